@@ -1,0 +1,119 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (TEST INFRASTRUCTURE).
+
+Run in the build container only (needs /root/reference):
+    python -m oracle.make_goldens
+Every array below is an output of the reference's own network/{posenet,fpn,anchors,utils}.py
+executed by the container's torch (CPU fp32), with seeded inputs (numpy PCG64) and the seeded
+weight sets of oracle/weights.py.  The entire_net ('both') branch needs a pth_nms; the
+reference's cffi binary is unusable, so oracle/nms_oracle.c stands in (recorded in `meta`).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import refshim, weights
+from .nms_oracle import nms_gpu_semantics, nms_cpu_semantics, nms_numpy_bruteforce
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def image(seed, shape):
+    return np.random.Generator(np.random.PCG64(seed)).standard_normal(shape, dtype=np.float32)
+
+
+def run_model(layers, kind, hw, batch, seed_img, full=True):
+    w = weights.make_weights(layers, kind, seed=0)
+    m = refshim.build_reference_model(layers, w)
+    x = torch.from_numpy(image(seed_img, (batch, 3) + hw))
+    out = {}
+    with torch.no_grad():
+        heat, saved = m([x, "keypoint_subnet"])
+        out["kp_heat"] = heat.numpy()
+        for i, s in enumerate(saved[:4]):
+            out["kp_saved%d" % i] = s.numpy()
+        _, (cls, reg, anc) = m([x, "detection_subnet"])
+        out["det_cls"], out["det_reg"], out["det_anchors"] = cls.numpy(), reg.numpy(), anc.numpy()
+        heat2, (sc, cl, bx) = m((x, "both"))
+        out["both_heat"] = heat2.numpy()
+        out["both_scores"], out["both_classes"], out["both_boxes"] = sc.numpy(), cl.numpy(), bx.numpy()
+    if not full:  # 480x640: keep the file small -- strided samples of the big maps
+        for k in ("kp_heat", "both_heat", "kp_saved0", "kp_saved1", "kp_saved2", "kp_saved3"):
+            out[k] = np.ascontiguousarray(out[k][:, :, ::4, ::4])
+        out["det_reg"] = np.ascontiguousarray(out["det_reg"][:, ::5])
+        out["det_anchors"] = np.ascontiguousarray(out["det_anchors"][:, ::5])
+    return out
+
+
+def nms_cases():
+    """Synthetic dets with the cfg3 recipe at small N plus edge cases."""
+    cases = {}
+    rng = np.random.Generator(np.random.PCG64(7))
+    for n_gt, per in ((5, 8), (20, 13), (100, 41)):
+        w = rng.uniform(20, 120, n_gt); h = rng.uniform(60, 300, n_gt)
+        cx = rng.uniform(0, 640, n_gt); cy = rng.uniform(0, 480, n_gt)
+        rows = []
+        for g in range(n_gt):
+            jw = w[g] * rng.uniform(0.9, 1.1, per); jh = h[g] * rng.uniform(0.9, 1.1, per)
+            jx = cx[g] + w[g] * rng.uniform(-0.1, 0.1, per); jy = cy[g] + h[g] * rng.uniform(-0.1, 0.1, per)
+            rows.append(np.stack([jx - jw / 2, jy - jh / 2, jx + jw / 2, jy + jh / 2], 1))
+        b = np.concatenate(rows, 0)
+        b[:, 0::2] = np.clip(b[:, 0::2], 0, 640); b[:, 1::2] = np.clip(b[:, 1::2], 0, 480)
+        s = rng.permutation(np.linspace(0.0501, 0.9999, len(b)))
+        cases["cfg3_%d" % len(b)] = np.concatenate([b, s[:, None]], 1).astype(np.float32)
+    cases["single"] = np.array([[10, 10, 50, 60, 0.9]], np.float32)
+    cases["identical"] = np.tile(np.array([[10, 10, 50, 60, 0.5]], np.float32), (70, 1))
+    cases["identical"][:, 4] = np.linspace(0.9, 0.1, 70)
+    cases["n65"] = cases["cfg3_260"][:65].copy()
+    cases["n128"] = cases["cfg3_260"][:128].copy()
+    return cases
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    meta = {"torch": torch.__version__, "numpy": np.__version__, "reference": refshim.REF_ROOT,
+            "nms_in_both_branch": "oracle/nms_oracle.c (reference cffi binary unusable)",
+            "weights": "oracle.weights.make_weights(layers, kind, seed=0)", "image": "PCG64(seed).standard_normal"}
+    ref = refshim.import_reference()
+    # anchors straight from the reference module
+    from network.anchors import Anchors
+    anc = {}
+    for hw in ((480, 640), (64, 96), (100, 130), (32, 32)):
+        anc["%dx%d" % hw] = Anchors()(torch.zeros(1, 3, *hw)).numpy()[0]
+    np.savez_compressed(os.path.join(OUT, "anchors.npz"), **anc)
+    # decode + clip straight from the reference modules
+    from network.utils import BBoxTransform, ClipBoxes
+    rng = np.random.Generator(np.random.PCG64(3))
+    a = torch.from_numpy(anc["64x96"])[None]
+    d = torch.from_numpy(rng.standard_normal((2, a.shape[1], 4), dtype=np.float32) * 2)
+    boxes = ClipBoxes()(BBoxTransform()(a, d), torch.zeros(2, 3, 64, 96))
+    np.savez_compressed(os.path.join(OUT, "decode.npz"), anchors=a.numpy(), deltas=d.numpy(), boxes=boxes.numpy())
+    # network forwards
+    runs = [("r50_cond_64x96_b2", 50, "conditioned", (64, 96), 2, 11, True),
+            ("r50_refinit_64x96_b1", 50, "refinit", (64, 96), 1, 12, True),
+            ("r101_cond_64x96_b1", 101, "conditioned", (64, 96), 1, 13, True),
+            ("r50_cond_480x640_b1", 50, "conditioned", (480, 640), 1, 14, False)]
+    for name, layers, kind, hw, b, seed, full in runs:
+        out = run_model(layers, kind, hw, b, seed, full)
+        out["meta"] = np.array(json.dumps(dict(meta, layers=layers, kind=kind, hw=hw, batch=b, img_seed=seed, full=full)))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+        print(name, {k: v.shape for k, v in out.items() if k != "meta"}, "K=%d" % len(out["both_scores"]))
+    # NMS cases: keep lists from the C restatement (cross-checked against brute-force numpy)
+    nm = {}
+    for k, dets in nms_cases().items():
+        for thr in (0.5, 0.3):
+            kg = nms_gpu_semantics(dets, thr)
+            assert np.array_equal(kg, nms_numpy_bruteforce(dets, thr)), k
+            kc = nms_cpu_semantics(dets, thr)
+            assert np.array_equal(kc, nms_numpy_bruteforce(dets, thr, ge=True)), k
+            nm["%s_dets" % k] = dets
+            nm["%s_keep_gt_%g" % (k, thr)] = kg
+            nm["%s_keep_ge_%g" % (k, thr)] = kc
+    np.savez_compressed(os.path.join(OUT, "nms.npz"), **nm)
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

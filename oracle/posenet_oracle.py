@@ -1,0 +1,255 @@
+"""Functional fp32 restatement of the reference forward (TEST INFRASTRUCTURE).
+
+Every function takes a flat state dict `sd` (name -> torch tensor, the reference's
+state_dict keys) and mirrors one reference routine; citations are into /root/reference.
+torch is used here only as the fp32 array library the reference itself calls
+(conv2d / batch_norm / max_pool2d are the third-party arithmetic, see oracle/__init__).
+
+Pinned against the real reference modules by oracle/make_goldens.py (container-side) and
+tests/test_oracle_vs_reference.py; tests/golden/*.npz hold the reference's outputs.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .anchors_oracle import anchors_for_image
+from .nms_oracle import nms_gpu_semantics
+
+BLOCKS = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
+
+
+def _conv(sd, name, x, stride=1, pad=0):
+    return F.conv2d(x, sd[name + ".weight"], sd.get(name + ".bias"), stride=stride, padding=pad)
+
+
+def _bn(sd, name, x):
+    # eval-mode BatchNorm2d, eps 1e-5 (fpn.py:15; poseNet.freeze_bn posenet.py:220-224)
+    return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"],
+                        sd[name + ".weight"], sd[name + ".bias"], False, 0.0, 1e-5)
+
+
+def bottleneck(sd, p, x, stride):
+    """fpn.py:28-34."""
+    out = F.relu(_bn(sd, p + "bn1", _conv(sd, p + "conv1", x)))
+    out = F.relu(_bn(sd, p + "bn2", _conv(sd, p + "conv2", out, stride=stride, pad=1)))
+    out = _bn(sd, p + "bn3", _conv(sd, p + "conv3", out))
+    if (p + "downsample.0.weight") in sd:
+        sc = _bn(sd, p + "downsample.1", _conv(sd, p + "downsample.0", x, stride=stride))
+    else:
+        sc = x
+    return F.relu(out + sc)
+
+
+def upsample_add(x, y):
+    """fpn.py:84-95: nearest upsample of x to y's size, plus y."""
+    return F.interpolate(x, size=y.shape[2:], mode="nearest") + y
+
+
+def backbone(sd, layers, x, pre="fpn."):
+    """fpn.py:99-105."""
+    c1 = F.relu(_bn(sd, pre + "bn1", _conv(sd, pre + "conv1", x, stride=2, pad=3)))
+    c = F.max_pool2d(c1, kernel_size=3, stride=2, padding=1)
+    feats = []
+    for li, (nblk, stride) in enumerate(zip(BLOCKS[layers], (1, 2, 2, 2)), start=1):
+        for b in range(nblk):
+            c = bottleneck(sd, "%slayer%d.%d." % (pre, li, b), c, stride if b == 0 else 1)
+        feats.append(c)
+    return feats  # c2, c3, c4, c5
+
+
+def detection_neck(sd, c3, c4, c5, pre="fpn."):
+    """fpn.py:107-114."""
+    p6 = _conv(sd, pre + "conv6", c5, stride=2, pad=1)
+    p7 = _conv(sd, pre + "conv7", F.relu(p6), stride=2, pad=1)
+    p5 = _conv(sd, pre + "latlayer1", c5)
+    p4 = upsample_add(p5, _conv(sd, pre + "latlayer2", c4))
+    p3 = upsample_add(p4, _conv(sd, pre + "latlayer3", c3))
+    p5 = _conv(sd, pre + "toplayer0", p5, pad=1)
+    p4 = _conv(sd, pre + "toplayer1", p4, pad=1)
+    p3 = _conv(sd, pre + "toplayer2", p3, pad=1)
+    return [p3, p4, p5, p6, p7]
+
+
+def keypoint_neck(sd, c2, c3, c4, c5, pre="fpn."):
+    """fpn.py:117-124."""
+    fp5 = _conv(sd, pre + "toplayer", c5)
+    fp4 = upsample_add(fp5, _conv(sd, pre + "flatlayer1", c4))
+    fp3 = upsample_add(fp4, _conv(sd, pre + "flatlayer2", c3))
+    fp2 = upsample_add(fp3, _conv(sd, pre + "flatlayer3", c2))
+    fp4 = _conv(sd, pre + "smooth1", fp4, pad=1)
+    fp3 = _conv(sd, pre + "smooth2", fp3, pad=1)
+    fp2 = _conv(sd, pre + "smooth3", fp2, pad=1)
+    return [fp2, fp3, fp4, fp5]
+
+
+def keypoint_head(sd, p2, p3, p4, p5):
+    """posenet.py:243-257 / 302-315."""
+    q5 = _conv(sd, "convs1", _conv(sd, "convt1", p5, pad=1), pad=1)
+    q4 = _conv(sd, "convs2", _conv(sd, "convt2", p4, pad=1), pad=1)
+    q3 = _conv(sd, "convs3", _conv(sd, "convt3", p3, pad=1), pad=1)
+    q2 = _conv(sd, "convs4", _conv(sd, "convt4", p2, pad=1), pad=1)
+    q5 = F.interpolate(q5, scale_factor=8, mode="nearest")
+    q4 = F.interpolate(q4, scale_factor=4, mode="nearest")
+    q3 = F.interpolate(q3, scale_factor=2, mode="nearest")
+    cat = torch.cat((q5, q4, q3, q2), 1)
+    return _conv(sd, "convfin", F.relu(_conv(sd, "conv2", cat, pad=1)))
+
+
+def intermediate_heads(sd, p2, p3, p4, p5):
+    """posenet.py:296-299."""
+    return [
+        _conv(sd, "convfin_k2", p2),
+        F.interpolate(_conv(sd, "convfin_k3", p3), scale_factor=2, mode="nearest"),
+        F.interpolate(_conv(sd, "convfin_k4", p4), scale_factor=4, mode="nearest"),
+        F.interpolate(_conv(sd, "convfin_k5", p5), scale_factor=8, mode="nearest"),
+    ]
+
+
+def retina_head(sd, head, feat, sigmoid):
+    """posenet.py:51-69 (RegressionModel.forward) / :96-117 (ClassificationModel.forward)."""
+    out = feat
+    for n in ("conv1", "conv2", "conv3", "conv4"):
+        out = F.relu(_conv(sd, "%s.%s" % (head, n), out, pad=1))
+    out = _conv(sd, head + ".output", out, pad=1)
+    if sigmoid:
+        out = torch.sigmoid(out)
+    out = out.permute(0, 2, 3, 1).contiguous()
+    return out.view(out.shape[0], -1, 1 if sigmoid else 4)
+
+
+def detection_heads(sd, feats):
+    """posenet.py:262-263."""
+    reg = torch.cat([retina_head(sd, "regressionModel", f, False) for f in feats], dim=1)
+    cls = torch.cat([retina_head(sd, "classificationModel", f, True) for f in feats], dim=1)
+    return cls, reg
+
+
+def decode_boxes(anchors, deltas):
+    """network/utils.py:19-43 (BBoxTransform.forward), mean 0, std [.1,.1,.2,.2]."""
+    std = torch.tensor([0.1, 0.1, 0.2, 0.2], dtype=torch.float32, device=deltas.device)
+    widths = anchors[:, :, 2] - anchors[:, :, 0]
+    heights = anchors[:, :, 3] - anchors[:, :, 1]
+    ctr_x = anchors[:, :, 0] + 0.5 * widths
+    ctr_y = anchors[:, :, 1] + 0.5 * heights
+    dx = deltas[:, :, 0] * std[0] + 0
+    dy = deltas[:, :, 1] * std[1] + 0
+    dw = deltas[:, :, 2] * std[2] + 0
+    dh = deltas[:, :, 3] * std[3] + 0
+    pcx = ctr_x + dx * widths
+    pcy = ctr_y + dy * heights
+    pw = torch.exp(dw) * widths
+    ph = torch.exp(dh) * heights
+    return torch.stack([pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw, pcy + 0.5 * ph], dim=2)
+
+
+def clip_boxes(boxes, height, width):
+    """network/utils.py:51-61 (only these four clamps)."""
+    boxes = boxes.clone()
+    boxes[:, :, 0] = torch.clamp(boxes[:, :, 0], min=0)
+    boxes[:, :, 1] = torch.clamp(boxes[:, :, 1], min=0)
+    boxes[:, :, 2] = torch.clamp(boxes[:, :, 2], max=width)
+    boxes[:, :, 3] = torch.clamp(boxes[:, :, 3], max=height)
+    return boxes
+
+
+def postprocess_image(cls_i, boxes_i, score_thresh=0.05, iou_thresh=0.5, ge=False):
+    """posenet.py:269-285 for ONE image: filter > 0.05, NMS, gather.
+
+    cls_i [A,1], boxes_i [A,4] (decoded + clipped).  Returns (scores[K], classes[K] int64,
+    boxes[K,4], keep_idx[K] int64 = indices into the filtered set, descending score)."""
+    scores = cls_i.max(dim=1)[0]
+    m = scores > score_thresh
+    if int(m.sum()) == 0:
+        z = torch.zeros(0)
+        return z, torch.zeros(0, dtype=torch.int64), torch.zeros(0, 4), torch.zeros(0, dtype=torch.int64)
+    fcls, fbox, fsc = cls_i[m], boxes_i[m], scores[m]
+    dets = torch.cat([fbox, fsc[:, None]], dim=1).cpu().numpy().astype(np.float32)
+    keep = torch.from_numpy(nms_gpu_semantics(dets, iou_thresh, ge=ge))
+    ksc, kcl = fcls[keep].max(dim=1)
+    return ksc, kcl, fbox[keep], keep
+
+
+def forward(sd, layers, img, subnet_name):
+    """posenet.py:226-285 dispatch.  img fp32 NCHW."""
+    H, W = img.shape[2:]
+    if subnet_name == "prn_subnet":
+        return prn_forward(sd, img)
+    c2, c3, c4, c5 = backbone(sd, layers, img)
+    if subnet_name == "keypoint_subnet":
+        p2, p3, p4, p5 = keypoint_neck(sd, c2, c3, c4, c5)
+        saved = intermediate_heads(sd, p2, p3, p4, p5)
+        heat = keypoint_head(sd, p2, p3, p4, p5)
+        saved.append(heat)
+        return heat, saved
+    if subnet_name == "detection_subnet":
+        feats = detection_neck(sd, c3, c4, c5)
+        cls, reg = detection_heads(sd, feats)
+        anchors = torch.from_numpy(anchors_for_image(H, W))[None].to(img.device)
+        return [], [cls, reg, anchors]
+    # entire_net
+    p2, p3, p4, p5 = keypoint_neck(sd, c2, c3, c4, c5)
+    heat = keypoint_head(sd, p2, p3, p4, p5)
+    feats = detection_neck(sd, c3, c4, c5)
+    cls, reg = detection_heads(sd, feats)
+    anchors = torch.from_numpy(anchors_for_image(H, W))[None].to(img.device)
+    boxes = clip_boxes(decode_boxes(anchors, reg), H, W)
+    ksc, kcl, kbox, _ = postprocess_image(cls[0], boxes[0])
+    return heat, [ksc, kcl, kbox], dict(cls=cls, reg=reg, boxes=boxes)
+
+
+def prn_forward(sd, x):
+    """posenet.py:337-350 (eval mode: dropout is identity)."""
+    res = x.reshape(x.shape[0], -1)
+    out = F.relu(F.linear(res, sd["prn.dens1.weight"], sd["prn.dens1.bias"]))
+    out = F.relu(F.linear(out, sd["prn.bneck.weight"], sd["prn.bneck.bias"]))
+    out = F.relu(F.linear(out, sd["prn.dens2.weight"], sd["prn.dens2.bias"]))
+    out = torch.softmax(out + res, dim=1)
+    out = out.view(x.shape[0], x.shape[1], x.shape[2], 17)
+    return out, [out]
+
+
+def conv_flops_entire(layers, H=480, W=640):
+    """Algorithmic conv FLOPs/img of the entire_net graph (2*MAC), SURVEY.md 8(d)."""
+    from .weights import param_spec
+
+    spec = param_spec(layers)
+    total = 0.0
+    # spatial size of each conv's OUTPUT, derived from the graph
+    h4, w4 = H // 4, W // 4
+    def out_hw(name):
+        if name == "fpn.conv1":
+            return H // 2, W // 2
+        if name.startswith("fpn.layer"):
+            li = int(name[len("fpn.layer")])
+            b = int(name.split(".")[2])
+            s = (1, 2, 4, 8)[li - 1]
+            hh, ww = h4 // s, w4 // s
+            if li > 1 and b == 0 and name.endswith("conv1"):
+                return hh * 2, ww * 2  # stride sits on conv2 (fpn.py:16)
+            return hh, ww
+        m = {"fpn.conv6": 64, "fpn.conv7": 128, "fpn.latlayer1": 32, "fpn.latlayer2": 16, "fpn.latlayer3": 8,
+             "fpn.toplayer0": 32, "fpn.toplayer1": 16, "fpn.toplayer2": 8, "fpn.toplayer": 32,
+             "fpn.flatlayer1": 16, "fpn.flatlayer2": 8, "fpn.flatlayer3": 4, "fpn.smooth1": 16,
+             "fpn.smooth2": 8, "fpn.smooth3": 4, "convt1": 32, "convs1": 32, "convt2": 16, "convs2": 16,
+             "convt3": 8, "convs3": 8, "convt4": 4, "convs4": 4, "conv2": 4, "convfin": 4}
+        if name in m:
+            d = m[name]
+            return -(-H // d), -(-W // d)
+        return None
+    for k, shp in spec.items():
+        if not (k.endswith(".weight") and len(shp) == 4):
+            continue
+        name = k[:-len(".weight")]
+        if name.startswith("convfin_k"):
+            continue  # keypoint_subnet mode only
+        mac = shp[0] * shp[1] * shp[2] * shp[3]
+        if name.startswith(("regressionModel", "classificationModel")):
+            cells = sum((-(-H // d)) * (-(-W // d)) for d in (8, 16, 32, 64, 128))
+            total += 2.0 * mac * cells
+            continue
+        hw = out_hw(name)
+        assert hw is not None, name
+        total += 2.0 * mac * hw[0] * hw[1]
+    return total

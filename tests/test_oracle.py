@@ -1,0 +1,116 @@
+"""CPU tests: the oracle restatement against the committed golden vectors (made from the reference)
+and, where /root/reference is present, against the live reference modules."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import anchors_oracle, nms_oracle, posenet_oracle as po, refshim, weights
+
+torch.set_grad_enabled(False)
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_anchors_bit_exact(golden_dir):
+    g = _load(golden_dir, "anchors.npz")
+    for key in g.files:
+        h, w = map(int, key.split("x"))
+        a = anchors_oracle.anchors_for_image(h, w)
+        assert a.dtype == np.float32 and a.shape == g[key].shape
+        assert np.array_equal(a.view(np.uint32), g[key].view(np.uint32)), key
+    assert anchors_oracle.anchors_for_image(480, 640).shape == (57600, 4)
+
+
+def test_decode_clip(golden_dir):
+    g = _load(golden_dir, "decode.npz")
+    b = po.clip_boxes(po.decode_boxes(torch.from_numpy(g["anchors"]), torch.from_numpy(g["deltas"])), 64, 96)
+    assert np.array_equal(b.numpy(), g["boxes"])
+
+
+def test_nms_goldens_and_bruteforce(golden_dir):
+    g = _load(golden_dir, "nms.npz")
+    names = sorted({k[: -len("_dets")] for k in g.files if k.endswith("_dets")})
+    assert names
+    for n in names:
+        dets = g[n + "_dets"]
+        for thr in (0.5, 0.3):
+            kg = nms_oracle.nms_gpu_semantics(dets, thr)
+            kc = nms_oracle.nms_cpu_semantics(dets, thr)
+            assert np.array_equal(kg, g["%s_keep_gt_%g" % (n, thr)])
+            assert np.array_equal(kc, g["%s_keep_ge_%g" % (n, thr)])
+            assert np.array_equal(kg, nms_oracle.nms_numpy_bruteforce(dets, thr))
+
+
+def test_nms_known_answers():
+    # IoU with the +1 convention: boxes [0,0,9,9] and [0,0,9,19]: inter 100, union 200 -> exactly 0.5
+    d = np.array([[0, 0, 9, 9, 0.9], [0, 0, 9, 19, 0.8], [100, 100, 120, 120, 0.7]], np.float32)
+    assert nms_oracle.nms_gpu_semantics(d, 0.5).tolist() == [0, 1, 2]      # '>' keeps the tie
+    assert nms_oracle.nms_cpu_semantics(d, 0.5).tolist() == [0, 2]         # '>=' suppresses it
+    assert nms_oracle.nms_gpu_semantics(d, 0.5, ge=True).tolist() == [0, 2]
+    assert nms_oracle.nms_gpu_semantics(np.zeros((0, 5), np.float32), 0.5).shape == (0,)
+    # order: descending score, indices refer to the input rows
+    d2 = d[[2, 0, 1]]
+    assert nms_oracle.nms_gpu_semantics(d2, 0.5).tolist() == [1, 2, 0]
+    # mask/reduce decomposition equals the fused entry point
+    rng = np.random.default_rng(0)
+    xy = rng.uniform(0, 200, (300, 2)); wh = rng.uniform(5, 80, (300, 2))
+    dets = np.concatenate([xy, xy + wh, rng.permutation(300)[:, None] / 300.0], 1).astype(np.float32)
+    order = nms_oracle.stable_desc_order(dets[:, 4])
+    m = nms_oracle.nms_mask(dets[order], 0.5)
+    assert np.array_equal(order[nms_oracle.reduce_mask(m, 300)], nms_oracle.nms_gpu_semantics(dets, 0.5))
+
+
+@pytest.mark.parametrize("name", ["r50_cond_64x96_b2", "r50_refinit_64x96_b1", "r101_cond_64x96_b1"])
+def test_network_restatement_vs_golden(golden_dir, name):
+    g = _load(golden_dir, name + ".npz")
+    meta = json.loads(str(g["meta"]))
+    sd = weights.to_torch_state_dict(weights.make_weights(meta["layers"], meta["kind"], seed=0))
+    x = torch.from_numpy(np.random.Generator(np.random.PCG64(meta["img_seed"])).standard_normal(
+        (meta["batch"], 3) + tuple(meta["hw"]), dtype=np.float32))
+    heat, saved = po.forward(sd, meta["layers"], x, "keypoint_subnet")
+    # same torch build, same op sequence -> identical; a different oneDNN path may reorder sums
+    tol = dict(rtol=1e-4, atol=1e-5 * float(np.abs(g["kp_heat"]).max()))
+    np.testing.assert_allclose(heat.numpy(), g["kp_heat"], **tol)
+    for i in range(4):
+        np.testing.assert_allclose(saved[i].numpy(), g["kp_saved%d" % i], rtol=1e-4,
+                                   atol=1e-5 * float(np.abs(g["kp_saved%d" % i]).max()))
+    _, (cls, reg, anc) = po.forward(sd, meta["layers"], x, "detection_subnet")
+    np.testing.assert_allclose(cls.numpy(), g["det_cls"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(reg.numpy(), g["det_reg"], rtol=1e-4, atol=1e-5 * float(np.abs(g["det_reg"]).max()))
+    assert np.array_equal(anc.numpy(), g["det_anchors"])
+    heat2, (sc, cl, bx), _ = po.forward(sd, meta["layers"], x, "both")
+    np.testing.assert_allclose(heat2.numpy(), g["both_heat"], **tol)
+    assert sc.shape == g["both_scores"].shape
+    if len(sc):
+        np.testing.assert_allclose(sc.numpy(), g["both_scores"], rtol=1e-4)
+        np.testing.assert_allclose(bx.numpy(), g["both_boxes"], rtol=1e-4, atol=1e-3)
+        assert np.array_equal(cl.numpy(), g["both_classes"])
+
+
+def test_param_spec_counts():
+    assert len(weights.param_spec(50)) == 402 and len(weights.param_spec(101)) == 708
+    assert abs(po.conv_flops_entire(101) / 1e9 - 270.12) < 0.01
+    assert abs(po.conv_flops_entire(50) / 1e9 - 224.67) < 0.01
+
+
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference not present")
+def test_live_reference_keys_and_forward():
+    w = weights.make_weights(50, "conditioned", seed=0)
+    m = refshim.build_reference_model(50, w)
+    spec = weights.param_spec(50)
+    assert list(m.state_dict().keys()) == list(spec.keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(spec[k]), k
+    x = torch.from_numpy(np.random.Generator(np.random.PCG64(5)).standard_normal((1, 3, 64, 64), dtype=np.float32))
+    sd = weights.to_torch_state_dict(w)
+    heat, saved = m([x, "keypoint_subnet"])
+    oh, osv = po.forward(sd, 50, x, "keypoint_subnet")
+    assert torch.equal(heat, oh) and all(torch.equal(a, b) for a, b in zip(saved, osv))
+    h2, (s, c, b) = m((x, "both"))
+    oh2, (os_, oc, ob), _ = po.forward(sd, 50, x, "both")
+    assert torch.equal(h2, oh2) and torch.equal(s, os_) and torch.equal(b, ob)
