@@ -1,0 +1,141 @@
+/* mpn_b200.h -- C ABI of libmpn_b200.so, the B200 (sm_100a) hot path of MultiPoseNet.
+ *
+ * The reference's only native boundary is lib/nms (cffi):
+ *     int cpu_nms(THLongTensor* keep_out, THLongTensor* num_out, THFloatTensor* boxes,
+ *                 THLongTensor* order, THFloatTensor* areas, float thresh);        lib/nms/src/nms.h:1
+ *     int gpu_nms(THLongTensor* keep_out, THLongTensor* num_out, THCudaTensor* boxes,
+ *                 float thresh);                                                   lib/nms/src/nms_cuda.h:1
+ * everything else on the path is a torch.nn call from network/posenet.py / network/fpn.py.  This
+ * header therefore (1) mirrors gpu_nms/cpu_nms on plain pointers (mpn_nms*), and (2) exposes one entry
+ * point per torch.nn call-site family of the path (conv2d+epilogue, max-pool, layout, decode/filter)
+ * so the Python host mirror of network/posenet.py can drive them with raw device pointers.
+ *
+ * Conventions: plain `extern "C"`, raw DEVICE pointers unless a parameter says host, sizes as ints,
+ * an explicit stream (void* = cudaStream_t; NULL = legacy default stream), caller-owned outputs and
+ * workspaces, no global mutable state (error text is thread-local).  Return 0 = success, <0 = error
+ * (text via mpn_last_error()).  The reference's "1 = success" convention (nms.c:68) is restored by the
+ * Python shim lib/nms/pth_nms.py.
+ */
+#ifndef MPN_B200_H_
+#define MPN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPN_OK 0
+#define MPN_ERR_ARG (-1)
+#define MPN_ERR_CUDA (-2)
+#define MPN_ERR_UNSUPPORTED (-3)
+
+/* Activation storage formats (NHWC, channel stride given separately). */
+#define MPN_FMT_F32 0    /* one fp32 plane                    -> CUDA-core fp32 path           */
+#define MPN_FMT_BF16 1   /* one bf16 plane                    -> tcgen05 single-pass bf16      */
+#define MPN_FMT_BF16X2 2 /* bf16 hi plane + bf16 lo plane     -> tcgen05 3-pass split (~fp32)  */
+
+/* Output modes of a conv epilogue. */
+#define MPN_OUT_ACT 0      /* activation format `fmt`, NHWC                                   */
+#define MPN_OUT_F32_NHWC 1 /* fp32 [N, OH*rep, OW*rep, Cout] (== permute(0,2,3,1), posenet.py:67,111) */
+#define MPN_OUT_F32_NCHW 2 /* fp32 [N, Cout, OH*rep, OW*rep] (the boundary layout of the heat maps)   */
+
+/* Epilogue flags. */
+#define MPN_EPI_RELU 1
+#define MPN_EPI_SIGMOID 2
+
+typedef struct mpn_conv_desc {
+  /* problem: y = epilogue(conv2d(x, w)); torch.nn.Conv2d semantics (cross-correlation, zero pad) */
+  int N, H, W, Cin;          /* input  [N,H,W,Cin]  (NHWC)                                    */
+  int Cout, R, S;            /* filter [Cout][R][S][Cin] for tcgen05, [R][S][Cin][CoutPad] for fp32 */
+  int stride, pad;
+  int OH, OW;                /* (H + 2*pad - R)/stride + 1                                    */
+  int fmt;                   /* MPN_FMT_* of x, residual, upsample source and MPN_OUT_ACT output */
+  int in_cstride;            /* channel stride (elements per pixel) of x                      */
+  int flags;                 /* MPN_EPI_*                                                     */
+  /* epilogue, applied in this order: v = acc*scale[c] + bias[c]; v += residual; v += up; relu/sigmoid */
+  int res_cstride;           /* residual [N,OH,OW,res_cstride] (0 = none)                     */
+  int up_h, up_w, up_cstride;/* nearest-upsampled addend [N,up_h,up_w,up_cstride] (0 = none), fpn.py:84-95 */
+  int out_mode;              /* MPN_OUT_*                                                     */
+  int out_cstride;           /* channels per pixel of the destination (>= out_coffset+Cout)   */
+  int out_coffset;           /* first destination channel (concat writes, posenet.py:254)     */
+  int out_rep;               /* nearest-upsample replication factor on store: 1,2,4,8 (posenet.py:180-182) */
+  long long out_nstride;     /* elements between images in the destination (0 = dense)        */
+  int w_cout_pad;            /* fp32 path: padded Cout of the [R][S][Cin][CoutPad] filter     */
+  int reserved;
+} mpn_conv_desc;
+
+typedef struct mpn_conv_ptrs {
+  const void* x_hi;   const void* x_lo;     /* lo planes only for MPN_FMT_BF16X2 */
+  const void* w_hi;   const void* w_lo;
+  const float* scale; const float* bias;    /* per-Cout fp32, either may be NULL */
+  const void* res_hi; const void* res_lo;
+  const void* up_hi;  const void* up_lo;
+  void* y_hi;         void* y_lo;
+} mpn_conv_ptrs;
+
+const char* mpn_last_error(void);
+int mpn_version(void);
+/* 1 if the current device can run the tcgen05 kernels (compute capability 10.x). */
+int mpn_device_supports_tcgen05(void);
+
+/* ---- conv2d (+BN-fold/bias/residual/upsample-add/ReLU/sigmoid): fpn.py:14-25,42-74,99-124,
+ *      posenet.py:37-49,79-92,165-187.  fmt F32 -> CUDA-core kernel, BF16/BF16X2 -> tcgen05+TMA. */
+int mpn_conv2d_fwd(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream);
+/* fp32-input variant used for the stem: x is fp32 NHWC (Cin may be 3), output in d->fmt. */
+int mpn_conv2d_fwd_f32in(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream);
+
+/* ---- filter packing (host-side weights are torch OIHW fp32 on the device) */
+/* OIHW fp32 -> [R][S][Cin][CoutPad] fp32 (zero padded) */
+int mpn_pack_filter_f32(const float* w_oihw, float* dst, int Cout, int Cin, int R, int S, int CoutPad, void* stream);
+/* OIHW fp32 -> [Cout][R][S][Cin] bf16 hi (+ lo = bf16(w - hi) if dst_lo != NULL) */
+int mpn_pack_filter_bf16(const float* w_oihw, void* dst_hi, void* dst_lo, int Cout, int Cin, int R, int S, void* stream);
+/* BatchNorm (eval) fold: scale = gamma/sqrt(var+eps), bias = beta - mean*scale   (fpn.py:15-19,25,43) */
+int mpn_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                float* scale, float* bias, int C, void* stream);
+
+/* ---- layout / elementwise */
+/* fp32 NCHW -> NHWC in `fmt` (dst_lo for BF16X2); cstride >= C, padding channels are zeroed */
+int mpn_nchw_to_nhwc(const float* src, void* dst_hi, void* dst_lo, int N, int C, int H, int W, int cstride, int fmt, void* stream);
+/* NHWC `fmt` -> fp32 NCHW (first C channels) */
+int mpn_nhwc_to_nchw(const void* src_hi, const void* src_lo, float* dst, int N, int C, int H, int W, int cstride, int fmt, void* stream);
+/* F.max_pool2d(kernel 3, stride 2, pad 1) on NHWC (fpn.py:100) */
+int mpn_maxpool3x3s2(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H, int W, int C, int fmt, void* stream);
+/* y = relu(x) on n elements (fpn.py:108: conv7(F.relu(p6))) */
+int mpn_relu(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, long long n, int fmt, void* stream);
+
+/* ---- detection post-process: anchors.py:21-37, utils.py:19-61, posenet.py:269-285, lib/nms */
+/* number of anchors for an image (levels 3..7, 9 per cell) */
+int mpn_num_anchors(int H, int W);
+/* HOST output [A,4] fp32, bit-identical to Anchors.forward (float64 math, cast to fp32) */
+int mpn_generate_anchors(int H, int W, float* anchors_host);
+/* boxes[b,a,:] = clip(decode(anchors[a], reg[b,a,:])); device pointers; reg [B,A,4], boxes [B,A,4];
+ * H <= 0 or W <= 0: decode only (no clipping) */
+int mpn_decode_clip(const float* anchors, const float* reg, float* boxes, int B, int A, int H, int W, void* stream);
+/* Per image: select a where cls[b,a] > score_thresh (order preserved, posenet.py:271-279), sort by
+ * score descending (stable), NMS (IoU > iou_thresh, or >= if ge), and write
+ *   cand_idx  [B,max_cand] int32 : anchor index of each candidate in filtered order
+ *   cand_cnt  [B]          int32 : number of candidates (N_s)
+ *   keep_idx  [B,max_cand] int64 : kept indices INTO THE FILTERED SET, descending score (== pth_nms)
+ *   keep_cnt  [B]          int32
+ *   out_scores[B,max_cand] fp32, out_boxes [B,max_cand,4] fp32 : gathered per kept index
+ * Candidates beyond max_cand are dropped (cand_cnt still reports the true count so the host can detect it).
+ * workspace: mpn_detect_workspace_bytes(B, A, max_cand) bytes of device memory. */
+size_t mpn_detect_workspace_bytes(int B, int A, int max_cand);
+int mpn_filter_sort_nms(const float* cls, const float* boxes, int B, int A, float score_thresh, float iou_thresh, int ge,
+                        int max_cand, int32_t* cand_idx, int32_t* cand_cnt, int64_t* keep_idx, int32_t* keep_cnt,
+                        float* out_scores, float* out_boxes, void* workspace, size_t workspace_bytes, void* stream);
+/* pth_nms equivalents on raw device memory.  dets [n,5] (x1,y1,x2,y2,score), any order.
+ * keep [n] int64 (device), num_out [1] int32 (device). Mirrors gpu_nms (ge=0) / cpu_nms (ge=1) + the
+ * sort/gather of pth_nms.py:25-44. workspace: mpn_nms_workspace_bytes(n). */
+size_t mpn_nms_workspace_bytes(int n);
+int mpn_nms(const float* dets, int n, float iou_thresh, int ge, int64_t* keep, int32_t* num_out,
+            void* workspace, size_t workspace_bytes, void* stream);
+/* mask stage alone on already-sorted dets (== _nms() of nms_kernel.cu:73): mask [n, ceil(n/64)] u64 */
+int mpn_nms_mask(const float* sorted_dets, int n, float iou_thresh, int ge, uint64_t* mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPN_B200_H_ */

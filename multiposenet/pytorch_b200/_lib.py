@@ -1,0 +1,82 @@
+"""ctypes binding of the C ABI in include/mpn_b200.h (libmpn_b200.so, built in-tree by csrc/build.py).
+
+No fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmpn_b200.so")
+
+FMT_F32, FMT_BF16, FMT_BF16X2 = 0, 1, 2
+OUT_ACT, OUT_F32_NHWC, OUT_F32_NCHW = 0, 1, 2
+EPI_RELU, EPI_SIGMOID = 1, 2
+
+c_void_p, c_int, c_float, c_size_t, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_longlong
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in (
+        "N", "H", "W", "Cin", "Cout", "R", "S", "stride", "pad", "OH", "OW", "fmt", "in_cstride", "flags",
+        "res_cstride", "up_h", "up_w", "up_cstride", "out_mode", "out_cstride", "out_coffset", "out_rep")] + [
+        ("out_nstride", c_ll), ("w_cout_pad", c_int), ("reserved", c_int)]
+
+
+class ConvPtrs(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "x_hi", "x_lo", "w_hi", "w_lo", "scale", "bias", "res_hi", "res_lo", "up_hi", "up_lo", "y_hi", "y_lo")]
+
+
+class MpnError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGS = {
+    "mpn_last_error": (ctypes.c_char_p, []),
+    "mpn_version": (c_int, []),
+    "mpn_device_supports_tcgen05": (c_int, []),
+    "mpn_conv2d_fwd": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvPtrs), c_void_p]),
+    "mpn_conv2d_fwd_f32in": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvPtrs), c_void_p]),
+    "mpn_pack_filter_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_pack_filter_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_fold_bn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "mpn_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_relu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "mpn_num_anchors": (c_int, [c_int, c_int]),
+    "mpn_generate_anchors": (c_int, [c_int, c_int, c_void_p]),
+    "mpn_decode_clip": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_detect_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mpn_filter_sort_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mpn_nms_workspace_bytes": (c_size_t, [c_int]),
+    "mpn_nms": (c_int, [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mpn_nms_mask": (c_int, [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p]),
+}
+
+EXPORTS = tuple(_SIGS.keys())
+
+
+def lib():
+    """The loaded library; raises MpnError if it has not been built (python __graft_entry__.py / csrc/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MpnError("libmpn_b200.so is missing (%s). Build it with `python -m multiposenet.pytorch_b200.csrc.build` "
+                           "or __graft_entry__.build(); there is no CPU / eager fallback." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)  # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().mpn_last_error()
+        raise MpnError("%s failed (%d): %s" % (what or "mpn call", rc, msg.decode() if msg else "?"))

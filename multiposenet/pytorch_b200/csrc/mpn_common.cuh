@@ -1,0 +1,59 @@
+// Shared helpers for libmpn_b200.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../../include/mpn_b200.h"
+
+void mpn_set_error(const char* fmt, ...);
+
+#define MPN_CHECK_ARG(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      mpn_set_error(__VA_ARGS__);           \
+      return MPN_ERR_ARG;                   \
+    }                                       \
+  } while (0)
+
+#define MPN_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      mpn_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return MPN_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define MPN_LAUNCH_OK() MPN_CUDA_OK(cudaGetLastError())
+
+static inline int mpn_divup(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- activation element access shared by the CUDA-core kernels ---------------------------------
+__device__ __forceinline__ float mpn_bf16_bits_to_float(unsigned short b) { return __uint_as_float(((unsigned)b) << 16); }
+
+__device__ __forceinline__ float mpn_load_act(const void* hi, const void* lo, long long idx, int fmt) {
+  if (fmt == MPN_FMT_F32) return ((const float*)hi)[idx];
+  float v = __bfloat162float(((const __nv_bfloat16*)hi)[idx]);
+  if (fmt == MPN_FMT_BF16X2) v += __bfloat162float(((const __nv_bfloat16*)lo)[idx]);
+  return v;
+}
+
+__device__ __forceinline__ void mpn_store_act(void* hi, void* lo, long long idx, int fmt, float v) {
+  if (fmt == MPN_FMT_F32) {
+    ((float*)hi)[idx] = v;
+  } else {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    ((__nv_bfloat16*)hi)[idx] = h;
+    if (fmt == MPN_FMT_BF16X2) ((__nv_bfloat16*)lo)[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// PyTorch legacy 'nearest' source index (fpn.py:95 F.upsample(size=...)): floor(dst * in/out) clamped
+__device__ __forceinline__ int mpn_nearest_src(int dst, int in_size, int out_size) {
+  if (out_size == 2 * in_size) return dst >> 1;
+  float scale = (float)in_size / (float)out_size;
+  int s = (int)floorf((float)dst * scale);
+  return s < in_size - 1 ? s : in_size - 1;
+}

@@ -1,0 +1,564 @@
+// tcgen05 + TMA implicit-GEMM convolution for sm_100a (NHWC bf16 planes, fp32 accumulation in TMEM).
+//
+//   D[pixel, cout] = sum_{tap (r,s)} sum_{c}  X[n, oh*stride + r - pad, ow*stride + s - pad, c] * W[cout, r, s, c]
+//
+// GEMM view: M = a TW x TH x TN box of output pixels (<= 128 rows), N = BN output channels, K walks
+// the filter taps and 64-channel blocks.  For every (tap, channel block) ONE 4-D TMA box load brings
+// the shifted input window [64ch, TW, TH, TN] into a 128B-swizzled K-major shared-memory tile; the
+// zero padding of the convolution is the TMA out-of-bounds fill, and stride-2 convolutions read one of
+// four "phase" views of the input (tensor maps with doubled pixel strides and an offset base), so no
+// im2col buffer ever exists in HBM.  The filter is a plain 2-D [Cout, R*S*Cin] K-major tensor.
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer           (mbarrier full/empty ring of STAGES stages)
+//   warp 1 lane 0 : tcgen05.mma issuer     (accumulators double-buffered in TMEM, 2 x BN columns)
+//   warp 2        : TMEM allocate / free
+//   warps 4..7    : epilogue: tcgen05.ld -> BN-fold scale/bias, residual, nearest-upsample add, ReLU/
+//                   sigmoid -> bf16 (hi/lo) NHWC, or fp32 NHWC / NCHW, optionally replicated x2/x4/x8
+// Precision modes: MPN_FMT_BF16   one bf16 plane per operand, one MMA per K step;
+//                  MPN_FMT_BF16X2 hi/lo bf16 planes (x = hi + lo to ~2^-17), three MMAs per K step
+//                  (hi*hi + lo*hi + hi*lo) accumulated in fp32 -> fp32-grade parity with the reference.
+#include <cuda.h>
+
+#include "mpn_common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;           // bf16 elements = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int BAR_BYTES = 256;
+
+struct Maps {
+  CUtensorMap a[2][4];  // [plane hi/lo][phase hp*2+wp]
+  CUtensorMap b[2];     // [plane]
+};
+
+struct TcParams {
+  int N, OH, OW, Cout;
+  int TW, TH, TN, rows;
+  int tiles_w, tiles_h, tiles_n, tiles_co, total_tiles;
+  int R, S, stride, pad, kb_per_tap, Cin;
+  int phase_empty;  // bit p set: phase view p has no pixels (tiny maps) -> load an all-OOB box instead
+  const float* scale;
+  const float* bias;
+  const __nv_bfloat16* res_hi;
+  const __nv_bfloat16* res_lo;
+  int res_cstride;
+  const __nv_bfloat16* up_hi;
+  const __nv_bfloat16* up_lo;
+  int up_h, up_w, up_cstride;
+  int flags, out_mode, out_cstride, out_coffset, out_rep;
+  long long out_nstride;
+  void* y_hi;
+  void* y_lo;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("mpn conv_tc: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+
+#define TMEM_LD_32x32b_X32(taddr, v)                                                                                     \
+  asm volatile(                                                                                                          \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                          \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                          \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),      \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),           \
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),          \
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                        \
+      : "r"(taddr)                                                                                                       \
+      : "memory")
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_lo_f(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+// add 32 bf16 channels at ptr (16-byte aligned) into v
+__device__ __forceinline__ void add_bf16x32(float* v, const __nv_bfloat16* ptr) {
+  const uint4* q = reinterpret_cast<const uint4*>(ptr);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t = __ldg(q + i);
+    v[i * 8 + 0] += bf16_lo_f(t.x); v[i * 8 + 1] += bf16_hi_f(t.x);
+    v[i * 8 + 2] += bf16_lo_f(t.y); v[i * 8 + 3] += bf16_hi_f(t.y);
+    v[i * 8 + 4] += bf16_lo_f(t.z); v[i * 8 + 5] += bf16_hi_f(t.z);
+    v[i * 8 + 6] += bf16_lo_f(t.w); v[i * 8 + 7] += bf16_hi_f(t.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool SPLIT, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ Maps maps, const TcParams P) {
+  constexpr int PLANES = SPLIT ? 2 : 1;
+  constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + B_TILE_BYTES);
+  constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k_iters = P.R * P.S * P.kb_per_tap;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int p = 0; p < PLANES; ++p) {
+      prefetch_tmap(&maps.b[p]);
+      prefetch_tmap(&maps.a[p][0]);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0 && lane == 0) {
+    // =============================== TMA producer ===============================
+    const uint32_t tx_bytes = (uint32_t)PLANES * (uint32_t)(P.rows * BLOCK_K * 2 + B_TILE_BYTES);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int co_t = tile % P.tiles_co;
+      int mt = tile / P.tiles_co;
+      const int tw_i = mt % P.tiles_w;
+      mt /= P.tiles_w;
+      const int th_i = mt % P.tiles_h;
+      const int tn_i = mt / P.tiles_h;
+      const int ow0 = tw_i * P.TW, oh0 = th_i * P.TH, n0 = tn_i * P.TN, co0 = co_t * BN;
+      for (int tap = 0; tap < P.R * P.S; ++tap) {
+        const int r = tap / P.S, s = tap - r * P.S;
+        const int dh = r - P.pad, dw = s - P.pad;
+        int ph = 0, hc, wc;
+        if (P.stride == 1) {
+          hc = oh0 + dh;
+          wc = ow0 + dw;
+        } else {  // stride 2: input row 2*oh + dh lives in phase view (dh & 1) at row oh + (dh - (dh&1))/2
+          const int hp = dh & 1, wp = dw & 1;
+          hc = oh0 + (dh - hp) / 2;
+          wc = ow0 + (dw - wp) / 2;
+          ph = hp * 2 + wp;
+        }
+        if ((P.phase_empty >> ph) & 1) {  // view without pixels: any fully out-of-range box reads zeros
+          ph = 0;
+          hc = 1 << 24;
+        }
+        for (int kb = 0; kb < P.kb_per_tap; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), tx_bytes);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + PLANES * A_TILE_BYTES;
+          const int kcol = tap * P.Cin + kb * BLOCK_K;
+#pragma unroll
+          for (int p = 0; p < PLANES; ++p) {
+            tma_load_4d(sa + p * A_TILE_BYTES, &maps.a[p][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
+            tma_load_2d(sb + p * B_TILE_BYTES, &maps.b[p], full_bar(stage), kcol, co0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // =============================== MMA issuer ===============================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int ki = 0; ki < num_k_iters; ++ki) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        const uint32_t sb = sa + PLANES * A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          const uint64_t a_hi = make_sdesc(sa + k * 32);
+          const uint64_t b_hi = make_sdesc(sb + k * 32);
+          umma_bf16(d_tmem, a_hi, b_hi, IDESC, (ki > 0 || k > 0) ? 1u : 0u);
+          if (SPLIT) {
+            const uint64_t a_lo = make_sdesc(sa + A_TILE_BYTES + k * 32);
+            const uint64_t b_lo = make_sdesc(sb + B_TILE_BYTES + k * 32);
+            umma_bf16(d_tmem, a_lo, b_hi, IDESC, 1u);
+            umma_bf16(d_tmem, a_hi, b_lo, IDESC, 1u);
+          }
+        }
+        umma_commit(empty_bar(stage));                       // frees the smem stage when the MMAs retire
+        if (ki == num_k_iters - 1) umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===============================
+    const int q = warp & 3;             // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;      // tile row = pixel
+    const int tw = row % P.TW;
+    const int th = (row / P.TW) % P.TH;
+    const int tn = row / (P.TW * P.TH);
+    const int rep = P.out_rep, OHr = P.OH * rep, OWr = P.OW * rep;
+    const long long nstride = P.out_nstride > 0 ? P.out_nstride
+                              : (P.out_mode == MPN_OUT_F32_NCHW ? (long long)P.Cout * OHr * OWr : (long long)OHr * OWr * P.out_cstride);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int co_t = tile % P.tiles_co;
+      int mt = tile / P.tiles_co;
+      const int tw_i = mt % P.tiles_w;
+      mt /= P.tiles_w;
+      const int th_i = mt % P.tiles_h;
+      const int tn_i = mt / P.tiles_h;
+      const int ow = tw_i * P.TW + tw, oh = th_i * P.TH + th, n = tn_i * P.TN + tn;
+      const int co0 = co_t * BN;
+      const bool valid = row < P.rows && ow < P.OW && oh < P.OH && n < P.N;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const long long pix = valid ? ((long long)n * P.OH + oh) * P.OW + ow : 0;
+      long long up_pix = 0;
+      if (valid && P.up_cstride > 0)
+        up_pix = ((long long)n * P.up_h + mpn_nearest_src(oh, P.up_h, P.OH)) * P.up_w + mpn_nearest_src(ow, P.up_w, P.OW);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int cbase = co0 + c0;
+        if (cbase >= P.Cout) break;  // warp-uniform
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+        TMEM_LD_32x32b_X32(taddr, raw);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!valid) continue;
+        const int nc = min(32, P.Cout - cbase);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (P.scale) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < nc) v[j] = __fmul_rn(v[j], __ldg(P.scale + cbase + j));
+        }
+        if (P.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < nc) v[j] = __fadd_rn(v[j], __ldg(P.bias + cbase + j));
+        }
+        if (P.res_cstride > 0) {
+          add_bf16x32(v, P.res_hi + pix * P.res_cstride + cbase);
+          if (SPLIT) add_bf16x32(v, P.res_lo + pix * P.res_cstride + cbase);
+        }
+        if (P.up_cstride > 0) {
+          add_bf16x32(v, P.up_hi + up_pix * P.up_cstride + cbase);
+          if (SPLIT) add_bf16x32(v, P.up_lo + up_pix * P.up_cstride + cbase);
+        }
+        if (P.flags & MPN_EPI_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (P.flags & MPN_EPI_SIGMOID) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+        }
+        if (P.out_mode == MPN_OUT_ACT) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            hi[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+            if (SPLIT) lo[j] = pack_bf16(v[2 * j] - bf16_lo_f(hi[j]), v[2 * j + 1] - bf16_hi_f(hi[j]));
+          }
+          for (int ry = 0; ry < rep; ++ry)
+            for (int rx = 0; rx < rep; ++rx) {
+              const long long o = (long long)n * nstride + ((long long)(oh * rep + ry) * OWr + (ow * rep + rx)) * P.out_cstride +
+                                  P.out_coffset + cbase;
+              uint4* dh = reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_hi + o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              if (SPLIT) {
+                uint4* dl = reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_lo + o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              }
+            }
+        } else if (P.out_mode == MPN_OUT_F32_NHWC) {
+          for (int ry = 0; ry < rep; ++ry)
+            for (int rx = 0; rx < rep; ++rx) {
+              float* dst = (float*)P.y_hi + (long long)n * nstride +
+                           ((long long)(oh * rep + ry) * OWr + (ow * rep + rx)) * P.out_cstride + P.out_coffset + cbase;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < nc) dst[j] = v[j];
+            }
+        } else {  // fp32 NCHW: for a fixed channel the 32 lanes hold neighbouring pixels -> coalesced rows
+          for (int ry = 0; ry < rep; ++ry)
+            for (int rx = 0; rx < rep; ++rx) {
+              float* dst = (float*)P.y_hi + (long long)n * nstride + (long long)(P.out_coffset + cbase) * OHr * OWr +
+                           (long long)(oh * rep + ry) * OWr + (ow * rep + rx);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < nc) dst[(long long)j * OHr * OWr] = v[j];
+            }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  // =============================== teardown ===============================
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;  // resolved once; the value is immutable afterwards
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int encode(EncodeTiledFn fn, CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+           const cuuint32_t* box) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mpn_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], rank > 2 ? (unsigned long long)dims[2] : 0ULL,
+                  rank > 3 ? (unsigned long long)dims[3] : 0ULL, box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return MPN_ERR_CUDA;
+  }
+  return MPN_OK;
+}
+
+// Pick the pixel box (TW x TH x TN <= 128) that wastes the fewest MMA rows.
+void choose_tile(int N, int OH, int OW, int* TW, int* TH, int* TN) {
+  double best = -1.0;
+  int bw = 1, bh = 1, bn = 1;
+  for (int tw = 1; tw <= 128 && tw <= OW; ++tw) {
+    for (int th = 1; th * tw <= 128 && th <= OH; ++th) {
+      int tn = 1;
+      if (tw == OW && th == OH) {
+        tn = 128 / (tw * th);
+        if (tn > N) tn = N;
+        if (tn < 1) tn = 1;
+      }
+      long long tiles = (long long)((OW + tw - 1) / tw) * ((OH + th - 1) / th) * ((N + tn - 1) / tn);
+      double util = (double)N * OH * OW / (double)(tiles * 128);
+      // prefer wide rows (longer contiguous pixel runs per TMA box row and coalesced NCHW stores)
+      double score = util + 1e-4 * tw;
+      if (score > best) { best = score; bw = tw; bh = th; bn = tn; }
+    }
+  }
+  *TW = bw; *TH = bh; *TN = bn;
+}
+
+template <int BN, bool SPLIT>
+int launch(const Maps& maps, const TcParams& P, cudaStream_t st) {
+  constexpr int PLANES = SPLIT ? 2 : 1;
+  constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + BN * BLOCK_K * 2);
+  constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES) / STAGE_BYTES;
+  constexpr int STAGES = MAXS > 8 ? 8 : MAXS;
+  static_assert(STAGES >= 2, "not enough shared memory for a 2-stage ring");
+  static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier area too small");
+  const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+  auto kern = conv_tc_kernel<BN, SPLIT, STAGES>;
+  MPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int dev = 0, sms = 148;
+  MPN_CUDA_OK(cudaGetDevice(&dev));
+  MPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int grid = P.total_tiles < sms ? P.total_tiles : sms;
+  kern<<<grid, NUM_THREADS, smem, st>>>(maps, P);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+}  // namespace
+
+int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream) {
+  const bool split = d->fmt == MPN_FMT_BF16X2;
+  MPN_CHECK_ARG(d->stride == 1 || d->stride == 2, "conv(tcgen05): stride must be 1 or 2");
+  MPN_CHECK_ARG(d->Cin % BLOCK_K == 0, "conv(tcgen05): Cin must be a multiple of 64 (got %d)", d->Cin);
+  MPN_CHECK_ARG(d->in_cstride % 8 == 0, "conv(tcgen05): in_cstride must be a multiple of 8");
+  MPN_CHECK_ARG(!split || (p->x_lo && p->w_lo), "conv(tcgen05): BF16X2 needs lo planes of x and w");
+  MPN_CHECK_ARG(d->res_cstride % 8 == 0 && d->up_cstride % 8 == 0, "conv(tcgen05): residual/upsample channel strides must be multiples of 8");
+  if (d->out_mode == MPN_OUT_ACT)
+    MPN_CHECK_ARG(d->Cout % 32 == 0 && d->out_cstride % 8 == 0 && d->out_coffset % 8 == 0,
+                  "conv(tcgen05): activation outputs need Cout %% 32 == 0 and 16-byte aligned channel offsets");
+  if (d->res_cstride > 0 || d->up_cstride > 0) MPN_CHECK_ARG(d->Cout % 32 == 0, "conv(tcgen05): residual/upsample add needs Cout %% 32 == 0");
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    mpn_set_error("conv(tcgen05): cuTensorMapEncodeTiled entry point not available");
+    return MPN_ERR_CUDA;
+  }
+
+  TcParams P;
+  memset(&P, 0, sizeof(P));
+  P.N = d->N; P.OH = d->OH; P.OW = d->OW; P.Cout = d->Cout;
+  choose_tile(d->N, d->OH, d->OW, &P.TW, &P.TH, &P.TN);
+  P.rows = P.TW * P.TH * P.TN;
+  P.tiles_w = mpn_divup(d->OW, P.TW);
+  P.tiles_h = mpn_divup(d->OH, P.TH);
+  P.tiles_n = mpn_divup(d->N, P.TN);
+  int BN = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
+  if (split && BN == 256) BN = 128;  // keep a 3-stage ring in split mode
+  P.tiles_co = mpn_divup(d->Cout, BN);
+  long long total = (long long)P.tiles_w * P.tiles_h * P.tiles_n * P.tiles_co;
+  MPN_CHECK_ARG(total < (1LL << 31), "conv(tcgen05): too many tiles");
+  P.total_tiles = (int)total;
+  P.R = d->R; P.S = d->S; P.stride = d->stride; P.pad = d->pad; P.Cin = d->Cin; P.kb_per_tap = d->Cin / BLOCK_K;
+  P.scale = p->scale; P.bias = p->bias;
+  P.res_hi = (const __nv_bfloat16*)p->res_hi; P.res_lo = (const __nv_bfloat16*)p->res_lo; P.res_cstride = d->res_cstride;
+  P.up_hi = (const __nv_bfloat16*)p->up_hi; P.up_lo = (const __nv_bfloat16*)p->up_lo;
+  P.up_h = d->up_h; P.up_w = d->up_w; P.up_cstride = d->up_cstride;
+  P.flags = d->flags; P.out_mode = d->out_mode; P.out_cstride = d->out_cstride; P.out_coffset = d->out_coffset;
+  P.out_rep = d->out_rep; P.out_nstride = d->out_nstride;
+  P.y_hi = p->y_hi; P.y_lo = p->y_lo;
+
+  alignas(64) Maps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int planes = split ? 2 : 1;
+  const int st = d->stride;
+  const int nphase = st == 1 ? 1 : 4;
+  for (int pl = 0; pl < planes; ++pl) {
+    const char* xb = (const char*)(pl == 0 ? p->x_hi : p->x_lo);
+    for (int ph = 0; ph < nphase; ++ph) {
+      const int hp = ph >> 1, wp = ph & 1;
+      const int Hp = (d->H - hp + st - 1) / st, Wp = (d->W - wp + st - 1) / st;
+      if (Hp <= 0 || Wp <= 0) {
+        P.phase_empty |= 1 << ph;
+        continue;
+      }
+      cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)d->N};
+      cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * st * 2ULL, (cuuint64_t)d->W * d->in_cstride * st * 2ULL,
+                               (cuuint64_t)d->H * d->W * d->in_cstride * 2ULL};
+      cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
+      const char* base = xb + ((long long)hp * d->W + wp) * d->in_cstride * 2LL;
+      int rc = encode(fn, &maps.a[pl][ph], base, 4, dims, strides, box);
+      if (rc) return rc;
+    }
+    MPN_CHECK_ARG(!(P.phase_empty & 1), "conv(tcgen05): empty input");
+    const cuuint64_t K = (cuuint64_t)d->R * d->S * d->Cin;
+    cuuint64_t wdims[2] = {K, (cuuint64_t)d->Cout};
+    cuuint64_t wstrides[1] = {K * 2ULL};
+    cuuint32_t wbox[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN};
+    int rc = encode(fn, &maps.b[pl], pl == 0 ? p->w_hi : p->w_lo, 2, wdims, wstrides, wbox);
+    if (rc) return rc;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (split) {
+    switch (BN) {
+      case 128: return launch<128, true>(maps, P, s);
+      case 64: return launch<64, true>(maps, P, s);
+      default: return launch<32, true>(maps, P, s);
+    }
+  }
+  switch (BN) {
+    case 256: return launch<256, false>(maps, P, s);
+    case 128: return launch<128, false>(maps, P, s);
+    case 64: return launch<64, false>(maps, P, s);
+    default: return launch<32, false>(maps, P, s);
+  }
+}

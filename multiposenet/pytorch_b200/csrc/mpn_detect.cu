@@ -1,0 +1,421 @@
+// Detection post-process on the device: anchors, box decode + clip, score filter, stable descending
+// radix sort, bit-mask IoU and the greedy reduction -- the reference's
+//   Anchors.forward (network/anchors.py:21-37)  [float64 host math, cached by the caller]
+//   BBoxTransform / ClipBoxes (network/utils.py:19-61)
+//   score > 0.05 boolean indexing (network/posenet.py:269-279)
+//   pth_nms -> gpu_nms -> nms_kernel + the serial host loop (lib/nms/pth_nms.py:25-44,
+//     src/nms_cuda.c:17-67, src/cuda/nms_kernel.cu:16-70)
+// without the reference's device->host mask copy and host loop.  Integer results are bit-exact with
+// oracle/nms_oracle.c: the IoU arithmetic uses explicit round-to-nearest intrinsics in the reference's
+// operation order (no FMA contraction is possible in devIoU either).
+#include <cub/cub.cuh>
+#include <math.h>
+
+#include "mpn_common.cuh"
+
+namespace {
+
+constexpr int kLevels[5] = {3, 4, 5, 6, 7};
+
+// ---------------------------------------------------------------------------------------------
+__global__ void decode_clip_kernel(const float* __restrict__ anchors, const float* __restrict__ reg, float* __restrict__ boxes,
+                                   int B, int A, float Hf, float Wf, int clip) {
+  long long total = (long long)B * A;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int a = (int)(i % A);
+    float4 an = reinterpret_cast<const float4*>(anchors)[a];
+    float4 dl = reinterpret_cast<const float4*>(reg)[i];
+    // utils.py:21-29 -- every product and sum is a separate fp32 op in torch, so no FMA here
+    float w = __fsub_rn(an.z, an.x), h = __fsub_rn(an.w, an.y);
+    float cx = __fadd_rn(an.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
+    float dx = __fadd_rn(__fmul_rn(dl.x, 0.1f), 0.f), dy = __fadd_rn(__fmul_rn(dl.y, 0.1f), 0.f);
+    float dw = __fadd_rn(__fmul_rn(dl.z, 0.2f), 0.f), dh = __fadd_rn(__fmul_rn(dl.w, 0.2f), 0.f);
+    float pcx = __fadd_rn(cx, __fmul_rn(dx, w)), pcy = __fadd_rn(cy, __fmul_rn(dy, h));
+    float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+    float4 o;
+    o.x = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+    o.y = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+    o.z = __fadd_rn(pcx, __fmul_rn(0.5f, pw));
+    o.w = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+    if (clip) {
+      o.x = fmaxf(o.x, 0.f);  // utils.py:56-57
+      o.y = fmaxf(o.y, 0.f);
+      o.z = fminf(o.z, Wf);   // utils.py:59-60
+      o.w = fminf(o.w, Hf);
+    }
+    reinterpret_cast<float4*>(boxes)[i] = o;
+  }
+}
+
+// One CTA per image walks the A scores in order; survivors keep their relative order
+// (boolean indexing semantics).  rank_in = position in the filtered set, key = score.
+__global__ void __launch_bounds__(1024) filter_compact_kernel(const float* __restrict__ cls, int A, float thr, int max_cand,
+                                                             int32_t* __restrict__ cand_idx, int32_t* __restrict__ cand_cnt,
+                                                             float* __restrict__ keys, int32_t* __restrict__ ranks) {
+  __shared__ int warp_sums[32];
+  __shared__ int running;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) running = 0;
+  __syncthreads();
+  const float* s = cls + (long long)b * A;
+  for (int base = 0; base < A; base += 1024) {
+    int a = base + tid;
+    float v = a < A ? s[a] : 0.f;
+    bool keep = a < A && v > thr;
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    int within = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_sums[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0;
+    int tot = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < 32; ++w2) {
+      int c = warp_sums[w2];
+      before += (w2 < wid) ? c : 0;
+      tot += c;
+    }
+    int pos = running + before + within;
+    if (keep && pos < max_cand) {
+      cand_idx[(long long)b * max_cand + pos] = a;
+      keys[(long long)b * max_cand + pos] = v;
+      ranks[(long long)b * max_cand + pos] = pos;
+    }
+    __syncthreads();
+    if (tid == 0) running += tot;
+    __syncthreads();
+  }
+  if (tid == 0) cand_cnt[b] = running;
+}
+
+__global__ void iota_dets_kernel(const float* __restrict__ dets, int n, float* keys, int32_t* ranks, int32_t* cand_idx,
+                                 int32_t* cand_cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = dets[(long long)i * 5 + 4];
+    ranks[i] = i;
+    cand_idx[i] = i;
+  }
+  if (i == 0) cand_cnt[0] = n;
+}
+
+__global__ void segments_kernel(const int32_t* cand_cnt, int B, int max_cand, int* seg_begin, int* seg_end) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    int c = cand_cnt[b];
+    seg_begin[b] = b * max_cand;
+    seg_end[b] = b * max_cand + (c < max_cand ? c : max_cand);
+  }
+}
+
+// sdets[b][j] = (box of the j-th best candidate, score)
+__global__ void gather_sorted_kernel(const float* __restrict__ boxes, int box_stride, long long box_image_stride,
+                                     const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_cnt,
+                                     const float* __restrict__ keys_sorted, const int32_t* __restrict__ ranks_sorted,
+                                     int max_cand, float* __restrict__ sdets) {
+  const int b = blockIdx.y;
+  int n = cand_cnt[b];
+  n = n < max_cand ? n : max_cand;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    long long o = (long long)b * max_cand + j;
+    int a = cand_idx[(long long)b * max_cand + ranks_sorted[o]];
+    const float* bx = boxes + (long long)b * box_image_stride + (long long)a * box_stride;
+    float* d = sdets + o * 5;
+    d[0] = bx[0]; d[1] = bx[1]; d[2] = bx[2]; d[3] = bx[3];
+    d[4] = keys_sorted[o];
+  }
+}
+
+__device__ __forceinline__ float dev_iou(const float* a, const float* b) {
+  // nms_kernel.cu:16-24, operation for operation
+  float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
+  float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+  float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+  float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+  float interS = __fmul_rn(width, height);
+  float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a[2], a[0]), 1.f), __fadd_rn(__fsub_rn(a[3], a[1]), 1.f));
+  float Sb = __fmul_rn(__fadd_rn(__fsub_rn(b[2], b[0]), 1.f), __fadd_rn(__fsub_rn(b[3], b[1]), 1.f));
+  return __fdiv_rn(interS, __fsub_rn(__fadd_rn(Sa, Sb), interS));
+}
+
+// grid (col_block, row_block, image); only col_block >= row_block is computed (the reduction never
+// reads the lower triangle, nms_cuda.c:52).  64 threads: thread t owns row box row_block*64+t.
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sdets, const int32_t* __restrict__ cand_cnt,
+                                                     int n_fixed, int max_cand, int cb_stride, float thr, int ge,
+                                                     unsigned long long* __restrict__ mask) {
+  const int b = blockIdx.z;
+  int n = cand_cnt ? cand_cnt[b] : n_fixed;
+  n = n < max_cand ? n : max_cand;
+  const int row_start = blockIdx.y, col_start = blockIdx.x;
+  if (col_start < row_start) return;
+  if (row_start * 64 >= n || col_start * 64 >= n) return;
+  const int row_size = min(n - row_start * 64, 64), col_size = min(n - col_start * 64, 64);
+  const float* dets = sdets + (long long)b * max_cand * 5;
+  __shared__ float block_boxes[64 * 5];
+  if (threadIdx.x < col_size) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) block_boxes[threadIdx.x * 5 + k] = dets[(long long)(64 * col_start + threadIdx.x) * 5 + k];
+  }
+  __syncthreads();
+  if (threadIdx.x < row_size) {
+    const int cur = 64 * row_start + threadIdx.x;
+    float cb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cb[k] = dets[(long long)cur * 5 + k];
+    unsigned long long t = 0;
+    int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
+    for (int i = start; i < col_size; ++i) {
+      float v = dev_iou(cb, block_boxes + i * 5);
+      if (ge ? (v >= thr) : (v > thr)) t |= 1ULL << i;
+    }
+    mask[((long long)b * max_cand + cur) * cb_stride + col_start] = t;
+  }
+}
+
+// One CTA per image: the serial host loop of nms_cuda.c:46-58, 64 boxes at a time.
+__global__ void __launch_bounds__(128) nms_reduce_kernel(const unsigned long long* __restrict__ mask,
+                                                        const int32_t* __restrict__ cand_cnt, int max_cand, int cb_stride,
+                                                        const int32_t* __restrict__ ranks_sorted,
+                                                        const float* __restrict__ sdets, int64_t* __restrict__ keep_idx,
+                                                        int32_t* __restrict__ keep_cnt, float* __restrict__ out_scores,
+                                                        float* __restrict__ out_boxes) {
+  extern __shared__ unsigned long long remv[];  // cb_stride words
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long keepbits_s;
+  __shared__ int kept_total;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  int n = cand_cnt[b];
+  n = n < max_cand ? n : max_cand;
+  const int col_blocks = (n + 63) / 64;
+  for (int j = tid; j < cb_stride; j += blockDim.x) remv[j] = 0ULL;
+  if (tid == 0) kept_total = 0;
+  __syncthreads();
+  const unsigned long long* m = mask + (long long)b * max_cand * cb_stride;
+  for (int rb = 0; rb < col_blocks; ++rb) {
+    const int rows = min(n - rb * 64, 64);
+    if (tid < 64) diag[tid] = tid < rows ? m[(long long)(rb * 64 + tid) * cb_stride + rb] : 0ULL;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long cur = remv[rb], kb = 0ULL;
+      for (int t = 0; t < rows; ++t) {
+        if (!((cur >> t) & 1ULL)) {
+          kb |= 1ULL << t;
+          cur |= diag[t];
+        }
+      }
+      keepbits_s = kb;
+    }
+    __syncthreads();
+    const unsigned long long kb = keepbits_s;
+    // later column blocks: OR in the rows of every kept box of this block
+    for (int j = rb + 1 + tid; j < col_blocks; j += blockDim.x) {
+      unsigned long long acc = remv[j];
+      unsigned long long bits = kb;
+      while (bits) {
+        int t = __ffsll((long long)bits) - 1;
+        bits &= bits - 1;
+        acc |= m[(long long)(rb * 64 + t) * cb_stride + j];
+      }
+      remv[j] = acc;
+    }
+    // emit the kept boxes of this block in order
+    if (tid < 64 && ((kb >> tid) & 1ULL)) {
+      int pos = kept_total + __popcll(kb & ((1ULL << tid) - 1ULL));
+      long long o = (long long)b * max_cand;
+      int srt = rb * 64 + tid;  // position in the sorted list
+      keep_idx[o + pos] = (int64_t)ranks_sorted[o + srt];
+      if (out_scores) out_scores[o + pos] = sdets[(o + srt) * 5 + 4];
+      if (out_boxes) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out_boxes[(o + pos) * 4 + k] = sdets[(o + srt) * 5 + k];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) kept_total += __popcll(kb);
+    __syncthreads();
+  }
+  if (tid == 0) keep_cnt[b] = kept_total;
+}
+
+struct Workspace {
+  float* keys_in;
+  float* keys_out;
+  int32_t* ranks_in;
+  int32_t* ranks_out;
+  int* seg_begin;
+  int* seg_end;
+  float* sdets;
+  unsigned long long* mask;
+  void* cub_temp;
+  size_t cub_bytes;
+  size_t total;
+};
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t cub_temp_bytes(int B, int max_cand) {
+  size_t bytes = 0;
+  cub::DeviceSegmentedRadixSort::SortPairsDescending((void*)nullptr, bytes, (const float*)nullptr, (float*)nullptr,
+                                                     (const int32_t*)nullptr, (int32_t*)nullptr, B * max_cand, B,
+                                                     (const int*)nullptr, (const int*)nullptr);
+  return bytes;
+}
+
+Workspace carve(void* base, int B, int max_cand) {
+  Workspace w;
+  size_t off = 0;
+  char* p = (char*)base;
+  size_t n = (size_t)B * max_cand;
+  int cb = (max_cand + 63) / 64;
+  auto take = [&](size_t bytes) {
+    char* q = p ? p + off : nullptr;
+    off += align256(bytes);
+    return q;
+  };
+  w.keys_in = (float*)take(n * 4);
+  w.keys_out = (float*)take(n * 4);
+  w.ranks_in = (int32_t*)take(n * 4);
+  w.ranks_out = (int32_t*)take(n * 4);
+  w.seg_begin = (int*)take((size_t)B * 4);
+  w.seg_end = (int*)take((size_t)B * 4);
+  w.sdets = (float*)take(n * 5 * 4);
+  w.mask = (unsigned long long*)take(n * cb * 8);
+  w.cub_bytes = cub_temp_bytes(B, max_cand);
+  w.cub_temp = take(w.cub_bytes);
+  w.total = off;
+  return w;
+}
+
+int run_core(const float* boxes, int box_stride, long long box_image_stride, int B, int max_cand, float iou_thr, int ge,
+             const int32_t* cand_idx, const int32_t* cand_cnt, int64_t* keep_idx, int32_t* keep_cnt, float* out_scores,
+             float* out_boxes, Workspace& w, cudaStream_t st) {
+  segments_kernel<<<mpn_divup(B, 128), 128, 0, st>>>(cand_cnt, B, max_cand, w.seg_begin, w.seg_end);
+  MPN_LAUNCH_OK();
+  size_t tb = w.cub_bytes;
+  MPN_CUDA_OK(cub::DeviceSegmentedRadixSort::SortPairsDescending(w.cub_temp, tb, w.keys_in, w.keys_out, w.ranks_in, w.ranks_out,
+                                                                 B * max_cand, B, w.seg_begin, w.seg_end, 0, 32, st));
+  dim3 gg(mpn_divup(max_cand, 256), B);
+  gather_sorted_kernel<<<gg, 256, 0, st>>>(boxes, box_stride, box_image_stride, cand_idx, cand_cnt, w.keys_out, w.ranks_out,
+                                           max_cand, w.sdets);
+  MPN_LAUNCH_OK();
+  const int cb = (max_cand + 63) / 64;
+  dim3 mg(cb, cb, B);
+  nms_mask_kernel<<<mg, 64, 0, st>>>(w.sdets, cand_cnt, 0, max_cand, cb, iou_thr, ge, w.mask);
+  MPN_LAUNCH_OK();
+  nms_reduce_kernel<<<B, 128, cb * sizeof(unsigned long long), st>>>(w.mask, cand_cnt, max_cand, cb, w.ranks_out, w.sdets,
+                                                                     keep_idx, keep_cnt, out_scores, out_boxes);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+}  // namespace
+
+extern "C" int mpn_num_anchors(int H, int W) {
+  if (H <= 0 || W <= 0) return 0;
+  long long a = 0;
+  for (int l : kLevels) {
+    int s = 1 << l;
+    a += (long long)((H + s - 1) / s) * ((W + s - 1) / s) * 9;
+  }
+  return (int)a;
+}
+
+extern "C" int mpn_generate_anchors(int H, int W, float* out) {
+  MPN_CHECK_ARG(H > 0 && W > 0 && out, "mpn_generate_anchors: bad argument");
+  const double ratios[3] = {0.5, 1.0, 2.0};
+  const double scales[3] = {pow(2.0, 0.0), pow(2.0, 1.0 / 3.0), pow(2.0, 2.0 / 3.0)};  // anchors.py:19
+  long long o = 0;
+  for (int l : kLevels) {
+    const int stride = 1 << l;
+    const double base_size = (double)(1 << (l + 2));  // anchors.py:15
+    double base[9][4];
+    for (int ri = 0; ri < 3; ++ri)
+      for (int si = 0; si < 3; ++si) {
+        double side = base_size * scales[si];   // anchors.py:55
+        double area = side * side;              // :58
+        double w = sqrt(area / ratios[ri]);     // :61
+        double h = w * ratios[ri];              // :62
+        double* b = base[ri * 3 + si];
+        b[0] = 0.0 - w * 0.5; b[1] = 0.0 - h * 0.5; b[2] = w - w * 0.5; b[3] = h - h * 0.5;  // :65-66
+      }
+    const int fh = (H + stride - 1) / stride, fw = (W + stride - 1) / stride;  // anchors.py:25
+    for (int y = 0; y < fh; ++y) {
+      const double sy = ((double)y + 0.5) * stride;  // anchors.py:108
+      for (int x = 0; x < fw; ++x) {
+        const double sx = ((double)x + 0.5) * stride;  // :107
+        for (int a = 0; a < 9; ++a) {
+          out[o++] = (float)(base[a][0] + sx);
+          out[o++] = (float)(base[a][1] + sy);
+          out[o++] = (float)(base[a][2] + sx);
+          out[o++] = (float)(base[a][3] + sy);
+        }
+      }
+    }
+  }
+  return MPN_OK;
+}
+
+extern "C" int mpn_decode_clip(const float* anchors, const float* reg, float* boxes, int B, int A, int H, int W, void* stream) {
+  MPN_CHECK_ARG(anchors && reg && boxes && B > 0 && A > 0, "mpn_decode_clip: bad argument");
+  const int clip = (H > 0 && W > 0) ? 1 : 0;  // H <= 0: decode only (BBoxTransform without ClipBoxes)
+  long long total = (long long)B * A;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  decode_clip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(anchors, reg, boxes, B, A, (float)H, (float)W, clip);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+extern "C" size_t mpn_detect_workspace_bytes(int B, int A, int max_cand) {
+  (void)A;
+  if (B <= 0 || max_cand <= 0) return 0;
+  return carve(nullptr, B, max_cand).total;
+}
+
+extern "C" int mpn_filter_sort_nms(const float* cls, const float* boxes, int B, int A, float score_thresh, float iou_thresh, int ge,
+                                   int max_cand, int32_t* cand_idx, int32_t* cand_cnt, int64_t* keep_idx, int32_t* keep_cnt,
+                                   float* out_scores, float* out_boxes, void* workspace, size_t workspace_bytes, void* stream) {
+  MPN_CHECK_ARG(cls && boxes && B > 0 && A > 0 && max_cand > 0, "mpn_filter_sort_nms: bad argument");
+  MPN_CHECK_ARG(cand_idx && cand_cnt && keep_idx && keep_cnt && workspace, "mpn_filter_sort_nms: null output/workspace");
+  MPN_CHECK_ARG((long long)B * max_cand < (1LL << 30), "mpn_filter_sort_nms: B*max_cand too large");
+  Workspace w = carve(workspace, B, max_cand);
+  MPN_CHECK_ARG(workspace_bytes >= w.total, "mpn_filter_sort_nms: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  filter_compact_kernel<<<B, 1024, 0, st>>>(cls, A, score_thresh, max_cand, cand_idx, cand_cnt, w.keys_in, w.ranks_in);
+  MPN_LAUNCH_OK();
+  return run_core(boxes, 4, (long long)A * 4, B, max_cand, iou_thresh, ge, cand_idx, cand_cnt, keep_idx, keep_cnt, out_scores,
+                  out_boxes, w, st);
+}
+
+extern "C" size_t mpn_nms_workspace_bytes(int n) {
+  if (n <= 0) return 256;
+  // extra: cand_idx[n] + cand_cnt[1]
+  return carve(nullptr, 1, n).total + align256((size_t)n * 4) + 256;
+}
+
+extern "C" int mpn_nms(const float* dets, int n, float iou_thresh, int ge, int64_t* keep, int32_t* num_out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  MPN_CHECK_ARG(n >= 0 && num_out, "mpn_nms: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    MPN_CUDA_OK(cudaMemsetAsync(num_out, 0, sizeof(int32_t), st));
+    return MPN_OK;
+  }
+  MPN_CHECK_ARG(dets && keep && workspace, "mpn_nms: null pointer");
+  MPN_CHECK_ARG(workspace_bytes >= mpn_nms_workspace_bytes(n), "mpn_nms: workspace too small");
+  Workspace w = carve(workspace, 1, n);
+  int32_t* cand_idx = (int32_t*)((char*)workspace + w.total);
+  int32_t* cand_cnt = (int32_t*)((char*)cand_idx + align256((size_t)n * 4));
+  iota_dets_kernel<<<mpn_divup(n, 256), 256, 0, st>>>(dets, n, w.keys_in, w.ranks_in, cand_idx, cand_cnt);
+  MPN_LAUNCH_OK();
+  return run_core(dets, 5, 0, 1, n, iou_thresh, ge, cand_idx, cand_cnt, keep, num_out, nullptr, nullptr, w, st);
+}
+
+extern "C" int mpn_nms_mask(const float* sorted_dets, int n, float iou_thresh, int ge, uint64_t* mask, void* stream) {
+  MPN_CHECK_ARG(sorted_dets && mask && n > 0, "mpn_nms_mask: bad argument");
+  const int cb = (n + 63) / 64;
+  dim3 mg(cb, cb, 1);
+  nms_mask_kernel<<<mg, 64, 0, (cudaStream_t)stream>>>(sorted_dets, nullptr, n, n, cb, iou_thresh, ge,
+                                                      (unsigned long long*)mask);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}

@@ -1,0 +1,207 @@
+// Layout conversion, filter packing, BN folding, max-pool, ReLU: the bandwidth-bound glue of the path.
+// All kernels are grid-stride, vector-friendly and launched on the caller's stream.
+#include <stdarg.h>
+#include <string.h>
+
+#include "mpn_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mpn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* mpn_last_error(void) { return g_err; }
+extern "C" int mpn_version(void) { return 100; }
+
+extern "C" int mpn_device_supports_tcgen05(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+static inline int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  const long long cap = 148LL * 16;  // 16 resident CTAs of 256 threads per SM, grid-stride beyond
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_filter_f32_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin, int R,
+                                       int S, int CoutPad) {
+  long long total = (long long)R * S * Cin * CoutPad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(i % CoutPad);
+    long long t = i / CoutPad;
+    int ci = (int)(t % Cin);
+    t /= Cin;
+    int s = (int)(t % S);
+    int r = (int)(t / S);
+    dst[i] = co < Cout ? w[(((long long)co * Cin + ci) * R + r) * S + s] : 0.f;
+  }
+}
+
+extern "C" int mpn_pack_filter_f32(const float* w, float* dst, int Cout, int Cin, int R, int S, int CoutPad, void* stream) {
+  MPN_CHECK_ARG(w && dst && Cout > 0 && Cin > 0 && R > 0 && S > 0 && CoutPad >= Cout, "mpn_pack_filter_f32: bad argument");
+  long long total = (long long)R * S * Cin * CoutPad;
+  pack_filter_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, dst, Cout, Cin, R, S, CoutPad);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+__global__ void pack_filter_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                        __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int R, int S) {
+  long long total = (long long)Cout * R * S * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int ci = (int)(i % Cin);
+    long long t = i / Cin;
+    int s = (int)(t % S);
+    t /= S;
+    int r = (int)(t % R);
+    int co = (int)(t / R);
+    float v = w[(((long long)co * Cin + ci) * R + r) * S + s];
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+extern "C" int mpn_pack_filter_bf16(const float* w, void* hi, void* lo, int Cout, int Cin, int R, int S, void* stream) {
+  MPN_CHECK_ARG(w && hi && Cout > 0 && Cin > 0 && R > 0 && S > 0, "mpn_pack_filter_bf16: bad argument");
+  long long total = (long long)Cout * R * S * Cin;
+  pack_filter_bf16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                                                 Cout, Cin, R, S);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+__global__ void fold_bn_kernel(const float* g, const float* b, const float* m, const float* v, float eps, float* scale,
+                               float* bias, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    // (x - mean) / sqrt(var + eps) * gamma + beta  ==  x*scale + bias
+    float s = __fdiv_rn(g[i], __fsqrt_rn(__fadd_rn(v[i], eps)));
+    scale[i] = s;
+    bias[i] = __fsub_rn(b[i], __fmul_rn(m[i], s));
+  }
+}
+
+extern "C" int mpn_fold_bn(const float* g, const float* b, const float* m, const float* v, float eps, float* scale,
+                           float* bias, int C, void* stream) {
+  MPN_CHECK_ARG(g && b && m && v && scale && bias && C > 0, "mpn_fold_bn: bad argument");
+  fold_bn_kernel<<<mpn_divup(C, 256), 256, 0, (cudaStream_t)stream>>>(g, b, m, v, eps, scale, bias, C);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC: one thread per (n, h, w, c) destination element, c fastest (coalesced writes);
+// reads are strided by H*W but the tensors this is used on are the 3-channel image and small maps.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* hi, void* lo, int N, int C, int H, int W,
+                                    int cstride, int fmt) {
+  long long total = (long long)N * H * W * cstride;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cstride);
+    long long p = i / cstride;
+    int w = (int)(p % W);
+    long long q = p / W;
+    int h = (int)(q % H);
+    int n = (int)(q / H);
+    float v = c < C ? src[(((long long)n * C + c) * H + h) * W + w] : 0.f;
+    mpn_store_act(hi, lo, i, fmt, v);
+  }
+}
+
+extern "C" int mpn_nchw_to_nhwc(const float* src, void* hi, void* lo, int N, int C, int H, int W, int cstride, int fmt,
+                                void* stream) {
+  MPN_CHECK_ARG(src && hi && N > 0 && C > 0 && H > 0 && W > 0 && cstride >= C, "mpn_nchw_to_nhwc: bad argument");
+  MPN_CHECK_ARG(fmt != MPN_FMT_BF16X2 || lo, "mpn_nchw_to_nhwc: BF16X2 needs a lo plane");
+  long long total = (long long)N * H * W * cstride;
+  nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, hi, lo, N, C, H, W, cstride, fmt);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+// NHWC -> NCHW fp32 through a 32x32 shared-memory transpose of the (pixel, channel) plane.
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ hi, const void* __restrict__ lo, float* __restrict__ dst,
+                                    int C, long long HW, int cstride, int fmt) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    long long p = p0 + j;
+    int c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (p < HW && c < C) ? mpn_load_act(hi, lo, ((long long)n * HW + p) * cstride + c, fmt) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j;
+    long long p = p0 + threadIdx.x;
+    if (p < HW && c < C) dst[((long long)n * C + c) * HW + p] = tile[threadIdx.x][j];
+  }
+}
+
+extern "C" int mpn_nhwc_to_nchw(const void* hi, const void* lo, float* dst, int N, int C, int H, int W, int cstride, int fmt,
+                                void* stream) {
+  MPN_CHECK_ARG(hi && dst && N > 0 && C > 0 && H > 0 && W > 0 && cstride >= C, "mpn_nhwc_to_nchw: bad argument");
+  long long HW = (long long)H * W;
+  dim3 grid(mpn_divup(HW, 32), mpn_divup(C, 32), N), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(hi, lo, dst, C, HW, cstride, fmt);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// max_pool2d(3, stride 2, pad 1), NHWC.  One thread per (pixel, 4-channel group); -inf padding.
+__global__ void maxpool3x3s2_kernel(const void* __restrict__ xhi, const void* __restrict__ xlo, void* yhi, void* ylo, int N,
+                                    int H, int W, int C, int OH, int OW, int fmt) {
+  long long total = (long long)N * OH * OW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    int ow = (int)(p % OW);
+    long long q = p / OW;
+    int oh = (int)(q % OH);
+    int n = (int)(q / OH);
+    float m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= W) continue;
+        m = fmaxf(m, mpn_load_act(xhi, xlo, (((long long)n * H + ih) * W + iw) * C + c, fmt));
+      }
+    }
+    mpn_store_act(yhi, ylo, i, fmt, m);
+  }
+}
+
+extern "C" int mpn_maxpool3x3s2(const void* xhi, const void* xlo, void* yhi, void* ylo, int N, int H, int W, int C, int fmt,
+                                void* stream) {
+  MPN_CHECK_ARG(xhi && yhi && N > 0 && H > 0 && W > 0 && C > 0, "mpn_maxpool3x3s2: bad argument");
+  int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  long long total = (long long)N * OH * OW * C;
+  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(xhi, xlo, yhi, ylo, N, H, W, C, OH, OW, fmt);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+__global__ void relu_kernel(const void* xhi, const void* xlo, void* yhi, void* ylo, long long n, int fmt) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    mpn_store_act(yhi, ylo, i, fmt, fmaxf(mpn_load_act(xhi, xlo, i, fmt), 0.f));
+}
+
+extern "C" int mpn_relu(const void* xhi, const void* xlo, void* yhi, void* ylo, long long n, int fmt, void* stream) {
+  MPN_CHECK_ARG(xhi && yhi && n > 0, "mpn_relu: bad argument");
+  relu_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(xhi, xlo, yhi, ylo, n, fmt);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}

@@ -1,0 +1,43 @@
+"""Register this package under the reference's import names.
+
+The reference's harness does `from network.posenet import poseNet` (evaluate/multipose_test.py:6,
+training/multipose_keypoint_train.py:11) and `from lib.nms.pth_nms import pth_nms`
+(network/posenet.py:16).  install_dropin() aliases those module names to this package's mirrors, so
+evaluate/ and training/ scripts import the B200 implementation without being edited.  Other
+`network.*` / `lib.*` submodules of a reference checkout on sys.path (joint_utils, net_utils, lib.utils)
+keep resolving to the checkout: only the hot-path modules are replaced.
+"""
+import importlib
+import sys
+import types
+
+
+def install_dropin(reference_root=None):
+    from .lib.nms import pth_nms as _pth
+    from .network import anchors as _anchors
+    from .network import fpn as _fpn
+    from .network import posenet as _posenet
+    from .network import utils as _utils
+
+    if reference_root and reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+
+    def _pkg(name):
+        m = sys.modules.get(name)
+        if m is None:
+            try:
+                m = importlib.import_module(name)  # a real package on sys.path (reference checkout)
+            except Exception:
+                m = types.ModuleType(name)
+                m.__path__ = []
+            sys.modules[name] = m
+        return m
+
+    for pkg in ("network", "lib", "lib.nms"):
+        _pkg(pkg)
+    for name, mod in (("network.posenet", _posenet), ("network.fpn", _fpn), ("network.anchors", _anchors),
+                      ("network.utils", _utils), ("lib.nms.pth_nms", _pth)):
+        sys.modules[name] = mod
+        parent, _, leaf = name.rpartition(".")
+        setattr(sys.modules[parent], leaf, mod)
+    return _posenet.poseNet

@@ -1,0 +1,238 @@
+"""Layer schedule of the hot path on top of the C ABI (the host half of the B200 design).
+
+Mirrors the reference call graph -- FPN.forward (network/fpn.py:97-126), the keypoint / detection /
+entire_net branches of poseNet.forward (network/posenet.py:226-335) -- as a flat sequence of
+libmpn_b200 launches on NHWC activations:
+
+  stem     : NCHW->NHWC, 7x7/2 conv + BN + ReLU (CUDA-core kernel, fp32 in), 3x3/2 max-pool
+  backbone : per Bottleneck 3 launches (4 with a projection shortcut); BN folded to scale/bias,
+             residual add + ReLU fused in conv3's epilogue
+  necks    : lateral 1x1 with the nearest-upsample-add fused in its epilogue, then 3x3 smooth
+  kp head  : convt/convs per level; convs writes straight into its channel slice of the 512-channel
+             concat buffer with the x8/x4/x2 nearest replication fused in the store; conv2+ReLU; convfin
+             writes fp32 NCHW directly
+  det head : shared tower on 5 levels; outputs land in the concatenated [B, A, 1|4] tensors
+  post     : decode+clip, filter, radix sort, bit-mask NMS, gather -- all on the device
+
+Precision modes (env MPN_PRECISION or Engine(precision=...)):
+  "bf16x3" (default) tcgen05, hi/lo bf16 split, 3 MMAs / K-step: fp32-grade parity (<1e-3)
+  "bf16"             tcgen05, single bf16 plane: fastest, ~1e-2 relative error after 100 layers
+  "fp32"             CUDA-core fp32 FMA kernel: exact-mode reference on the device
+"""
+import os
+
+import torch
+
+from . import ops
+from ._lib import FMT_BF16, FMT_BF16X2, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_NHWC
+
+DEFAULT_PRECISION = os.environ.get("MPN_PRECISION", "bf16x3")
+
+
+def _bn_tuple(bn):
+    return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+
+
+class Engine(object):
+    def __init__(self, model, precision=None):
+        self.model = model
+        self.precision = precision or DEFAULT_PRECISION
+        if self.precision not in ops.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(ops.PRECISIONS))
+        self.fmt = ops.PRECISIONS[self.precision]
+        self._packed = {}
+        self._sig = None
+        self.last_detections = None
+
+    # ------------------------------------------------------------------ weights
+    def _signature(self):
+        sig = []
+        for t in list(self.model.parameters()) + list(self.model.buffers()):
+            sig.append((t.data_ptr(), t._version))
+        return tuple(sig)
+
+    def _ensure_packed(self):
+        sig = self._signature()
+        if sig != self._sig:
+            self._packed = {}
+            self._sig = sig
+
+    def _pc(self, name, conv, bn=None, fmt=None):
+        fmt = self.fmt if fmt is None else fmt
+        key = (name, fmt)
+        pc = self._packed.get(key)
+        if pc is None:
+            if not conv.weight.is_cuda:
+                raise RuntimeError("poseNet must be on a CUDA device (no CPU path); call .cuda() first")
+            pc = ops.pack_conv(conv.weight, conv.bias, _bn_tuple(bn) if bn is not None else None, fmt)
+            self._packed[key] = pc
+        return pc
+
+    # ------------------------------------------------------------------ backbone
+    def backbone(self, img):
+        """fpn.py:99-105 -> c2, c3, c4, c5 (Act)."""
+        fpn = self.model.fpn
+        if not (img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3):
+            raise RuntimeError("expected a CUDA fp32 [B,3,H,W] image batch")
+        x = ops.act_from_nchw(img, FMT_F32)
+        # stem weights are always fp32-packed; the epilogue emits the engine's activation format
+        pc = self._stem_pc()
+        c1 = ops.conv2d(x, pc, stride=2, pad=3, relu=True, f32_input=True)
+        c = ops.maxpool3x3s2(c1)
+        feats = []
+        for li in range(1, 5):
+            layer = getattr(fpn, "layer%d" % li)
+            for bi, blk in enumerate(layer):
+                c = self._bottleneck("fpn.layer%d.%d" % (li, bi), blk, c)
+            feats.append(c)
+        return feats
+
+    def _stem_pc(self):
+        key = ("fpn.conv1", "stem", self.fmt)
+        pc = self._packed.get(key)
+        if pc is None:
+            fpn = self.model.fpn
+            if not fpn.conv1.weight.is_cuda:
+                raise RuntimeError("poseNet must be on a CUDA device (no CPU path); call .cuda() first")
+            pc = ops.pack_conv(fpn.conv1.weight, None, _bn_tuple(fpn.bn1), FMT_F32)
+            pc.fmt = self.fmt  # output / epilogue format
+            self._packed[key] = pc
+        return pc
+
+    def _bottleneck(self, name, blk, x):
+        """fpn.py:28-34."""
+        stride = blk.conv2.stride[0]
+        o = ops.conv2d(x, self._pc(name + ".conv1", blk.conv1, blk.bn1), relu=True)
+        o = ops.conv2d(o, self._pc(name + ".conv2", blk.conv2, blk.bn2), stride=stride, pad=1, relu=True)
+        if len(blk.downsample) > 0:
+            sc = ops.conv2d(x, self._pc(name + ".downsample", blk.downsample[0], blk.downsample[1]), stride=stride)
+        else:
+            sc = x
+        return ops.conv2d(o, self._pc(name + ".conv3", blk.conv3, blk.bn3), relu=True, residual=sc)
+
+    # ------------------------------------------------------------------ necks
+    def detection_neck(self, c3, c4, c5):
+        """fpn.py:107-114 -> [p3, p4, p5, p6, p7]."""
+        f = self.model.fpn
+        p6 = ops.conv2d(c5, self._pc("fpn.conv6", f.conv6), stride=2, pad=1)
+        p7 = ops.conv2d(ops.relu(p6), self._pc("fpn.conv7", f.conv7), stride=2, pad=1)
+        p5 = ops.conv2d(c5, self._pc("fpn.latlayer1", f.latlayer1))
+        p4 = ops.conv2d(c4, self._pc("fpn.latlayer2", f.latlayer2), up=p5)
+        p3 = ops.conv2d(c3, self._pc("fpn.latlayer3", f.latlayer3), up=p4)
+        p5 = ops.conv2d(p5, self._pc("fpn.toplayer0", f.toplayer0), pad=1)
+        p4 = ops.conv2d(p4, self._pc("fpn.toplayer1", f.toplayer1), pad=1)
+        p3 = ops.conv2d(p3, self._pc("fpn.toplayer2", f.toplayer2), pad=1)
+        return [p3, p4, p5, p6, p7]
+
+    def keypoint_neck(self, c2, c3, c4, c5):
+        """fpn.py:117-124 -> [fp2, fp3, fp4, fp5]."""
+        f = self.model.fpn
+        fp5 = ops.conv2d(c5, self._pc("fpn.toplayer", f.toplayer))
+        fp4 = ops.conv2d(c4, self._pc("fpn.flatlayer1", f.flatlayer1), up=fp5)
+        fp3 = ops.conv2d(c3, self._pc("fpn.flatlayer2", f.flatlayer2), up=fp4)
+        fp2 = ops.conv2d(c2, self._pc("fpn.flatlayer3", f.flatlayer3), up=fp3)
+        fp4 = ops.conv2d(fp4, self._pc("fpn.smooth1", f.smooth1), pad=1)
+        fp3 = ops.conv2d(fp3, self._pc("fpn.smooth2", f.smooth2), pad=1)
+        fp2 = ops.conv2d(fp2, self._pc("fpn.smooth3", f.smooth3), pad=1)
+        return [fp2, fp3, fp4, fp5]
+
+    # ------------------------------------------------------------------ heads
+    def keypoint_head(self, p2, p3, p4, p5):
+        """posenet.py:243-257: returns heat [B,18,H/4,W/4] fp32 NCHW."""
+        m = self.model
+        if not (p3.H * 2 == p2.H and p4.H * 4 == p2.H and p5.H * 8 == p2.H and p3.W * 2 == p2.W and p4.W * 4 == p2.W
+                and p5.W * 8 == p2.W):
+            raise RuntimeError("keypoint head needs H and W to be multiples of 32 (evaluate/tester.py:285 pads to 32)")
+        cat = ops.Act(self.fmt, p2.N, p2.H, p2.W, 512, p2.hi.device)
+        for src, t, s, rep, off in ((p5, "convt1", "convs1", 8, 0), (p4, "convt2", "convs2", 4, 128),
+                                    (p3, "convt3", "convs3", 2, 256), (p2, "convt4", "convs4", 1, 384)):
+            q = ops.conv2d(src, self._pc(t, getattr(m, t)), pad=1)
+            ops.conv2d(q, self._pc(s, getattr(m, s)), pad=1, out=cat, out_coffset=off, out_rep=rep)
+        h = ops.conv2d(cat, self._pc("conv2", m.conv2), pad=1, relu=True)
+        return ops.conv2d(h, self._pc("convfin", m.convfin), out_mode=OUT_F32_NCHW)
+
+    def intermediate_heads(self, p2, p3, p4, p5):
+        """posenet.py:296-299."""
+        m = self.model
+        outs = []
+        for src, name, rep in ((p2, "convfin_k2", 1), (p3, "convfin_k3", 2), (p4, "convfin_k4", 4), (p5, "convfin_k5", 8)):
+            outs.append(ops.conv2d(src, self._pc(name, getattr(m, name)), out_mode=OUT_F32_NCHW, out_rep=rep))
+        return outs
+
+    def detection_heads(self, feats):
+        """posenet.py:262-263 -> cls [B,A,1], reg [B,A,4] fp32 (levels concatenated in place)."""
+        m = self.model
+        B = feats[0].N
+        cells = [f.H * f.W for f in feats]
+        A = 9 * sum(cells)
+        dev = feats[0].hi.device
+        cls = torch.empty((B, A, 1), dtype=torch.float32, device=dev)
+        reg = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+        for head, out, per, sig in ((m.regressionModel, reg, 4, False), (m.classificationModel, cls, 1, True)):
+            hname = "regressionModel" if per == 4 else "classificationModel"
+            off = 0
+            for f, ncell in zip(feats, cells):
+                o = f
+                for n in ("conv1", "conv2", "conv3", "conv4"):
+                    o = ops.conv2d(o, self._pc("%s.%s" % (hname, n), getattr(head, n)), pad=1, relu=True)
+                ops.conv2d(o, self._pc(hname + ".output", head.output), pad=1, sigmoid=sig, out_mode=OUT_F32_NHWC,
+                           out_tensor=out, out_elem_offset=off * per, out_cstride=9 * per, out_nstride=A * per)
+                off += ncell * 9
+        return cls, reg
+
+    # ------------------------------------------------------------------ subnet entry points
+    @torch.no_grad()
+    def keypoint_forward(self, img):
+        self._ensure_packed()
+        c2, c3, c4, c5 = self.backbone(img)
+        p2, p3, p4, p5 = self.keypoint_neck(c2, c3, c4, c5)  # the unused detection neck is skipped (fpn.py:126)
+        saved = self.intermediate_heads(p2, p3, p4, p5)
+        heat = self.keypoint_head(p2, p3, p4, p5)
+        saved.append(heat)
+        return heat, saved
+
+    @torch.no_grad()
+    def detection_forward(self, img):
+        self._ensure_packed()
+        _, c3, c4, c5 = self.backbone(img)
+        cls, reg = self.detection_heads(self.detection_neck(c3, c4, c5))
+        anchors = ops.anchors_for(img.shape[2], img.shape[3], img.device)
+        return [], [cls, reg, anchors]
+
+    @torch.no_grad()
+    def fpn_forward(self, img):
+        """FPN.forward (fpn.py:97-126) with the reference's return structure, as fp32 NCHW tensors."""
+        self._ensure_packed()
+        c2, c3, c4, c5 = self.backbone(img)
+        kp = self.keypoint_neck(c2, c3, c4, c5)
+        det = self.detection_neck(c3, c4, c5)
+        return [[a.to_nchw() for a in kp], [a.to_nchw() for a in det]]
+
+    @torch.no_grad()
+    def entire_forward_device(self, img, score_thresh=0.05, iou_thresh=0.5, max_cand=4096, ge=False):
+        """Everything on the device, no host sync: returns (heat, cls, reg, boxes, Detections)."""
+        self._ensure_packed()
+        H, W = img.shape[2], img.shape[3]
+        c2, c3, c4, c5 = self.backbone(img)
+        heat = self.keypoint_head(*self.keypoint_neck(c2, c3, c4, c5))
+        cls, reg = self.detection_heads(self.detection_neck(c3, c4, c5))
+        boxes = ops.decode_clip(ops.anchors_for(H, W, img.device), reg, H, W)
+        det = ops.filter_sort_nms(cls, boxes, score_thresh, iou_thresh, ge=ge, max_cand=max_cand)
+        return heat, cls, reg, boxes, det
+
+    @torch.no_grad()
+    def entire_forward(self, img, max_cand=4096):
+        """posenet.py:236-285: (heat, [nms_scores, nms_class, boxes]) for image 0, like the reference;
+        the per-image results of the whole batch stay in self.last_detections."""
+        heat, cls, reg, boxes, det = self.entire_forward_device(img, max_cand=max_cand)
+        cnt = det.cand_cnt.cpu()
+        if int(cnt.max()) > det.max_cand:  # rare: more survivors than the fast-path capacity -> redo with room
+            det = ops.filter_sort_nms(cls, boxes, 0.05, 0.5, max_cand=int(cnt.max()))
+            cnt = det.cand_cnt.cpu()
+        self.last_detections = det
+        if int(cnt[0]) == 0:  # posenet.py:273-275 (CPU tensors, as in the reference)
+            return heat, [torch.zeros(0), torch.zeros(0), torch.zeros(0, 4)]
+        k = int(det.keep_cnt[0].item())
+        scores = det.scores[0, :k].clone()
+        classes = torch.zeros((k,), dtype=torch.int64, device=img.device)  # single class: argmax over 1 column
+        return heat, [scores, classes, det.boxes[0, :k].clone()]

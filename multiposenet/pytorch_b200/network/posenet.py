@@ -1,0 +1,244 @@
+"""Drop-in `poseNet` with the reference's module tree, state_dict and forward() contract.
+
+Mirror of /root/reference/network/posenet.py:
+  poseNet(layers, prn_node_count=1024, prn_coeff=2)            :154-211
+  forward([img_batch, subnet_name])                            :226-285
+      'keypoint_subnet'  -> (heat[B,18,H/4,W/4], [k2,k3,k4,k5 each [B,19,H/4,W/4], heat])   :288-318
+      'detection_subnet' -> ([], [cls[B,A,1], reg[B,A,4], anchors[1,A,4]])                  :320-335
+      'prn_subnet'       -> (out[B,56,36,17], [out])                                        :337-350
+      anything else      -> (heat, [nms_scores[K], nms_class[K], boxes[K,4]]) for image 0   :236-285
+  build_loss / freeze_bn                                        :220-224, :352-364
+Inference (no grad) runs on libmpn_b200's sm_100a kernels through ..engine.Engine; there is no eager
+PyTorch fallback: CPU tensors or a missing library raise.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import init
+
+from .. import engine as _engine
+from .. import ops as _ops
+from .fpn import FPN50, FPN101
+
+
+def nms(dets, thresh):
+    """posenet.py:19-22: dispatch to pth_nms."""
+    from ..lib.nms.pth_nms import pth_nms
+    return pth_nms(dets, thresh)
+
+
+class _ParamsOnly(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError("%s holds parameters only; use poseNet.forward" % type(self).__name__)
+
+
+class RegressionModel(_ParamsOnly):
+    def __init__(self, num_features_in, num_anchors=9, feature_size=256):
+        super().__init__()
+        self.conv1 = nn.Conv2d(num_features_in, feature_size, 3, padding=1)
+        self.act1 = nn.ReLU()
+        self.conv2 = nn.Conv2d(feature_size, feature_size, 3, padding=1)
+        self.act2 = nn.ReLU()
+        self.conv3 = nn.Conv2d(feature_size, feature_size, 3, padding=1)
+        self.act3 = nn.ReLU()
+        self.conv4 = nn.Conv2d(feature_size, feature_size, 3, padding=1)
+        self.act4 = nn.ReLU()
+        self.output = nn.Conv2d(feature_size, num_anchors * 4, 3, padding=1)
+
+
+class ClassificationModel(_ParamsOnly):
+    def __init__(self, num_features_in, num_anchors=9, num_classes=80, prior=0.01, feature_size=256):
+        super().__init__()
+        self.num_classes, self.num_anchors = num_classes, num_anchors
+        self.conv1 = nn.Conv2d(num_features_in, feature_size, 3, padding=1)
+        self.act1 = nn.ReLU()
+        self.conv2 = nn.Conv2d(feature_size, feature_size, 3, padding=1)
+        self.act2 = nn.ReLU()
+        self.conv3 = nn.Conv2d(feature_size, feature_size, 3, padding=1)
+        self.act3 = nn.ReLU()
+        self.conv4 = nn.Conv2d(feature_size, feature_size, 3, padding=1)
+        self.act4 = nn.ReLU()
+        self.output = nn.Conv2d(feature_size, num_anchors * num_classes, 3, padding=1)
+        self.output_act = nn.Sigmoid()
+
+
+class Flatten(nn.Module):
+    def forward(self, x):
+        return x.view(x.size(0), -1)
+
+
+class Add(nn.Module):
+    def forward(self, a, b):
+        return torch.add(a, b)
+
+
+class Concat(nn.Module):
+    def forward(self, a, b, c, d):
+        return torch.cat((a, b, c, d), 1)
+
+
+class PRN(nn.Module):
+    """posenet.py:130-152.  Off the conv hot path: three nn.Linear library calls."""
+
+    def __init__(self, node_count, coeff):
+        super().__init__()
+        self.flatten = Flatten()
+        self.height, self.width = coeff * 28, coeff * 18
+        n = self.height * self.width * 17
+        self.dens1 = nn.Linear(n, node_count)
+        self.bneck = nn.Linear(node_count, node_count)
+        self.dens2 = nn.Linear(node_count, n)
+        self.drop = nn.Dropout()
+        self.add = Add()
+        self.softmax = nn.Softmax(dim=1)
+
+    def forward(self, x):
+        res = self.flatten(x)
+        out = self.drop(F.relu(self.dens1(res)))
+        out = self.drop(F.relu(self.bneck(out)))
+        out = F.relu(self.dens2(out))
+        out = self.softmax(self.add(out, res))
+        return out.view(out.size(0), self.height, self.width, 17)
+
+
+class poseNet(nn.Module):
+    def __init__(self, layers, prn_node_count=1024, prn_coeff=2, precision=None):
+        super().__init__()
+        if layers == 101:
+            self.fpn = FPN101()
+        elif layers == 50:
+            self.fpn = FPN50()
+        else:
+            raise ValueError("layers must be 50 or 101")
+        self.layers = layers
+        # keypoint subnet: intermediate supervision heads, per-level towers, fusion
+        for k in (2, 3, 4, 5):
+            setattr(self, "convfin_k%d" % k, nn.Conv2d(256, 19, 1))
+        for i in (1, 2, 3, 4):
+            setattr(self, "convt%d" % i, nn.Conv2d(256, 128, 3, padding=1))
+        for i in (1, 2, 3, 4):
+            setattr(self, "convs%d" % i, nn.Conv2d(128, 128, 3, padding=1))
+        self.upsample1 = nn.Upsample(scale_factor=8, mode="nearest")
+        self.upsample2 = nn.Upsample(scale_factor=4, mode="nearest")
+        self.upsample3 = nn.Upsample(scale_factor=2, mode="nearest")
+        self.concat = Concat()
+        self.conv2 = nn.Conv2d(512, 256, 3, padding=1)
+        self.convfin = nn.Conv2d(256, 18, 1)
+        # detection subnet
+        self.regressionModel = RegressionModel(256)
+        self.classificationModel = ClassificationModel(256, num_classes=1)
+        from .anchors import Anchors
+        from .utils import BBoxTransform, ClipBoxes
+        self.anchors = Anchors()
+        self.regressBoxes = BBoxTransform()
+        self.clipBoxes = ClipBoxes()
+        # pose residual network
+        self.prn = PRN(prn_node_count, prn_coeff)
+        self._initialize_weights_norm()
+        prior = 0.01
+        with torch.no_grad():
+            self.classificationModel.output.weight.fill_(0)
+            self.classificationModel.output.bias.fill_(-math.log((1.0 - prior) / prior))
+            self.regressionModel.output.weight.fill_(0)
+            self.regressionModel.output.bias.fill_(0)
+        self.freeze_bn()
+        object.__setattr__(self, "_engines", {})
+        self._precision = precision
+
+    # -- reference API ---------------------------------------------------------------------------
+    def _initialize_weights_norm(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                init.normal_(m.weight, std=0.01)
+                if m.bias is not None:
+                    init.constant_(m.bias, 0.0)
+
+    def freeze_bn(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    def engine(self, precision=None):
+        precision = precision or self._precision or _engine.DEFAULT_PRECISION
+        # nn.DataParallel replicas share this dict (shallow __dict__ copy): key by module identity
+        engines = self.__dict__.setdefault("_engines", {})
+        key = (precision, id(self))
+        e = engines.get(key)
+        if e is None or e.model is not self:
+            if len(engines) > 32:
+                engines.clear()
+            e = _engine.Engine(self, precision)
+            engines[key] = e
+        return e
+
+    def forward(self, x):
+        img_batch, subnet_name = x
+        if subnet_name == "prn_subnet":
+            return self.prn_forward(img_batch)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError(
+                "libmpn_b200 round 1 implements the inference path (no_grad / eval); the training step "
+                "(dgrad/wgrad kernels + NCCL allreduce, SURVEY 8(a17)) is not built yet and there is no eager fallback")
+        eng = self.engine()
+        with torch.cuda.device(img_batch.device):
+            if subnet_name == "keypoint_subnet":
+                return eng.keypoint_forward(img_batch)
+            if subnet_name == "detection_subnet":
+                return eng.detection_forward(img_batch)
+            return eng.entire_forward(img_batch)
+
+    def keypoint_forward(self, img_batch):
+        return self.forward((img_batch, "keypoint_subnet"))
+
+    def detection_forward(self, img_batch):
+        return self.forward((img_batch, "detection_subnet"))
+
+    def prn_forward(self, img_batch):
+        out = self.prn(img_batch)
+        return out, [out]
+
+    @staticmethod
+    def build_loss(saved_for_loss, *args):
+        subnet_name = args[0]
+        if subnet_name == "keypoint_subnet":
+            return build_keypoint_loss(saved_for_loss, args[1], args[2])
+        if subnet_name == "detection_subnet":
+            raise NotImplementedError("detection training loss (network/losses.py) is outside the hot path (SURVEY 8(f) rank 4)")
+        if subnet_name == "prn_subnet":
+            return build_prn_loss(saved_for_loss, args[1])
+        return 0
+
+
+PoseNet = poseNet  # alias (BASELINE.json spells it with a capital P)
+
+
+def build_names():
+    names = []
+    for j in range(2, 6):
+        names += ["heatmap_loss_k%d" % j, "seg_loss_k%d" % j]
+    return names + ["heatmap_loss", "seg_loss"]
+
+
+def build_keypoint_loss(saved_for_loss, heat_temp, heat_weight):
+    """posenet.py:367-403: sum over the 5 maps of MSE(pred[:, :18] * w, w * gt), mean reduction."""
+    names = build_names()
+    log = OrderedDict()
+    total = 0
+    target = heat_weight * heat_temp
+    for j in range(5):
+        loss = F.mse_loss(saved_for_loss[j][:, :18] * heat_weight, target)
+        total = total + loss
+        log[names[2 * j]] = loss.item()
+    last = saved_for_loss[-1].detach()[:, :18]
+    log["max_ht"] = last.max().item()
+    log["min_ht"] = last.min().item()
+    return total, log
+
+
+def build_prn_loss(saved_for_loss, label):
+    """posenet.py:426-445."""
+    loss = F.binary_cross_entropy(saved_for_loss[0], label)
+    return loss, OrderedDict([("PRN loss", loss.item())])

@@ -1,0 +1,240 @@
+"""Host-side wrappers: torch tensors own the device memory, the C ABI does the work.
+
+torch is plumbing here (allocation, streams); every computation below is a libmpn_b200 call.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_RELU, EPI_SIGMOID, FMT_BF16, FMT_BF16X2, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_NHWC, ConvDesc,
+                   ConvPtrs, check)
+
+PRECISIONS = {"fp32": FMT_F32, "bf16": FMT_BF16, "bf16x3": FMT_BF16X2}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _dtype(fmt):
+    return torch.float32 if fmt == FMT_F32 else torch.bfloat16
+
+
+class Act(object):
+    """NHWC activation: `hi` (and `lo` for the split format) are [N,H,W,cstride] tensors."""
+    __slots__ = ("fmt", "N", "H", "W", "C", "cstride", "hi", "lo")
+
+    def __init__(self, fmt, N, H, W, C, device, cstride=None, zero=False):
+        self.fmt, self.N, self.H, self.W, self.C = fmt, N, H, W, C
+        self.cstride = C if cstride is None else cstride
+        mk = torch.zeros if zero else torch.empty
+        self.hi = mk((N, H, W, self.cstride), dtype=_dtype(fmt), device=device)
+        self.lo = mk((N, H, W, self.cstride), dtype=torch.bfloat16, device=device) if fmt == FMT_BF16X2 else None
+
+    def to_nchw(self):
+        out = torch.empty((self.N, self.C, self.H, self.W), dtype=torch.float32, device=self.hi.device)
+        check(_lib.lib().mpn_nhwc_to_nchw(_ptr(self.hi), _ptr(self.lo), _ptr(out), self.N, self.C, self.H, self.W,
+                                          self.cstride, self.fmt, _stream()), "mpn_nhwc_to_nchw")
+        return out
+
+
+def act_from_nchw(x, fmt, cstride=None):
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+    x = x.contiguous()
+    N, C, H, W = x.shape
+    a = Act(fmt, N, H, W, C, x.device, cstride=cstride)
+    check(_lib.lib().mpn_nchw_to_nhwc(_ptr(x), _ptr(a.hi), _ptr(a.lo), N, C, H, W, a.cstride, fmt, _stream()), "mpn_nchw_to_nhwc")
+    return a
+
+
+class PackedConv(object):
+    """Filter + per-channel epilogue constants of one nn.Conv2d (+ folded eval-mode BatchNorm2d)."""
+    __slots__ = ("Cout", "Cin", "R", "S", "fmt", "w_hi", "w_lo", "cout_pad", "scale", "bias")
+
+
+def pack_conv(weight, bias, bn, fmt):
+    """weight OIHW fp32 cuda; bias fp32 or None; bn = (gamma, beta, mean, var, eps) or None."""
+    L = _lib.lib()
+    w = weight.detach().contiguous()
+    assert w.is_cuda and w.dtype == torch.float32
+    pc = PackedConv()
+    pc.Cout, pc.Cin, pc.R, pc.S = w.shape
+    pc.fmt = fmt
+    dev = w.device
+    if fmt == FMT_F32:
+        pc.cout_pad = (pc.Cout + 63) // 64 * 64
+        pc.w_hi = torch.empty((pc.R, pc.S, pc.Cin, pc.cout_pad), dtype=torch.float32, device=dev)
+        pc.w_lo = None
+        check(L.mpn_pack_filter_f32(_ptr(w), _ptr(pc.w_hi), pc.Cout, pc.Cin, pc.R, pc.S, pc.cout_pad, _stream()), "mpn_pack_filter_f32")
+    else:
+        pc.cout_pad = pc.Cout
+        pc.w_hi = torch.empty((pc.Cout, pc.R, pc.S, pc.Cin), dtype=torch.bfloat16, device=dev)
+        pc.w_lo = torch.empty_like(pc.w_hi) if fmt == FMT_BF16X2 else None
+        check(L.mpn_pack_filter_bf16(_ptr(w), _ptr(pc.w_hi), _ptr(pc.w_lo), pc.Cout, pc.Cin, pc.R, pc.S, _stream()), "mpn_pack_filter_bf16")
+    npad = (pc.Cout + 63) // 64 * 64
+    if bn is not None:
+        gamma, beta, mean, var, eps = bn
+        pc.scale = torch.zeros(npad, dtype=torch.float32, device=dev)
+        pc.bias = torch.zeros(npad, dtype=torch.float32, device=dev)
+        check(L.mpn_fold_bn(_ptr(gamma.detach().contiguous()), _ptr(beta.detach().contiguous()), _ptr(mean.contiguous()),
+                            _ptr(var.contiguous()), float(eps), _ptr(pc.scale), _ptr(pc.bias), pc.Cout, _stream()), "mpn_fold_bn")
+        assert bias is None
+    else:
+        pc.scale = None
+        if bias is not None:
+            pc.bias = torch.zeros(npad, dtype=torch.float32, device=dev)
+            pc.bias[: pc.Cout].copy_(bias.detach())
+        else:
+            pc.bias = None
+    return pc
+
+
+def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=None, out=None, out_mode=OUT_ACT,
+           out_coffset=0, out_rep=1, out_tensor=None, out_elem_offset=0, out_cstride=None, out_nstride=0, f32_input=False):
+    """y = epilogue(conv2d(x, w)).  Returns the output Act (OUT_ACT) or the fp32 tensor written.
+
+    out          : existing Act to write into (concat buffers), else a new one is allocated
+    out_tensor   : fp32 tensor for OUT_F32_* (allocated if None); out_elem_offset shifts the base pointer
+    f32_input    : x is an fp32 NHWC Act while the output/epilogue use pc.fmt (stem)
+    """
+    L = _lib.lib()
+    fmt = pc.fmt
+    d = ConvDesc()
+    d.N, d.H, d.W, d.Cin = x.N, x.H, x.W, pc.Cin
+    assert x.C == pc.Cin, (x.C, pc.Cin)
+    d.Cout, d.R, d.S, d.stride, d.pad = pc.Cout, pc.R, pc.S, stride, pad
+    d.OH = (x.H + 2 * pad - pc.R) // stride + 1
+    d.OW = (x.W + 2 * pad - pc.S) // stride + 1
+    d.fmt = fmt
+    d.in_cstride = x.cstride
+    d.flags = (EPI_RELU if relu else 0) | (EPI_SIGMOID if sigmoid else 0)
+    d.out_mode, d.out_rep, d.out_coffset = out_mode, out_rep, out_coffset
+    d.w_cout_pad = pc.cout_pad
+    p = ConvPtrs()
+    p.x_hi, p.x_lo = _ptr(x.hi), _ptr(x.lo)
+    p.w_hi, p.w_lo = _ptr(pc.w_hi), _ptr(pc.w_lo)
+    p.scale, p.bias = _ptr(pc.scale), _ptr(pc.bias)
+    if residual is not None:
+        assert (residual.N, residual.H, residual.W, residual.C) == (x.N, d.OH, d.OW, pc.Cout) and residual.fmt == fmt
+        d.res_cstride = residual.cstride
+        p.res_hi, p.res_lo = _ptr(residual.hi), _ptr(residual.lo)
+    if up is not None:
+        assert up.N == x.N and up.C == pc.Cout and up.fmt == fmt
+        d.up_h, d.up_w, d.up_cstride = up.H, up.W, up.cstride
+        p.up_hi, p.up_lo = _ptr(up.hi), _ptr(up.lo)
+    ret = None
+    if out_mode == OUT_ACT:
+        if out is None:
+            out = Act(fmt, x.N, d.OH * out_rep, d.OW * out_rep, pc.Cout, x.hi.device)
+        assert out.fmt == fmt and out.N == x.N and out.H == d.OH * out_rep and out.W == d.OW * out_rep
+        d.out_cstride = out.cstride
+        p.y_hi, p.y_lo = _ptr(out.hi), _ptr(out.lo)
+        ret = out
+    else:
+        if out_tensor is None:
+            shape = ((x.N, pc.Cout, d.OH * out_rep, d.OW * out_rep) if out_mode == OUT_F32_NCHW
+                     else (x.N, d.OH * out_rep, d.OW * out_rep, pc.Cout))
+            out_tensor = torch.empty(shape, dtype=torch.float32, device=x.hi.device)
+        assert out_tensor.dtype == torch.float32 and out_tensor.is_contiguous()
+        d.out_cstride = pc.Cout if out_cstride is None else out_cstride
+        d.out_nstride = out_nstride
+        p.y_hi = ctypes.c_void_p(out_tensor.data_ptr() + 4 * out_elem_offset)
+        ret = out_tensor
+    fn = L.mpn_conv2d_fwd_f32in if f32_input else L.mpn_conv2d_fwd
+    check(fn(ctypes.byref(d), ctypes.byref(p), _stream()), "mpn_conv2d_fwd")
+    return ret
+
+
+def maxpool3x3s2(x):
+    OH, OW = (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1
+    y = Act(x.fmt, x.N, OH, OW, x.C, x.hi.device)
+    assert x.cstride == x.C
+    check(_lib.lib().mpn_maxpool3x3s2(_ptr(x.hi), _ptr(x.lo), _ptr(y.hi), _ptr(y.lo), x.N, x.H, x.W, x.C, x.fmt, _stream()), "mpn_maxpool3x3s2")
+    return y
+
+
+def relu(x):
+    y = Act(x.fmt, x.N, x.H, x.W, x.C, x.hi.device, cstride=x.cstride)
+    check(_lib.lib().mpn_relu(_ptr(x.hi), _ptr(x.lo), _ptr(y.hi), _ptr(y.lo), x.hi.numel(), x.fmt, _stream()), "mpn_relu")
+    return y
+
+
+_ANCHOR_CACHE = {}
+
+
+def anchors_for(H, W, device):
+    """[1,A,4] fp32 anchors (bit-identical to network/anchors.py), generated once per (H, W, device)."""
+    key = (int(H), int(W), str(device))
+    t = _ANCHOR_CACHE.get(key)
+    if t is None:
+        L = _lib.lib()
+        A = L.mpn_num_anchors(int(H), int(W))
+        host = torch.empty((1, A, 4), dtype=torch.float32)
+        check(L.mpn_generate_anchors(int(H), int(W), ctypes.c_void_p(host.data_ptr())), "mpn_generate_anchors")
+        t = host.to(device)
+        _ANCHOR_CACHE[key] = t
+    return t
+
+
+def decode_clip(anchors, reg, H, W):
+    B, A = reg.shape[0], reg.shape[1]
+    boxes = torch.empty((B, A, 4), dtype=torch.float32, device=reg.device)
+    check(_lib.lib().mpn_decode_clip(_ptr(anchors), _ptr(reg), _ptr(boxes), B, A, int(H), int(W), _stream()), "mpn_decode_clip")
+    return boxes
+
+
+class Detections(object):
+    __slots__ = ("cand_idx", "cand_cnt", "keep_idx", "keep_cnt", "scores", "boxes", "max_cand")
+
+
+def filter_sort_nms(cls, boxes, score_thresh=0.05, iou_thresh=0.5, ge=False, max_cand=4096):
+    """cls [B,A,1] or [B,A] fp32, boxes [B,A,4] fp32 -> Detections (device tensors, no host sync)."""
+    L = _lib.lib()
+    B, A = boxes.shape[0], boxes.shape[1]
+    max_cand = int(min(max(64, max_cand), A))
+    dev = boxes.device
+    det = Detections()
+    det.max_cand = max_cand
+    det.cand_idx = torch.empty((B, max_cand), dtype=torch.int32, device=dev)
+    det.cand_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    det.keep_idx = torch.empty((B, max_cand), dtype=torch.int64, device=dev)
+    det.keep_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    det.scores = torch.empty((B, max_cand), dtype=torch.float32, device=dev)
+    det.boxes = torch.empty((B, max_cand, 4), dtype=torch.float32, device=dev)
+    ws_bytes = L.mpn_detect_workspace_bytes(B, A, max_cand)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    check(L.mpn_filter_sort_nms(_ptr(cls.contiguous()), _ptr(boxes.contiguous()), B, A, float(score_thresh), float(iou_thresh),
+                                int(bool(ge)), max_cand, _ptr(det.cand_idx), _ptr(det.cand_cnt), _ptr(det.keep_idx),
+                                _ptr(det.keep_cnt), _ptr(det.scores), _ptr(det.boxes), _ptr(ws), ws_bytes, _stream()),
+          "mpn_filter_sort_nms")
+    return det
+
+
+def nms(dets, thresh, ge=False):
+    """dets [n,5] fp32 cuda -> int64 [K] indices into dets, descending score (pth_nms semantics)."""
+    L = _lib.lib()
+    assert dets.is_cuda and dets.dtype == torch.float32 and dets.dim() == 2 and dets.shape[1] == 5
+    n = dets.shape[0]
+    if n == 0:
+        return torch.zeros((0,), dtype=torch.int64, device=dets.device)
+    dets = dets.contiguous()
+    keep = torch.empty((n,), dtype=torch.int64, device=dets.device)
+    num = torch.zeros((1,), dtype=torch.int32, device=dets.device)
+    ws_bytes = L.mpn_nms_workspace_bytes(n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dets.device)
+    check(L.mpn_nms(_ptr(dets), n, float(thresh), int(bool(ge)), _ptr(keep), _ptr(num), _ptr(ws), ws_bytes, _stream()), "mpn_nms")
+    k = int(num.item())
+    return keep[:k]
+
+
+def nms_mask(sorted_dets, thresh, ge=False):
+    n = sorted_dets.shape[0]
+    cb = (n + 63) // 64
+    mask = torch.zeros((n, cb), dtype=torch.int64, device=sorted_dets.device)
+    check(_lib.lib().mpn_nms_mask(_ptr(sorted_dets.contiguous()), n, float(thresh), int(bool(ge)), _ptr(mask), _stream()), "mpn_nms_mask")
+    return mask

@@ -1,0 +1,68 @@
+"""GPU parity of the conv primitive (CUDA-core fp32 and tcgen05 bf16 / bf16x3) vs torch fp32 conv2d."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# (N, H, W, Cin, Cout, R, stride, pad, kwargs)
+SIMT_CASES = [
+    (2, 17, 23, 3, 64, 7, 2, 3, dict(bn=True, relu=True, bias=False)),           # stem
+    (2, 12, 20, 64, 64, 1, 1, 0, dict(bn=True, relu=True, bias=False)),
+    (1, 13, 9, 64, 128, 3, 2, 1, dict(bn=True, relu=True, bias=False)),
+    (2, 8, 8, 128, 256, 1, 1, 0, dict(bn=True, residual=True, relu=True, bias=False)),
+    (2, 10, 14, 96, 64, 1, 1, 0, dict(up=True)),
+    (1, 7, 9, 32, 18, 1, 1, 0, dict(out_mode=2, rep=4)),
+    (2, 6, 5, 64, 36, 3, 1, 1, dict(out_mode=1)),
+    (2, 6, 5, 64, 9, 3, 1, 1, dict(out_mode=1, sigmoid=True)),
+    (1, 5, 6, 64, 128, 3, 1, 1, dict(rep=2, coffset=128, ctotal=512)),
+]
+
+TC_CASES = [
+    (2, 16, 32, 64, 64, 1, 1, 0, dict(bn=True, relu=True, bias=False)),
+    (2, 16, 32, 64, 64, 3, 1, 1, dict(bn=True, relu=True, bias=False)),
+    (1, 30, 40, 256, 256, 3, 1, 1, dict()),
+    (2, 15, 20, 512, 128, 1, 1, 0, dict(bn=True, relu=True, bias=False)),
+    (2, 30, 40, 128, 128, 3, 2, 1, dict(bn=True, relu=True, bias=False)),          # stride-2 phase views
+    (2, 15, 20, 256, 512, 1, 2, 0, dict(bn=True, bias=False)),                      # projection shortcut
+    (2, 15, 21, 128, 128, 3, 2, 1, dict()),                                         # odd sizes, stride 2
+    (2, 8, 8, 128, 256, 1, 1, 0, dict(bn=True, residual=True, relu=True, bias=False)),
+    (2, 10, 14, 128, 256, 1, 1, 0, dict(up=True)),
+    (1, 16, 24, 256, 18, 1, 1, 0, dict(out_mode=2)),
+    (1, 4, 6, 256, 19, 1, 1, 0, dict(out_mode=2, rep=4)),
+    (2, 6, 5, 256, 36, 3, 1, 1, dict(out_mode=1)),
+    (2, 6, 5, 256, 9, 3, 1, 1, dict(out_mode=1, sigmoid=True)),
+    (1, 5, 6, 128, 128, 3, 1, 1, dict(rep=2, coffset=128, ctotal=512)),
+    (3, 2, 3, 2048, 256, 3, 2, 1, dict()),                                          # conv6 on a tiny map
+    (3, 1, 2, 256, 256, 3, 2, 1, dict()),                                           # conv7: empty phase views
+    (2, 60, 80, 64, 256, 1, 1, 0, dict(bn=True, relu=True, bias=False)),            # many tiles / persistence
+    (1, 24, 32, 512, 256, 3, 1, 1, dict(relu=True)),                                # long K loop (72 k-iters)
+]
+
+
+def _check(fmt, case, tol_rounded, tol_exact):
+    from gpu_util import conv_case, nerr, no_tf32
+    no_tf32()
+    N, H, W, Cin, Cout, R, stride, pad, kw = case
+    ours, ref_r, ref_e = conv_case(fmt, N, H, W, Cin, Cout, R, stride, pad, **kw)
+    assert ours.shape == ref_e.shape
+    assert torch.isfinite(ours).all()
+    er, ee = nerr(ours, ref_r), nerr(ours, ref_e)
+    assert er <= tol_rounded and ee <= tol_exact, "err vs rounded-operand ref %.3g (tol %.3g), vs fp32 ref %.3g (tol %.3g)" % (
+        er, tol_rounded, ee, tol_exact)
+
+
+@pytest.mark.parametrize("case", SIMT_CASES)
+def test_conv_fp32_cuda_core(case):
+    _check(0, case, 2e-5, 2e-5)
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_bf16x3(case):
+    # operands carry ~16 mantissa bits; bf16 hi/lo re-split of the output costs 2^-17
+    _check(2, case, 5e-5, 1e-4)
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_bf16(case):
+    # vs the same conv on bf16-rounded operands only accumulation order + bf16 output rounding differ
+    _check(1, case, 6e-3, 3e-2)
