@@ -182,6 +182,9 @@ class poseNet(nn.Module):
             raise NotImplementedError(
                 "libmpn_b200 round 1 implements the inference path (no_grad / eval); the training step "
                 "(dgrad/wgrad kernels + NCCL allreduce, SURVEY 8(a17)) is not built yet and there is no eager fallback")
+        if not (torch.is_tensor(img_batch) and img_batch.is_cuda):
+            raise RuntimeError("poseNet.forward needs a CUDA image batch: the path runs on libmpn_b200 (sm_100a) only, "
+                               "there is no CPU / eager fallback")
         eng = self.engine()
         with torch.cuda.device(img_batch.device):
             if subnet_name == "keypoint_subnet":

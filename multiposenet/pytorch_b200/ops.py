@@ -12,6 +12,10 @@ from ._lib import (EPI_RELU, EPI_SIGMOID, FMT_BF16, FMT_BF16X2, FMT_F32, OUT_ACT
 
 PRECISIONS = {"fp32": FMT_F32, "bf16": FMT_BF16, "bf16x3": FMT_BF16X2}
 
+# Launch accounting for bench.py: `launches` counts kernels launched through this module; when
+# `conv_events` is a list, every tensor-core / CUDA-core conv launch is bracketed by CUDA events.
+stats = {"launches": 0, "conv_events": None}
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -40,6 +44,7 @@ class Act(object):
         out = torch.empty((self.N, self.C, self.H, self.W), dtype=torch.float32, device=self.hi.device)
         check(_lib.lib().mpn_nhwc_to_nchw(_ptr(self.hi), _ptr(self.lo), _ptr(out), self.N, self.C, self.H, self.W,
                                           self.cstride, self.fmt, _stream()), "mpn_nhwc_to_nchw")
+        stats["launches"] += 1
         return out
 
 
@@ -49,6 +54,7 @@ def act_from_nchw(x, fmt, cstride=None):
     N, C, H, W = x.shape
     a = Act(fmt, N, H, W, C, x.device, cstride=cstride)
     check(_lib.lib().mpn_nchw_to_nhwc(_ptr(x), _ptr(a.hi), _ptr(a.lo), N, C, H, W, a.cstride, fmt, _stream()), "mpn_nchw_to_nhwc")
+    stats["launches"] += 1
     return a
 
 
@@ -146,7 +152,15 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
         p.y_hi = ctypes.c_void_p(out_tensor.data_ptr() + 4 * out_elem_offset)
         ret = out_tensor
     fn = L.mpn_conv2d_fwd_f32in if f32_input else L.mpn_conv2d_fwd
+    ev = stats["conv_events"]
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(fn(ctypes.byref(d), ctypes.byref(p), _stream()), "mpn_conv2d_fwd")
+    if ev is not None:
+        e1.record()
+        ev.append((e0, e1, 2.0 * x.N * d.OH * d.OW * pc.Cout * pc.Cin * pc.R * pc.S, bool(f32_input or fmt == FMT_F32)))
+    stats["launches"] += 1
     return ret
 
 
@@ -155,12 +169,14 @@ def maxpool3x3s2(x):
     y = Act(x.fmt, x.N, OH, OW, x.C, x.hi.device)
     assert x.cstride == x.C
     check(_lib.lib().mpn_maxpool3x3s2(_ptr(x.hi), _ptr(x.lo), _ptr(y.hi), _ptr(y.lo), x.N, x.H, x.W, x.C, x.fmt, _stream()), "mpn_maxpool3x3s2")
+    stats["launches"] += 1
     return y
 
 
 def relu(x):
     y = Act(x.fmt, x.N, x.H, x.W, x.C, x.hi.device, cstride=x.cstride)
     check(_lib.lib().mpn_relu(_ptr(x.hi), _ptr(x.lo), _ptr(y.hi), _ptr(y.lo), x.hi.numel(), x.fmt, _stream()), "mpn_relu")
+    stats["launches"] += 1
     return y
 
 
@@ -185,6 +201,7 @@ def decode_clip(anchors, reg, H, W):
     B, A = reg.shape[0], reg.shape[1]
     boxes = torch.empty((B, A, 4), dtype=torch.float32, device=reg.device)
     check(_lib.lib().mpn_decode_clip(_ptr(anchors), _ptr(reg), _ptr(boxes), B, A, int(H), int(W), _stream()), "mpn_decode_clip")
+    stats["launches"] += 1
     return boxes
 
 
@@ -212,6 +229,7 @@ def filter_sort_nms(cls, boxes, score_thresh=0.05, iou_thresh=0.5, ge=False, max
                                 int(bool(ge)), max_cand, _ptr(det.cand_idx), _ptr(det.cand_cnt), _ptr(det.keep_idx),
                                 _ptr(det.keep_cnt), _ptr(det.scores), _ptr(det.boxes), _ptr(ws), ws_bytes, _stream()),
           "mpn_filter_sort_nms")
+    stats["launches"] += 6  # filter/compact, segments, radix sort (>=1), gather, mask, reduce
     return det
 
 
