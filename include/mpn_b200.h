@@ -63,7 +63,10 @@ typedef struct mpn_conv_desc {
   int out_rep;               /* nearest-upsample replication factor on store: 1,2,4,8 (posenet.py:180-182) */
   long long out_nstride;     /* elements between images in the destination (0 = dense)        */
   int w_cout_pad;            /* fp32 path: padded Cout of the [R][S][Cin][CoutPad] filter     */
-  int reserved;
+  int in_wpitch;             /* pixels per input row in memory (0 = W); tcgen05 path only     */
+  int in_hpitch;             /* rows per input image in memory (0 = H); tcgen05 path only     */
+  int k_overlap;             /* 1: in_cstride < Cin is intended -- each "pixel" of Cin channels is a window of
+                                Cin/in_cstride neighbouring pixels (stem as a space-to-depth conv) */
 } mpn_conv_desc;
 
 typedef struct mpn_conv_ptrs {
@@ -94,6 +97,14 @@ int mpn_pack_filter_bf16(const float* w_oihw, void* dst_hi, void* dst_lo, int Co
 /* BatchNorm (eval) fold: scale = gamma/sqrt(var+eps), bias = beta - mean*scale   (fpn.py:15-19,25,43) */
 int mpn_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                 float* scale, float* bias, int C, void* stream);
+
+/* ---- tensor-core stem (fpn.py:99: 7x7/2 conv, 3 -> 64).  The image is re-laid as a zero-padded
+ * space-to-depth tensor X2[n, H/2+3, W/2+3, 16] (channel = (row parity, col parity, rgb), 12 used) in
+ * which the 7x7/2 conv is a 4x4/1 conv; one filter row (4 pixels x 16 ch = 64 contiguous elements) is one
+ * K block, so mpn_conv2d_fwd runs it with R=4, S=1, Cin=64, in_cstride=16, k_overlap=1. */
+int mpn_stem_pack_input(const float* img_nchw, void* dst_hi, void* dst_lo, int N, int H, int W, int fmt, void* stream);
+/* OIHW [64,3,7,7] fp32 -> [64][4][64] bf16 hi (+lo) matching that layout */
+int mpn_stem_pack_filter(const float* w_oihw, void* dst_hi, void* dst_lo, int Cout, void* stream);
 
 /* ---- layout / elementwise */
 /* fp32 NCHW -> NHWC in `fmt` (dst_lo for BF16X2); cstride >= C, padding channels are zeroed */

@@ -19,7 +19,7 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [(n, c_int) for n in (
         "N", "H", "W", "Cin", "Cout", "R", "S", "stride", "pad", "OH", "OW", "fmt", "in_cstride", "flags",
         "res_cstride", "up_h", "up_w", "up_cstride", "out_mode", "out_cstride", "out_coffset", "out_rep")] + [
-        ("out_nstride", c_ll), ("w_cout_pad", c_int), ("reserved", c_int)]
+        ("out_nstride", c_ll), ("w_cout_pad", c_int), ("in_wpitch", c_int), ("in_hpitch", c_int), ("k_overlap", c_int)]
 
 
 class ConvPtrs(ctypes.Structure):
@@ -42,6 +42,8 @@ _SIGS = {
     "mpn_pack_filter_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_pack_filter_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_fold_bn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "mpn_stem_pack_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_stem_pack_filter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mpn_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -156,7 +156,7 @@ int check_desc(const mpn_conv_desc* d, const mpn_conv_ptrs* p) {
                 "conv: bad problem size");
   MPN_CHECK_ARG(d->OH == (d->H + 2 * d->pad - d->R) / d->stride + 1 && d->OW == (d->W + 2 * d->pad - d->S) / d->stride + 1,
                 "conv: OH/OW do not match (H + 2*pad - R)/stride + 1");
-  MPN_CHECK_ARG(d->in_cstride >= d->Cin, "conv: in_cstride < Cin");
+  MPN_CHECK_ARG(d->in_cstride >= d->Cin || d->k_overlap, "conv: in_cstride < Cin");
   MPN_CHECK_ARG(d->out_rep == 1 || d->out_rep == 2 || d->out_rep == 4 || d->out_rep == 8, "conv: out_rep must be 1,2,4,8");
   MPN_CHECK_ARG(d->out_mode >= 0 && d->out_mode <= 2, "conv: bad out_mode");
   MPN_CHECK_ARG(d->out_mode == MPN_OUT_F32_NCHW || d->out_cstride >= d->out_coffset + d->Cout, "conv: out_cstride too small");
@@ -175,6 +175,7 @@ int launch_simt(const mpn_conv_desc* d, const mpn_conv_ptrs* p, int in_fmt, void
   int rc = check_desc(d, p);
   if (rc) return rc;
   MPN_CHECK_ARG(d->w_cout_pad >= d->Cout && d->w_cout_pad % 4 == 0, "conv(fp32): w_cout_pad must be >= Cout and a multiple of 4");
+  MPN_CHECK_ARG(!d->k_overlap && !d->in_wpitch && !d->in_hpitch, "conv(fp32): pitched / overlapped inputs are a tcgen05-path feature");
   MPN_CHECK_ARG(in_fmt != MPN_FMT_BF16X2 || p->x_lo, "conv: BF16X2 input needs x_lo");
   SimtParams P;
   P.d = *d;

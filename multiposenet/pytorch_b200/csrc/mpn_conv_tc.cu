@@ -522,6 +522,12 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   const int planes = split ? 2 : 1;
   const int st = d->stride;
   const int nphase = st == 1 ? 1 : 4;
+  const long long wpitch = d->in_wpitch > 0 ? d->in_wpitch : d->W;   // pixels per row in memory
+  const long long hpitch = d->in_hpitch > 0 ? d->in_hpitch : d->H;   // rows per image in memory
+  MPN_CHECK_ARG(wpitch >= d->W && hpitch >= d->H, "conv(tcgen05): pitches smaller than the logical size");
+  MPN_CHECK_ARG(!d->k_overlap || (st == 1 && d->Cin == BLOCK_K && d->in_cstride % 8 == 0 &&
+                                  wpitch >= d->W + d->Cin / d->in_cstride - 1),
+                "conv(tcgen05): k_overlap needs stride 1, Cin == 64 and a row pitch covering the window");
   for (int pl = 0; pl < planes; ++pl) {
     const char* xb = (const char*)(pl == 0 ? p->x_hi : p->x_lo);
     for (int ph = 0; ph < nphase; ++ph) {
@@ -532,10 +538,10 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
         continue;
       }
       cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)d->N};
-      cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * st * 2ULL, (cuuint64_t)d->W * d->in_cstride * st * 2ULL,
-                               (cuuint64_t)d->H * d->W * d->in_cstride * 2ULL};
+      cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * st * 2ULL, (cuuint64_t)wpitch * d->in_cstride * st * 2ULL,
+                               (cuuint64_t)hpitch * wpitch * d->in_cstride * 2ULL};
       cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
-      const char* base = xb + ((long long)hp * d->W + wp) * d->in_cstride * 2LL;
+      const char* base = xb + ((long long)hp * wpitch + wp) * d->in_cstride * 2LL;
       int rc = encode(fn, &maps.a[pl][ph], base, 4, dims, strides, box);
       if (rc) return rc;
     }

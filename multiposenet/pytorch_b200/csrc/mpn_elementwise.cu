@@ -205,3 +205,58 @@ extern "C" int mpn_relu(const void* xhi, const void* xlo, void* yhi, void* ylo, 
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core stem helpers (see mpn_b200.h).  X2[n][hp][wp][cc], cc = (ph*2+pw)*3 + c, hp = h/2 + 2.
+__global__ void stem_pack_input_kernel(const float* __restrict__ img, void* hi, void* lo, int N, int H, int W, int H2p, int W2p,
+                                       int fmt) {
+  long long total = (long long)N * H2p * W2p * 16;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cc = (int)(i & 15);
+    long long p = i >> 4;
+    int wp = (int)(p % W2p);
+    long long q = p / W2p;
+    int hp = (int)(q % H2p);
+    int n = (int)(q / H2p);
+    float v = 0.f;
+    if (cc < 12) {
+      int c = cc % 3, ph = (cc / 3) >> 1, pw = (cc / 3) & 1;
+      int ih = 2 * (hp - 2) + ph, iw = 2 * (wp - 2) + pw;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = img[(((long long)n * 3 + c) * H + ih) * W + iw];
+    }
+    mpn_store_act(hi, lo, i, fmt, v);
+  }
+}
+
+extern "C" int mpn_stem_pack_input(const float* img, void* hi, void* lo, int N, int H, int W, int fmt, void* stream) {
+  MPN_CHECK_ARG(img && hi && N > 0 && H > 0 && W > 0, "mpn_stem_pack_input: bad argument");
+  MPN_CHECK_ARG(fmt == MPN_FMT_BF16 || (fmt == MPN_FMT_BF16X2 && lo), "mpn_stem_pack_input: fmt must be BF16 or BF16X2 (with lo)");
+  int H2p = (H + 1) / 2 + 3, W2p = (W + 1) / 2 + 3;
+  long long total = (long long)N * H2p * W2p * 16;
+  stem_pack_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, hi, lo, N, H, W, H2p, W2p, fmt);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+__global__ void stem_pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* hi, __nv_bfloat16* lo, int Cout) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // [co][r2][k], k = s2*16 + cc
+  if (i >= Cout * 4 * 64) return;
+  int k = i & 63, r2 = (i >> 6) & 3, co = i >> 8;
+  int s2 = k >> 4, cc = k & 15;
+  float v = 0.f;
+  if (cc < 12) {
+    int c = cc % 3, ph = (cc / 3) >> 1, pw = (cc / 3) & 1;
+    int r = 2 * r2 + ph - 1, s = 2 * s2 + pw - 1;  // tap of the 7x7 filter this (row, pixel, parity) slot holds
+    if (r >= 0 && r < 7 && s >= 0 && s < 7) v = w[((co * 3 + c) * 7 + r) * 7 + s];
+  }
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+extern "C" int mpn_stem_pack_filter(const float* w, void* hi, void* lo, int Cout, void* stream) {
+  MPN_CHECK_ARG(w && hi && Cout > 0, "mpn_stem_pack_filter: bad argument");
+  stem_pack_filter_kernel<<<mpn_divup(Cout * 256, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Cout);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}

@@ -27,6 +27,8 @@ from . import ops
 from ._lib import FMT_BF16, FMT_BF16X2, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_NHWC
 
 DEFAULT_PRECISION = os.environ.get("MPN_PRECISION", "bf16x3")
+USE_GRAPHS = os.environ.get("MPN_CUDA_GRAPH", "0") == "1"
+TC_STEM = os.environ.get("MPN_TC_STEM", "1") == "1"
 
 
 def _bn_tuple(bn):
@@ -42,6 +44,8 @@ class Engine(object):
         self.fmt = ops.PRECISIONS[self.precision]
         self._packed = {}
         self._sig = None
+        self._graphs = {}
+        self._graph_sig = None
         self.last_detections = None
 
     # ------------------------------------------------------------------ weights
@@ -74,10 +78,18 @@ class Engine(object):
         fpn = self.model.fpn
         if not (img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3):
             raise RuntimeError("expected a CUDA fp32 [B,3,H,W] image batch")
-        x = ops.act_from_nchw(img, FMT_F32)
-        # stem weights are always fp32-packed; the epilogue emits the engine's activation format
-        pc = self._stem_pc()
-        c1 = ops.conv2d(x, pc, stride=2, pad=3, relu=True, f32_input=True)
+        if self.fmt != FMT_F32 and TC_STEM:
+            # tensor-core stem: 7x7/2 on the image == 4x4/1 on the zero-padded space-to-depth tensor
+            key = ("fpn.conv1", "tcstem", self.fmt)
+            pc = self._packed.get(key)
+            if pc is None:
+                pc = ops.pack_stem_filter(fpn.conv1.weight, _bn_tuple(fpn.bn1), self.fmt)
+                self._packed[key] = pc
+            c1 = ops.conv2d(ops.stem_pack_input(img, self.fmt), pc, relu=True)
+        else:
+            x = ops.act_from_nchw(img, FMT_F32)
+            # fp32-packed stem filter on the CUDA-core kernel; the epilogue emits the engine's activation format
+            c1 = ops.conv2d(x, self._stem_pc(), stride=2, pad=3, relu=True, f32_input=True)
         c = ops.maxpool3x3s2(c1)
         feats = []
         for li in range(1, 5):
@@ -220,11 +232,46 @@ class Engine(object):
         det = ops.filter_sort_nms(cls, boxes, score_thresh, iou_thresh, ge=ge, max_cand=max_cand)
         return heat, cls, reg, boxes, det
 
+    # ------------------------------------------------------------------ CUDA-graph replay of a whole step
+    def graphed(self, kind, img, **kw):
+        """Run `kind` ('entire', 'keypoint', 'detection') through a captured CUDA graph of its launch
+        sequence (captured on first use per input shape; ~250 launches replayed with one driver call).
+        The returned tensors are the graph's static outputs: they are overwritten by the next replay."""
+        key = (kind, tuple(img.shape), str(img.device), tuple(sorted(kw.items())))
+        self._ensure_packed()
+        if getattr(self, "_graph_sig", None) != self._sig:
+            self._graphs, self._graph_sig = {}, self._sig  # weights changed -> recapture
+        g = self._graphs.get(key)
+        fn = {"entire": self.entire_forward_device, "keypoint": self.keypoint_forward, "detection": self.detection_forward}[kind]
+        if g is None:
+            static_in = torch.empty_like(img)
+            static_in.copy_(img)
+            side = torch.cuda.Stream(device=img.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up off the capture: packs filters, caches anchors, sizes func attributes
+                for _ in range(2):
+                    fn(static_in, **kw)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = fn(static_in, **kw)
+            g = (graph, static_in, out)
+            self._graphs[key] = g
+        graph, static_in, out = g
+        static_in.copy_(img, non_blocking=True)
+        graph.replay()
+        return out
+
     @torch.no_grad()
     def entire_forward(self, img, max_cand=4096):
         """posenet.py:236-285: (heat, [nms_scores, nms_class, boxes]) for image 0, like the reference;
         the per-image results of the whole batch stay in self.last_detections."""
-        heat, cls, reg, boxes, det = self.entire_forward_device(img, max_cand=max_cand)
+        if USE_GRAPHS:
+            heat, cls, reg, boxes, det = self.graphed("entire", img, max_cand=max_cand)
+            heat = heat.clone()  # static graph output -> caller-owned
+        else:
+            heat, cls, reg, boxes, det = self.entire_forward_device(img, max_cand=max_cand)
         cnt = det.cand_cnt.cpu()
         if int(cnt.max()) > det.max_cand:  # rare: more survivors than the fast-path capacity -> redo with room
             det = ops.filter_sort_nms(cls, boxes, 0.05, 0.5, max_cand=int(cnt.max()))

@@ -31,14 +31,16 @@ def _dtype(fmt):
 
 class Act(object):
     """NHWC activation: `hi` (and `lo` for the split format) are [N,H,W,cstride] tensors."""
-    __slots__ = ("fmt", "N", "H", "W", "C", "cstride", "hi", "lo")
+    __slots__ = ("fmt", "N", "H", "W", "C", "cstride", "hi", "lo", "wpitch", "k_overlap")
 
-    def __init__(self, fmt, N, H, W, C, device, cstride=None, zero=False):
+    def __init__(self, fmt, N, H, W, C, device, cstride=None, zero=False, wpitch=0, k_overlap=0):
         self.fmt, self.N, self.H, self.W, self.C = fmt, N, H, W, C
         self.cstride = C if cstride is None else cstride
+        self.wpitch, self.k_overlap = wpitch, k_overlap  # see mpn_conv_desc.in_wpitch / k_overlap
         mk = torch.zeros if zero else torch.empty
-        self.hi = mk((N, H, W, self.cstride), dtype=_dtype(fmt), device=device)
-        self.lo = mk((N, H, W, self.cstride), dtype=torch.bfloat16, device=device) if fmt == FMT_BF16X2 else None
+        shape = (N, H, wpitch if wpitch else W, self.cstride)
+        self.hi = mk(shape, dtype=_dtype(fmt), device=device)
+        self.lo = mk(shape, dtype=torch.bfloat16, device=device) if fmt == FMT_BF16X2 else None
 
     def to_nchw(self):
         out = torch.empty((self.N, self.C, self.H, self.W), dtype=torch.float32, device=self.hi.device)
@@ -118,6 +120,7 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
     d.OW = (x.W + 2 * pad - pc.S) // stride + 1
     d.fmt = fmt
     d.in_cstride = x.cstride
+    d.in_wpitch, d.k_overlap = x.wpitch, x.k_overlap
     d.flags = (EPI_RELU if relu else 0) | (EPI_SIGMOID if sigmoid else 0)
     d.out_mode, d.out_rep, d.out_coffset = out_mode, out_rep, out_coffset
     d.w_cout_pad = pc.cout_pad
@@ -162,6 +165,37 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
         ev.append((e0, e1, 2.0 * x.N * d.OH * d.OW * pc.Cout * pc.Cin * pc.R * pc.S, bool(f32_input or fmt == FMT_F32)))
     stats["launches"] += 1
     return ret
+
+
+def stem_pack_input(img, fmt):
+    """fp32 NCHW image -> zero-padded space-to-depth Act [N, H/2+3, W/2 (+3 pitch), 64-wide windows of 16 ch]
+    (mpn_stem_pack_input); with pack_stem_filter the 7x7/2 stem becomes a tcgen05 conv (R=4, S=1, Cin=64)."""
+    assert img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3
+    img = img.contiguous()
+    N, _, H, W = img.shape
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    a = Act(fmt, N, H2 + 3, W2, 64, img.device, cstride=16, wpitch=W2 + 3, k_overlap=1)
+    check(_lib.lib().mpn_stem_pack_input(_ptr(img), _ptr(a.hi), _ptr(a.lo), N, H, W, fmt, _stream()), "mpn_stem_pack_input")
+    stats["launches"] += 1
+    return a
+
+
+def pack_stem_filter(weight, bn, fmt):
+    L = _lib.lib()
+    w = weight.detach().contiguous()
+    assert tuple(w.shape[1:]) == (3, 7, 7)
+    pc = PackedConv()
+    pc.Cout, pc.Cin, pc.R, pc.S, pc.fmt, pc.cout_pad = w.shape[0], 64, 4, 1, fmt, w.shape[0]
+    pc.w_hi = torch.empty((pc.Cout, 4, 1, 64), dtype=torch.bfloat16, device=w.device)
+    pc.w_lo = torch.empty_like(pc.w_hi) if fmt == FMT_BF16X2 else None
+    check(L.mpn_stem_pack_filter(_ptr(w), _ptr(pc.w_hi), _ptr(pc.w_lo), pc.Cout, _stream()), "mpn_stem_pack_filter")
+    gamma, beta, mean, var, eps = bn
+    npad = (pc.Cout + 63) // 64 * 64
+    pc.scale = torch.zeros(npad, dtype=torch.float32, device=w.device)
+    pc.bias = torch.zeros(npad, dtype=torch.float32, device=w.device)
+    check(L.mpn_fold_bn(_ptr(gamma.detach().contiguous()), _ptr(beta.detach().contiguous()), _ptr(mean.contiguous()),
+                        _ptr(var.contiguous()), float(eps), _ptr(pc.scale), _ptr(pc.bias), pc.Cout, _stream()), "mpn_fold_bn")
+    return pc
 
 
 def maxpool3x3s2(x):
