@@ -86,6 +86,59 @@ class ClockSampler(object):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def available_cpus():
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:  # cgroup v2 quota
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return n
+
+
+def pick_cpu_threads(sd):
+    """The oracle port runs on torch's CPU (oneDNN) kernels; on a many-core host the best thread count is not
+    always 'all of them' (oversubscription).  Probe a small forward at a few counts and keep the fastest."""
+    from oracle import posenet_oracle as po
+    navail = available_cpus()
+    cands = sorted({navail, max(1, navail // 2), max(1, navail // 4), min(navail, 32), min(navail, 16), min(navail, 8)}, reverse=True)
+    x = torch.randn(1, 3, 160, 224)
+    best = (None, 1e30)
+    for t in cands:
+        torch.set_num_threads(t)
+        with torch.no_grad():
+            po.forward(sd, LAYERS, x, "keypoint_subnet")
+            t0 = time.perf_counter()
+            po.forward(sd, LAYERS, x, "keypoint_subnet")
+            dt = time.perf_counter() - t0
+        if dt < best[1]:
+            best = (t, dt)
+    torch.set_num_threads(best[0])
+    return best[0], navail
+
+
+def calibrate_cls_bias(model, dev, target=3600):
+    """Synthetic-weight construction: shift the class-head bias so that ~`target` of the
+    57600 anchors per image pass the 0.05 score filter on N(0,1) images."""
+    import math
+    x = torch.from_numpy(np.random.Generator(np.random.PCG64(99)).standard_normal((2, 3, H, W), dtype=np.float32)).to(dev)
+    with torch.no_grad():
+        _, (cls, _, _) = model((x, "detection_subnet"))
+    p = cls[:, :, 0].double().clamp(1e-12, 1 - 1e-12)
+    logit = torch.log(p / (1 - p))
+    q = 1.0 - float(target) / logit.shape[1]
+    cut = float(torch.quantile(logit.flatten()[:: max(1, logit.numel() // 2000000)].float(), q))
+    shift = math.log(0.05 / 0.95) - cut
+    with torch.no_grad():
+        model.classificationModel.output.bias += shift
+    return shift
+
+
 def cpu_reference_step(sd, x):
     """The reference graph (oracle port) on the host: entire_net incl. NMS for the images in x."""
     from oracle import posenet_oracle as po
@@ -97,9 +150,9 @@ def run_reference(args, rank, world):
     from oracle import weights
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count())
     w = weights.make_weights(LAYERS, "conditioned", seed=0)
     sd = weights.to_torch_state_dict(w)
+    nthreads, navail = pick_cpu_threads(sd)
     nimg = 1
     x = torch.from_numpy(np.random.Generator(np.random.PCG64(0)).standard_normal((nimg, 3, H, W), dtype=np.float32))
     steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
@@ -110,7 +163,7 @@ def run_reference(args, rank, world):
         t0 = time.perf_counter(); cpu_reference_step(sd, x); ts.append(time.perf_counter() - t0)
     med = float(np.median(ts))
     v = nimg / med
-    sample = "%d step(s) of %d image(s) (R101 entire_net + NMS, batch %d; full workload is batch 32/GPU)" % (steps, nimg, nimg)
+    sample = "%d step(s) of %d image(s) (R101 entire_net + NMS, batch %d; full workload is batch 32/GPU); %d of %d host threads (fastest of a probe)" % (steps, nimg, nimg, nthreads, navail)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -130,6 +183,7 @@ def main():
     ap.add_argument("--layers", type=int, default=LAYERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (0 = eager launches)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -153,9 +207,11 @@ def main():
     model = poseNet(args.layers, precision=args.precision)
     w = load_weights_into(model, args.layers)
     model = model.to(dev).eval()
+    bias_shift = calibrate_cls_bias(model, dev)
     eng = model.engine()
     flops_img = po.conv_flops_entire(args.layers, H, W)
-    MAXC = 8192
+    import multiposenet.pytorch_b200.engine as engine_mod
+    engine_mod.USE_GRAPHS = bool(args.graph)  # the public forward() replays a captured graph as well
 
     # synthetic input: 3 distinct batches rotated so no step re-reads the previous step's input from L2
     rng = np.random.Generator(np.random.PCG64(1234 + rank))
@@ -163,6 +219,8 @@ def main():
     devin = [h.to(dev) for h in host]
 
     def step_device(i):
+        if args.graph:  # one cudaGraphLaunch replays the ~250 launches of the step
+            return eng.graphed("entire", devin[i % len(devin)], max_cand=MAXC)
         return eng.entire_forward_device(devin[i % len(devin)], max_cand=MAXC)
 
     def barrier():
@@ -170,12 +228,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # eager probe: launch count per step and the candidate capacity the NMS stage needs
+    n0 = ops.stats["launches"]
+    heat, cls, reg, boxes, det = eng.entire_forward_device(devin[0], max_cand=8192)
+    launches_per_step = ops.stats["launches"] - n0
+    torch.cuda.synchronize()
+    worst = max(int(eng.entire_forward_device(d_, max_cand=8192)[4].cand_cnt.max()) for d_ in devin)
+    MAXC = 4096 if worst <= 4096 else 8192
     for _ in range(args.warmup):
         out = step_device(_)
     barrier()
-    n0 = ops.stats["launches"]
-    out = step_device(0)
-    launches_per_step = ops.stats["launches"] - n0
     heat, cls, reg, boxes, det = out
     torch.cuda.synchronize()
     n_s = det.cand_cnt.float().mean().item()
@@ -230,7 +292,7 @@ def main():
         nprof = 2
         ops.stats["conv_events"] = evs = []
         for i in range(nprof):
-            step_device(i)
+            eng.entire_forward_device(devin[i % len(devin)], max_cand=MAXC)  # eager: events around each launch
         torch.cuda.synchronize()
         ops.stats["conv_events"] = None
         tc = [(a.elapsed_time(b), f) for a, b, f, simt in evs if not simt]
@@ -249,12 +311,14 @@ def main():
     fast = None
     if not args.no_fast and args.precision == "bf16x3":
         feng = model.engine("bf16")
+        fstep = (lambda i: feng.graphed("entire", devin[i % 2], max_cand=MAXC)) if args.graph else \
+                (lambda i: feng.entire_forward_device(devin[i % 2], max_cand=MAXC))
         for i in range(3):
-            feng.entire_forward_device(devin[i % 2], max_cand=MAXC)
+            fstep(i)
         barrier()
         e0.record()
         for i in range(args.steps):
-            feng.entire_forward_device(devin[i % 2], max_cand=MAXC)
+            fstep(i)
         e1.record()
         barrier()
         fast = {"precision": "bf16 single pass (fails the 1e-3 parity bar, ~1e-2)",
@@ -265,8 +329,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import weights
-        torch.set_num_threads(os.cpu_count())
         sd = weights.to_torch_state_dict(w)
+        sd["classificationModel.output.bias"] = model.classificationModel.output.bias.detach().cpu().clone()
+        nthreads, navail = pick_cpu_threads(sd)
         x1 = host[0][:1].clone()
         cpu_reference_step(sd, x1)
         ts = []
@@ -274,7 +339,7 @@ def main():
         while len(ts) < 5 and time.perf_counter() - t_start < 25:
             t0 = time.perf_counter(); cpu_reference_step(sd, x1); ts.append(time.perf_counter() - t0)
         cpu = {"value": 1.0 / float(np.median(ts)), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "%d timed forwards of 1 image (R%d entire_net + NMS) after 1 warm-up; full step is %d images" % (len(ts), args.layers, B)}
+               "sample": "%d timed forwards of 1 image (R%d entire_net + NMS) after 1 warm-up; full step is %d images; %d of %d host threads" % (len(ts), args.layers, B, nthreads, navail)}
 
     if rank == 0:
         line = {
@@ -284,7 +349,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": "R%d-FPN entire_net fwd (keypoint + RetinaNet heads) + decode/filter/NMS, batch %d/GPU, 3x480x640"
                                    % (args.layers, B), "global_batch": B * world, "parallelism": "dp%d (image shards, no collective)" % world,
-                       "precision": args.precision, "candidates_per_image": n_s, "kept_per_image": n_k, "max_cand": MAXC,
+                       "precision": args.precision, "candidates_per_image": n_s, "kept_per_image": n_k, "max_cand": MAXC, "cuda_graph": bool(args.graph),
+                       "cls_bias_shift": bias_shift,
                        "l2": "2 rotating input batches; activations >5 GB/step >> 126 MB L2, no explicit flush",
                        "gflop_per_image": flops_img / 1e9},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,

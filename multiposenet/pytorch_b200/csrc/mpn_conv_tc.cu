@@ -30,6 +30,7 @@ constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_THREADS = 256;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 256;
+constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32 accumulators, 16B chunks XOR-swizzled
 
 struct Maps {
   CUtensorMap a[2][4];  // [plane hi/lo][phase hp*2+wp]
@@ -158,8 +159,17 @@ __device__ __forceinline__ void add_bf16x32(float* v, const __nv_bfloat16* ptr) 
   }
 }
 
+// add 8 bf16 channels at ptr (16-byte aligned) into v
+__device__ __forceinline__ void add_bf16x8(float* v, const __nv_bfloat16* ptr) {
+  const uint4 t = __ldg(reinterpret_cast<const uint4*>(ptr));
+  v[0] += bf16_lo_f(t.x); v[1] += bf16_hi_f(t.x);
+  v[2] += bf16_lo_f(t.y); v[3] += bf16_hi_f(t.y);
+  v[4] += bf16_lo_f(t.z); v[5] += bf16_hi_f(t.z);
+  v[6] += bf16_lo_f(t.w); v[7] += bf16_hi_f(t.w);
+}
+
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool SPLIT, int STAGES>
+template <int BN, bool SPLIT, int STAGES, bool F32OUT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ Maps maps, const TcParams P) {
   constexpr int PLANES = SPLIT ? 2 : 1;
   constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
@@ -177,6 +187,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  uint8_t* epi_stage = smem_gen + STAGES * STAGE_BYTES + BAR_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k_iters = P.R * P.S * P.kb_per_tap;
@@ -321,6 +332,73 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
         TMEM_LD_32x32b_X32(taddr, raw);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if constexpr (!F32OUT) {
+          // ---- coalescing transpose: thread-per-row accumulators -> shared (swizzled) -> 4 lanes per row,
+          // so every global load/store instruction of the warp covers 8 rows x 64 contiguous bytes.
+          float* stg = reinterpret_cast<float*>(epi_stage + (warp - 4) * EPI_STAGE_BYTES);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+                make_uint4(raw[4 * c], raw[4 * c + 1], raw[4 * c + 2], raw[4 * c + 3]);
+          __syncwarp();
+          const int g = lane & 3;            // 8-channel group of this lane
+          const int ch = cbase + 8 * g;
+          float sc[8], bi[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            sc[j] = P.scale ? __ldg(P.scale + ch + j) : 1.f;
+            bi[j] = P.bias ? __ldg(P.bias + ch + j) : 0.f;
+          }
+#pragma unroll 1
+          for (int i = 0; i < 4; ++i) {
+            const int rr = (lane >> 2) + 8 * i;  // row of this warp's 32
+            const int trow = q * 32 + rr;
+            const int tw2 = trow % P.TW, th2 = (trow / P.TW) % P.TH, tn2 = trow / (P.TW * P.TH);
+            const int ow2 = tw_i * P.TW + tw2, oh2 = th_i * P.TH + th2, n2 = tn_i * P.TN + tn2;
+            if (!(trow < P.rows && ow2 < P.OW && oh2 < P.OH && n2 < P.N)) continue;
+            const uint4 f0 = *reinterpret_cast<const uint4*>(stg + rr * 32 + (((2 * g) ^ (rr & 7)) << 2));
+            const uint4 f1 = *reinterpret_cast<const uint4*>(stg + rr * 32 + (((2 * g + 1) ^ (rr & 7)) << 2));
+            float v[8] = {__uint_as_float(f0.x), __uint_as_float(f0.y), __uint_as_float(f0.z), __uint_as_float(f0.w),
+                          __uint_as_float(f1.x), __uint_as_float(f1.y), __uint_as_float(f1.z), __uint_as_float(f1.w)};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __fadd_rn(__fmul_rn(v[j], sc[j]), bi[j]);
+            const long long pix2 = ((long long)n2 * P.OH + oh2) * P.OW + ow2;
+            if (P.res_cstride > 0) {
+              add_bf16x8(v, P.res_hi + pix2 * P.res_cstride + ch);
+              if (SPLIT) add_bf16x8(v, P.res_lo + pix2 * P.res_cstride + ch);
+            }
+            if (P.up_cstride > 0) {
+              const long long up2 = ((long long)n2 * P.up_h + mpn_nearest_src(oh2, P.up_h, P.OH)) * P.up_w +
+                                    mpn_nearest_src(ow2, P.up_w, P.OW);
+              add_bf16x8(v, P.up_hi + up2 * P.up_cstride + ch);
+              if (SPLIT) add_bf16x8(v, P.up_lo + up2 * P.up_cstride + ch);
+            }
+            if (P.flags & MPN_EPI_RELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (P.flags & MPN_EPI_SIGMOID) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+            }
+            uint4 hi4, lo4;
+            hi4.x = pack_bf16(v[0], v[1]); hi4.y = pack_bf16(v[2], v[3]); hi4.z = pack_bf16(v[4], v[5]); hi4.w = pack_bf16(v[6], v[7]);
+            if (SPLIT) {
+              lo4.x = pack_bf16(v[0] - bf16_lo_f(hi4.x), v[1] - bf16_hi_f(hi4.x));
+              lo4.y = pack_bf16(v[2] - bf16_lo_f(hi4.y), v[3] - bf16_hi_f(hi4.y));
+              lo4.z = pack_bf16(v[4] - bf16_lo_f(hi4.z), v[5] - bf16_hi_f(hi4.z));
+              lo4.w = pack_bf16(v[6] - bf16_lo_f(hi4.w), v[7] - bf16_hi_f(hi4.w));
+            }
+            for (int ry = 0; ry < rep; ++ry)
+              for (int rx = 0; rx < rep; ++rx) {
+                const long long o = (long long)n2 * nstride + ((long long)(oh2 * rep + ry) * OWr + (ow2 * rep + rx)) * P.out_cstride +
+                                    P.out_coffset + ch;
+                *reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_hi + o) = hi4;
+                if (SPLIT) *reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_lo + o) = lo4;
+              }
+          }
+          __syncwarp();  // staging is rewritten by the next chunk
+        } else {
         if (!valid) continue;
         const int nc = min(32, P.Cout - cbase);
         float v[32];
@@ -350,27 +428,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
         }
-        if (P.out_mode == MPN_OUT_ACT) {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            hi[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-            if (SPLIT) lo[j] = pack_bf16(v[2 * j] - bf16_lo_f(hi[j]), v[2 * j + 1] - bf16_hi_f(hi[j]));
-          }
-          for (int ry = 0; ry < rep; ++ry)
-            for (int rx = 0; rx < rep; ++rx) {
-              const long long o = (long long)n * nstride + ((long long)(oh * rep + ry) * OWr + (ow * rep + rx)) * P.out_cstride +
-                                  P.out_coffset + cbase;
-              uint4* dh = reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_hi + o);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-              if (SPLIT) {
-                uint4* dl = reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_lo + o);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-              }
-            }
-        } else if (P.out_mode == MPN_OUT_F32_NHWC) {
+        if (P.out_mode == MPN_OUT_F32_NHWC) {
           for (int ry = 0; ry < rep; ++ry)
             for (int rx = 0; rx < rep; ++rx) {
               float* dst = (float*)P.y_hi + (long long)n * nstride +
@@ -387,6 +445,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               for (int j = 0; j < 32; ++j) if (j < nc) dst[(long long)j * OHr * OWr] = v[j];
             }
         }
+        }  // F32OUT
       }
       tc_fence_before();
       __syncwarp();
@@ -455,16 +514,16 @@ void choose_tile(int N, int OH, int OW, int* TW, int* TH, int* TN) {
   *TW = bw; *TH = bh; *TN = bn;
 }
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool F32OUT>
 int launch(const Maps& maps, const TcParams& P, cudaStream_t st) {
   constexpr int PLANES = SPLIT ? 2 : 1;
   constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + BN * BLOCK_K * 2);
-  constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES) / STAGE_BYTES;
+  constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - 4 * EPI_STAGE_BYTES) / STAGE_BYTES;
   constexpr int STAGES = MAXS > 8 ? 8 : MAXS;
   static_assert(STAGES >= 2, "not enough shared memory for a 2-stage ring");
   static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier area too small");
-  const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
-  auto kern = conv_tc_kernel<BN, SPLIT, STAGES>;
+  const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + 4 * EPI_STAGE_BYTES;
+  auto kern = conv_tc_kernel<BN, SPLIT, STAGES, F32OUT>;
   MPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int dev = 0, sms = 148;
   MPN_CUDA_OK(cudaGetDevice(&dev));
@@ -554,17 +613,23 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
     if (rc) return rc;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  const bool f32out = d->out_mode != MPN_OUT_ACT;
+  if (f32out) {  // head outputs (18/19/36/9 channels): the thread-per-row fp32 store path, small-N tiles only
+    MPN_CHECK_ARG(BN <= 64, "conv(tcgen05): fp32 outputs are built for Cout <= 64 (got %d)", d->Cout);
+    if (split) return BN == 64 ? launch<64, true, true>(maps, P, s) : launch<32, true, true>(maps, P, s);
+    return BN == 64 ? launch<64, false, true>(maps, P, s) : launch<32, false, true>(maps, P, s);
+  }
   if (split) {
     switch (BN) {
-      case 128: return launch<128, true>(maps, P, s);
-      case 64: return launch<64, true>(maps, P, s);
-      default: return launch<32, true>(maps, P, s);
+      case 128: return launch<128, true, false>(maps, P, s);
+      case 64: return launch<64, true, false>(maps, P, s);
+      default: return launch<32, true, false>(maps, P, s);
     }
   }
   switch (BN) {
-    case 256: return launch<256, false>(maps, P, s);
-    case 128: return launch<128, false>(maps, P, s);
-    case 64: return launch<64, false>(maps, P, s);
-    default: return launch<32, false>(maps, P, s);
+    case 256: return launch<256, false, false>(maps, P, s);
+    case 128: return launch<128, false, false>(maps, P, s);
+    case 64: return launch<64, false, false>(maps, P, s);
+    default: return launch<32, false, false>(maps, P, s);
   }
 }

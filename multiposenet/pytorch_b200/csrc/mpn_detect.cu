@@ -137,16 +137,21 @@ __device__ __forceinline__ float dev_iou(const float* a, const float* b) {
   return __fdiv_rn(interS, __fsub_rn(__fadd_rn(Sa, Sb), interS));
 }
 
-// grid (col_block, row_block, image); only col_block >= row_block is computed (the reduction never
+// grid (upper-triangle block pair, 1, image): only col_block >= row_block exists (the reduction never
 // reads the lower triangle, nms_cuda.c:52).  64 threads: thread t owns row box row_block*64+t.
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sdets, const int32_t* __restrict__ cand_cnt,
-                                                     int n_fixed, int max_cand, int cb_stride, float thr, int ge,
-                                                     unsigned long long* __restrict__ mask) {
+                                                     int n_fixed, int max_cand, int cb_stride, int cb_grid, float thr,
+                                                     int ge, unsigned long long* __restrict__ mask) {
   const int b = blockIdx.z;
   int n = cand_cnt ? cand_cnt[b] : n_fixed;
   n = n < max_cand ? n : max_cand;
-  const int row_start = blockIdx.y, col_start = blockIdx.x;
-  if (col_start < row_start) return;
+  // blockIdx.x enumerates the upper triangle of the cb_grid x cb_grid block matrix row by row
+  int row_start = 0, t = blockIdx.x;
+  while (t >= cb_grid - row_start) {
+    t -= cb_grid - row_start;
+    ++row_start;
+  }
+  const int col_start = row_start + t;
   if (row_start * 64 >= n || col_start * 64 >= n) return;
   const int row_size = min(n - row_start * 64, 64), col_size = min(n - col_start * 64, 64);
   const float* dets = sdets + (long long)b * max_cand * 5;
@@ -298,8 +303,8 @@ int run_core(const float* boxes, int box_stride, long long box_image_stride, int
                                            max_cand, w.sdets);
   MPN_LAUNCH_OK();
   const int cb = (max_cand + 63) / 64;
-  dim3 mg(cb, cb, B);
-  nms_mask_kernel<<<mg, 64, 0, st>>>(w.sdets, cand_cnt, 0, max_cand, cb, iou_thr, ge, w.mask);
+  dim3 mg(cb * (cb + 1) / 2, 1, B);
+  nms_mask_kernel<<<mg, 64, 0, st>>>(w.sdets, cand_cnt, 0, max_cand, cb, cb, iou_thr, ge, w.mask);
   MPN_LAUNCH_OK();
   nms_reduce_kernel<<<B, 128, cb * sizeof(unsigned long long), st>>>(w.mask, cand_cnt, max_cand, cb, w.ranks_out, w.sdets,
                                                                      keep_idx, keep_cnt, out_scores, out_boxes);
@@ -413,8 +418,8 @@ extern "C" int mpn_nms(const float* dets, int n, float iou_thresh, int ge, int64
 extern "C" int mpn_nms_mask(const float* sorted_dets, int n, float iou_thresh, int ge, uint64_t* mask, void* stream) {
   MPN_CHECK_ARG(sorted_dets && mask && n > 0, "mpn_nms_mask: bad argument");
   const int cb = (n + 63) / 64;
-  dim3 mg(cb, cb, 1);
-  nms_mask_kernel<<<mg, 64, 0, (cudaStream_t)stream>>>(sorted_dets, nullptr, n, n, cb, iou_thresh, ge,
+  dim3 mg(cb * (cb + 1) / 2, 1, 1);
+  nms_mask_kernel<<<mg, 64, 0, (cudaStream_t)stream>>>(sorted_dets, nullptr, n, n, cb, cb, iou_thresh, ge,
                                                       (unsigned long long*)mask);
   MPN_LAUNCH_OK();
   return MPN_OK;

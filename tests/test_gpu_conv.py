@@ -66,3 +66,24 @@ def test_conv_tcgen05_bf16x3(case):
 def test_conv_tcgen05_bf16(case):
     # vs the same conv on bf16-rounded operands only accumulation order + bf16 output rounding differ
     _check(1, case, 6e-3, 3e-2)
+
+
+@pytest.mark.parametrize("fmt,tol", [(2, 1e-4), (1, 2e-2)])
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 50, 70), (2, 33, 47)])
+def test_tensor_core_stem_vs_torch(fmt, tol, shape):
+    """fpn.py:99: 7x7/2 conv + BN + ReLU as a tcgen05 conv over the space-to-depth image."""
+    import torch.nn.functional as F
+    from gpu_util import nerr, no_tf32
+    from multiposenet.pytorch_b200 import ops
+    no_tf32()
+    N, H, W = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, 3, H, W, generator=g).cuda()
+    w = (torch.randn(64, 3, 7, 7, generator=g) / 12.0).cuda()
+    bn = (torch.rand(64, generator=g).cuda() + 0.5, torch.randn(64, generator=g).cuda() * 0.1,
+          torch.randn(64, generator=g).cuda() * 0.1, torch.rand(64, generator=g).cuda() + 0.5, 1e-5)
+    ref = F.relu(F.batch_norm(F.conv2d(x, w, None, stride=2, padding=3), bn[2], bn[3], bn[0], bn[1], False, 0.0, 1e-5))
+    pc = ops.pack_stem_filter(w, bn, fmt)
+    y = ops.conv2d(ops.stem_pack_input(x, fmt), pc, relu=True).to_nchw()
+    assert y.shape == ref.shape
+    assert nerr(y, ref) <= tol

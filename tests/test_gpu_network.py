@@ -113,3 +113,19 @@ def test_dropin_surface():
         m([torch.zeros(1, 3, 64, 64), "keypoint_subnet"])  # CPU tensors: no fallback
     for k in [k for k in sys.modules if k.startswith(("network", "lib.nms"))]:
         pass
+
+
+def test_cuda_graph_replay_matches_eager():
+    from gpu_util import image, load_model
+    m, _ = load_model(50, "conditioned", "bf16x3")
+    eng = m.engine()
+    x1, x2 = image(21, (2, 3, 96, 128)), image(22, (2, 3, 96, 128))
+    for x in (x1, x2, x1):
+        heat_e, cls_e, reg_e, boxes_e, det_e = eng.entire_forward_device(x, max_cand=4096)
+        keep_e = det_e.keep_idx.clone(); cnt_e = det_e.keep_cnt.clone(); heat_e = heat_e.clone()
+        heat_g, cls_g, reg_g, boxes_g, det_g = eng.graphed("entire", x, max_cand=4096)
+        torch.cuda.synchronize()
+        assert torch.equal(heat_g, heat_e)
+        assert torch.equal(det_g.keep_cnt, cnt_e)
+        k = int(cnt_e[0])
+        assert torch.equal(det_g.keep_idx[0, :k], keep_e[0, :k])
