@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--layers", type=int, default=LAYERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true")
+    ap.add_argument("--streams", type=int, default=None, help="branch-level side streams (default: engine default = on)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (0 = eager launches)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -212,6 +213,9 @@ def main():
     flops_img = po.conv_flops_entire(args.layers, H, W)
     import multiposenet.pytorch_b200.engine as engine_mod
     engine_mod.USE_GRAPHS = bool(args.graph)  # the public forward() replays a captured graph as well
+    if args.streams is not None:
+        engine_mod.USE_STREAMS = bool(args.streams)
+    streams_default = engine_mod.USE_STREAMS
 
     # synthetic input: 3 distinct batches rotated so no step re-reads the previous step's input from L2
     rng = np.random.Generator(np.random.PCG64(1234 + rank))
@@ -263,24 +267,39 @@ def main():
     # ---- end to end through the public API: pinned host -> device -> model((img,'both')) -> host
     heat_host = torch.empty((B, 18, H // 4, W // 4), dtype=torch.float32).pin_memory()
 
-    def step_e2e(i):
-        x = host[i % len(host)].to(dev, non_blocking=True)
-        with torch.no_grad():
-            hm, (sc, cl, bx) = model((x, "both"))
-        heat_host.copy_(hm, non_blocking=True)
-        d = eng.last_detections
-        outs = [d.keep_cnt.cpu(), d.scores.cpu(), d.boxes.cpu()]
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def prefetch(i):
+        """H2D of batch i from pinned host memory on a copy stream (overlaps the previous batch's compute)."""
+        with torch.cuda.stream(copy_stream):
+            x = host[i % len(host)].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return x, ev
+
+    def run_e2e(nsteps):
+        outs = None
+        nxt = prefetch(0)
+        for i in range(nsteps):
+            x, ev = nxt
+            torch.cuda.current_stream().wait_event(ev)
+            x.record_stream(torch.cuda.current_stream())
+            if i + 1 < nsteps:
+                nxt = prefetch(i + 1)
+            with torch.no_grad():
+                hm, (sc, cl, bx) = model((x, "both"))  # the public call; syncs on the candidate counts
+            heat_host.copy_(hm, non_blocking=True)
+            d = eng.last_detections
+            outs = [d.keep_cnt.cpu(), d.scores.cpu(), d.boxes.cpu()]
         torch.cuda.synchronize()
         return outs
 
-    for i in range(2):
-        outs = step_e2e(i)
+    outs = run_e2e(2)
     d2h = heat_host.numel() * 4 + sum(o.numel() * o.element_size() for o in outs) + 4 * B
     h2d = host[0].numel() * 4
     barrier()
     e0.record()
-    for i in range(args.steps):
-        step_e2e(i)
+    run_e2e(args.steps)
     e1.record()
     barrier()
     e2e_value = shard.whole_job_rate(B * args.steps, e0.elapsed_time(e1), dev)
@@ -290,11 +309,13 @@ def main():
     if rank == 0:
         pk, pk_src = peaks()
         nprof = 2
+        engine_mod.USE_STREAMS = False  # serial launches: clean per-kernel durations
         ops.stats["conv_events"] = evs = []
         for i in range(nprof):
             eng.entire_forward_device(devin[i % len(devin)], max_cand=MAXC)  # eager: events around each launch
         torch.cuda.synchronize()
         ops.stats["conv_events"] = None
+        engine_mod.USE_STREAMS = streams_default
         tc = [(a.elapsed_time(b), f) for a, b, f, simt in evs if not simt]
         conv_ms = sum(t for t, _ in tc) / nprof
         nconv = len(tc) // nprof
@@ -349,7 +370,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "R%d-FPN entire_net fwd (keypoint + RetinaNet heads) + decode/filter/NMS, batch %d/GPU, 3x480x640"
                                    % (args.layers, B), "global_batch": B * world, "parallelism": "dp%d (image shards, no collective)" % world,
-                       "precision": args.precision, "candidates_per_image": n_s, "kept_per_image": n_k, "max_cand": MAXC, "cuda_graph": bool(args.graph),
+                       "precision": args.precision, "candidates_per_image": n_s, "kept_per_image": n_k, "max_cand": MAXC, "cuda_graph": bool(args.graph), "branch_streams": streams_default,
                        "cls_bias_shift": bias_shift,
                        "l2": "2 rotating input batches; activations >5 GB/step >> 126 MB L2, no explicit flush",
                        "gflop_per_image": flops_img / 1e9},

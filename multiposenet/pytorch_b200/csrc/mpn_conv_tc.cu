@@ -9,12 +9,13 @@
 // four "phase" views of the input (tensor maps with doubled pixel strides and an offset base), so no
 // im2col buffer ever exists in HBM.  The filter is a plain 2-D [Cout, R*S*Cin] K-major tensor.
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+// Warp roles (384 threads, 1 CTA/SM, persistent over tiles):
 //   warp 0 lane 0 : TMA producer           (mbarrier full/empty ring of STAGES stages)
 //   warp 1 lane 0 : tcgen05.mma issuer     (accumulators double-buffered in TMEM, 2 x BN columns)
 //   warp 2        : TMEM allocate / free
-//   warps 4..7    : epilogue: tcgen05.ld -> BN-fold scale/bias, residual, nearest-upsample add, ReLU/
-//                   sigmoid -> bf16 (hi/lo) NHWC, or fp32 NHWC / NCHW, optionally replicated x2/x4/x8
+//   warps 4..11   : epilogue (two warps per TMEM lane quarter): tcgen05.ld -> swizzled smem transpose -> BN-fold
+//                   scale/bias, residual, nearest-upsample add, ReLU/sigmoid -> bf16 (hi/lo) NHWC with
+//                   64-byte row segments per 4 lanes, or fp32 NHWC / NCHW heads, optionally replicated x2/x4/x8
 // Precision modes: MPN_FMT_BF16   one bf16 plane per operand, one MMA per K step;
 //                  MPN_FMT_BF16X2 hi/lo bf16 planes (x = hi + lo to ~2^-17), three MMAs per K step
 //                  (hi*hi + lo*hi + hi*lo) accumulated in fp32 -> fp32-grade parity with the reference.
@@ -27,7 +28,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;           // bf16 elements = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
+constexpr int NUM_EPI_WARPS = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 256;
 constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32 accumulators, 16B chunks XOR-swizzled
@@ -139,6 +141,15 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
       : "r"(taddr)                                                                                                       \
       : "memory")
 
+#define TMEM_LD_32x32b_X16(taddr, v)                                                                                     \
+  asm volatile(                                                                                                          \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                                          \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                                   \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),      \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                         \
+      : "r"(taddr)                                                                                                       \
+      : "memory")
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -157,6 +168,13 @@ __device__ __forceinline__ void add_bf16x32(float* v, const __nv_bfloat16* ptr) 
     v[i * 8 + 4] += bf16_lo_f(t.z); v[i * 8 + 5] += bf16_hi_f(t.z);
     v[i * 8 + 6] += bf16_lo_f(t.w); v[i * 8 + 7] += bf16_hi_f(t.w);
   }
+}
+
+__device__ __forceinline__ void add_bf16x8_reg(float* v, const uint4& t) {
+  v[0] += bf16_lo_f(t.x); v[1] += bf16_hi_f(t.x);
+  v[2] += bf16_lo_f(t.y); v[3] += bf16_hi_f(t.y);
+  v[4] += bf16_lo_f(t.z); v[5] += bf16_hi_f(t.z);
+  v[6] += bf16_lo_f(t.w); v[7] += bf16_hi_f(t.w);
 }
 
 // add 8 bf16 channels at ptr (16-byte aligned) into v
@@ -204,7 +222,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), NUM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -296,12 +314,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       }
     }
   } else if (warp >= 4) {
-    // =============================== epilogue ===============================
-    const int q = warp & 3;             // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;      // tile row = pixel
-    const int tw = row % P.TW;
-    const int th = (row / P.TW) % P.TH;
-    const int tn = row / (P.TW * P.TH);
+    // =============================== epilogue (8 warps) ===============================
+    // Two warps per TMEM lane quarter (one per SM sub-partition pair): warp w owns quarter w&3 and the
+    // 32-column chunks of parity (w-4)>>2, so each scheduler has two independent instruction streams.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int rep = P.out_rep, OHr = P.OH * rep, OWr = P.OW * rep;
     const long long nstride = P.out_nstride > 0 ? P.out_nstride
                               : (P.out_mode == MPN_OUT_F32_NCHW ? (long long)P.Cout * OHr * OWr : (long long)OHr * OWr * P.out_cstride);
@@ -315,63 +332,82 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       mt /= P.tiles_w;
       const int th_i = mt % P.tiles_h;
       const int tn_i = mt / P.tiles_h;
-      const int ow = tw_i * P.TW + tw, oh = th_i * P.TH + th, n = tn_i * P.TN + tn;
       const int co0 = co_t * BN;
-      const bool valid = row < P.rows && ow < P.OW && oh < P.OH && n < P.N;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const long long pix = valid ? ((long long)n * P.OH + oh) * P.OW + ow : 0;
-      long long up_pix = 0;
-      if (valid && P.up_cstride > 0)
-        up_pix = ((long long)n * P.up_h + mpn_nearest_src(oh, P.up_h, P.OH)) * P.up_w + mpn_nearest_src(ow, P.up_w, P.OW);
+      if constexpr (!F32OUT) {
+        // ---- per-tile row bookkeeping for the coalesced phase: lane serves rows (lane>>2) + 8*i, i = 0..3
+        long long obase[4];  // destination element offset of (n, oh*rep, ow*rep, out_coffset)
+        int pixv[4];         // flat output pixel index, or -1 if the row is outside the tensor
+        int upv[4];          // flat pixel index in the upsample source
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int trow = q * 32 + (lane >> 2) + 8 * i;
+          const int tw2 = trow % P.TW, th2 = (trow / P.TW) % P.TH, tn2 = trow / (P.TW * P.TH);
+          const int ow2 = tw_i * P.TW + tw2, oh2 = th_i * P.TH + th2, n2 = tn_i * P.TN + tn2;
+          const bool ok = trow < P.rows && ow2 < P.OW && oh2 < P.OH && n2 < P.N;
+          pixv[i] = ok ? (n2 * P.OH + oh2) * P.OW + ow2 : -1;
+          obase[i] = (long long)n2 * nstride + ((long long)(oh2 * rep) * OWr + ow2 * rep) * P.out_cstride + P.out_coffset;
+          upv[i] = 0;
+          if (ok && P.up_cstride > 0)
+            upv[i] = (n2 * P.up_h + mpn_nearest_src(oh2, P.up_h, P.OH)) * P.up_w + mpn_nearest_src(ow2, P.up_w, P.OW);
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        float* stg = reinterpret_cast<float*>(epi_stage + (warp - 4) * EPI_STAGE_BYTES);
+        const int g = lane & 3;  // 8-channel group of this lane in the coalesced phase
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int cbase = co0 + c0;
-        if (cbase >= P.Cout) break;  // warp-uniform
-        uint32_t raw[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
-        TMEM_LD_32x32b_X32(taddr, raw);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if constexpr (!F32OUT) {
-          // ---- coalescing transpose: thread-per-row accumulators -> shared (swizzled) -> 4 lanes per row,
-          // so every global load/store instruction of the warp covers 8 rows x 64 contiguous bytes.
-          float* stg = reinterpret_cast<float*>(epi_stage + (warp - 4) * EPI_STAGE_BYTES);
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          const int cbase = co0 + c0;
+          if (cbase >= P.Cout) break;  // warp-uniform
+          uint32_t raw[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+          TMEM_LD_32x32b_X32(taddr, raw);
+          // prefetch the residual / upsample operands of this chunk while the TMEM load is in flight
+          const int ch = cbase + 8 * g;
+          uint4 rh[4], rl[4], uh[4], ul[4];
+          if (P.res_cstride > 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const long long o = (long long)(pixv[i] < 0 ? 0 : pixv[i]) * P.res_cstride + ch;
+              rh[i] = __ldg(reinterpret_cast<const uint4*>(P.res_hi + o));
+              if (SPLIT) rl[i] = __ldg(reinterpret_cast<const uint4*>(P.res_lo + o));
+            }
+          }
+          if (P.up_cstride > 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const long long o = (long long)upv[i] * P.up_cstride + ch;
+              uh[i] = __ldg(reinterpret_cast<const uint4*>(P.up_hi + o));
+              if (SPLIT) ul[i] = __ldg(reinterpret_cast<const uint4*>(P.up_lo + o));
+            }
+          }
+          float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, bi0 = make_float4(0.f, 0.f, 0.f, 0.f), bi1 = bi0;
+          if (P.scale) { sc0 = __ldg(reinterpret_cast<const float4*>(P.scale + ch)); sc1 = __ldg(reinterpret_cast<const float4*>(P.scale + ch + 4)); }
+          if (P.bias) { bi0 = __ldg(reinterpret_cast<const float4*>(P.bias + ch)); bi1 = __ldg(reinterpret_cast<const float4*>(P.bias + ch + 4)); }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // thread-per-row accumulators -> swizzled staging -> 4 lanes per row (coalesced 64-byte row segments)
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             *reinterpret_cast<uint4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) =
                 make_uint4(raw[4 * c], raw[4 * c + 1], raw[4 * c + 2], raw[4 * c + 3]);
           __syncwarp();
-          const int g = lane & 3;            // 8-channel group of this lane
-          const int ch = cbase + 8 * g;
-          float sc[8], bi[8];
+          const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+          const float biv[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            sc[j] = P.scale ? __ldg(P.scale + ch + j) : 1.f;
-            bi[j] = P.bias ? __ldg(P.bias + ch + j) : 0.f;
-          }
-#pragma unroll 1
           for (int i = 0; i < 4; ++i) {
-            const int rr = (lane >> 2) + 8 * i;  // row of this warp's 32
-            const int trow = q * 32 + rr;
-            const int tw2 = trow % P.TW, th2 = (trow / P.TW) % P.TH, tn2 = trow / (P.TW * P.TH);
-            const int ow2 = tw_i * P.TW + tw2, oh2 = th_i * P.TH + th2, n2 = tn_i * P.TN + tn2;
-            if (!(trow < P.rows && ow2 < P.OW && oh2 < P.OH && n2 < P.N)) continue;
+            const int rr = (lane >> 2) + 8 * i;
             const uint4 f0 = *reinterpret_cast<const uint4*>(stg + rr * 32 + (((2 * g) ^ (rr & 7)) << 2));
             const uint4 f1 = *reinterpret_cast<const uint4*>(stg + rr * 32 + (((2 * g + 1) ^ (rr & 7)) << 2));
             float v[8] = {__uint_as_float(f0.x), __uint_as_float(f0.y), __uint_as_float(f0.z), __uint_as_float(f0.w),
                           __uint_as_float(f1.x), __uint_as_float(f1.y), __uint_as_float(f1.z), __uint_as_float(f1.w)};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __fadd_rn(__fmul_rn(v[j], sc[j]), bi[j]);
-            const long long pix2 = ((long long)n2 * P.OH + oh2) * P.OW + ow2;
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], scv[j], biv[j]);
             if (P.res_cstride > 0) {
-              add_bf16x8(v, P.res_hi + pix2 * P.res_cstride + ch);
-              if (SPLIT) add_bf16x8(v, P.res_lo + pix2 * P.res_cstride + ch);
+              add_bf16x8_reg(v, rh[i]);
+              if (SPLIT) add_bf16x8_reg(v, rl[i]);
             }
             if (P.up_cstride > 0) {
-              const long long up2 = ((long long)n2 * P.up_h + mpn_nearest_src(oh2, P.up_h, P.OH)) * P.up_w +
-                                    mpn_nearest_src(ow2, P.up_w, P.OW);
-              add_bf16x8(v, P.up_hi + up2 * P.up_cstride + ch);
-              if (SPLIT) add_bf16x8(v, P.up_lo + up2 * P.up_cstride + ch);
+              add_bf16x8_reg(v, uh[i]);
+              if (SPLIT) add_bf16x8_reg(v, ul[i]);
             }
             if (P.flags & MPN_EPI_RELU) {
 #pragma unroll
@@ -389,63 +425,66 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               lo4.z = pack_bf16(v[4] - bf16_lo_f(hi4.z), v[5] - bf16_hi_f(hi4.z));
               lo4.w = pack_bf16(v[6] - bf16_lo_f(hi4.w), v[7] - bf16_hi_f(hi4.w));
             }
-            for (int ry = 0; ry < rep; ++ry)
-              for (int rx = 0; rx < rep; ++rx) {
-                const long long o = (long long)n2 * nstride + ((long long)(oh2 * rep + ry) * OWr + (ow2 * rep + rx)) * P.out_cstride +
-                                    P.out_coffset + ch;
-                *reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_hi + o) = hi4;
-                if (SPLIT) *reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_lo + o) = lo4;
+            if (pixv[i] >= 0) {
+              if (rep == 1) {
+                *reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_hi + obase[i] + ch) = hi4;
+                if (SPLIT) *reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_lo + obase[i] + ch) = lo4;
+              } else {
+                for (int ry = 0; ry < rep; ++ry)
+                  for (int rx = 0; rx < rep; ++rx) {
+                    const long long o = obase[i] + ((long long)ry * OWr + rx) * P.out_cstride + ch;
+                    *reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_hi + o) = hi4;
+                    if (SPLIT) *reinterpret_cast<uint4*>((__nv_bfloat16*)P.y_lo + o) = lo4;
+                  }
               }
+            }
           }
-          __syncwarp();  // staging is rewritten by the next chunk
-        } else {
-        if (!valid) continue;
-        const int nc = min(32, P.Cout - cbase);
-        float v[32];
+          __syncwarp();  // the staging tile is rewritten by the next chunk
+        }
+      } else {
+        // ---- fp32 outputs (heads: Cout <= 64): thread-per-row, 16 columns at a time
+        const int row = q * 32 + lane;
+        const int tw = row % P.TW, th = (row / P.TW) % P.TH, tn = row / (P.TW * P.TH);
+        const int ow = tw_i * P.TW + tw, oh = th_i * P.TH + th, n = tn_i * P.TN + tn;
+        const bool valid = row < P.rows && ow < P.OW && oh < P.OH && n < P.N;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = half * 16; c0 < BN; c0 += 32) {
+          const int cbase = co0 + c0;
+          if (cbase >= P.Cout) break;  // warp-uniform
+          uint32_t raw[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+          TMEM_LD_32x32b_X16(taddr, raw);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (!valid) continue;
+          const int nc = min(16, P.Cout - cbase);
+          float v[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (P.scale) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < nc) v[j] = __fmul_rn(v[j], __ldg(P.scale + cbase + j));
-        }
-        if (P.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < nc) v[j] = __fadd_rn(v[j], __ldg(P.bias + cbase + j));
-        }
-        if (P.res_cstride > 0) {
-          add_bf16x32(v, P.res_hi + pix * P.res_cstride + cbase);
-          if (SPLIT) add_bf16x32(v, P.res_lo + pix * P.res_cstride + cbase);
-        }
-        if (P.up_cstride > 0) {
-          add_bf16x32(v, P.up_hi + up_pix * P.up_cstride + cbase);
-          if (SPLIT) add_bf16x32(v, P.up_lo + up_pix * P.up_cstride + cbase);
-        }
-        if (P.flags & MPN_EPI_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (P.flags & MPN_EPI_SIGMOID) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
-        }
-        if (P.out_mode == MPN_OUT_F32_NHWC) {
+          for (int j = 0; j < 16; ++j) {
+            v[j] = __uint_as_float(raw[j]);
+            if (j < nc) {
+              if (P.scale) v[j] *= __ldg(P.scale + cbase + j);
+              if (P.bias) v[j] += __ldg(P.bias + cbase + j);
+            }
+            if (P.flags & MPN_EPI_RELU) v[j] = fmaxf(v[j], 0.f);
+            if (P.flags & MPN_EPI_SIGMOID) v[j] = 1.f / (1.f + expf(-v[j]));
+          }
           for (int ry = 0; ry < rep; ++ry)
             for (int rx = 0; rx < rep; ++rx) {
-              float* dst = (float*)P.y_hi + (long long)n * nstride +
-                           ((long long)(oh * rep + ry) * OWr + (ow * rep + rx)) * P.out_cstride + P.out_coffset + cbase;
+              if (P.out_mode == MPN_OUT_F32_NHWC) {
+                float* dst = (float*)P.y_hi + (long long)n * nstride +
+                             ((long long)(oh * rep + ry) * OWr + (ow * rep + rx)) * P.out_cstride + P.out_coffset + cbase;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < nc) dst[j] = v[j];
-            }
-        } else {  // fp32 NCHW: for a fixed channel the 32 lanes hold neighbouring pixels -> coalesced rows
-          for (int ry = 0; ry < rep; ++ry)
-            for (int rx = 0; rx < rep; ++rx) {
-              float* dst = (float*)P.y_hi + (long long)n * nstride + (long long)(P.out_coffset + cbase) * OHr * OWr +
-                           (long long)(oh * rep + ry) * OWr + (ow * rep + rx);
+                for (int j = 0; j < 16; ++j) if (j < nc) dst[j] = v[j];
+              } else {  // NCHW: for a fixed channel the 32 lanes are neighbouring pixels -> coalesced rows
+                float* dst = (float*)P.y_hi + (long long)n * nstride + (long long)(P.out_coffset + cbase) * OHr * OWr +
+                             (long long)(oh * rep + ry) * OWr + (ow * rep + rx);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < nc) dst[(long long)j * OHr * OWr] = v[j];
+                for (int j = 0; j < 16; ++j) if (j < nc) dst[(long long)j * OHr * OWr] = v[j];
+              }
             }
         }
-        }  // F32OUT
       }
       tc_fence_before();
       __syncwarp();
@@ -518,11 +557,11 @@ template <int BN, bool SPLIT, bool F32OUT>
 int launch(const Maps& maps, const TcParams& P, cudaStream_t st) {
   constexpr int PLANES = SPLIT ? 2 : 1;
   constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + BN * BLOCK_K * 2);
-  constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - 4 * EPI_STAGE_BYTES) / STAGE_BYTES;
+  constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - NUM_EPI_WARPS * EPI_STAGE_BYTES) / STAGE_BYTES;
   constexpr int STAGES = MAXS > 8 ? 8 : MAXS;
   static_assert(STAGES >= 2, "not enough shared memory for a 2-stage ring");
   static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier area too small");
-  const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + 4 * EPI_STAGE_BYTES;
+  const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
   auto kern = conv_tc_kernel<BN, SPLIT, STAGES, F32OUT>;
   MPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int dev = 0, sms = 148;

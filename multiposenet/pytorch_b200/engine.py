@@ -29,6 +29,7 @@ from ._lib import FMT_BF16, FMT_BF16X2, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_
 DEFAULT_PRECISION = os.environ.get("MPN_PRECISION", "bf16x3")
 USE_GRAPHS = os.environ.get("MPN_CUDA_GRAPH", "0") == "1"
 TC_STEM = os.environ.get("MPN_TC_STEM", "1") == "1"
+USE_STREAMS = os.environ.get("MPN_STREAMS", "1") == "1"
 
 
 def _bn_tuple(bn):
@@ -46,7 +47,19 @@ class Engine(object):
         self._sig = None
         self._graphs = {}
         self._graph_sig = None
+        self._streams = {}
         self.last_detections = None
+
+    def _side(self, i, device):
+        """Side streams for the independent branches of the graph (keypoint head | detection neck+class tower |
+        box tower): the persistent conv kernels own whole SMs, so a second stream fills the tail of each launch
+        and lets the small pyramid levels of the two towers run side by side."""
+        key = (i, str(device))
+        st = self._streams.get(key)
+        if st is None:
+            st = torch.cuda.Stream(device=device)
+            self._streams[key] = st
+        return st
 
     # ------------------------------------------------------------------ weights
     def _signature(self):
@@ -171,25 +184,36 @@ class Engine(object):
             outs.append(ops.conv2d(src, self._pc(name, getattr(m, name)), out_mode=OUT_F32_NCHW, out_rep=rep))
         return outs
 
+    def _tower(self, head, hname, feats, out, per, sigmoid):
+        cells = [f.H * f.W for f in feats]
+        A = 9 * sum(cells)
+        off = 0
+        for f, ncell in zip(feats, cells):
+            o = f
+            for n in ("conv1", "conv2", "conv3", "conv4"):
+                o = ops.conv2d(o, self._pc("%s.%s" % (hname, n), getattr(head, n)), pad=1, relu=True)
+            ops.conv2d(o, self._pc(hname + ".output", head.output), pad=1, sigmoid=sigmoid, out_mode=OUT_F32_NHWC,
+                       out_tensor=out, out_elem_offset=off * per, out_cstride=9 * per, out_nstride=A * per)
+            off += ncell * 9
+
     def detection_heads(self, feats):
         """posenet.py:262-263 -> cls [B,A,1], reg [B,A,4] fp32 (levels concatenated in place)."""
         m = self.model
         B = feats[0].N
-        cells = [f.H * f.W for f in feats]
-        A = 9 * sum(cells)
+        A = 9 * sum(f.H * f.W for f in feats)
         dev = feats[0].hi.device
         cls = torch.empty((B, A, 1), dtype=torch.float32, device=dev)
         reg = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
-        for head, out, per, sig in ((m.regressionModel, reg, 4, False), (m.classificationModel, cls, 1, True)):
-            hname = "regressionModel" if per == 4 else "classificationModel"
-            off = 0
-            for f, ncell in zip(feats, cells):
-                o = f
-                for n in ("conv1", "conv2", "conv3", "conv4"):
-                    o = ops.conv2d(o, self._pc("%s.%s" % (hname, n), getattr(head, n)), pad=1, relu=True)
-                ops.conv2d(o, self._pc(hname + ".output", head.output), pad=1, sigmoid=sig, out_mode=OUT_F32_NHWC,
-                           out_tensor=out, out_elem_offset=off * per, out_cstride=9 * per, out_nstride=A * per)
-                off += ncell * 9
+        if USE_STREAMS:
+            cur, side = torch.cuda.current_stream(), self._side(1, dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._tower(m.regressionModel, "regressionModel", feats, reg, 4, False)
+            self._tower(m.classificationModel, "classificationModel", feats, cls, 1, True)
+            cur.wait_stream(side)
+        else:
+            self._tower(m.regressionModel, "regressionModel", feats, reg, 4, False)
+            self._tower(m.classificationModel, "classificationModel", feats, cls, 1, True)
         return cls, reg
 
     # ------------------------------------------------------------------ subnet entry points
@@ -226,10 +250,23 @@ class Engine(object):
         self._ensure_packed()
         H, W = img.shape[2], img.shape[3]
         c2, c3, c4, c5 = self.backbone(img)
-        heat = self.keypoint_head(*self.keypoint_neck(c2, c3, c4, c5))
-        cls, reg = self.detection_heads(self.detection_neck(c3, c4, c5))
-        boxes = ops.decode_clip(ops.anchors_for(H, W, img.device), reg, H, W)
-        det = ops.filter_sort_nms(cls, boxes, score_thresh, iou_thresh, ge=ge, max_cand=max_cand)
+        anchors = ops.anchors_for(H, W, img.device)
+
+        def detect_branch():
+            cls, reg = self.detection_heads(self.detection_neck(c3, c4, c5))
+            boxes = ops.decode_clip(anchors, reg, H, W)
+            return cls, reg, boxes, ops.filter_sort_nms(cls, boxes, score_thresh, iou_thresh, ge=ge, max_cand=max_cand)
+
+        if USE_STREAMS:
+            cur, side = torch.cuda.current_stream(), self._side(0, img.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                cls, reg, boxes, det = detect_branch()
+            heat = self.keypoint_head(*self.keypoint_neck(c2, c3, c4, c5))
+            cur.wait_stream(side)
+        else:
+            heat = self.keypoint_head(*self.keypoint_neck(c2, c3, c4, c5))
+            cls, reg, boxes, det = detect_branch()
         return heat, cls, reg, boxes, det
 
     # ------------------------------------------------------------------ CUDA-graph replay of a whole step

@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--layers", type=int, default=101)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
+    import multiposenet.pytorch_b200.engine as E
+    E.USE_STREAMS = False  # serial launches: clean per-kernel durations
     dev = torch.device("cuda")
     m = poseNet(a.layers, precision=a.precision)
     bench.load_weights_into(m, a.layers)
