@@ -20,6 +20,7 @@
 //                  MPN_FMT_BF16X2 hi/lo bf16 planes (x = hi + lo to ~2^-17), three MMAs per K step
 //                  (hi*hi + lo*hi + hi*lo) accumulated in fp32 -> fp32-grade parity with the reference.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "mpn_common.cuh"
 
@@ -37,6 +38,7 @@ constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32 a
 struct Maps {
   CUtensorMap a[2][4];  // [plane hi/lo][phase hp*2+wp]
   CUtensorMap b[2];     // [plane]
+  CUtensorMap r[2];     // [plane] residual operand, used only for L2 prefetch (no swizzle)
 };
 
 struct TcParams {
@@ -44,6 +46,7 @@ struct TcParams {
   int TW, TH, TN, rows;
   int tiles_w, tiles_h, tiles_n, tiles_co, total_tiles;
   int R, S, stride, pad, kb_per_tap, Cin;
+  int res_prefetch;  // 1: maps.r[] describe the residual tensor -> producer prefetches its tiles into L2
   int phase_empty;  // bit p set: phase view p has no pixels (tiny maps) -> load an all-OOB box instead
   const float* scale;
   const float* bias;
@@ -100,6 +103,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -248,6 +255,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const int th_i = mt % P.tiles_h;
       const int tn_i = mt / P.tiles_h;
       const int ow0 = tw_i * P.TW, oh0 = th_i * P.TH, n0 = tn_i * P.TN, co0 = co_t * BN;
+      if (P.res_prefetch) {
+        // pull the residual tile the epilogue will add into L2: this tile's on the first round (short lead),
+        // then always the NEXT tile's, a whole tile time ahead of its epilogue
+        if (tile == (int)blockIdx.x) {
+#pragma unroll
+          for (int p = 0; p < PLANES; ++p) tma_prefetch_l2_4d(&maps.r[p], co0, ow0, oh0, n0);
+        }
+        const int nt = tile + gridDim.x;
+        if (nt < P.total_tiles) {
+          const int nco = nt % P.tiles_co;
+          int nm = nt / P.tiles_co;
+          const int ntw = nm % P.tiles_w;
+          nm /= P.tiles_w;
+          const int nth = nm % P.tiles_h, ntn = nm / P.tiles_h;
+#pragma unroll
+          for (int p = 0; p < PLANES; ++p) tma_prefetch_l2_4d(&maps.r[p], nco * BN, ntw * P.TW, nth * P.TH, ntn * P.TN);
+        }
+      }
       for (int tap = 0; tap < P.R * P.S; ++tap) {
         const int r = tap / P.S, s = tap - r * P.S;
         const int dh = r - P.pad, dw = s - P.pad;
@@ -517,10 +542,10 @@ EncodeTiledFn get_encode_fn() {
 }
 
 int encode(EncodeTiledFn fn, CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-           const cuuint32_t* box) {
+           const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     mpn_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]", (int)r, rank,
@@ -601,7 +626,8 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   P.tiles_h = mpn_divup(d->OH, P.TH);
   P.tiles_n = mpn_divup(d->N, P.TN);
   int BN = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
-  if (split && BN == 256) BN = 128;  // keep a 3-stage ring in split mode
+  static const bool split256 = getenv("MPN_SPLIT_BN256") && atoi(getenv("MPN_SPLIT_BN256")) != 0;  // experiment switch
+  if (split && BN == 256 && !split256) BN = 128;  // keep a 3-stage ring in split mode
   P.tiles_co = mpn_divup(d->Cout, BN);
   long long total = (long long)P.tiles_w * P.tiles_h * P.tiles_n * P.tiles_co;
   MPN_CHECK_ARG(total < (1LL << 31), "conv(tcgen05): too many tiles");
@@ -651,6 +677,17 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
     int rc = encode(fn, &maps.b[pl], pl == 0 ? p->w_hi : p->w_lo, 2, wdims, wstrides, wbox);
     if (rc) return rc;
   }
+  if (d->res_cstride > 0 && d->out_mode == MPN_OUT_ACT) {
+    for (int pl = 0; pl < planes; ++pl) {
+      cuuint64_t rdims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->OW, (cuuint64_t)d->OH, (cuuint64_t)d->N};
+      cuuint64_t rstr[3] = {(cuuint64_t)d->res_cstride * 2ULL, (cuuint64_t)d->OW * d->res_cstride * 2ULL,
+                            (cuuint64_t)d->OH * d->OW * d->res_cstride * 2ULL};
+      cuuint32_t rbox[4] = {(cuuint32_t)(BN < d->Cout ? BN : d->Cout), (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
+      int rc = encode(fn, &maps.r[pl], pl == 0 ? p->res_hi : p->res_lo, 4, rdims, rstr, rbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (rc) return rc;
+    }
+    P.res_prefetch = 1;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   const bool f32out = d->out_mode != MPN_OUT_ACT;
   if (f32out) {  // head outputs (18/19/36/9 channels): the thread-per-row fp32 store path, small-N tiles only
@@ -660,6 +697,7 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   }
   if (split) {
     switch (BN) {
+      case 256: return launch<256, true, false>(maps, P, s);
       case 128: return launch<128, true, false>(maps, P, s);
       case 64: return launch<64, true, false>(maps, P, s);
       default: return launch<32, true, false>(maps, P, s);

@@ -29,7 +29,7 @@ from ._lib import FMT_BF16, FMT_BF16X2, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_
 DEFAULT_PRECISION = os.environ.get("MPN_PRECISION", "bf16x3")
 USE_GRAPHS = os.environ.get("MPN_CUDA_GRAPH", "0") == "1"
 TC_STEM = os.environ.get("MPN_TC_STEM", "1") == "1"
-USE_STREAMS = os.environ.get("MPN_STREAMS", "1") == "1"
+USE_STREAMS = os.environ.get("MPN_STREAMS", "0") == "1"  # measured: no gain on B200 (r01c), kept as an option
 
 
 def _bn_tuple(bn):

@@ -129,3 +129,20 @@ def test_cuda_graph_replay_matches_eager():
         assert torch.equal(det_g.keep_cnt, cnt_e)
         k = int(cnt_e[0])
         assert torch.equal(det_g.keep_idx[0, :k], keep_e[0, :k])
+
+
+@pytest.mark.parametrize("hw", [(100, 130), (75, 50)])
+def test_detection_subnet_ragged_sizes_vs_oracle(hw):
+    """Odd image sizes: ceil-shaped pyramid levels, non-2x nearest upsample-add (fpn.py:84-95), 1x1 P7."""
+    from gpu_util import image, load_model, nerr, no_tf32
+    from oracle import posenet_oracle as po, weights
+    no_tf32()
+    m, w = load_model(50, "conditioned", "bf16x3")
+    x = image(31, (2, 3) + hw)
+    with torch.no_grad():
+        _, (cls, reg, anc) = m([x, "detection_subnet"])
+        sd = {k: v.cuda() for k, v in weights.to_torch_state_dict(w).items()}
+        _, (ocls, oreg, oanc) = po.forward(sd, 50, x, "detection_subnet")
+    assert cls.shape == ocls.shape and reg.shape == oreg.shape
+    assert torch.equal(anc, oanc)
+    assert nerr(cls, ocls) <= 1e-3 and nerr(reg, oreg) <= 1e-3
