@@ -626,8 +626,15 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   P.tiles_h = mpn_divup(d->OH, P.TH);
   P.tiles_n = mpn_divup(d->N, P.TN);
   int BN = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
-  static const bool split256 = getenv("MPN_SPLIT_BN256") && atoi(getenv("MPN_SPLIT_BN256")) != 0;  // experiment switch
-  if (split && BN == 256 && !split256) BN = 128;  // keep a 3-stage ring in split mode
+  // Split mode: 256-wide tiles (2-stage ring, 96 B/cycle of smem operand traffic per MMA instead of 128) win
+  // whenever the 128-wide tiling needs more than one round of CTAs (measured r01c: 3x3 convs 435 -> 525 TFLOP/s);
+  // launches that fit in one round keep BN = 128 for twice the CTAs.  MPN_SPLIT_BN256 = 0/1 forces either.
+  static const int split256 = getenv("MPN_SPLIT_BN256") ? atoi(getenv("MPN_SPLIT_BN256")) : -1;
+  if (split && BN == 256) {
+    const long long tiles128 = (long long)P.tiles_w * P.tiles_h * P.tiles_n * mpn_divup(d->Cout, 128);
+    const bool use256 = split256 >= 0 ? split256 != 0 : tiles128 > 148;
+    if (!use256) BN = 128;
+  }
   P.tiles_co = mpn_divup(d->Cout, BN);
   long long total = (long long)P.tiles_w * P.tiles_h * P.tiles_n * P.tiles_co;
   MPN_CHECK_ARG(total < (1LL << 31), "conv(tcgen05): too many tiles");

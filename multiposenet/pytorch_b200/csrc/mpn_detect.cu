@@ -168,8 +168,16 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
     for (int k = 0; k < 4; ++k) cb[k] = dets[(long long)cur * 5 + k];
     unsigned long long t = 0;
     int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
+    const bool fast_ok = thr > 1e-3f;  // the shortcuts below assume a positive threshold
     for (int i = start; i < col_size; ++i) {
-      float v = dev_iou(cb, block_boxes + i * 5);
+      const float* bb = block_boxes + i * 5;
+      if (fast_ok) {
+        // disjoint boxes: interS == 0 exactly -> IoU is 0 (or NaN for a 0/0 union): never above a positive threshold
+        float w = __fadd_rn(__fsub_rn(fminf(cb[2], bb[2]), fmaxf(cb[0], bb[0])), 1.f);
+        float h = __fadd_rn(__fsub_rn(fminf(cb[3], bb[3]), fmaxf(cb[1], bb[1])), 1.f);
+        if (!(w > 0.f) || !(h > 0.f)) continue;
+      }
+      float v = dev_iou(cb, bb);
       if (ge ? (v >= thr) : (v > thr)) t |= 1ULL << i;
     }
     mask[((long long)b * max_cand + cur) * cb_stride + col_start] = t;

@@ -184,11 +184,83 @@ __global__ void maxpool3x3s2_kernel(const void* __restrict__ xhi, const void* __
   }
 }
 
+// bf16 planes, 8 channels (one 16-byte vector) per thread; hi/lo pairs are compared as hi+lo values.
+template <bool SPLIT>
+__global__ void maxpool3x3s2_bf16_kernel(const uint4* __restrict__ xhi, const uint4* __restrict__ xlo, uint4* __restrict__ yhi,
+                                         uint4* __restrict__ ylo, int N, int H, int W, int C8, int OH, int OW) {
+  long long total = (long long)N * OH * OW * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C8);
+    long long p = i / C8;
+    int ow = (int)(p % OW);
+    long long q = p / OW;
+    int oh = (int)(q % OH);
+    int n = (int)(q / OH);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= W) continue;
+        long long o = (((long long)n * H + ih) * W + iw) * C8 + c;
+        uint4 h = __ldg(xhi + o);
+        const unsigned hv[4] = {h.x, h.y, h.z, h.w};
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[2 * j] = __uint_as_float(hv[j] << 16);
+          v[2 * j + 1] = __uint_as_float(hv[j] & 0xFFFF0000u);
+        }
+        if (SPLIT) {
+          uint4 l = __ldg(xlo + o);
+          const unsigned lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[2 * j] += __uint_as_float(lv[j] << 16);
+            v[2 * j + 1] += __uint_as_float(lv[j] & 0xFFFF0000u);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+      }
+    }
+    unsigned oh4[4], ol4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(m[2 * j], m[2 * j + 1]);
+      oh4[j] = *reinterpret_cast<unsigned*>(&t);
+      if (SPLIT) {
+        __nv_bfloat162 u = __floats2bfloat162_rn(m[2 * j] - __uint_as_float(oh4[j] << 16),
+                                                 m[2 * j + 1] - __uint_as_float(oh4[j] & 0xFFFF0000u));
+        ol4[j] = *reinterpret_cast<unsigned*>(&u);
+      }
+    }
+    yhi[i] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
+    if (SPLIT) ylo[i] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+  }
+}
+
 extern "C" int mpn_maxpool3x3s2(const void* xhi, const void* xlo, void* yhi, void* ylo, int N, int H, int W, int C, int fmt,
                                 void* stream) {
   MPN_CHECK_ARG(xhi && yhi && N > 0 && H > 0 && W > 0 && C > 0, "mpn_maxpool3x3s2: bad argument");
   int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   long long total = (long long)N * OH * OW * C;
+  if (fmt != MPN_FMT_F32 && C % 8 == 0) {
+    long long t8 = total / 8;
+    if (fmt == MPN_FMT_BF16X2)
+      maxpool3x3s2_bf16_kernel<true><<<grid_for(t8, 256), 256, 0, (cudaStream_t)stream>>>(
+          (const uint4*)xhi, (const uint4*)xlo, (uint4*)yhi, (uint4*)ylo, N, H, W, C / 8, OH, OW);
+    else
+      maxpool3x3s2_bf16_kernel<false><<<grid_for(t8, 256), 256, 0, (cudaStream_t)stream>>>(
+          (const uint4*)xhi, nullptr, (uint4*)yhi, nullptr, N, H, W, C / 8, OH, OW);
+    MPN_LAUNCH_OK();
+    return MPN_OK;
+  }
   maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(xhi, xlo, yhi, ylo, N, H, W, C, OH, OW, fmt);
   MPN_LAUNCH_OK();
   return MPN_OK;
