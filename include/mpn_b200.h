@@ -116,6 +116,11 @@ int mpn_maxpool3x3s2(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo,
 /* y = relu(x) on n elements (fpn.py:108: conv7(F.relu(p6))) */
 int mpn_relu(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, long long n, int fmt, void* stream);
 
+/* out[r,:] = softmax(a[r,:] + res[r,:]) over D columns (posenet.py:147-148 / 345-346: Add then Softmax(dim=1)).
+ * a: activation planes `fmt` with row stride a_stride elements; res, out: fp32 [P, D] dense. */
+int mpn_add_softmax_rows(const void* a_hi, const void* a_lo, const float* res, float* out, int P, int D, int a_stride, int fmt,
+                         void* stream);
+
 /* ---- detection post-process: anchors.py:21-37, utils.py:19-61, posenet.py:269-285, lib/nms */
 /* number of anchors for an image (levels 3..7, 9 per cell) */
 int mpn_num_anchors(int H, int W);

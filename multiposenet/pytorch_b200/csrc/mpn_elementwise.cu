@@ -332,3 +332,55 @@ extern "C" int mpn_stem_pack_filter(const float* w, void* hi, void* lo, int Cout
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// PRN tail: out = softmax(a + res) per row (posenet.py:147-148).  One 512-thread CTA per row; the row
+// (34272 floats for the reference's 56x36x17 grid) is streamed three times from L2: max, sum, normalise.
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(512) add_softmax_rows_kernel(const void* __restrict__ ahi, const void* __restrict__ alo,
+                                                               const float* __restrict__ res, float* __restrict__ out, int D,
+                                                               int a_stride, int fmt) {
+  __shared__ float red[16];
+  const long long r = blockIdx.x;
+  const float* rr = res + r * D;
+  float* oo = out + r * D;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    float v = mpn_load_act(ahi, alo, r * a_stride + j, fmt) + rr[j];
+    oo[j] = v;  // staged in the output row
+    m = fmaxf(m, v);
+  }
+  m = block_reduce(m, red, true);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    float e = expf(oo[j] - m);
+    oo[j] = e;
+    s += e;
+  }
+  s = block_reduce(s, red, false);
+  const float inv = 1.f / s;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) oo[j] = oo[j] * inv;
+}
+
+extern "C" int mpn_add_softmax_rows(const void* ahi, const void* alo, const float* res, float* out, int P, int D, int a_stride,
+                                    int fmt, void* stream) {
+  MPN_CHECK_ARG(ahi && res && out && P > 0 && D > 0 && a_stride >= D, "mpn_add_softmax_rows: bad argument");
+  MPN_CHECK_ARG(fmt != MPN_FMT_BF16X2 || alo, "mpn_add_softmax_rows: BF16X2 needs a lo plane");
+  add_softmax_rows_kernel<<<P, 512, 0, (cudaStream_t)stream>>>(ahi, alo, res, out, D, a_stride, fmt);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}

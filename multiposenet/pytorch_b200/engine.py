@@ -269,6 +269,42 @@ class Engine(object):
             cls, reg, boxes, det = detect_branch()
         return heat, cls, reg, boxes, det
 
+    # ------------------------------------------------------------------ pose residual network
+    @torch.no_grad()
+    def prn_forward(self, x):
+        """posenet.py:337-350 (eval: dropout = identity) for a whole batch of persons at once:
+        flatten -> FC+ReLU -> FC+ReLU -> FC+ReLU -> +input -> softmax, the three FCs as 1x1 convs on the
+        tcgen05 kernel (a person = a pixel), K padded to a multiple of 64."""
+        self._ensure_packed()
+        prn = self.model.prn
+        if not (x.is_cuda and x.dtype == torch.float32):
+            raise RuntimeError("expected a CUDA fp32 [P, H, W, 17] batch")
+        P = x.shape[0]
+        res = x.reshape(P, -1).contiguous()
+        D = res.shape[1]
+        if self.fmt == FMT_F32:
+            raise NotImplementedError("PRN runs on the tcgen05 path (precision bf16x3 or bf16)")
+        Dp = (D + 63) // 64 * 64
+
+        def pc(name, lin, cin_pad):
+            key = (name, "prn", self.fmt)
+            p_ = self._packed.get(key)
+            if p_ is None:
+                w = lin.weight.detach()
+                if cin_pad != w.shape[1]:
+                    w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[1]))
+                p_ = ops.pack_conv(w.reshape(w.shape[0], w.shape[1], 1, 1).contiguous(), lin.bias, None, self.fmt)
+                self._packed[key] = p_
+            return p_
+
+        # a person = one 1x1 "image" with D channels, zero-padded to Dp (NCHW [P,Dp,1,1] == NHWC [P,1,1,Dp])
+        a = ops.act_from_nchw(torch.nn.functional.pad(res, (0, Dp - D)).view(P, Dp, 1, 1), self.fmt)
+        h = ops.conv2d(a, pc("prn.dens1", prn.dens1, Dp), relu=True)
+        h = ops.conv2d(h, pc("prn.bneck", prn.bneck, prn.bneck.weight.shape[1]), relu=True)
+        o = ops.conv2d(h, pc("prn.dens2", prn.dens2, prn.dens2.weight.shape[1]), relu=True)
+        out = ops.add_softmax_rows(o, res)
+        return out.view(P, prn.height, prn.width, 17)
+
     # ------------------------------------------------------------------ CUDA-graph replay of a whole step
     def graphed(self, kind, img, **kw):
         """Run `kind` ('entire', 'keypoint', 'detection') through a captured CUDA graph of its launch

@@ -200,7 +200,11 @@ class poseNet(nn.Module):
         return self.forward((img_batch, "detection_subnet"))
 
     def prn_forward(self, img_batch):
-        out = self.prn(img_batch)
+        if img_batch.is_cuda and not (torch.is_grad_enabled() and self.training):
+            with torch.cuda.device(img_batch.device):
+                out = self.engine().prn_forward(img_batch)  # batched, tensor cores
+        else:
+            out = self.prn(img_batch)  # training of the PRN (nn.Linear library calls), SURVEY 8(f)
         return out, [out]
 
     @staticmethod

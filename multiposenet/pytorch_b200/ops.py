@@ -198,6 +198,16 @@ def pack_stem_filter(weight, bn, fmt):
     return pc
 
 
+def add_softmax_rows(a, res):
+    """softmax(a + res, dim=1): a = Act viewed as [P, D(+pad)] rows, res fp32 [P, D]."""
+    P, D = res.shape
+    out = torch.empty((P, D), dtype=torch.float32, device=res.device)
+    check(_lib.lib().mpn_add_softmax_rows(_ptr(a.hi), _ptr(a.lo), _ptr(res.contiguous()), _ptr(out), P, D, a.cstride, a.fmt, _stream()),
+          "mpn_add_softmax_rows")
+    stats["launches"] += 1
+    return out
+
+
 def maxpool3x3s2(x):
     OH, OW = (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1
     y = Act(x.fmt, x.N, OH, OW, x.C, x.hi.device)

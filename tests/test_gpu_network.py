@@ -146,3 +146,25 @@ def test_detection_subnet_ragged_sizes_vs_oracle(hw):
     assert cls.shape == ocls.shape and reg.shape == oreg.shape
     assert torch.equal(anc, oanc)
     assert nerr(cls, ocls) <= 1e-3 and nerr(reg, oreg) <= 1e-3
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-3), ("bf16", 5e-2)])
+def test_prn_batched_vs_oracle(precision, tol):
+    """posenet.py:337-350 on the tensor-core path (small PRN: coeff 1, 256 nodes; K = 8568 is not a multiple of 64)."""
+    from gpu_util import nerr, no_tf32
+    from multiposenet.pytorch_b200 import poseNet
+    from oracle import posenet_oracle as po
+    no_tf32()
+    torch.manual_seed(0)
+    m = poseNet(50, prn_node_count=256, prn_coeff=1, precision=precision).cuda().eval()
+    with torch.no_grad():
+        for lin in (m.prn.dens1, m.prn.bneck, m.prn.dens2):
+            lin.weight.normal_(0, 1.0 / lin.weight.shape[1] ** 0.5)
+            lin.bias.normal_(0, 0.1)
+    x = torch.rand(37, 28, 18, 17, device="cuda") * 3
+    with torch.no_grad():
+        out, saved = m([x, "prn_subnet"])
+        want, _ = po.prn_forward({k: v for k, v in m.state_dict().items()}, x)
+    assert out.shape == (37, 28, 18, 17) and saved[0] is out
+    assert nerr(out, want) <= tol
+    assert torch.allclose(out.reshape(37, -1).sum(1), torch.ones(37, device="cuda"), atol=1e-4)
