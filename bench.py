@@ -30,6 +30,10 @@ import torch
 LAYERS = 101
 H, W = 480, 640
 METRIC = "images/sec (3x480x640) full PoseNet fwd+NMS"
+# Class-head bias shift that puts ~3700 of the 57600 anchors per N(0,1) image above the 0.05 score filter for the
+# seeded R101 "conditioned" weights (SURVEY 8(d) cfg3 regime).  Calibrated once with calibrate_cls_bias() on the
+# B200 (profiles/r01d_bench_n1.json: cls_bias_shift) and frozen so both arms of the bench use identical weights.
+CLS_BIAS_SHIFT = {101: -0.7387505}
 
 
 def load_weights_into(model, layers):
@@ -61,7 +65,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -152,6 +156,7 @@ def run_reference(args, rank, world):
         return
     w = weights.make_weights(LAYERS, "conditioned", seed=0)
     sd = weights.to_torch_state_dict(w)
+    sd["classificationModel.output.bias"] = sd["classificationModel.output.bias"] + CLS_BIAS_SHIFT[LAYERS]
     nthreads, navail = pick_cpu_threads(sd)
     nimg = 1
     x = torch.from_numpy(np.random.Generator(np.random.PCG64(0)).standard_normal((nimg, 3, H, W), dtype=np.float32))
@@ -175,7 +180,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("MPN_PRECISION", "bf16x3"))
@@ -208,7 +213,12 @@ def main():
     model = poseNet(args.layers, precision=args.precision)
     w = load_weights_into(model, args.layers)
     model = model.to(dev).eval()
-    bias_shift = calibrate_cls_bias(model, dev)
+    if args.layers in CLS_BIAS_SHIFT:
+        bias_shift = CLS_BIAS_SHIFT[args.layers]
+        with torch.no_grad():
+            model.classificationModel.output.bias += bias_shift
+    else:
+        bias_shift = calibrate_cls_bias(model, dev)
     eng = model.engine()
     flops_img = po.conv_flops_entire(args.layers, H, W)
     import multiposenet.pytorch_b200.engine as engine_mod
