@@ -286,14 +286,16 @@ class Engine(object):
             raise NotImplementedError("PRN runs on the tcgen05 path (precision bf16x3 or bf16)")
         Dp = (D + 63) // 64 * 64
 
-        def pc(name, lin, cin_pad):
+        def pc(name, lin, cin_pad, cout_pad=None):
             key = (name, "prn", self.fmt)
             p_ = self._packed.get(key)
             if p_ is None:
-                w = lin.weight.detach()
-                if cin_pad != w.shape[1]:
-                    w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[1]))
-                p_ = ops.pack_conv(w.reshape(w.shape[0], w.shape[1], 1, 1).contiguous(), lin.bias, None, self.fmt)
+                w, b = lin.weight.detach(), lin.bias.detach()
+                cout_pad = cout_pad or w.shape[0]
+                if cin_pad != w.shape[1] or cout_pad != w.shape[0]:  # zero rows / columns: exact
+                    w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[1], 0, cout_pad - w.shape[0]))
+                    b = torch.nn.functional.pad(b, (0, cout_pad - b.shape[0]))
+                p_ = ops.pack_conv(w.reshape(w.shape[0], w.shape[1], 1, 1).contiguous(), b, None, self.fmt)
                 self._packed[key] = p_
             return p_
 
@@ -301,7 +303,7 @@ class Engine(object):
         a = ops.act_from_nchw(torch.nn.functional.pad(res, (0, Dp - D)).view(P, Dp, 1, 1), self.fmt)
         h = ops.conv2d(a, pc("prn.dens1", prn.dens1, Dp), relu=True)
         h = ops.conv2d(h, pc("prn.bneck", prn.bneck, prn.bneck.weight.shape[1]), relu=True)
-        o = ops.conv2d(h, pc("prn.dens2", prn.dens2, prn.dens2.weight.shape[1]), relu=True)
+        o = ops.conv2d(h, pc("prn.dens2", prn.dens2, prn.dens2.weight.shape[1], Dp), relu=True)  # [P, Dp], first D used
         out = ops.add_softmax_rows(o, res)
         return out.view(P, prn.height, prn.width, 17)
 
