@@ -121,6 +121,45 @@ int mpn_relu(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, long lo
 int mpn_add_softmax_rows(const void* a_hi, const void* a_lo, const float* res, float* out, int P, int D, int a_stride, int fmt,
                          void* stream);
 
+/* ---- training step of the keypoint subnet (posenet.py:367-403 loss, BatchNorm2d in train mode,
+ *      the autograd backward of fpn.py / posenet.py).  Activations are dense NHWC (cstride == C) unless noted. */
+/* dW[Cout][R][S][Cin] fp32 = sum_pixels dY (x) X  -- tcgen05, MN-major operands, split-K over pixels with fp32 atomics.
+ * d = the FORWARD conv descriptor; p->x_* = forward input, p->res_* (+ d->res_cstride) = dY. */
+int mpn_conv2d_wgrad(const mpn_conv_desc* d, const mpn_conv_ptrs* p, float* dw, void* stream);
+/* data-gradient filter of a conv: OIHW fp32 -> [Cin][R][S][CoutPad] bf16 hi(+lo), taps flipped; dX = conv(dY, W') with
+ * pad' = R-1-pad runs on mpn_conv2d_fwd (stride-2 convs: dY zero-inserted first, mpn_zero_insert2). */
+int mpn_pack_filter_dgrad_bf16(const float* w_oihw, void* dst_hi, void* dst_lo, int Cout, int Cin, int R, int S, int CoutPad, void* stream);
+int mpn_unpack_filter_grad(const float* g_corsci, float* out_oihw, int Cout, int Cin, int R, int S, void* stream);
+int mpn_stem_unpack_filter_grad(const float* g_stem, float* out_oihw, int Cout, void* stream);
+int mpn_zero_insert2(const void* dy_hi, const void* dy_lo, void* out_hi, void* out_lo, int N, int OH, int OW, int C, int H, int W, int fmt, void* stream);
+/* per-channel sums (fp64 accumulators): bias gradients, BN statistics */
+int mpn_channel_sums(const void* x_hi, const void* x_lo, long long pixels, int C, int cstride, int coffset, int fmt,
+                     double* sum, double* sumsq_or_null, void* stream);
+int mpn_double_to_float(const double* a, float* out, int n, float scale, void* stream);
+/* BatchNorm2d, training mode (fpn.py:15-25 under model.train(), trainer.py:170-174): batch mean / biased variance,
+ * running-stat update (momentum 0.1, unbiased variance), normalise (+residual, +ReLU), and the backward pass.
+ * workspace: 2*C doubles. */
+int mpn_bn_stats(const void* y_hi, const void* y_lo, long long pixels, int C, int fmt, float* mean, float* var, double* workspace, void* stream);
+int mpn_bn_update_running(const float* mean, const float* var, float* running_mean, float* running_var, long long n, float momentum, int C, void* stream);
+int mpn_bn_apply(const void* y_hi, const void* y_lo, const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                 const void* res_hi, const void* res_lo, int relu, void* z_hi, void* z_lo, long long pixels, int C, int fmt, void* stream);
+/* g = dz * (z > 0 if relu); dy = gamma*invstd*(g - mean(g) - yhat*mean(g*yhat)); dgamma = sum g*yhat; dbeta = sum g;
+ * g_out (optional) receives g (the gradient of the residual / shortcut input). */
+int mpn_bn_backward(const void* dz_hi, const void* dz_lo, const void* z_hi, const void* z_lo, const void* y_hi, const void* y_lo,
+                    const float* mean, const float* var, const float* gamma, float eps, int relu, long long pixels, int C, int fmt,
+                    void* dy_hi, void* dy_lo, void* g_hi, void* g_lo, float* dgamma, float* dbeta, double* workspace, void* stream);
+int mpn_relu_backward(const void* dz_hi, const void* dz_lo, const void* z_hi, const void* z_lo, void* out_hi, void* out_lo, long long n, int fmt, void* stream);
+int mpn_add_act(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo, long long n, int fmt, void* stream);
+int mpn_maxpool3x3s2_backward(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, void* dx_hi, void* dx_lo,
+                              int N, int H, int W, int C, int fmt, void* stream);
+/* backward of a nearest upsample by an integer factor r: coarse = sum of the r x r fine block (channel slice of the fine tensor) */
+int mpn_block_sum(const void* fine_hi, const void* fine_lo, int f_cstride, int f_coffset, void* coarse_hi, void* coarse_lo,
+                  int N, int h, int w, int C, int r, int fmt, void* stream);
+/* weighted MSE of one supervised heat map (posenet.py:380-387): *loss += mean((pred*w - gt*w)^2) over [B,18,H,W];
+ * dpred (NHWC, Cd >= 18 channels, extra channels zero) = grad_scale * d loss / d pred. pred fp32 NCHW [B,Cp,H,W]. */
+int mpn_mse_heatmap_loss(const float* pred, const float* gt, const float* weight, int B, int Cp, int H, int W, double* loss,
+                         void* dpred_hi, void* dpred_lo, int Cd, int fmt, float grad_scale, void* stream);
+
 /* ---- detection post-process: anchors.py:21-37, utils.py:19-61, posenet.py:269-285, lib/nms */
 /* number of anchors for an image (levels 3..7, 9 per cell) */
 int mpn_num_anchors(int H, int W);

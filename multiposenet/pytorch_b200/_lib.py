@@ -48,6 +48,24 @@ _SIGS = {
     "mpn_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_relu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "mpn_conv2d_wgrad": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvPtrs), c_void_p, c_void_p]),
+    "mpn_pack_filter_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_unpack_filter_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_stem_unpack_filter_grad": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "mpn_zero_insert2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_channel_sums": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mpn_double_to_float": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    "mpn_bn_stats": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mpn_bn_update_running": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_int, c_void_p]),
+    "mpn_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
+                             c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
+    "mpn_bn_backward": (c_int, [c_void_p] * 6 + [c_void_p, c_void_p, c_void_p, c_float, c_int, c_ll, c_int, c_int] + [c_void_p] * 8),
+    "mpn_relu_backward": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_void_p]),
+    "mpn_add_act": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_void_p]),
+    "mpn_maxpool3x3s2_backward": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_block_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_mse_heatmap_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_int, c_float, c_void_p]),
     "mpn_add_softmax_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_num_anchors": (c_int, [c_int, c_int]),
     "mpn_generate_anchors": (c_int, [c_int, c_int, c_void_p]),

@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["mpn_elementwise.cu", "mpn_conv_simt.cu", "mpn_conv_tc.cu", "mpn_detect.cu"]
+SOURCES = ["mpn_elementwise.cu", "mpn_conv_simt.cu", "mpn_conv_tc.cu", "mpn_detect.cu", "mpn_train.cu", "mpn_wgrad_tc.cu"]
 OUT = os.path.join(HERE, "libmpn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -15,7 +15,7 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(HERE, s) for s in SOURCES] + [os.path.join(HERE, "mpn_common.cuh"),
+    deps = [os.path.join(HERE, s) for s in SOURCES] + [os.path.join(HERE, "mpn_common.cuh"), os.path.join(HERE, "mpn_tc_ptx.cuh"),
                                                         os.path.join(HERE, "..", "..", "..", "include", "mpn_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
