@@ -174,14 +174,34 @@ class poseNet(nn.Module):
             engines[key] = e
         return e
 
+    def train_engine(self, precision=None):
+        from ..train_engine import TrainEngine
+        precision = precision or self._precision or _engine.DEFAULT_PRECISION
+        engines = self.__dict__.setdefault("_engines", {})
+        key = ("train", precision, id(self))
+        e = engines.get(key)
+        if e is None or e.model is not self:
+            e = TrainEngine(self, precision)
+            engines[key] = e
+        return e
+
     def forward(self, x):
         img_batch, subnet_name = x
         if subnet_name == "prn_subnet":
             return self.prn_forward(img_batch)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError(
-                "libmpn_b200 round 1 implements the inference path (no_grad / eval); the training step "
-                "(dgrad/wgrad kernels + NCCL allreduce, SURVEY 8(a17)) is not built yet and there is no eager fallback")
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            if subnet_name != "keypoint_subnet":
+                raise NotImplementedError(
+                    "only the keypoint-subnet training step (BASELINE config 4, SURVEY 8(a17)) has backward kernels; "
+                    "detection-subnet training (network/losses.py) is SURVEY 8(f) rank 4 and there is no eager fallback")
+            if not (torch.is_tensor(img_batch) and img_batch.is_cuda):
+                raise RuntimeError("poseNet.forward needs a CUDA image batch (no CPU / eager fallback)")
+            from ..train_engine import KeypointTrainFunction
+            teng = self.train_engine()
+            params = [p for _, p in teng.trainable_parameters()]
+            with torch.cuda.device(img_batch.device):
+                outs = KeypointTrainFunction.apply(teng, img_batch, *params)
+            return outs[4], [outs[0], outs[1], outs[2], outs[3], outs[4]]
         if not (torch.is_tensor(img_batch) and img_batch.is_cuda):
             raise RuntimeError("poseNet.forward needs a CUDA image batch: the path runs on libmpn_b200 (sm_100a) only, "
                                "there is no CPU / eager fallback")

@@ -1,0 +1,236 @@
+"""Training step of the keypoint subnet on the C ABI (BASELINE config 4).
+
+Reference: `Trainer._train_one_epoch` (training/trainer.py:239-262) runs
+    output, saved_for_loss = model([img, 'keypoint_subnet'])        # BN in TRAIN mode (trainer.py:170-174)
+    loss, log = model.module.build_loss(saved_for_loss, 'keypoint_subnet', heat, heat_weight)   (posenet.py:367-403)
+    loss.backward(); optimizer.step()
+with the detection neck / heads / PRN frozen (training/multipose_keypoint_train.py:78-89).
+
+Here the forward saves what the backward needs (raw conv outputs y, batch statistics, activations z), and the backward
+is an explicit reverse schedule of libmpn_b200 launches:
+    BN backward (two per-channel reductions + one elementwise pass), ReLU masks folded into it
+    data gradients  = the forward tcgen05 conv kernel on the flipped / transposed filter (stride 2: zero-inserted dY)
+    weight gradients = mpn_conv2d_wgrad (tcgen05, MN-major operands, split-K fp32 atomics)
+    bias gradients  = per-channel sums; max-pool / nearest-upsample / concat-slice backward kernels
+Gradient accumulation where a tensor has two consumers rides on the conv epilogue's residual input.
+`KeypointTrainFunction` exposes this as a torch.autograd.Function so the reference's loop above works unchanged;
+`TrainEngine.train_step` is the fused variant (loss kernel included) used by bench.py.  Data parallel: one process per
+GPU, per-rank batch statistics (nn.DataParallel semantics, no SyncBN), one NCCL allreduce over the flat fp32 gradient.
+"""
+import torch
+
+from . import ops
+from . import train_ops as T
+from ._lib import FMT_F32, OUT_ACT, OUT_F32_NCHW
+
+
+class _Saved(object):
+    pass
+
+
+class TrainEngine(object):
+    def __init__(self, model, precision="bf16x3"):
+        if precision not in ("bf16x3", "bf16"):
+            raise ValueError("training runs on the tcgen05 path: precision must be bf16x3 or bf16")
+        self.model = model
+        self.precision = precision
+        self.fmt = ops.PRECISIONS[precision]
+        self.grads = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _pc(self, conv):
+        """Unfolded filter (+bias) of the CURRENT weights (they change every step)."""
+        return ops.pack_conv(conv.weight, conv.bias, None, self.fmt)
+
+    def _conv(self, x, conv, **kw):
+        return ops.conv2d(x, self._pc(conv), stride=conv.stride[0], pad=conv.padding[0], **kw)
+
+    def _conv_grads(self, name, conv, x, dy, need_dx=True, residual=None, dx_hw=None):
+        """Accumulate dW / db of `conv` (x -> y, dy given, possibly with zero-padded extra channels); return dX."""
+        Cout, _, R, S = conv.weight.shape
+        stride, pad = conv.stride[0], conv.padding[0]
+        dw = T.conv_wgrad(x, dy, Cout, R, S, stride, pad)
+        self.grads[name + ".weight"] = T.unpack_filter_grad(dw)
+        if conv.bias is not None:
+            self.grads[name + ".bias"] = T.channel_sum(dy, C=Cout)
+        if not need_dx:
+            return None
+        return T.conv_dgrad(dy, conv.weight, stride, pad, dx_hw or (x.H, x.W), self.fmt, residual=residual)
+
+    def _bn_grads(self, name, dgamma, dbeta):
+        self.grads[name + ".weight"] = dgamma
+        self.grads[name + ".bias"] = dbeta
+
+    # ------------------------------------------------------------------ forward (train mode)
+    def forward(self, img):
+        m, fpn = self.model, self.model.fpn
+        S = _Saved()
+        S.img_hw = (img.shape[2], img.shape[3])
+        # stem (fpn.py:99-100)
+        S.xs = ops.stem_pack_input(img, self.fmt)
+        spc = ops.pack_stem_filter(fpn.conv1.weight, (torch.ones_like(fpn.bn1.weight), torch.zeros_like(fpn.bn1.bias),
+                                                      torch.zeros_like(fpn.bn1.running_mean), torch.ones_like(fpn.bn1.running_var), 0.0),
+                                   self.fmt)
+        spc.scale = spc.bias = None
+        y = ops.conv2d(S.xs, spc)
+        S.stem_z, S.stem_st = T.bn_train_forward(y, fpn.bn1, relu=True)
+        x = ops.maxpool3x3s2(S.stem_z)
+        S.pool = x
+        S.blocks = []
+        feats = []
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(fpn, "layer%d" % li)):
+                b = _Saved()
+                b.name, b.blk, b.x = "fpn.layer%d.%d" % (li, bi), blk, x
+                y1 = self._conv(x, blk.conv1)
+                b.z1, b.st1 = T.bn_train_forward(y1, blk.bn1, relu=True)
+                y2 = self._conv(b.z1, blk.conv2)
+                b.z2, b.st2 = T.bn_train_forward(y2, blk.bn2, relu=True)
+                y3 = self._conv(b.z2, blk.conv3)
+                if len(blk.downsample) > 0:
+                    ys = self._conv(x, blk.downsample[0])
+                    s, b.std = T.bn_train_forward(ys, blk.downsample[1], relu=False)
+                else:
+                    s, b.std = x, None
+                x, b.st3 = T.bn_train_forward(y3, blk.bn3, relu=True, residual=s)
+                S.blocks.append(b)
+            feats.append(x)
+        S.c2, S.c3, S.c4, S.c5 = feats
+        # keypoint neck (fpn.py:117-124)
+        S.fp5 = self._conv(S.c5, fpn.toplayer)
+        S.fp4 = self._conv(S.c4, fpn.flatlayer1, up=S.fp5)
+        S.fp3 = self._conv(S.c3, fpn.flatlayer2, up=S.fp4)
+        S.fp2 = self._conv(S.c2, fpn.flatlayer3, up=S.fp3)
+        S.s4 = self._conv(S.fp4, fpn.smooth1)
+        S.s3 = self._conv(S.fp3, fpn.smooth2)
+        S.s2 = self._conv(S.fp2, fpn.smooth3)
+        ps = {2: S.s2, 3: S.s3, 4: S.s4, 5: S.fp5}
+        # intermediate supervision (posenet.py:296-299)
+        outs = []
+        for k, rep in ((2, 1), (3, 2), (4, 4), (5, 8)):
+            outs.append(self._conv(ps[k], getattr(m, "convfin_k%d" % k), out_mode=OUT_F32_NCHW, out_rep=rep))
+        # head (posenet.py:302-315)
+        S.cat = ops.Act(self.fmt, S.s2.N, S.s2.H, S.s2.W, 512, S.s2.hi.device)
+        S.q = {}
+        for i, (k, rep, off) in enumerate(((5, 8, 0), (4, 4, 128), (3, 2, 256), (2, 1, 384)), start=1):
+            S.q[i] = self._conv(ps[k], getattr(m, "convt%d" % i))
+            self._conv(S.q[i], getattr(m, "convs%d" % i), out=S.cat, out_coffset=off, out_rep=rep)
+        S.h = self._conv(S.cat, m.conv2, relu=True)
+        outs.append(self._conv(S.h, m.convfin, out_mode=OUT_F32_NCHW))
+        S.ps = ps
+        return outs, S
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, S, douts):
+        """douts: 5 Acts [B, H/4, W/4, 64] (channels >= 19/18 zero) = d loss / d (k2, k3, k4, k5, heat)."""
+        m, fpn = self.model, self.model.fpn
+        self.grads = {}
+        # head: convfin <- conv2(+ReLU) <- concat
+        d_h = self._conv_grads("convfin", m.convfin, S.h, douts[4])
+        d_hpre = T.relu_backward(d_h, S.h)
+        d_cat = self._conv_grads("conv2", m.conv2, S.cat, d_hpre)
+        dp = {}
+        for i, (k, rep, off) in enumerate(((5, 8, 0), (4, 4, 128), (3, 2, 256), (2, 1, 384)), start=1):
+            d_cs = T.block_sum(d_cat, rep, C=128, coffset=off)
+            d_q = self._conv_grads("convs%d" % i, getattr(m, "convs%d" % i), S.q[i], d_cs)
+            dp[k] = self._conv_grads("convt%d" % i, getattr(m, "convt%d" % i), S.ps[k], d_q)
+        # intermediate heads add into the same neck gradients (residual epilogue)
+        for j, (k, rep) in enumerate(((2, 1), (3, 2), (4, 4), (5, 8))):
+            d_small = T.block_sum(douts[j], rep) if rep > 1 else douts[j]
+            dp[k] = self._conv_grads("convfin_k%d" % k, getattr(m, "convfin_k%d" % k), S.ps[k], d_small, residual=dp[k])
+        # neck: smooth convs, then the top-down pathway
+        d_fp2 = self._conv_grads("fpn.smooth3", fpn.smooth3, S.fp2, dp[2])
+        d_fp3 = self._conv_grads("fpn.smooth2", fpn.smooth2, S.fp3, dp[3])
+        d_fp4 = self._conv_grads("fpn.smooth1", fpn.smooth1, S.fp4, dp[4])
+        d_c2 = self._conv_grads("fpn.flatlayer3", fpn.flatlayer3, S.c2, d_fp2)
+        d_fp3 = T.add(d_fp3, T.block_sum(d_fp2, 2))
+        d_c3 = self._conv_grads("fpn.flatlayer2", fpn.flatlayer2, S.c3, d_fp3)
+        d_fp4 = T.add(d_fp4, T.block_sum(d_fp3, 2))
+        d_c4 = self._conv_grads("fpn.flatlayer1", fpn.flatlayer1, S.c4, d_fp4)
+        d_fp5 = T.add(dp[5], T.block_sum(d_fp4, 2))
+        d_c5 = self._conv_grads("fpn.toplayer", fpn.toplayer, S.c5, d_fp5)
+        # backbone, last block first; the neck's contribution joins at each stage output
+        extra = {id(S.c4): d_c4, id(S.c3): d_c3, id(S.c2): d_c2}
+        d = d_c5
+        for b in reversed(S.blocks):
+            blk, name = b.blk, b.name
+            dy3, g, dg, db = T.bn_train_backward(d, b.st3, blk.bn3, want_g=True)
+            self._bn_grads(name + ".bn3", dg, db)
+            dz2 = self._conv_grads(name + ".conv3", blk.conv3, b.z2, dy3)
+            dy2, _, dg, db = T.bn_train_backward(dz2, b.st2, blk.bn2)
+            self._bn_grads(name + ".bn2", dg, db)
+            dz1 = self._conv_grads(name + ".conv2", blk.conv2, b.z1, dy2)
+            dy1, _, dg, db = T.bn_train_backward(dz1, b.st1, blk.bn1)
+            self._bn_grads(name + ".bn1", dg, db)
+            if b.std is not None:
+                dys, _, dg, db = T.bn_train_backward(g, b.std, blk.downsample[1])
+                self._bn_grads(name + ".downsample.1", dg, db)
+                dsc = self._conv_grads(name + ".downsample.0", blk.downsample[0], b.x, dys)
+            else:
+                dsc = g
+            d = self._conv_grads(name + ".conv1", blk.conv1, b.x, dy1, residual=dsc)
+            if id(b.x) in extra:  # b.x is a stage output (c2 / c3 / c4) that also feeds a lateral conv
+                d = T.add(d, extra[id(b.x)])
+        # stem
+        d_z = T.maxpool_backward(S.stem_z, d)
+        dy, _, dg, db = T.bn_train_backward(d_z, S.stem_st, fpn.bn1)
+        self._bn_grads("fpn.bn1", dg, db)
+        dw = T.conv_wgrad(S.xs, dy, 64, 4, 1, 1, 0)
+        self.grads["fpn.conv1.weight"] = T.stem_unpack_filter_grad(dw)
+        return self.grads
+
+    # ------------------------------------------------------------------ fused step
+    def forward_backward(self, img, heat_gt, heat_weight):
+        """One forward + backward with the fused weighted-MSE loss kernel (posenet.py:367-403: sum of 5 MSE terms).
+        Returns (loss fp64 [1] on device, outs, grads dict name -> tensor)."""
+        outs, S = self.forward(img)
+        loss = torch.zeros(1, dtype=torch.float64, device=img.device)
+        douts = [T.mse_heatmap_loss(o, heat_gt, heat_weight, loss, self.fmt, Cd=64) for o in outs]
+        grads = self.backward(S, douts)
+        return loss, outs, grads
+
+    def trainable_parameters(self):
+        return [(n, p) for n, p in self.model.named_parameters() if p.requires_grad]
+
+    def assign_grads(self, grads, world_size=1):
+        """Copy the step's gradients into param.grad (one NCCL allreduce over a flat fp32 buffer when world_size > 1)."""
+        named = [(n, p) for n, p in self.trainable_parameters() if n in grads]
+        flat = torch.cat([grads[n].reshape(-1) for n, _ in named])
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat /= world_size
+        off = 0
+        for n, p in named:
+            k = p.numel()
+            p.grad = flat[off:off + k].view_as(p)
+            off += k
+        return flat
+
+
+class KeypointTrainFunction(torch.autograd.Function):
+    """model([img, 'keypoint_subnet']) under torch.enable_grad() in train mode: the five supervised maps come out as
+    autograd-tracked fp32 tensors, so `build_loss(...).backward()` of the reference loop reaches the kernels above."""
+
+    @staticmethod
+    def forward(ctx, engine, img, *params):
+        outs, S = engine.forward(img)
+        ctx.engine, ctx.saved, ctx.names = engine, S, [n for n, _ in engine.trainable_parameters()]
+        ctx.out_shapes, ctx.device = [tuple(o.shape) for o in outs], img.device
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        eng, S = ctx.engine, ctx.saved
+        acts = []
+        for o_grad, o in zip(douts, ctx.out_shapes):
+            if o_grad is None:
+                o_grad = torch.zeros(o, dtype=torch.float32, device=ctx.device)
+            g = o_grad.contiguous().float()
+            pad = 64 - g.shape[1]
+            acts.append(ops.act_from_nchw(torch.nn.functional.pad(g, (0, 0, 0, 0, 0, pad)), eng.fmt))
+        grads = eng.backward(S, acts)
+        out = [None, None]
+        for n in ctx.names:
+            out.append(grads.get(n))
+        return tuple(out)

@@ -24,8 +24,13 @@ def _conv(sd, name, x, stride=1, pad=0):
     return F.conv2d(x, sd[name + ".weight"], sd.get(name + ".bias"), stride=stride, padding=pad)
 
 
+_BN_TRAIN = False  # forward_train_keypoint() flips this: batch statistics, as under model.train() (trainer.py:170-174)
+
+
 def _bn(sd, name, x):
-    # eval-mode BatchNorm2d, eps 1e-5 (fpn.py:15; poseNet.freeze_bn posenet.py:220-224)
+    # BatchNorm2d, eps 1e-5 (fpn.py:15); eval mode (poseNet.freeze_bn posenet.py:220-224) unless _BN_TRAIN
+    if _BN_TRAIN:
+        return F.batch_norm(x, None, None, sd[name + ".weight"], sd[name + ".bias"], True, 0.0, 1e-5)
     return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"],
                         sd[name + ".weight"], sd[name + ".bias"], False, 0.0, 1e-5)
 
@@ -197,6 +202,26 @@ def forward(sd, layers, img, subnet_name):
     boxes = clip_boxes(decode_boxes(anchors, reg), H, W)
     ksc, kcl, kbox, _ = postprocess_image(cls[0], boxes[0])
     return heat, [ksc, kcl, kbox], dict(cls=cls, reg=reg, boxes=boxes)
+
+
+def forward_train_keypoint(sd, layers, img):
+    """keypoint_subnet forward with BatchNorm in TRAIN mode (the reference's training configuration,
+    training/trainer.py:170-174).  Returns the 5 supervised maps [k2, k3, k4, k5, heat]."""
+    global _BN_TRAIN
+    _BN_TRAIN = True
+    try:
+        heat, saved = forward(sd, layers, img, "keypoint_subnet")
+    finally:
+        _BN_TRAIN = False
+    return saved
+
+
+def keypoint_loss(saved, heat_gt, heat_weight):
+    """posenet.py:367-403: sum over the 5 maps of MSELoss(mean)(pred[:, :18] * w, w * gt)."""
+    total = 0
+    for s in saved:
+        total = total + F.mse_loss(s[:, :18] * heat_weight, heat_weight * heat_gt)
+    return total
 
 
 def prn_forward(sd, x):

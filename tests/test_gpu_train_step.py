@@ -1,0 +1,97 @@
+"""GPU parity of the whole keypoint-subnet training step vs torch autograd on the oracle restatement (BN train mode)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(layers=50, hw=(64, 96), B=2):
+    from gpu_util import image, load_model, no_tf32
+    no_tf32()
+    m, w = load_model(layers, "conditioned", "bf16x3")
+    x = image(41, (B, 3) + hw)
+    g = torch.Generator().manual_seed(9)
+    gt = torch.rand(B, 18, hw[0] // 4, hw[1] // 4, generator=g).cuda()
+    wt = (torch.rand(B, 18, hw[0] // 4, hw[1] // 4, generator=g) > 0.2).float().cuda()
+    return m, w, x, gt, wt
+
+
+def _reference_grads(w, layers, x, gt, wt):
+    from oracle import posenet_oracle as po, weights
+    sd = {k: v.cuda() for k, v in weights.to_torch_state_dict(w).items()}
+    for k, v in sd.items():
+        if v.dtype == torch.float32 and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+    saved = po.forward_train_keypoint(sd, layers, x)
+    loss = po.keypoint_loss(saved, gt, wt)
+    loss.backward()
+    return float(loss), [s.detach() for s in saved], {k: v.grad for k, v in sd.items() if v.grad is not None}
+
+
+def test_fused_train_step_vs_autograd():
+    from gpu_util import nerr
+    m, w, x, gt, wt = _problem()
+    m.train()
+    loss_ref, saved_ref, gref = _reference_grads(w, 50, x, gt, wt)
+    eng = m.train_engine()
+    loss, outs, grads = eng.forward_backward(x, gt, wt)
+    torch.cuda.synchronize()
+    for a, b in zip(outs, saved_ref):
+        assert nerr(a, b) <= 1e-3
+    assert abs(float(loss) - loss_ref) <= 1e-4 * max(1.0, abs(loss_ref))
+    frozen = ("fpn.conv6", "fpn.conv7", "fpn.latlayer", "fpn.toplayer0", "fpn.toplayer1", "fpn.toplayer2",
+              "regressionModel", "classificationModel", "prn")
+    checked = 0
+    worst = (0.0, None)
+    for k, g in gref.items():
+        if k.startswith(frozen):
+            assert k not in grads
+            continue
+        assert k in grads, "missing gradient for %s" % k
+        assert grads[k].shape == g.shape, k
+        if float(g.abs().max()) == 0.0:
+            continue
+        e = nerr(grads[k], g)
+        if e > worst[0]:
+            worst = (e, k)
+        checked += 1
+    print("checked %d gradients, worst normalized error %.3g at %s" % (checked, worst[0], worst[1]))
+    assert checked > 150 and worst[0] <= 3e-3, worst
+    # BN running statistics moved exactly like torch's (momentum 0.1, unbiased variance)
+    assert int(m.fpn.bn1.num_batches_tracked) == 1
+
+
+def test_reference_training_loop_surface():
+    """The reference's loop (trainer.py:245-259): forward, build_loss, zero_grad, backward, Adam step."""
+    from gpu_util import nerr
+    from multiposenet.pytorch_b200 import poseNet
+    m, w, x, gt, wt = _problem()
+    m.train()
+    for name, mod in m.named_children():  # multipose_keypoint_train.py:78-89 freezes the detection subnet and the PRN
+        if name in ("regressionModel", "classificationModel", "prn"):
+            for p in mod.parameters():
+                p.requires_grad = False
+    for name, mod in m.fpn.named_children():
+        if name in ("conv6", "conv7", "latlayer1", "latlayer2", "latlayer3", "toplayer0", "toplayer1", "toplayer2"):
+            for p in mod.parameters():
+                p.requires_grad = False
+    opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-4)
+    loss_ref, _, gref = _reference_grads(w, 50, x, gt, wt)
+    out, saved = m([x, "keypoint_subnet"])
+    loss, log = poseNet.build_loss(saved, "keypoint_subnet", gt, wt)
+    opt.zero_grad()
+    loss.backward()
+    assert abs(float(loss) - loss_ref) <= 1e-4 * max(1.0, abs(loss_ref))
+    assert nerr(m.conv2.weight.grad, gref["conv2.weight"]) <= 3e-3
+    assert nerr(m.fpn.layer1[0].conv1.weight.grad, gref["fpn.layer1.0.conv1.weight"]) <= 3e-3
+    assert nerr(m.fpn.conv1.weight.grad, gref["fpn.conv1.weight"]) <= 3e-3
+    assert m.regressionModel.conv1.weight.grad is None
+    before = m.conv2.weight.detach().clone()
+    opt.step()
+    assert not torch.equal(before, m.conv2.weight)
+    assert "heatmap_loss" in log and "max_ht" in log
+    # second step runs with the updated weights (filters are re-packed every step)
+    out2, saved2 = m([x, "keypoint_subnet"])
+    loss2, _ = poseNet.build_loss(saved2, "keypoint_subnet", gt, wt)
+    assert float(loss2) < float(loss)
