@@ -177,6 +177,90 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def freeze_for_keypoint_training(model):
+    """training/multipose_keypoint_train.py:78-89: detection neck / heads and the PRN are frozen."""
+    for name, mod in model.fpn.named_children():
+        if name in ("conv6", "conv7", "latlayer1", "latlayer2", "latlayer3", "toplayer0", "toplayer1", "toplayer2"):
+            for p in mod.parameters():
+                p.requires_grad = False
+    for name, mod in model.named_children():
+        if name in ("regressionModel", "classificationModel", "prn"):
+            for p in mod.parameters():
+                p.requires_grad = False
+
+
+def run_train(args, rank, world, local):
+    """BASELINE config 4: keypoint-subnet training step (fwd + bwd + NCCL gradient allreduce + Adam), batch 16/GPU."""
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from multiposenet.pytorch_b200 import poseNet, shard
+    from oracle import posenet_oracle as po
+    B = args.batch if args.batch != 32 else 16
+    model = poseNet(args.layers, precision=args.precision)
+    load_weights_into(model, args.layers)
+    model = model.to(dev).train()
+    freeze_for_keypoint_training(model)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+    eng = model.train_engine()
+    rng = np.random.Generator(np.random.PCG64(4321 + rank))
+    x = torch.from_numpy(rng.standard_normal((B, 3, H, W), dtype=np.float32)).to(dev)
+    gt = torch.from_numpy(rng.random((B, 18, H // 4, W // 4), dtype=np.float32)).to(dev)
+    wt = torch.from_numpy((rng.random((B, 18, H // 4, W // 4)) > 0.2).astype(np.float32)).to(dev)
+
+    def step():
+        loss, outs, grads = eng.forward_backward(x, gt, wt)
+        eng.assign_grads(grads, world)   # one NCCL allreduce over the flat fp32 gradient (no-op at world 1)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses = []
+    for _ in range(max(args.warmup, 3)):
+        losses.append(step())
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        losses.append(step())
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    value = shard.whole_job_rate(B * args.steps, ms, dev)
+    ms = shard.max_over_ranks(ms, dev)
+    nparam = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    fwd_gflop = (po.conv_flops_entire(args.layers, H, W) - 0) / 1e9  # upper bound; the trainable sub-graph is 198.2 (R101)
+    if rank == 0:
+        pk, pk_src = peaks()
+        alg = 3.0 * 198.23e9 if args.layers == 101 else 3.0 * 152.78e9  # fwd + dgrad + wgrad of the keypoint sub-graph (SURVEY 8(d))
+        ach = alg * B * world * args.steps / (ms / 1e3) / 1e12 / world
+        print(json.dumps({
+            "mode": "train", "metric": "images/sec keypoint-subnet training step (fwd+bwd+allreduce+Adam), 3x480x640", "value": value,
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "wall_ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "R%d keypoint_subnet train step, batch %d/GPU, BN train mode, Adam lr 1e-4" % (args.layers, B),
+                       "global_batch": B * world, "parallelism": "dp%d, one NCCL allreduce of %d fp32 gradients (%.1f MB) per step" % (
+                           world, nparam, nparam * 4 / 1e6)},
+            "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk.get("bf16_tflops_sustained"), "unit": "TFLOP/s",
+                         "frac": ach / pk.get("bf16_tflops_sustained"), "note": "per-GPU algorithmic FLOPs = 3 x forward of the trainable graph"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,6 +272,7 @@ def main():
     ap.add_argument("--layers", type=int, default=LAYERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train = BASELINE config 4 (extra line, not the headline)")
     ap.add_argument("--streams", type=int, default=None, help="branch-level side streams (default: engine default = on)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (0 = eager launches)")
     args = ap.parse_args()
@@ -196,6 +281,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.mode == "train":
+        return run_train(args, rank, world, local)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist

@@ -40,3 +40,32 @@ def whole_job_rate(images_this_rank, elapsed_ms_local, device=None):
     """images/s of the whole job: all ranks' images over the slowest rank's device time."""
     slowest = max_over_ranks(elapsed_ms_local, device)
     return sum_over_ranks(images_this_rank, device) / (slowest / 1e3)
+
+
+def allreduce_mean_(flat):
+    """In-place mean over ranks of a flat gradient buffer: the ONE collective of the training step.
+    NCCL on CUDA tensors, gloo on CPU tensors; identity without an initialised process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= dist.get_world_size()
+    return flat
+
+
+def flatten_grads(named_grads):
+    """[(name, tensor)] -> (flat fp32 buffer, [(name, shape, offset)])."""
+    parts, index, off = [], [], 0
+    for n, g in named_grads:
+        parts.append(g.reshape(-1).float())
+        index.append((n, tuple(g.shape), off))
+        off += g.numel()
+    return torch.cat(parts) if parts else torch.zeros(0), index
+
+
+def unflatten_grads(flat, index):
+    out = {}
+    for n, shape, off in index:
+        k = 1
+        for d in shape:
+            k *= d
+        out[n] = flat[off:off + k].view(shape)
+    return out

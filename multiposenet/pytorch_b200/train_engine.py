@@ -36,6 +36,7 @@ class TrainEngine(object):
         self.precision = precision
         self.fmt = ops.PRECISIONS[precision]
         self.grads = {}
+        self.trace = None  # dict -> records d loss / d (block output) during backward (diagnostics)
 
     # ------------------------------------------------------------------ helpers
     def _pc(self, conv):
@@ -154,6 +155,8 @@ class TrainEngine(object):
         d = d_c5
         for b in reversed(S.blocks):
             blk, name = b.blk, b.name
+            if self.trace is not None:
+                self.trace[name] = d.to_nchw()  # gradient w.r.t. this block's output
             dy3, g, dg, db = T.bn_train_backward(d, b.st3, blk.bn3, want_g=True)
             self._bn_grads(name + ".bn3", dg, db)
             dz2 = self._conv_grads(name + ".conv3", blk.conv3, b.z2, dy3)
@@ -184,27 +187,40 @@ class TrainEngine(object):
         """One forward + backward with the fused weighted-MSE loss kernel (posenet.py:367-403: sum of 5 MSE terms).
         Returns (loss fp64 [1] on device, outs, grads dict name -> tensor)."""
         outs, S = self.forward(img)
+        self.last_saved = S
         loss = torch.zeros(1, dtype=torch.float64, device=img.device)
         douts = [T.mse_heatmap_loss(o, heat_gt, heat_weight, loss, self.fmt, Cd=64) for o in outs]
         grads = self.backward(S, douts)
         return loss, outs, grads
 
+    def relu_masks(self, S):
+        """The {0,1} ReLU patterns of a saved forward, in the order the graph applies them (fp32 NCHW tensors):
+        stem, then (relu1, relu2, relu_out) per bottleneck, then the head's conv2.  Test support."""
+        acts = [S.stem_z]
+        for b in S.blocks:
+            acts += [b.z1, b.z2, b.st3.z]
+        acts.append(S.h)
+        return [(a.to_nchw() > 0).float() for a in acts]
+
+    def pool_indices(self, S):
+        """Flat arg-max indices (into H*W of the stem activation) chosen by the 3x3/2 max-pool of the saved forward."""
+        z = S.stem_z.to_nchw()
+        return torch.nn.functional.max_pool2d(z, 3, 2, 1, return_indices=True)[1]
+
     def trainable_parameters(self):
         return [(n, p) for n, p in self.model.named_parameters() if p.requires_grad]
 
     def assign_grads(self, grads, world_size=1):
-        """Copy the step's gradients into param.grad (one NCCL allreduce over a flat fp32 buffer when world_size > 1)."""
+        """Copy the step's gradients into param.grad; with several ranks, ONE allreduce (NCCL) over the flat fp32
+        buffer first (reference: DataParallel's reduce-add onto GPU 0, training/trainer.py:170)."""
+        from . import shard
         named = [(n, p) for n, p in self.trainable_parameters() if n in grads]
-        flat = torch.cat([grads[n].reshape(-1) for n, _ in named])
+        flat, index = shard.flatten_grads([(n, grads[n]) for n, _ in named])
         if world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            flat /= world_size
-        off = 0
+            shard.allreduce_mean_(flat)
+        by_name = shard.unflatten_grads(flat, index)
         for n, p in named:
-            k = p.numel()
-            p.grad = flat[off:off + k].view_as(p)
-            off += k
+            p.grad = by_name[n].view_as(p)
         return flat
 
 
@@ -215,6 +231,7 @@ class KeypointTrainFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, img, *params):
         outs, S = engine.forward(img)
+        engine.last_saved = S
         ctx.engine, ctx.saved, ctx.names = engine, S, [n for n, _ in engine.trainable_parameters()]
         ctx.out_shapes, ctx.device = [tuple(o.shape) for o in outs], img.device
         return tuple(outs)

@@ -24,6 +24,10 @@ def _conv(sd, name, x, stride=1, pad=0):
     return F.conv2d(x, sd[name + ".weight"], sd.get(name + ".bias"), stride=stride, padding=pad)
 
 
+RELU_MASKS = None  # iterator of {0,1} tensors: _relu(x) = x * mask (lets a test impose ANOTHER implementation's ReLU
+                   # pattern so that a handful of sign flips at |x| ~ 1e-4 do not dominate a max-norm gradient comparison)
+POOL_INDICES = None  # same idea for the stem max-pool: impose another implementation's arg-max selection
+TRACE = None       # set to a dict to record block outputs (tests / debugging only)
 _BN_TRAIN = False  # forward_train_keypoint() flips this: batch statistics, as under model.train() (trainer.py:170-174)
 
 
@@ -35,16 +39,24 @@ def _bn(sd, name, x):
                         sd[name + ".weight"], sd[name + ".bias"], False, 0.0, 1e-5)
 
 
+def _relu(x):
+    if RELU_MASKS is None:
+        return F.relu(x)
+    m = next(RELU_MASKS)
+    assert m.shape == x.shape, (m.shape, x.shape)
+    return x * m.to(x.dtype)
+
+
 def bottleneck(sd, p, x, stride):
     """fpn.py:28-34."""
-    out = F.relu(_bn(sd, p + "bn1", _conv(sd, p + "conv1", x)))
-    out = F.relu(_bn(sd, p + "bn2", _conv(sd, p + "conv2", out, stride=stride, pad=1)))
+    out = _relu(_bn(sd, p + "bn1", _conv(sd, p + "conv1", x)))
+    out = _relu(_bn(sd, p + "bn2", _conv(sd, p + "conv2", out, stride=stride, pad=1)))
     out = _bn(sd, p + "bn3", _conv(sd, p + "conv3", out))
     if (p + "downsample.0.weight") in sd:
         sc = _bn(sd, p + "downsample.1", _conv(sd, p + "downsample.0", x, stride=stride))
     else:
         sc = x
-    return F.relu(out + sc)
+    return _relu(out + sc)
 
 
 def upsample_add(x, y):
@@ -54,12 +66,19 @@ def upsample_add(x, y):
 
 def backbone(sd, layers, x, pre="fpn."):
     """fpn.py:99-105."""
-    c1 = F.relu(_bn(sd, pre + "bn1", _conv(sd, pre + "conv1", x, stride=2, pad=3)))
-    c = F.max_pool2d(c1, kernel_size=3, stride=2, padding=1)
+    c1 = _relu(_bn(sd, pre + "bn1", _conv(sd, pre + "conv1", x, stride=2, pad=3)))
+    if POOL_INDICES is None:
+        c = F.max_pool2d(c1, kernel_size=3, stride=2, padding=1)
+    else:
+        idx = POOL_INDICES
+        c = c1.flatten(2).gather(2, idx.flatten(2)).view(idx.shape)
     feats = []
     for li, (nblk, stride) in enumerate(zip(BLOCKS[layers], (1, 2, 2, 2)), start=1):
         for b in range(nblk):
             c = bottleneck(sd, "%slayer%d.%d." % (pre, li, b), c, stride if b == 0 else 1)
+            if TRACE is not None and c.requires_grad:  # diagnostics: keep each block output and its gradient
+                c.retain_grad()
+                TRACE["%slayer%d.%d" % (pre, li, b)] = c
         feats.append(c)
     return feats  # c2, c3, c4, c5
 
@@ -99,7 +118,7 @@ def keypoint_head(sd, p2, p3, p4, p5):
     q4 = F.interpolate(q4, scale_factor=4, mode="nearest")
     q3 = F.interpolate(q3, scale_factor=2, mode="nearest")
     cat = torch.cat((q5, q4, q3, q2), 1)
-    return _conv(sd, "convfin", F.relu(_conv(sd, "conv2", cat, pad=1)))
+    return _conv(sd, "convfin", _relu(_conv(sd, "conv2", cat, pad=1)))
 
 
 def intermediate_heads(sd, p2, p3, p4, p5):

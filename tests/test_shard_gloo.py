@@ -22,6 +22,12 @@ def test_shard_range_partitions():
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the training step's single collective: flat gradient mean over ranks
+    grads = [("a.weight", torch.full((2, 3), float(rank + 1))), ("b.bias", torch.arange(4.0) * (rank + 1))]
+    flat, index = shard.flatten_grads(grads)
+    shard.allreduce_mean_(flat)
+    back = shard.unflatten_grads(flat, index)
+    assert torch.allclose(back["a.weight"], torch.full((2, 3), 1.5)) and torch.allclose(back["b.bias"], torch.arange(4.0) * 1.5)
     b, e = shard.shard_range(33, rank, world)
     slow = shard.max_over_ranks(10.0 * (rank + 1))
     rate = shard.whole_job_rate(e - b, 10.0 * (rank + 1))
