@@ -275,6 +275,210 @@ __global__ void stem_unpack_filter_grad_kernel(const float* __restrict__ g, floa
   out[i] = g[(co * 4 + r2) * 64 + s2 * 16 + cc];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Vectorised bf16 / bf16x2 variants (8 channels = one 16-byte vector per thread).  The scalar kernels above stay as
+// the generic (fp32 / odd channel count) path.
+template <bool SPLIT>
+__device__ __forceinline__ void load8(const uint4* __restrict__ hi, const uint4* __restrict__ lo, long long i, float* v) {
+  const uint4 h = __ldg(hi + i);
+  const unsigned hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __uint_as_float(hv[j] << 16);
+    v[2 * j + 1] = __uint_as_float(hv[j] & 0xFFFF0000u);
+  }
+  if (SPLIT) {
+    const uint4 l = __ldg(lo + i);
+    const unsigned lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] += __uint_as_float(lv[j] << 16);
+      v[2 * j + 1] += __uint_as_float(lv[j] & 0xFFFF0000u);
+    }
+  }
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ void store8(uint4* hi, uint4* lo, long long i, const float* v) {
+  unsigned oh[4], ol[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    oh[j] = *reinterpret_cast<unsigned*>(&t);
+    if (SPLIT) {
+      __nv_bfloat162 u = __floats2bfloat162_rn(v[2 * j] - __uint_as_float(oh[j] << 16), v[2 * j + 1] - __uint_as_float(oh[j] & 0xFFFF0000u));
+      ol[j] = *reinterpret_cast<unsigned*>(&u);
+    }
+  }
+  hi[i] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+  if (SPLIT) lo[i] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+}
+
+constexpr int VPIX = 256;  // pixels per CTA in the vectorised reductions
+
+// per-channel sum / sum of squares; dense channels (C8 = C/8 vectors per pixel), 256 threads
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) channel_stats_v8_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo,
+                                                               long long pixels, int C8, double* __restrict__ sum,
+                                                               double* __restrict__ sumsq) {
+  extern __shared__ float sh[];  // [2][C]
+  const int C = C8 * 8;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  const long long p0 = (long long)blockIdx.x * VPIX;
+  const long long p1 = p0 + VPIX < pixels ? p0 + VPIX : pixels;
+  const int groups = C8 < 256 ? C8 : 256;        // channel groups handled concurrently
+  const int lanes = 256 / groups;                // pixel lanes per group
+  const int lane = threadIdx.x / groups;
+  for (int cg = threadIdx.x % groups; cg < C8; cg += groups) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    if (lane < lanes)
+      for (long long p = p0 + lane; p < p1; p += lanes) {
+        float v[8];
+        load8<SPLIT>(hi, lo, p * C8 + cg, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[cg * 8 + j], s[j]);
+      atomicAdd(&sh[C + cg * 8 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    atomicAdd(sum + c, (double)sh[c]);
+    if (sumsq) atomicAdd(sumsq + c, (double)sh[C + c]);
+  }
+}
+
+template <bool SPLIT>
+__global__ void bn_apply_v8_kernel(const uint4* __restrict__ yhi, const uint4* __restrict__ ylo, const float* __restrict__ mean,
+                                   const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, const uint4* __restrict__ rhi, const uint4* __restrict__ rlo, int relu, uint4* zhi,
+                                   uint4* zlo, long long total8, int C8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % C8) * 8;
+    float v[8], r[8];
+    load8<SPLIT>(yhi, ylo, i, v);
+    if (rhi) load8<SPLIT>(rhi, rlo, i, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float invstd = rsqrtf(var[c0 + j] + eps);
+      float o = (v[j] - mean[c0 + j]) * invstd * gamma[c0 + j] + beta[c0 + j];
+      if (rhi) o += r[j];
+      v[j] = relu ? fmaxf(o, 0.f) : o;
+    }
+    store8<SPLIT>(zhi, zlo, i, v);
+  }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_v8_kernel(const uint4* __restrict__ dzhi, const uint4* __restrict__ dzlo,
+                                                               const uint4* __restrict__ zhi, const uint4* __restrict__ zlo,
+                                                               const uint4* __restrict__ yhi, const uint4* __restrict__ ylo,
+                                                               const float* __restrict__ mean, const float* __restrict__ var,
+                                                               float eps, int relu, long long pixels, int C8,
+                                                               double* __restrict__ s1, double* __restrict__ s2) {
+  extern __shared__ float sh[];  // [2][C]
+  const int C = C8 * 8;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  const long long p0 = (long long)blockIdx.x * VPIX;
+  const long long p1 = p0 + VPIX < pixels ? p0 + VPIX : pixels;
+  const int groups = C8 < 256 ? C8 : 256;
+  const int lanes = 256 / groups;
+  const int lane = threadIdx.x / groups;
+  for (int cg = threadIdx.x % groups; cg < C8; cg += groups) {
+    float a[8], b[8], m[8], is[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = b[j] = 0.f;
+      m[j] = mean[cg * 8 + j];
+      is[j] = rsqrtf(var[cg * 8 + j] + eps);
+    }
+    if (lane < lanes)
+      for (long long p = p0 + lane; p < p1; p += lanes) {
+        float g[8], z[8], y[8];
+        load8<SPLIT>(dzhi, dzlo, p * C8 + cg, g);
+        if (relu) load8<SPLIT>(zhi, zlo, p * C8 + cg, z);
+        load8<SPLIT>(yhi, ylo, p * C8 + cg, y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = (relu && !(z[j] > 0.f)) ? 0.f : g[j];
+          a[j] += gg;
+          b[j] = fmaf(gg, (y[j] - m[j]) * is[j], b[j]);
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[cg * 8 + j], a[j]);
+      atomicAdd(&sh[C + cg * 8 + j], b[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    atomicAdd(s1 + c, (double)sh[c]);
+    atomicAdd(s2 + c, (double)sh[C + c]);
+  }
+}
+
+template <bool SPLIT>
+__global__ void bn_bwd_apply_v8_kernel(const uint4* __restrict__ dzhi, const uint4* __restrict__ dzlo, const uint4* __restrict__ zhi,
+                                       const uint4* __restrict__ zlo, const uint4* __restrict__ yhi, const uint4* __restrict__ ylo,
+                                       const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
+                                       float eps, int relu, const double* __restrict__ s1, const double* __restrict__ s2, double n,
+                                       uint4* dyhi, uint4* dylo, uint4* ghi, uint4* glo, long long total8, int C8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % C8) * 8;
+    float g[8], z[8], y[8], o[8];
+    load8<SPLIT>(dzhi, dzlo, i, g);
+    if (relu) load8<SPLIT>(zhi, zlo, i, z);
+    load8<SPLIT>(yhi, ylo, i, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float invstd = rsqrtf(var[c] + eps);
+      if (relu && !(z[j] > 0.f)) g[j] = 0.f;
+      const float yhat = (y[j] - mean[c]) * invstd;
+      o[j] = gamma[c] * invstd * (g[j] - (float)(s1[c] / n) - yhat * (float)(s2[c] / n));
+    }
+    store8<SPLIT>(dyhi, dylo, i, o);
+    if (ghi) store8<SPLIT>(ghi, glo, i, g);
+  }
+}
+
+template <bool SPLIT>
+__global__ void relu_bwd_v8_kernel(const uint4* __restrict__ dzhi, const uint4* __restrict__ dzlo, const uint4* __restrict__ zhi,
+                                   const uint4* __restrict__ zlo, uint4* ohi, uint4* olo, long long total8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    float g[8], z[8];
+    load8<SPLIT>(dzhi, dzlo, i, g);
+    load8<SPLIT>(zhi, zlo, i, z);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (!(z[j] > 0.f)) g[j] = 0.f;
+    store8<SPLIT>(ohi, olo, i, g);
+  }
+}
+
+template <bool SPLIT>
+__global__ void add_act_v8_kernel(const uint4* __restrict__ ahi, const uint4* __restrict__ alo, const uint4* __restrict__ bhi,
+                                  const uint4* __restrict__ blo, uint4* ohi, uint4* olo, long long total8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    load8<SPLIT>(ahi, alo, i, a);
+    load8<SPLIT>(bhi, blo, i, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    store8<SPLIT>(ohi, olo, i, a);
+  }
+}
+
+inline bool vec_ok(int fmt, int C) { return (fmt == MPN_FMT_BF16 || fmt == MPN_FMT_BF16X2) && C % 8 == 0 && C <= 4096; }
+
 }  // namespace
 
 #define ST ((cudaStream_t)stream)
@@ -284,6 +488,16 @@ extern "C" int mpn_channel_sums(const void* hi, const void* lo, long long pixels
   MPN_CHECK_ARG(hi && sum && pixels > 0 && C > 0 && cstride >= coffset + C, "mpn_channel_sums: bad argument");
   MPN_CUDA_OK(cudaMemsetAsync(sum, 0, sizeof(double) * C, ST));
   if (sumsq) MPN_CUDA_OK(cudaMemsetAsync(sumsq, 0, sizeof(double) * C, ST));
+  if (vec_ok(fmt, C) && cstride == C && coffset == 0) {
+    const int grid = mpn_divup(pixels, VPIX);
+    const size_t smem = sizeof(float) * 2 * C;
+    if (fmt == MPN_FMT_BF16X2)
+      channel_stats_v8_kernel<true><<<grid, 256, smem, ST>>>((const uint4*)hi, (const uint4*)lo, pixels, C / 8, sum, sumsq);
+    else
+      channel_stats_v8_kernel<false><<<grid, 256, smem, ST>>>((const uint4*)hi, nullptr, pixels, C / 8, sum, sumsq);
+    MPN_LAUNCH_OK();
+    return MPN_OK;
+  }
   channel_stats_kernel<<<mpn_divup(pixels, PIX_PER_BLOCK), 256, 0, ST>>>(hi, lo, pixels, C, cstride, coffset, fmt, sum, sumsq);
   MPN_LAUNCH_OK();
   return MPN_OK;
@@ -312,6 +526,17 @@ extern "C" int mpn_bn_apply(const void* yhi, const void* ylo, const float* mean,
                             long long pixels, int C, int fmt, void* stream) {
   MPN_CHECK_ARG(yhi && mean && var && gamma && beta && zhi && pixels > 0 && C > 0, "mpn_bn_apply: bad argument");
   long long total = pixels * C;
+  if (vec_ok(fmt, C)) {
+    const long long t8 = total / 8;
+    if (fmt == MPN_FMT_BF16X2)
+      bn_apply_v8_kernel<true><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)yhi, (const uint4*)ylo, mean, var, gamma, beta, eps,
+                                                                  (const uint4*)rhi, (const uint4*)rlo, relu, (uint4*)zhi, (uint4*)zlo, t8, C / 8);
+    else
+      bn_apply_v8_kernel<false><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)yhi, nullptr, mean, var, gamma, beta, eps,
+                                                                   (const uint4*)rhi, nullptr, relu, (uint4*)zhi, nullptr, t8, C / 8);
+    MPN_LAUNCH_OK();
+    return MPN_OK;
+  }
   bn_apply_kernel<<<grid_for(total, 256), 256, 0, ST>>>(yhi, ylo, mean, var, gamma, beta, eps, rhi, rlo, relu, zhi, zlo, total, C, fmt);
   MPN_LAUNCH_OK();
   return MPN_OK;
@@ -326,13 +551,34 @@ extern "C" int mpn_bn_backward(const void* dzhi, const void* dzlo, const void* z
   double* s1 = workspace;
   double* s2 = workspace + C;
   MPN_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * C, ST));
-  bn_bwd_reduce_kernel<<<mpn_divup(pixels, PIX_PER_BLOCK), 256, 0, ST>>>(dzhi, dzlo, zhi, zlo, yhi, ylo, mean, var, eps, relu, pixels,
-                                                                          C, fmt, s1, s2);
-  MPN_LAUNCH_OK();
   long long total = pixels * C;
-  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dzhi, dzlo, zhi, zlo, yhi, ylo, mean, var, gamma, eps, relu, s1, s2,
-                                                           (double)pixels, dyhi, dylo, ghi, glo, total, C, fmt);
-  MPN_LAUNCH_OK();
+  if (vec_ok(fmt, C)) {
+    const int grid = mpn_divup(pixels, VPIX);
+    const size_t smem = sizeof(float) * 2 * C;
+    const long long t8 = total / 8;
+    if (fmt == MPN_FMT_BF16X2) {
+      bn_bwd_reduce_v8_kernel<true><<<grid, 256, smem, ST>>>((const uint4*)dzhi, (const uint4*)dzlo, (const uint4*)zhi, (const uint4*)zlo,
+                                                             (const uint4*)yhi, (const uint4*)ylo, mean, var, eps, relu, pixels, C / 8, s1, s2);
+      bn_bwd_apply_v8_kernel<true><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)dzhi, (const uint4*)dzlo, (const uint4*)zhi,
+                                                                      (const uint4*)zlo, (const uint4*)yhi, (const uint4*)ylo, mean, var, gamma,
+                                                                      eps, relu, s1, s2, (double)pixels, (uint4*)dyhi, (uint4*)dylo,
+                                                                      (uint4*)ghi, (uint4*)glo, t8, C / 8);
+    } else {
+      bn_bwd_reduce_v8_kernel<false><<<grid, 256, smem, ST>>>((const uint4*)dzhi, nullptr, (const uint4*)zhi, nullptr, (const uint4*)yhi,
+                                                              nullptr, mean, var, eps, relu, pixels, C / 8, s1, s2);
+      bn_bwd_apply_v8_kernel<false><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)dzhi, nullptr, (const uint4*)zhi, nullptr,
+                                                                       (const uint4*)yhi, nullptr, mean, var, gamma, eps, relu, s1, s2,
+                                                                       (double)pixels, (uint4*)dyhi, nullptr, (uint4*)ghi, nullptr, t8, C / 8);
+    }
+    MPN_LAUNCH_OK();
+  } else {
+    bn_bwd_reduce_kernel<<<mpn_divup(pixels, PIX_PER_BLOCK), 256, 0, ST>>>(dzhi, dzlo, zhi, zlo, yhi, ylo, mean, var, eps, relu, pixels,
+                                                                            C, fmt, s1, s2);
+    MPN_LAUNCH_OK();
+    bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dzhi, dzlo, zhi, zlo, yhi, ylo, mean, var, gamma, eps, relu, s1, s2,
+                                                             (double)pixels, dyhi, dylo, ghi, glo, total, C, fmt);
+    MPN_LAUNCH_OK();
+  }
   if (dgamma) double_to_float_kernel<<<mpn_divup(C, 256), 256, 0, ST>>>(s2, dgamma, C, 1.f);
   if (dbeta) double_to_float_kernel<<<mpn_divup(C, 256), 256, 0, ST>>>(s1, dbeta, C, 1.f);
   MPN_LAUNCH_OK();
@@ -349,6 +595,16 @@ extern "C" int mpn_double_to_float(const double* a, float* out, int n, float sca
 extern "C" int mpn_relu_backward(const void* dzhi, const void* dzlo, const void* zhi, const void* zlo, void* ohi, void* olo,
                                  long long n, int fmt, void* stream) {
   MPN_CHECK_ARG(dzhi && zhi && ohi && n > 0, "mpn_relu_backward: bad argument");
+  if ((fmt == MPN_FMT_BF16 || fmt == MPN_FMT_BF16X2) && n % 8 == 0) {
+    if (fmt == MPN_FMT_BF16X2)
+      relu_bwd_v8_kernel<true><<<grid_for(n / 8, 256), 256, 0, ST>>>((const uint4*)dzhi, (const uint4*)dzlo, (const uint4*)zhi,
+                                                                      (const uint4*)zlo, (uint4*)ohi, (uint4*)olo, n / 8);
+    else
+      relu_bwd_v8_kernel<false><<<grid_for(n / 8, 256), 256, 0, ST>>>((const uint4*)dzhi, nullptr, (const uint4*)zhi, nullptr, (uint4*)ohi,
+                                                                       nullptr, n / 8);
+    MPN_LAUNCH_OK();
+    return MPN_OK;
+  }
   relu_bwd_kernel<<<grid_for(n, 256), 256, 0, ST>>>(dzhi, dzlo, zhi, zlo, ohi, olo, n, fmt);
   MPN_LAUNCH_OK();
   return MPN_OK;
@@ -357,6 +613,16 @@ extern "C" int mpn_relu_backward(const void* dzhi, const void* dzlo, const void*
 extern "C" int mpn_add_act(const void* ahi, const void* alo, const void* bhi, const void* blo, void* ohi, void* olo, long long n,
                            int fmt, void* stream) {
   MPN_CHECK_ARG(ahi && bhi && ohi && n > 0, "mpn_add_act: bad argument");
+  if ((fmt == MPN_FMT_BF16 || fmt == MPN_FMT_BF16X2) && n % 8 == 0) {
+    if (fmt == MPN_FMT_BF16X2)
+      add_act_v8_kernel<true><<<grid_for(n / 8, 256), 256, 0, ST>>>((const uint4*)ahi, (const uint4*)alo, (const uint4*)bhi, (const uint4*)blo,
+                                                                     (uint4*)ohi, (uint4*)olo, n / 8);
+    else
+      add_act_v8_kernel<false><<<grid_for(n / 8, 256), 256, 0, ST>>>((const uint4*)ahi, nullptr, (const uint4*)bhi, nullptr, (uint4*)ohi,
+                                                                      nullptr, n / 8);
+    MPN_LAUNCH_OK();
+    return MPN_OK;
+  }
   add_act_kernel<<<grid_for(n, 256), 256, 0, ST>>>(ahi, alo, bhi, blo, ohi, olo, n, fmt);
   MPN_LAUNCH_OK();
   return MPN_OK;
