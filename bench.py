@@ -211,7 +211,10 @@ def run_train(args, rank, world, local):
     wt = torch.from_numpy((rng.random((B, 18, H // 4, W // 4)) > 0.2).astype(np.float32)).to(dev)
 
     def step():
-        loss, outs, grads = eng.forward_backward(x, gt, wt)
+        if args.graph:
+            loss, outs, grads = eng.graphed_forward_backward(x, gt, wt)  # one cudaGraphLaunch for fwd + bwd
+        else:
+            loss, outs, grads = eng.forward_backward(x, gt, wt)
         eng.assign_grads(grads, world)   # one NCCL allreduce over the flat fp32 gradient (no-op at world 1)
         opt.step()
         return loss
@@ -252,7 +255,7 @@ def run_train(args, rank, world, local):
             "wall_ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "R%d keypoint_subnet train step, batch %d/GPU, BN train mode, Adam lr 1e-4" % (args.layers, B),
-                       "global_batch": B * world, "parallelism": "dp%d, one NCCL allreduce of %d fp32 gradients (%.1f MB) per step" % (
+                       "global_batch": B * world, "cuda_graph": bool(args.graph), "parallelism": "dp%d, one NCCL allreduce of %d fp32 gradients (%.1f MB) per step" % (
                            world, nparam, nparam * 4 / 1e6)},
             "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk.get("bf16_tflops_sustained"), "unit": "TFLOP/s",

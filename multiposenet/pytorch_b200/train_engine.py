@@ -207,6 +207,40 @@ class TrainEngine(object):
         z = S.stem_z.to_nchw()
         return torch.nn.functional.max_pool2d(z, 3, 2, 1, return_indices=True)[1]
 
+    def graphed_forward_backward(self, img, heat_gt, heat_weight):
+        """forward_backward replayed from a CUDA graph (captured on first use per input shape): the ~2000 launches
+        of a step become one driver call, which matters because the eager step is bound by Python launch overhead.
+        The filters are re-packed from the live weights INSIDE the graph, so optimizer updates are seen.
+        Returned tensors are the graph's static outputs (overwritten by the next replay)."""
+        key = (tuple(img.shape), str(img.device))
+        g = getattr(self, "_graphs", {}).get(key)
+        if g is None:
+            if not hasattr(self, "_graphs"):
+                self._graphs = {}
+            sx, sg, sw = torch.empty_like(img), torch.empty_like(heat_gt), torch.empty_like(heat_weight)
+            sx.copy_(img); sg.copy_(heat_gt); sw.copy_(heat_weight)
+            bn_state = [(m, m.running_mean.clone(), m.running_var.clone(), m.num_batches_tracked.clone())
+                        for m in self.model.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+            side = torch.cuda.Stream(device=img.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.forward_backward(sx, sg, sw)  # warm-up off the capture (function attributes, allocator pools)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for m, rm, rv, nb in bn_state:  # the warm-up must not count as a training step
+                m.running_mean.copy_(rm); m.running_var.copy_(rv); m.num_batches_tracked.copy_(nb)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.forward_backward(sx, sg, sw)
+            for m, rm, rv, nb in bn_state:  # capture does not execute, but keep the invariant explicit
+                m.running_mean.copy_(rm); m.running_var.copy_(rv); m.num_batches_tracked.copy_(nb)
+            g = (graph, sx, sg, sw, out)
+            self._graphs[key] = g
+        graph, sx, sg, sw, out = g
+        sx.copy_(img, non_blocking=True); sg.copy_(heat_gt, non_blocking=True); sw.copy_(heat_weight, non_blocking=True)
+        graph.replay()
+        return out
+
     def trainable_parameters(self):
         return [(n, p) for n, p in self.model.named_parameters() if p.requires_grad]
 

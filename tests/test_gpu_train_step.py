@@ -109,3 +109,22 @@ def test_reference_training_loop_surface():
     out2, saved2 = m([x, "keypoint_subnet"])
     loss2, _ = poseNet.build_loss(saved2, "keypoint_subnet", gt, wt)
     assert float(loss2) < float(loss)
+
+
+def test_graphed_train_step_matches_eager():
+    from gpu_util import nerr
+    m, w, x, gt, wt = _problem()
+    m.train()
+    eng = m.train_engine()
+    loss_e, outs_e, grads_e = eng.forward_backward(x, gt, wt)
+    ref = {k: v.clone() for k, v in grads_e.items()}
+    loss_e = float(loss_e)
+    nb = int(m.fpn.bn1.num_batches_tracked)
+    for _ in range(2):
+        loss_g, outs_g, grads_g = eng.graphed_forward_backward(x, gt, wt)
+    torch.cuda.synchronize()
+    assert abs(float(loss_g) - loss_e) <= 1e-6 * max(1.0, abs(loss_e))
+    assert set(grads_g) == set(ref)
+    # fp32 atomics in wgrad / the BN reductions make the summation order vary between runs: tolerance, not equality
+    assert max(nerr(grads_g[k], ref[k]) for k in ref if float(ref[k].abs().max()) > 0) <= 1e-4
+    assert int(m.fpn.bn1.num_batches_tracked) == nb + 2  # the capture/warm-up runs did not count as steps
