@@ -226,7 +226,7 @@ def run_train(args, rank, world, local):
 
     losses = []
     for _ in range(max(args.warmup, 3)):
-        losses.append(step())
+        losses.append(step().clone())
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -235,7 +235,7 @@ def run_train(args, rank, world, local):
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        losses.append(step())
+        losses.append(step().clone())
     e1.record()
     barrier()
     wall = time.perf_counter() - t0

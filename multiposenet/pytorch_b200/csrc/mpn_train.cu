@@ -315,7 +315,7 @@ __device__ __forceinline__ void store8(uint4* hi, uint4* lo, long long i, const 
   if (SPLIT) lo[i] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
 }
 
-constexpr int VPIX = 256;  // pixels per CTA in the vectorised reductions
+constexpr int VPIX = 512;  // pixels per CTA in the vectorised reductions
 
 // per-channel sum / sum of squares; dense channels (C8 = C/8 vectors per pixel), 256 threads
 template <bool SPLIT>
@@ -342,10 +342,20 @@ __global__ void __launch_bounds__(256) channel_stats_v8_kernel(const uint4* __re
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
       }
+    // threads of a warp that own the same channel group sit `groups` apart: fold them with shuffles first
+    for (int o = groups; o < 32; o <<= 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[cg * 8 + j], s[j]);
-      atomicAdd(&sh[C + cg * 8 + j], q[j]);
+      for (int j = 0; j < 8; ++j) {
+        s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+        q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+      }
+    }
+    if (groups >= 32 || (threadIdx.x & 31) < groups) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sh[cg * 8 + j], s[j]);
+        atomicAdd(&sh[C + cg * 8 + j], q[j]);
+      }
     }
   }
   __syncthreads();
@@ -413,10 +423,19 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v8_kernel(const uint4* __re
           b[j] = fmaf(gg, (y[j] - m[j]) * is[j], b[j]);
         }
       }
+    for (int o = groups; o < 32; o <<= 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[cg * 8 + j], a[j]);
-      atomicAdd(&sh[C + cg * 8 + j], b[j]);
+      for (int j = 0; j < 8; ++j) {
+        a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+        b[j] += __shfl_xor_sync(0xffffffffu, b[j], o);
+      }
+    }
+    if (groups >= 32 || (threadIdx.x & 31) < groups) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sh[cg * 8 + j], a[j]);
+        atomicAdd(&sh[C + cg * 8 + j], b[j]);
+      }
     }
   }
   __syncthreads();
@@ -477,7 +496,10 @@ __global__ void add_act_v8_kernel(const uint4* __restrict__ ahi, const uint4* __
   }
 }
 
-inline bool vec_ok(int fmt, int C) { return (fmt == MPN_FMT_BF16 || fmt == MPN_FMT_BF16X2) && C % 8 == 0 && C <= 4096; }
+inline bool vec_ok(int fmt, int C) {
+  const int c8 = C / 8;
+  return (fmt == MPN_FMT_BF16 || fmt == MPN_FMT_BF16X2) && C % 8 == 0 && C <= 4096 && (c8 & (c8 - 1)) == 0;  // power-of-two groups
+}
 
 }  // namespace
 
