@@ -315,53 +315,51 @@ __device__ __forceinline__ void store8(uint4* hi, uint4* lo, long long i, const 
   if (SPLIT) lo[i] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
 }
 
-constexpr int VPIX = 512;  // pixels per CTA in the vectorised reductions
 
-// per-channel sum / sum of squares; dense channels (C8 = C/8 vectors per pixel), 256 threads
+// per-channel sum / sum of squares; dense channels (C8 = C/8 vectors per pixel), 256 threads.
+// grid = (pixel chunks, channel slices of <= 32 vectors): small-spatial / wide layers still fill the machine.
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) channel_stats_v8_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo,
-                                                               long long pixels, int C8, double* __restrict__ sum,
+                                                               long long pixels, int C8, int vpix, double* __restrict__ sum,
                                                                double* __restrict__ sumsq) {
-  extern __shared__ float sh[];  // [2][C]
-  const int C = C8 * 8;
-  for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.f;
+  __shared__ float sh[2][256];
+  sh[0][threadIdx.x] = 0.f;
+  sh[1][threadIdx.x] = 0.f;
   __syncthreads();
-  const long long p0 = (long long)blockIdx.x * VPIX;
-  const long long p1 = p0 + VPIX < pixels ? p0 + VPIX : pixels;
-  const int groups = C8 < 256 ? C8 : 256;        // channel groups handled concurrently
-  const int lanes = 256 / groups;                // pixel lanes per group
-  const int lane = threadIdx.x / groups;
-  for (int cg = threadIdx.x % groups; cg < C8; cg += groups) {
-    float s[8], q[8];
+  const int groups = C8 < 32 ? C8 : 32;          // channel vectors of this CTA's slice (power of two)
+  const int cg = blockIdx.y * 32 + (threadIdx.x % groups);
+  const int lanes = 256 / groups, lane = threadIdx.x / groups;
+  const long long p0 = (long long)blockIdx.x * vpix;
+  const long long p1 = p0 + vpix < pixels ? p0 + vpix : pixels;
+  float s[8], q[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    if (lane < lanes)
-      for (long long p = p0 + lane; p < p1; p += lanes) {
-        float v[8];
-        load8<SPLIT>(hi, lo, p * C8 + cg, v);
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  for (long long p = p0 + lane; p < p1; p += lanes) {
+    float v[8];
+    load8<SPLIT>(hi, lo, p * C8 + cg, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
-      }
-    // threads of a warp that own the same channel group sit `groups` apart: fold them with shuffles first
-    for (int o = groups; o < 32; o <<= 1) {
+    for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+  }
+  for (int o = groups; o < 32; o <<= 1) {  // same-slice threads of a warp sit `groups` apart
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-        q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
-      }
+    for (int j = 0; j < 8; ++j) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+      q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
     }
-    if (groups >= 32 || (threadIdx.x & 31) < groups) {
+  }
+  if (groups >= 32 || (threadIdx.x & 31) < groups) {
+    const int g = threadIdx.x % groups;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sh[cg * 8 + j], s[j]);
-        atomicAdd(&sh[C + cg * 8 + j], q[j]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[0][g * 8 + j], s[j]);
+      atomicAdd(&sh[1][g * 8 + j], q[j]);
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
-    atomicAdd(sum + c, (double)sh[c]);
-    if (sumsq) atomicAdd(sumsq + c, (double)sh[C + c]);
+  if (threadIdx.x < groups * 8) {
+    const int c = blockIdx.y * 256 + threadIdx.x;
+    atomicAdd(sum + c, (double)sh[0][threadIdx.x]);
+    if (sumsq) atomicAdd(sumsq + c, (double)sh[1][threadIdx.x]);
   }
 }
 
@@ -391,57 +389,56 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v8_kernel(const uint4* __re
                                                                const uint4* __restrict__ zhi, const uint4* __restrict__ zlo,
                                                                const uint4* __restrict__ yhi, const uint4* __restrict__ ylo,
                                                                const float* __restrict__ mean, const float* __restrict__ var,
-                                                               float eps, int relu, long long pixels, int C8,
+                                                               float eps, int relu, long long pixels, int C8, int vpix,
                                                                double* __restrict__ s1, double* __restrict__ s2) {
-  extern __shared__ float sh[];  // [2][C]
-  const int C = C8 * 8;
-  for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.f;
+  __shared__ float sh[2][256];
+  sh[0][threadIdx.x] = 0.f;
+  sh[1][threadIdx.x] = 0.f;
   __syncthreads();
-  const long long p0 = (long long)blockIdx.x * VPIX;
-  const long long p1 = p0 + VPIX < pixels ? p0 + VPIX : pixels;
-  const int groups = C8 < 256 ? C8 : 256;
-  const int lanes = 256 / groups;
-  const int lane = threadIdx.x / groups;
-  for (int cg = threadIdx.x % groups; cg < C8; cg += groups) {
-    float a[8], b[8], m[8], is[8];
+  const int groups = C8 < 32 ? C8 : 32;
+  const int cg = blockIdx.y * 32 + (threadIdx.x % groups);
+  const int lanes = 256 / groups, lane = threadIdx.x / groups;
+  const long long p0 = (long long)blockIdx.x * vpix;
+  const long long p1 = p0 + vpix < pixels ? p0 + vpix : pixels;
+  float a[8], b[8], m[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = b[j] = 0.f;
+    m[j] = mean[cg * 8 + j];
+    is[j] = rsqrtf(var[cg * 8 + j] + eps);
+  }
+  for (long long p = p0 + lane; p < p1; p += lanes) {
+    float g[8], z[8], y[8];
+    load8<SPLIT>(dzhi, dzlo, p * C8 + cg, g);
+    if (relu) load8<SPLIT>(zhi, zlo, p * C8 + cg, z);
+    load8<SPLIT>(yhi, ylo, p * C8 + cg, y);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      a[j] = b[j] = 0.f;
-      m[j] = mean[cg * 8 + j];
-      is[j] = rsqrtf(var[cg * 8 + j] + eps);
+      const float gg = (relu && !(z[j] > 0.f)) ? 0.f : g[j];
+      a[j] += gg;
+      b[j] = fmaf(gg, (y[j] - m[j]) * is[j], b[j]);
     }
-    if (lane < lanes)
-      for (long long p = p0 + lane; p < p1; p += lanes) {
-        float g[8], z[8], y[8];
-        load8<SPLIT>(dzhi, dzlo, p * C8 + cg, g);
-        if (relu) load8<SPLIT>(zhi, zlo, p * C8 + cg, z);
-        load8<SPLIT>(yhi, ylo, p * C8 + cg, y);
+  }
+  for (int o = groups; o < 32; o <<= 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float gg = (relu && !(z[j] > 0.f)) ? 0.f : g[j];
-          a[j] += gg;
-          b[j] = fmaf(gg, (y[j] - m[j]) * is[j], b[j]);
-        }
-      }
-    for (int o = groups; o < 32; o <<= 1) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
-        b[j] += __shfl_xor_sync(0xffffffffu, b[j], o);
-      }
+    for (int j = 0; j < 8; ++j) {
+      a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+      b[j] += __shfl_xor_sync(0xffffffffu, b[j], o);
     }
-    if (groups >= 32 || (threadIdx.x & 31) < groups) {
+  }
+  if (groups >= 32 || (threadIdx.x & 31) < groups) {
+    const int g2 = threadIdx.x % groups;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sh[cg * 8 + j], a[j]);
-        atomicAdd(&sh[C + cg * 8 + j], b[j]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[0][g2 * 8 + j], a[j]);
+      atomicAdd(&sh[1][g2 * 8 + j], b[j]);
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
-    atomicAdd(s1 + c, (double)sh[c]);
-    atomicAdd(s2 + c, (double)sh[C + c]);
+  if (threadIdx.x < groups * 8) {
+    const int c = blockIdx.y * 256 + threadIdx.x;
+    atomicAdd(s1 + c, (double)sh[0][threadIdx.x]);
+    atomicAdd(s2 + c, (double)sh[1][threadIdx.x]);
   }
 }
 
@@ -496,6 +493,84 @@ __global__ void add_act_v8_kernel(const uint4* __restrict__ ahi, const uint4* __
   }
 }
 
+
+// max_pool2d(3,2,1) backward, 8 channels per thread.  A window's arg-max is the FIRST maximum in row-major order
+// (ATen semantics); it is recognised by comparing against the pooled value and checking the earlier window positions.
+template <bool SPLIT>
+__global__ void maxpool_bwd_v8_kernel(const uint4* __restrict__ xhi, const uint4* __restrict__ xlo, const uint4* __restrict__ dyhi,
+                                      const uint4* __restrict__ dylo, uint4* dxhi, uint4* dxlo, int N, int H, int W, int C8, int OH,
+                                      int OW) {
+  long long total = (long long)N * H * W * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long long p = i / C8;
+    const int iw = (int)(p % W);
+    long long q = p / W;
+    const int ih = (int)(q % H);
+    const int n = (int)(q / H);
+    float xv[8], acc[8];
+    load8<SPLIT>(xhi, xlo, i, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int oh = ih / 2; oh <= (ih + 1) / 2 && oh < OH; ++oh)
+      for (int ow = iw / 2; ow <= (iw + 1) / 2 && ow < OW; ++ow) {
+        // is (ih, iw) the first maximum of window (oh, ow)?  per channel: not beaten by any element, not tied by an earlier one
+        bool win[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[j] = true;
+        for (int r = 0; r < 3; ++r) {
+          const int y = 2 * oh - 1 + r;
+          if (y < 0 || y >= H) continue;
+          for (int s2 = 0; s2 < 3; ++s2) {
+            const int x = 2 * ow - 1 + s2;
+            if (x < 0 || x >= W || (y == ih && x == iw)) continue;
+            float v[8];
+            load8<SPLIT>(xhi, xlo, (((long long)n * H + y) * W + x) * C8 + c, v);
+            const bool earlier = (y < ih) || (y == ih && x < iw);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) win[j] = win[j] && (earlier ? (v[j] < xv[j]) : (v[j] <= xv[j]));
+          }
+        }
+        float g[8];
+        load8<SPLIT>(dyhi, dylo, (((long long)n * OH + oh) * OW + ow) * C8 + c, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += win[j] ? g[j] : 0.f;
+      }
+    store8<SPLIT>(dxhi, dxlo, i, acc);
+  }
+}
+
+template <bool SPLIT>
+__global__ void zero_insert2_v8_kernel(const uint4* __restrict__ dyhi, const uint4* __restrict__ dylo, uint4* ohi, uint4* olo, int N,
+                                       int OH, int OW, int C8, int H, int W) {
+  long long total = (long long)N * H * W * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long long p = i / C8;
+    const int x = (int)(p % W);
+    long long q = p / W;
+    const int y = (int)(q % H);
+    const int n = (int)(q / H);
+    uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+    if (!(y & 1) && !(x & 1) && (y >> 1) < OH && (x >> 1) < OW) {
+      const long long o = (((long long)n * OH + (y >> 1)) * OW + (x >> 1)) * C8 + c;
+      h = __ldg(dyhi + o);
+      if (SPLIT) l = __ldg(dylo + o);
+    }
+    ohi[i] = h;
+    if (SPLIT) olo[i] = l;
+  }
+}
+
+// pixels per CTA of the per-channel reductions: aim at >= 4 CTAs per SM over the (pixel chunk, channel slice) grid
+inline int reduce_vpix(long long pixels, int C8) {
+  const long long slices = C8 < 32 ? 1 : C8 / 32;
+  long long v = pixels * slices / (148 * 4);
+  if (v > 512) v = 512;
+  if (v < 32) v = 32;
+  return (int)v;
+}
+
 inline bool vec_ok(int fmt, int C) {
   const int c8 = C / 8;
   return (fmt == MPN_FMT_BF16 || fmt == MPN_FMT_BF16X2) && C % 8 == 0 && C <= 4096 && (c8 & (c8 - 1)) == 0;  // power-of-two groups
@@ -511,12 +586,12 @@ extern "C" int mpn_channel_sums(const void* hi, const void* lo, long long pixels
   MPN_CUDA_OK(cudaMemsetAsync(sum, 0, sizeof(double) * C, ST));
   if (sumsq) MPN_CUDA_OK(cudaMemsetAsync(sumsq, 0, sizeof(double) * C, ST));
   if (vec_ok(fmt, C) && cstride == C && coffset == 0) {
-    const int grid = mpn_divup(pixels, VPIX);
-    const size_t smem = sizeof(float) * 2 * C;
+    const int vpix = reduce_vpix(pixels, C / 8);
+    dim3 grid(mpn_divup(pixels, vpix), C / 8 < 32 ? 1 : C / 8 / 32);
     if (fmt == MPN_FMT_BF16X2)
-      channel_stats_v8_kernel<true><<<grid, 256, smem, ST>>>((const uint4*)hi, (const uint4*)lo, pixels, C / 8, sum, sumsq);
+      channel_stats_v8_kernel<true><<<grid, 256, 0, ST>>>((const uint4*)hi, (const uint4*)lo, pixels, C / 8, vpix, sum, sumsq);
     else
-      channel_stats_v8_kernel<false><<<grid, 256, smem, ST>>>((const uint4*)hi, nullptr, pixels, C / 8, sum, sumsq);
+      channel_stats_v8_kernel<false><<<grid, 256, 0, ST>>>((const uint4*)hi, nullptr, pixels, C / 8, vpix, sum, sumsq);
     MPN_LAUNCH_OK();
     return MPN_OK;
   }
@@ -575,19 +650,19 @@ extern "C" int mpn_bn_backward(const void* dzhi, const void* dzlo, const void* z
   MPN_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * C, ST));
   long long total = pixels * C;
   if (vec_ok(fmt, C)) {
-    const int grid = mpn_divup(pixels, VPIX);
-    const size_t smem = sizeof(float) * 2 * C;
+    const int vpix = reduce_vpix(pixels, C / 8);
+    dim3 grid(mpn_divup(pixels, vpix), C / 8 < 32 ? 1 : C / 8 / 32);
     const long long t8 = total / 8;
     if (fmt == MPN_FMT_BF16X2) {
-      bn_bwd_reduce_v8_kernel<true><<<grid, 256, smem, ST>>>((const uint4*)dzhi, (const uint4*)dzlo, (const uint4*)zhi, (const uint4*)zlo,
-                                                             (const uint4*)yhi, (const uint4*)ylo, mean, var, eps, relu, pixels, C / 8, s1, s2);
+      bn_bwd_reduce_v8_kernel<true><<<grid, 256, 0, ST>>>((const uint4*)dzhi, (const uint4*)dzlo, (const uint4*)zhi, (const uint4*)zlo,
+                                                          (const uint4*)yhi, (const uint4*)ylo, mean, var, eps, relu, pixels, C / 8, vpix, s1, s2);
       bn_bwd_apply_v8_kernel<true><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)dzhi, (const uint4*)dzlo, (const uint4*)zhi,
                                                                       (const uint4*)zlo, (const uint4*)yhi, (const uint4*)ylo, mean, var, gamma,
                                                                       eps, relu, s1, s2, (double)pixels, (uint4*)dyhi, (uint4*)dylo,
                                                                       (uint4*)ghi, (uint4*)glo, t8, C / 8);
     } else {
-      bn_bwd_reduce_v8_kernel<false><<<grid, 256, smem, ST>>>((const uint4*)dzhi, nullptr, (const uint4*)zhi, nullptr, (const uint4*)yhi,
-                                                              nullptr, mean, var, eps, relu, pixels, C / 8, s1, s2);
+      bn_bwd_reduce_v8_kernel<false><<<grid, 256, 0, ST>>>((const uint4*)dzhi, nullptr, (const uint4*)zhi, nullptr, (const uint4*)yhi,
+                                                           nullptr, mean, var, eps, relu, pixels, C / 8, vpix, s1, s2);
       bn_bwd_apply_v8_kernel<false><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)dzhi, nullptr, (const uint4*)zhi, nullptr,
                                                                        (const uint4*)yhi, nullptr, mean, var, gamma, eps, relu, s1, s2,
                                                                        (double)pixels, (uint4*)dyhi, nullptr, (uint4*)ghi, nullptr, t8, C / 8);
@@ -655,6 +730,16 @@ extern "C" int mpn_maxpool3x3s2_backward(const void* xhi, const void* xlo, const
   MPN_CHECK_ARG(xhi && dyhi && dxhi && N > 0 && H > 0 && W > 0 && C > 0, "mpn_maxpool3x3s2_backward: bad argument");
   int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   long long total = (long long)N * H * W * C;
+  if ((fmt == MPN_FMT_BF16 || fmt == MPN_FMT_BF16X2) && C % 8 == 0) {
+    if (fmt == MPN_FMT_BF16X2)
+      maxpool_bwd_v8_kernel<true><<<grid_for(total / 8, 256), 256, 0, ST>>>((const uint4*)xhi, (const uint4*)xlo, (const uint4*)dyhi,
+                                                                             (const uint4*)dylo, (uint4*)dxhi, (uint4*)dxlo, N, H, W, C / 8, OH, OW);
+    else
+      maxpool_bwd_v8_kernel<false><<<grid_for(total / 8, 256), 256, 0, ST>>>((const uint4*)xhi, nullptr, (const uint4*)dyhi, nullptr,
+                                                                              (uint4*)dxhi, nullptr, N, H, W, C / 8, OH, OW);
+    MPN_LAUNCH_OK();
+    return MPN_OK;
+  }
   maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(xhi, xlo, dyhi, dylo, dxhi, dxlo, N, H, W, C, OH, OW, fmt);
   MPN_LAUNCH_OK();
   return MPN_OK;
@@ -673,6 +758,16 @@ extern "C" int mpn_zero_insert2(const void* dyhi, const void* dylo, void* ohi, v
                                 int fmt, void* stream) {
   MPN_CHECK_ARG(dyhi && ohi && N > 0 && OH > 0 && OW > 0 && C > 0 && H >= 2 * OH - 1 && W >= 2 * OW - 1, "mpn_zero_insert2: bad argument");
   long long total = (long long)N * H * W * C;
+  if ((fmt == MPN_FMT_BF16 || fmt == MPN_FMT_BF16X2) && C % 8 == 0) {
+    if (fmt == MPN_FMT_BF16X2)
+      zero_insert2_v8_kernel<true><<<grid_for(total / 8, 256), 256, 0, ST>>>((const uint4*)dyhi, (const uint4*)dylo, (uint4*)ohi, (uint4*)olo,
+                                                                              N, OH, OW, C / 8, H, W);
+    else
+      zero_insert2_v8_kernel<false><<<grid_for(total / 8, 256), 256, 0, ST>>>((const uint4*)dyhi, nullptr, (uint4*)ohi, nullptr, N, OH, OW,
+                                                                               C / 8, H, W);
+    MPN_LAUNCH_OK();
+    return MPN_OK;
+  }
   zero_insert2_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dyhi, dylo, ohi, olo, N, OH, OW, C, H, W, fmt);
   MPN_LAUNCH_OK();
   return MPN_OK;

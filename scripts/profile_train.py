@@ -1,5 +1,5 @@
 """Kernel-time table of one training step (torch.profiler / CUPTI, eager launches)."""
-import os, sys
+import os, re, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
@@ -27,7 +27,8 @@ rows = {}
 for e in prof.events():
     if e.device_type.name != "CUDA":
         continue
-    k = e.name.split("(")[0][:70]
+    k = re.sub(r"\(anonymous namespace\)::|<unnamed>::|^void ", "", e.name)
+    k = re.sub(r"\(.*$", "", k)[:70]
     r = rows.setdefault(k, [0, 0.0])
     r[0] += 1; r[1] += e.device_time
 tot = sum(v[1] for v in rows.values())

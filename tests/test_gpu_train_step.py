@@ -123,7 +123,7 @@ def test_graphed_train_step_matches_eager():
     for _ in range(2):
         loss_g, outs_g, grads_g = eng.graphed_forward_backward(x, gt, wt)
     torch.cuda.synchronize()
-    assert abs(float(loss_g) - loss_e) <= 1e-6 * max(1.0, abs(loss_e))
+    assert abs(float(loss_g) - loss_e) <= 1e-5 * max(1.0, abs(loss_e))
     assert set(grads_g) == set(ref)
     # Summation order varies between runs (fp32/fp64 atomics), which moves a pre-activation of magnitude ~1e-8 across
     # zero now and then; one flipped ReLU unit shows up as an O(0.1) max-norm outlier on a few tensors.  Compare robustly:
