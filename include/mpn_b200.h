@@ -142,12 +142,14 @@ int mpn_double_to_float(const double* a, float* out, int n, float scale, void* s
 int mpn_bn_stats(const void* y_hi, const void* y_lo, long long pixels, int C, int fmt, float* mean, float* var, double* workspace, void* stream);
 int mpn_bn_update_running(const float* mean, const float* var, float* running_mean, float* running_var, long long n, float momentum, int C, void* stream);
 int mpn_bn_apply(const void* y_hi, const void* y_lo, const float* mean, const float* var, const float* gamma, const float* beta, float eps,
-                 const void* res_hi, const void* res_lo, int relu, void* z_hi, void* z_lo, long long pixels, int C, int fmt, void* stream);
+                 const void* res_hi, const void* res_lo, int relu, void* z_hi, void* z_lo, long long pixels, int C, int fmt,
+                 float* coef_workspace /* 3*C floats */, void* stream);
 /* g = dz * (z > 0 if relu); dy = gamma*invstd*(g - mean(g) - yhat*mean(g*yhat)); dgamma = sum g*yhat; dbeta = sum g;
  * g_out (optional) receives g (the gradient of the residual / shortcut input). */
 int mpn_bn_backward(const void* dz_hi, const void* dz_lo, const void* z_hi, const void* z_lo, const void* y_hi, const void* y_lo,
                     const float* mean, const float* var, const float* gamma, float eps, int relu, long long pixels, int C, int fmt,
-                    void* dy_hi, void* dy_lo, void* g_hi, void* g_lo, float* dgamma, float* dbeta, double* workspace, void* stream);
+                    void* dy_hi, void* dy_lo, void* g_hi, void* g_lo, float* dgamma, float* dbeta, double* workspace,
+                    float* coef_workspace /* 3*C floats */, void* stream);
 int mpn_relu_backward(const void* dz_hi, const void* dz_lo, const void* z_hi, const void* z_lo, void* out_hi, void* out_lo, long long n, int fmt, void* stream);
 int mpn_add_act(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo, long long n, int fmt, void* stream);
 int mpn_maxpool3x3s2_backward(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, void* dx_hi, void* dx_lo,

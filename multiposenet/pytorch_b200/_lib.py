@@ -58,8 +58,8 @@ _SIGS = {
     "mpn_bn_stats": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpn_bn_update_running": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_int, c_void_p]),
     "mpn_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
-                             c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
-    "mpn_bn_backward": (c_int, [c_void_p] * 6 + [c_void_p, c_void_p, c_void_p, c_float, c_int, c_ll, c_int, c_int] + [c_void_p] * 8),
+                             c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p]),
+    "mpn_bn_backward": (c_int, [c_void_p] * 6 + [c_void_p, c_void_p, c_void_p, c_float, c_int, c_ll, c_int, c_int] + [c_void_p] * 9),
     "mpn_relu_backward": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_void_p]),
     "mpn_add_act": (c_int, [c_void_p] * 6 + [c_ll, c_int, c_void_p]),
     "mpn_maxpool3x3s2_backward": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -363,20 +363,32 @@ __global__ void __launch_bounds__(256) channel_stats_v8_kernel(const uint4* __re
   }
 }
 
+// coef[0..C) = gamma*invstd, coef[C..2C) = beta - mean*gamma*invstd
+__global__ void bn_fwd_coef_kernel(const float* mean, const float* var, const float* gamma, const float* beta, float eps, float* coef, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float a = gamma[c] * rsqrtf(var[c] + eps);
+    coef[c] = a;
+    coef[C + c] = beta[c] - mean[c] * a;
+  }
+}
+
 template <bool SPLIT>
-__global__ void bn_apply_v8_kernel(const uint4* __restrict__ yhi, const uint4* __restrict__ ylo, const float* __restrict__ mean,
-                                   const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float eps, const uint4* __restrict__ rhi, const uint4* __restrict__ rlo, int relu, uint4* zhi,
+__global__ void bn_apply_v8_kernel(const uint4* __restrict__ yhi, const uint4* __restrict__ ylo, const float* __restrict__ coef, int C,
+                                   const uint4* __restrict__ rhi, const uint4* __restrict__ rlo, int relu, uint4* zhi,
                                    uint4* zlo, long long total8, int C8) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % C8) * 8;
     float v[8], r[8];
     load8<SPLIT>(yhi, ylo, i, v);
     if (rhi) load8<SPLIT>(rhi, rlo, i, r);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(coef + c0)), a1 = __ldg(reinterpret_cast<const float4*>(coef + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(coef + C + c0)), b1 = __ldg(reinterpret_cast<const float4*>(coef + C + c0 + 4));
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float invstd = rsqrtf(var[c0 + j] + eps);
-      float o = (v[j] - mean[c0 + j]) * invstd * gamma[c0 + j] + beta[c0 + j];
+      float o = fmaf(v[j], a[j], b[j]);
       if (rhi) o += r[j];
       v[j] = relu ? fmaxf(o, 0.f) : o;
     }
@@ -442,25 +454,45 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v8_kernel(const uint4* __re
   }
 }
 
+// dy = A*g + Bc*y + D per channel:  A = gamma*invstd, Bc = -A*invstd*m2, D = -A*m1 + A*invstd*m2*mean   (m1 = s1/n, m2 = s2/n)
+__global__ void bn_bwd_coef_kernel(const float* mean, const float* var, const float* gamma, float eps, const double* s1, const double* s2,
+                                   double n, float* coef, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float invstd = rsqrtf(var[c] + eps);
+    const float A = gamma[c] * invstd;
+    const float m1 = (float)(s1[c] / n), m2 = (float)(s2[c] / n);
+    coef[c] = A;
+    coef[C + c] = -A * invstd * m2;
+    coef[2 * C + c] = -A * m1 + A * invstd * m2 * mean[c];
+  }
+}
+
 template <bool SPLIT>
 __global__ void bn_bwd_apply_v8_kernel(const uint4* __restrict__ dzhi, const uint4* __restrict__ dzlo, const uint4* __restrict__ zhi,
                                        const uint4* __restrict__ zlo, const uint4* __restrict__ yhi, const uint4* __restrict__ ylo,
-                                       const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
-                                       float eps, int relu, const double* __restrict__ s1, const double* __restrict__ s2, double n,
-                                       uint4* dyhi, uint4* dylo, uint4* ghi, uint4* glo, long long total8, int C8) {
+                                       const float* __restrict__ coef, int C, int relu, uint4* dyhi, uint4* dylo, uint4* ghi, uint4* glo,
+                                       long long total8, int C8) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % C8) * 8;
     float g[8], z[8], y[8], o[8];
     load8<SPLIT>(dzhi, dzlo, i, g);
     if (relu) load8<SPLIT>(zhi, zlo, i, z);
     load8<SPLIT>(yhi, ylo, i, y);
+    float A[8], Bc[8], D[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(coef + c0 + 4 * h));
+      const float4 t1 = __ldg(reinterpret_cast<const float4*>(coef + C + c0 + 4 * h));
+      const float4 t2 = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4 * h));
+      A[4 * h] = t0.x; A[4 * h + 1] = t0.y; A[4 * h + 2] = t0.z; A[4 * h + 3] = t0.w;
+      Bc[4 * h] = t1.x; Bc[4 * h + 1] = t1.y; Bc[4 * h + 2] = t1.z; Bc[4 * h + 3] = t1.w;
+      D[4 * h] = t2.x; D[4 * h + 1] = t2.y; D[4 * h + 2] = t2.z; D[4 * h + 3] = t2.w;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float invstd = rsqrtf(var[c] + eps);
       if (relu && !(z[j] > 0.f)) g[j] = 0.f;
-      const float yhat = (y[j] - mean[c]) * invstd;
-      o[j] = gamma[c] * invstd * (g[j] - (float)(s1[c] / n) - yhat * (float)(s2[c] / n));
+      o[j] = fmaf(A[j], g[j], fmaf(Bc[j], y[j], D[j]));
     }
     store8<SPLIT>(dyhi, dylo, i, o);
     if (ghi) store8<SPLIT>(ghi, glo, i, g);
@@ -620,17 +652,19 @@ extern "C" int mpn_bn_update_running(const float* mean, const float* var, float*
 
 extern "C" int mpn_bn_apply(const void* yhi, const void* ylo, const float* mean, const float* var, const float* gamma,
                             const float* beta, float eps, const void* rhi, const void* rlo, int relu, void* zhi, void* zlo,
-                            long long pixels, int C, int fmt, void* stream) {
+                            long long pixels, int C, int fmt, float* coef, void* stream) {
   MPN_CHECK_ARG(yhi && mean && var && gamma && beta && zhi && pixels > 0 && C > 0, "mpn_bn_apply: bad argument");
   long long total = pixels * C;
   if (vec_ok(fmt, C)) {
     const long long t8 = total / 8;
+    MPN_CHECK_ARG(coef, "mpn_bn_apply: coefficient workspace (3*C floats) missing");
+    bn_fwd_coef_kernel<<<mpn_divup(C, 256), 256, 0, ST>>>(mean, var, gamma, beta, eps, coef, C);
     if (fmt == MPN_FMT_BF16X2)
-      bn_apply_v8_kernel<true><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)yhi, (const uint4*)ylo, mean, var, gamma, beta, eps,
-                                                                  (const uint4*)rhi, (const uint4*)rlo, relu, (uint4*)zhi, (uint4*)zlo, t8, C / 8);
+      bn_apply_v8_kernel<true><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)yhi, (const uint4*)ylo, coef, C, (const uint4*)rhi,
+                                                                  (const uint4*)rlo, relu, (uint4*)zhi, (uint4*)zlo, t8, C / 8);
     else
-      bn_apply_v8_kernel<false><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)yhi, nullptr, mean, var, gamma, beta, eps,
-                                                                   (const uint4*)rhi, nullptr, relu, (uint4*)zhi, nullptr, t8, C / 8);
+      bn_apply_v8_kernel<false><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)yhi, nullptr, coef, C, (const uint4*)rhi, nullptr, relu,
+                                                                   (uint4*)zhi, nullptr, t8, C / 8);
     MPN_LAUNCH_OK();
     return MPN_OK;
   }
@@ -642,8 +676,8 @@ extern "C" int mpn_bn_apply(const void* yhi, const void* ylo, const float* mean,
 extern "C" int mpn_bn_backward(const void* dzhi, const void* dzlo, const void* zhi, const void* zlo, const void* yhi, const void* ylo,
                                const float* mean, const float* var, const float* gamma, float eps, int relu, long long pixels, int C,
                                int fmt, void* dyhi, void* dylo, void* ghi, void* glo, float* dgamma, float* dbeta,
-                               double* workspace, void* stream) {
-  MPN_CHECK_ARG(dzhi && yhi && mean && var && gamma && dyhi && workspace && pixels > 0 && C > 0, "mpn_bn_backward: bad argument");
+                               double* workspace, float* coef, void* stream) {
+  MPN_CHECK_ARG(dzhi && yhi && mean && var && gamma && dyhi && workspace && coef && pixels > 0 && C > 0, "mpn_bn_backward: bad argument");
   MPN_CHECK_ARG(!relu || zhi, "mpn_bn_backward: relu mask needs z");
   double* s1 = workspace;
   double* s2 = workspace + C;
@@ -656,16 +690,17 @@ extern "C" int mpn_bn_backward(const void* dzhi, const void* dzlo, const void* z
     if (fmt == MPN_FMT_BF16X2) {
       bn_bwd_reduce_v8_kernel<true><<<grid, 256, 0, ST>>>((const uint4*)dzhi, (const uint4*)dzlo, (const uint4*)zhi, (const uint4*)zlo,
                                                           (const uint4*)yhi, (const uint4*)ylo, mean, var, eps, relu, pixels, C / 8, vpix, s1, s2);
+      bn_bwd_coef_kernel<<<mpn_divup(C, 256), 256, 0, ST>>>(mean, var, gamma, eps, s1, s2, (double)pixels, coef, C);
       bn_bwd_apply_v8_kernel<true><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)dzhi, (const uint4*)dzlo, (const uint4*)zhi,
-                                                                      (const uint4*)zlo, (const uint4*)yhi, (const uint4*)ylo, mean, var, gamma,
-                                                                      eps, relu, s1, s2, (double)pixels, (uint4*)dyhi, (uint4*)dylo,
-                                                                      (uint4*)ghi, (uint4*)glo, t8, C / 8);
+                                                                      (const uint4*)zlo, (const uint4*)yhi, (const uint4*)ylo, coef, C, relu,
+                                                                      (uint4*)dyhi, (uint4*)dylo, (uint4*)ghi, (uint4*)glo, t8, C / 8);
     } else {
       bn_bwd_reduce_v8_kernel<false><<<grid, 256, 0, ST>>>((const uint4*)dzhi, nullptr, (const uint4*)zhi, nullptr, (const uint4*)yhi,
                                                            nullptr, mean, var, eps, relu, pixels, C / 8, vpix, s1, s2);
+      bn_bwd_coef_kernel<<<mpn_divup(C, 256), 256, 0, ST>>>(mean, var, gamma, eps, s1, s2, (double)pixels, coef, C);
       bn_bwd_apply_v8_kernel<false><<<grid_for(t8, 256), 256, 0, ST>>>((const uint4*)dzhi, nullptr, (const uint4*)zhi, nullptr,
-                                                                       (const uint4*)yhi, nullptr, mean, var, gamma, eps, relu, s1, s2,
-                                                                       (double)pixels, (uint4*)dyhi, nullptr, (uint4*)ghi, nullptr, t8, C / 8);
+                                                                       (const uint4*)yhi, nullptr, coef, C, relu, (uint4*)dyhi, nullptr,
+                                                                       (uint4*)ghi, nullptr, t8, C / 8);
     }
     MPN_LAUNCH_OK();
   } else {

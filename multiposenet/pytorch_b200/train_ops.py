@@ -124,10 +124,11 @@ def bn_train_forward(y, bn, relu, residual=None, update_running=True):
                                       float(bn.momentum), C, _stream()), "mpn_bn_update_running")
         bn.num_batches_tracked += 1
     z = _like(y)
+    coef = torch.empty((3 * C,), dtype=torch.float32, device=dev)
     check(L.mpn_bn_apply(_ptr(y.hi), _ptr(y.lo), _ptr(st.mean), _ptr(st.var), _ptr(bn.weight.detach()), _ptr(bn.bias.detach()),
                          float(bn.eps), _ptr(residual.hi) if residual is not None else None,
                          _ptr(residual.lo) if residual is not None else None, int(relu), _ptr(z.hi), _ptr(z.lo), pixels, C,
-                         y.fmt, _stream()), "mpn_bn_apply")
+                         y.fmt, _ptr(coef), _stream()), "mpn_bn_apply")
     st.y, st.z, st.relu, st.eps = y, z, bool(relu), float(bn.eps)
     return z, st
 
@@ -142,10 +143,11 @@ def bn_train_backward(dz, st, bn, want_g=False):
     dgamma = torch.empty((C,), dtype=torch.float32, device=dev)
     dbeta = torch.empty((C,), dtype=torch.float32, device=dev)
     ws = torch.empty((2 * C,), dtype=torch.float64, device=dev)
+    coef = torch.empty((3 * C,), dtype=torch.float32, device=dev)
     check(L.mpn_bn_backward(_ptr(dz.hi), _ptr(dz.lo), _ptr(st.z.hi), _ptr(st.z.lo), _ptr(y.hi), _ptr(y.lo), _ptr(st.mean),
                             _ptr(st.var), _ptr(bn.weight.detach()), st.eps, int(st.relu), pixels, C, y.fmt, _ptr(dy.hi), _ptr(dy.lo),
                             _ptr(g.hi) if g is not None else None, _ptr(g.lo) if (g is not None and g.lo is not None) else None,
-                            _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream()), "mpn_bn_backward")
+                            _ptr(dgamma), _ptr(dbeta), _ptr(ws), _ptr(coef), _stream()), "mpn_bn_backward")
     return dy, g, dgamma, dbeta
 
 
