@@ -322,9 +322,11 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256) channel_stats_v8_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo,
                                                                long long pixels, int C8, int vpix, double* __restrict__ sum,
                                                                double* __restrict__ sumsq) {
-  __shared__ float sh[2][256];
-  sh[0][threadIdx.x] = 0.f;
-  sh[1][threadIdx.x] = 0.f;
+  // fp64 accumulators: the cross-thread sums must not depend on the (non-deterministic) order of the atomics, otherwise
+  // batch statistics differ in the last fp32 bit from run to run and the bf16 hi/lo re-split turns that into ~1e-5 jitter
+  __shared__ double sh[2][256];
+  sh[0][threadIdx.x] = 0.0;
+  sh[1][threadIdx.x] = 0.0;
   __syncthreads();
   const int groups = C8 < 32 ? C8 : 32;          // channel vectors of this CTA's slice (power of two)
   const int cg = blockIdx.y * 32 + (threadIdx.x % groups);
@@ -351,15 +353,15 @@ __global__ void __launch_bounds__(256) channel_stats_v8_kernel(const uint4* __re
     const int g = threadIdx.x % groups;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[0][g * 8 + j], s[j]);
-      atomicAdd(&sh[1][g * 8 + j], q[j]);
+      atomicAdd(&sh[0][g * 8 + j], (double)s[j]);
+      atomicAdd(&sh[1][g * 8 + j], (double)q[j]);
     }
   }
   __syncthreads();
   if (threadIdx.x < groups * 8) {
     const int c = blockIdx.y * 256 + threadIdx.x;
-    atomicAdd(sum + c, (double)sh[0][threadIdx.x]);
-    if (sumsq) atomicAdd(sumsq + c, (double)sh[1][threadIdx.x]);
+    atomicAdd(sum + c, sh[0][threadIdx.x]);
+    if (sumsq) atomicAdd(sumsq + c, sh[1][threadIdx.x]);
   }
 }
 
@@ -403,9 +405,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v8_kernel(const uint4* __re
                                                                const float* __restrict__ mean, const float* __restrict__ var,
                                                                float eps, int relu, long long pixels, int C8, int vpix,
                                                                double* __restrict__ s1, double* __restrict__ s2) {
-  __shared__ float sh[2][256];
-  sh[0][threadIdx.x] = 0.f;
-  sh[1][threadIdx.x] = 0.f;
+  // fp64 accumulators: the cross-thread sums must not depend on the (non-deterministic) order of the atomics, otherwise
+  // batch statistics differ in the last fp32 bit from run to run and the bf16 hi/lo re-split turns that into ~1e-5 jitter
+  __shared__ double sh[2][256];
+  sh[0][threadIdx.x] = 0.0;
+  sh[1][threadIdx.x] = 0.0;
   __syncthreads();
   const int groups = C8 < 32 ? C8 : 32;
   const int cg = blockIdx.y * 32 + (threadIdx.x % groups);
@@ -442,15 +446,15 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v8_kernel(const uint4* __re
     const int g2 = threadIdx.x % groups;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[0][g2 * 8 + j], a[j]);
-      atomicAdd(&sh[1][g2 * 8 + j], b[j]);
+      atomicAdd(&sh[0][g2 * 8 + j], (double)a[j]);
+      atomicAdd(&sh[1][g2 * 8 + j], (double)b[j]);
     }
   }
   __syncthreads();
   if (threadIdx.x < groups * 8) {
     const int c = blockIdx.y * 256 + threadIdx.x;
-    atomicAdd(s1 + c, (double)sh[0][threadIdx.x]);
-    atomicAdd(s2 + c, (double)sh[1][threadIdx.x]);
+    atomicAdd(s1 + c, sh[0][threadIdx.x]);
+    atomicAdd(s2 + c, sh[1][threadIdx.x]);
   }
 }
 

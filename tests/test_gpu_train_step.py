@@ -118,6 +118,7 @@ def test_graphed_train_step_matches_eager():
     eng = m.train_engine()
     loss_e, outs_e, grads_e = eng.forward_backward(x, gt, wt)
     ref = {k: v.clone() for k, v in grads_e.items()}
+    outs_ref = [o.clone() for o in outs_e]
     loss_e = float(loss_e)
     nb = int(m.fpn.bn1.num_batches_tracked)
     for _ in range(2):
@@ -125,10 +126,10 @@ def test_graphed_train_step_matches_eager():
     torch.cuda.synchronize()
     assert abs(float(loss_g) - loss_e) <= 1e-5 * max(1.0, abs(loss_e))
     assert set(grads_g) == set(ref)
-    # Summation order varies between runs (fp32/fp64 atomics), which moves a pre-activation of magnitude ~1e-8 across
-    # zero now and then; one flipped ReLU unit shows up as an O(0.1) max-norm outlier on a few tensors.  Compare robustly:
+    # The forward is reproducible (fp64 cross-thread accumulation of the batch statistics); the weight gradients carry
+    # fp32 atomic-order noise only.  A graph replay must therefore agree with the eager step to ~1e-5.
     errs = sorted(nerr(grads_g[k], ref[k]) for k in ref if float(ref[k].abs().max()) > 0)
-    assert errs[len(errs) // 2] <= 1e-5, errs[len(errs) // 2]
-    l2 = max(float((grads_g[k].double() - ref[k].double()).norm() / ref[k].double().norm()) for k in ref if float(ref[k].abs().max()) > 0)
-    print("graph vs eager: median max-norm err %.2e, worst max-norm %.2e, worst relative L2 %.2e" % (errs[len(errs) // 2], errs[-1], l2))
+    print("graph vs eager: median max-norm err %.2e, worst %.2e" % (errs[len(errs) // 2], errs[-1]))
+    assert all(torch.equal(a, b) for a, b in zip(outs_g, outs_ref)), "forward not reproducible"
+    assert errs[-1] <= 1e-4, errs[-1]
     assert int(m.fpn.bn1.num_batches_tracked) == nb + 2  # the capture/warm-up runs did not count as steps
