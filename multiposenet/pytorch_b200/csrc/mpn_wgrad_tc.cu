@@ -24,6 +24,7 @@ constexpr int BOX_BYTES = KROWS * 128;         // one [64 pixels x 64 channels] 
 constexpr int WG_THREADS = 256;
 constexpr int WG_SMEM_LIMIT = 227 * 1024;
 constexpr int WG_BAR_BYTES = 256;
+constexpr int WG_EPI_STAGE = 4096;  // per epilogue warp: 32 x 32 fp32 tile, 16-byte chunks XOR-swizzled
 
 struct WMaps {
   CUtensorMap dy[2];    // [plane]
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  uint8_t* epi_stage = smem_gen + STAGES * STAGE_BYTES + WG_BAR_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -199,8 +201,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int co = co_t * 128 + q * 32 + lane;
-      float* dst_row = P.dw + ((long long)co * taps + tap) * P.Cin + ci_t * BN;
+      const int co_base = co_t * 128 + q * 32;  // first output channel (dW row) of this warp
+      float* stg = reinterpret_cast<float*>(epi_stage + (warp - 4) * WG_EPI_STAGE);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (ci_t * BN + c0 >= P.Cin) break;
@@ -208,12 +210,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
         TMEM_LD_32x32b_X32(taddr, raw);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (co < P.Cout && kb1 > kb0) {
-          const int nc = min(32, P.Cin - (ci_t * BN + c0));
+        // thread-per-row accumulators -> swizzled staging -> lane-per-column, so each RED instruction of the warp
+        // adds 32 consecutive floats of one dW row (one 128-byte L2 transaction instead of 32 scattered ones)
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nc) atomicAdd(dst_row + c0 + j, __uint_as_float(raw[j]));
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+              make_uint4(raw[4 * c], raw[4 * c + 1], raw[4 * c + 2], raw[4 * c + 3]);
+        __syncwarp();
+        const int ci = ci_t * BN + c0 + lane;
+        if (ci < P.Cin && kb1 > kb0) {
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int co = co_base + rr;
+            if (co >= P.Cout) break;
+            const float v = stg[rr * 32 + ((((lane >> 2) ^ (rr & 7))) << 2) + (lane & 3)];
+            atomicAdd(P.dw + ((long long)co * taps + tap) * P.Cin + ci, v);
+          }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -251,10 +265,10 @@ template <int BN, bool SPLIT>
 int launch_wgrad(const WMaps& maps, const WParams& P, cudaStream_t st) {
   constexpr int PLANES = SPLIT ? 2 : 1;
   constexpr int STAGE_BYTES = PLANES * (2 + BN / 64) * BOX_BYTES;
-  constexpr int MAXS = (WG_SMEM_LIMIT - 1024 - WG_BAR_BYTES) / STAGE_BYTES;
+  constexpr int MAXS = (WG_SMEM_LIMIT - 1024 - WG_BAR_BYTES - 4 * WG_EPI_STAGE) / STAGE_BYTES;
   constexpr int STAGES = MAXS > 6 ? 6 : MAXS;
   static_assert(STAGES >= 2, "wgrad: need a 2-stage ring");
-  const int smem = STAGES * STAGE_BYTES + 1024 + WG_BAR_BYTES;
+  const int smem = STAGES * STAGE_BYTES + 1024 + WG_BAR_BYTES + 4 * WG_EPI_STAGE;
   auto kern = wgrad_tc_kernel<BN, SPLIT, STAGES>;
   MPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int dev = 0, sms = 148;
@@ -302,7 +316,7 @@ extern "C" int mpn_conv2d_wgrad(const mpn_conv_desc* d, const mpn_conv_ptrs* p, 
   P.co_tiles = mpn_divup(d->Cout, 128);
   P.ci_tiles = mpn_divup(d->Cin, BN);
   const int base_items = P.co_tiles * P.ci_tiles * d->R * d->S;
-  int kc = mpn_divup(2 * 148, base_items);
+  int kc = mpn_divup(148, base_items);  // ~one wave of work items: every extra pixel chunk costs a full tile of atomics
   if (kc > P.kblocks) kc = P.kblocks;
   if (kc < 1) kc = 1;
   P.kb_per_chunk = mpn_divup(P.kblocks, kc);
