@@ -189,18 +189,27 @@ class poseNet(nn.Module):
         img_batch, subnet_name = x
         if subnet_name == "prn_subnet":
             return self.prn_forward(img_batch)
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+        bn_batch_stats = self.training and self.fpn.bn1.training  # model.train() without freeze_bn (trainer.py:170-174)
+        wants_grad = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
+        if wants_grad or (bn_batch_stats and subnet_name == "keypoint_subnet"):
             if subnet_name != "keypoint_subnet":
                 raise NotImplementedError(
                     "only the keypoint-subnet training step (BASELINE config 4, SURVEY 8(a17)) has backward kernels; "
                     "detection-subnet training (network/losses.py) is SURVEY 8(f) rank 4 and there is no eager fallback")
+            if not bn_batch_stats:
+                raise NotImplementedError("keypoint-subnet training with frozen BatchNorm (freeze_bn() in train mode) is not "
+                                          "built: the reference trains this subnet with batch statistics (trainer.py:170-174)")
             if not (torch.is_tensor(img_batch) and img_batch.is_cuda):
                 raise RuntimeError("poseNet.forward needs a CUDA image batch (no CPU / eager fallback)")
             from ..train_engine import KeypointTrainFunction
             teng = self.train_engine()
-            params = [p for _, p in teng.trainable_parameters()]
             with torch.cuda.device(img_batch.device):
-                outs = KeypointTrainFunction.apply(teng, img_batch, *params)
+                if wants_grad:
+                    params = [p for _, p in teng.trainable_parameters()]
+                    outs = KeypointTrainFunction.apply(teng, img_batch, *params)
+                else:  # train mode under no_grad: batch statistics (and running-stat updates), nothing saved
+                    with torch.no_grad():
+                        outs, _ = teng.forward(img_batch)
             return outs[4], [outs[0], outs[1], outs[2], outs[3], outs[4]]
         if not (torch.is_tensor(img_batch) and img_batch.is_cuda):
             raise RuntimeError("poseNet.forward needs a CUDA image batch: the path runs on libmpn_b200 (sm_100a) only, "

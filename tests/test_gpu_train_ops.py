@@ -6,6 +6,12 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _grad_enabled():
+    with torch.enable_grad():
+        yield
+
+
 def _setup():
     from gpu_util import no_tf32
     no_tf32()

@@ -6,6 +6,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _grad_enabled():
+    with torch.enable_grad():
+        yield
+
+
 def _problem(layers=50, hw=(64, 96), B=2):
     from gpu_util import image, load_model, no_tf32
     no_tf32()

@@ -9,7 +9,12 @@ import torch
 
 from oracle import anchors_oracle, nms_oracle, posenet_oracle as po, refshim, weights
 
-torch.set_grad_enabled(False)
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    with torch.no_grad():
+        yield
 
 
 def _load(golden_dir, name):
