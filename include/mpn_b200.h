@@ -106,6 +106,12 @@ int mpn_stem_pack_input(const float* img_nchw, void* dst_hi, void* dst_lo, int N
 /* OIHW [64,3,7,7] fp32 -> [64][4][64] bf16 hi (+lo) matching that layout */
 int mpn_stem_pack_filter(const float* w_oihw, void* dst_hi, void* dst_lo, int Cout, void* stream);
 
+/* ---- input side: resnet_preprocess of datasets/coco_data/preprocessing.py:15-26 on the device.
+ * img: uint8 [N,H,W,3] BGR (cv2.imread layout).  Bit-identical to the numpy code (fp32 divide / subtract / divide). */
+int mpn_preprocess_u8_nchw(const unsigned char* img_nhwc_bgr, float* out_nchw, int N, int H, int W, void* stream);
+/* ... fused into mpn_stem_pack_input: uint8 image -> normalised, zero-padded space-to-depth stem operand */
+int mpn_stem_pack_input_u8(const unsigned char* img_nhwc_bgr, void* dst_hi, void* dst_lo, int N, int H, int W, int fmt, void* stream);
+
 /* ---- layout / elementwise */
 /* fp32 NCHW -> NHWC in `fmt` (dst_lo for BF16X2); cstride >= C, padding channels are zeroed */
 int mpn_nchw_to_nhwc(const float* src, void* dst_hi, void* dst_lo, int N, int C, int H, int W, int cstride, int fmt, void* stream);

@@ -384,3 +384,67 @@ extern "C" int mpn_add_softmax_rows(const void* ahi, const void* alo, const floa
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// resnet_preprocess (datasets/coco_data/preprocessing.py:15-26) on the device, for uint8 HWC BGR images as cv2.imread
+// returns them: out[c] = ((float(u8[2-c]) / 255) - mean[c]) / std[c] in fp32, operation for operation (no FMA, IEEE
+// division), so the result is bit-identical to the numpy code.
+__device__ __forceinline__ float resnet_preprocess_px(const unsigned char* __restrict__ px, int c) {
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  const float v = __fdiv_rn((float)px[2 - c], 255.f);  // BGR -> RGB
+  return __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+}
+
+__global__ void preprocess_u8_nchw_kernel(const unsigned char* __restrict__ img, float* __restrict__ out, int N, int H, int W) {
+  long long total = (long long)N * 3 * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int w = (int)(i % W);
+    long long t = i / W;
+    int h = (int)(t % H);
+    t /= H;
+    int c = (int)(t % 3);
+    int n = (int)(t / 3);
+    out[i] = resnet_preprocess_px(img + (((long long)n * H + h) * W + w) * 3, c);
+  }
+}
+
+extern "C" int mpn_preprocess_u8_nchw(const unsigned char* img_nhwc_bgr, float* out_nchw, int N, int H, int W, void* stream) {
+  MPN_CHECK_ARG(img_nhwc_bgr && out_nchw && N > 0 && H > 0 && W > 0, "mpn_preprocess_u8_nchw: bad argument");
+  long long total = (long long)N * 3 * H * W;
+  preprocess_u8_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img_nhwc_bgr, out_nchw, N, H, W);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+// the same, fused into the tensor-core stem's space-to-depth packing (see mpn_stem_pack_input)
+__global__ void stem_pack_input_u8_kernel(const unsigned char* __restrict__ img, void* hi, void* lo, int N, int H, int W, int H2p,
+                                          int W2p, int fmt) {
+  long long total = (long long)N * H2p * W2p * 16;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cc = (int)(i & 15);
+    long long p = i >> 4;
+    int wp = (int)(p % W2p);
+    long long q = p / W2p;
+    int hp = (int)(q % H2p);
+    int n = (int)(q / H2p);
+    float v = 0.f;
+    if (cc < 12) {
+      int c = cc % 3, ph = (cc / 3) >> 1, pw = (cc / 3) & 1;
+      int ih = 2 * (hp - 2) + ph, iw = 2 * (wp - 2) + pw;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = resnet_preprocess_px(img + (((long long)n * H + ih) * W + iw) * 3, c);
+    }
+    mpn_store_act(hi, lo, i, fmt, v);
+  }
+}
+
+extern "C" int mpn_stem_pack_input_u8(const unsigned char* img_nhwc_bgr, void* hi, void* lo, int N, int H, int W, int fmt,
+                                      void* stream) {
+  MPN_CHECK_ARG(img_nhwc_bgr && hi && N > 0 && H > 0 && W > 0, "mpn_stem_pack_input_u8: bad argument");
+  MPN_CHECK_ARG(fmt == MPN_FMT_BF16 || (fmt == MPN_FMT_BF16X2 && lo), "mpn_stem_pack_input_u8: fmt must be BF16 or BF16X2 (with lo)");
+  int H2p = (H + 1) / 2 + 3, W2p = (W + 1) / 2 + 3;
+  long long total = (long long)N * H2p * W2p * 16;
+  stem_pack_input_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img_nhwc_bgr, hi, lo, N, H, W, H2p, W2p, fmt);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}

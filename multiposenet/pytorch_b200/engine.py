@@ -89,8 +89,12 @@ class Engine(object):
     def backbone(self, img):
         """fpn.py:99-105 -> c2, c3, c4, c5 (Act)."""
         fpn = self.model.fpn
-        if not (img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3):
-            raise RuntimeError("expected a CUDA fp32 [B,3,H,W] image batch")
+        raw_u8 = img.is_cuda and img.dtype == torch.uint8 and img.dim() == 4 and img.shape[3] == 3
+        if raw_u8 and not (self.fmt != FMT_F32 and TC_STEM):
+            img = ops.resnet_preprocess_u8(img)  # extension: raw cv2 images, resnet_preprocess on the device
+            raw_u8 = False
+        if not raw_u8 and not (img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3):
+            raise RuntimeError("expected a CUDA fp32 [B,3,H,W] image batch (or uint8 [B,H,W,3] BGR raw images)")
         if self.fmt != FMT_F32 and TC_STEM:
             # tensor-core stem: 7x7/2 on the image == 4x4/1 on the zero-padded space-to-depth tensor
             key = ("fpn.conv1", "tcstem", self.fmt)
@@ -98,7 +102,8 @@ class Engine(object):
             if pc is None:
                 pc = ops.pack_stem_filter(fpn.conv1.weight, _bn_tuple(fpn.bn1), self.fmt)
                 self._packed[key] = pc
-            c1 = ops.conv2d(ops.stem_pack_input(img, self.fmt), pc, relu=True)
+            xs = ops.stem_pack_input_u8(img, self.fmt) if raw_u8 else ops.stem_pack_input(img, self.fmt)
+            c1 = ops.conv2d(xs, pc, relu=True)
         else:
             x = ops.act_from_nchw(img, FMT_F32)
             # fp32-packed stem filter on the CUDA-core kernel; the epilogue emits the engine's activation format
@@ -232,7 +237,8 @@ class Engine(object):
         self._ensure_packed()
         _, c3, c4, c5 = self.backbone(img)
         cls, reg = self.detection_heads(self.detection_neck(c3, c4, c5))
-        anchors = ops.anchors_for(img.shape[2], img.shape[3], img.device)
+        H, W = (img.shape[1], img.shape[2]) if img.dtype == torch.uint8 else (img.shape[2], img.shape[3])
+        anchors = ops.anchors_for(H, W, img.device)
         return [], [cls, reg, anchors]
 
     @torch.no_grad()
@@ -248,7 +254,7 @@ class Engine(object):
     def entire_forward_device(self, img, score_thresh=0.05, iou_thresh=0.5, max_cand=4096, ge=False):
         """Everything on the device, no host sync: returns (heat, cls, reg, boxes, Detections)."""
         self._ensure_packed()
-        H, W = img.shape[2], img.shape[3]
+        H, W = (img.shape[1], img.shape[2]) if img.dtype == torch.uint8 else (img.shape[2], img.shape[3])
         c2, c3, c4, c5 = self.backbone(img)
         anchors = ops.anchors_for(H, W, img.device)
 

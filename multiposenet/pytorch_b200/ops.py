@@ -180,6 +180,29 @@ def stem_pack_input(img, fmt):
     return a
 
 
+def resnet_preprocess_u8(img_u8):
+    """uint8 [N,H,W,3] BGR (cuda) -> fp32 [N,3,H,W], bit-identical to datasets/coco_data/preprocessing.py:15-26."""
+    assert img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[3] == 3
+    img_u8 = img_u8.contiguous()
+    N, H, W, _ = img_u8.shape
+    out = torch.empty((N, 3, H, W), dtype=torch.float32, device=img_u8.device)
+    check(_lib.lib().mpn_preprocess_u8_nchw(_ptr(img_u8), _ptr(out), N, H, W, _stream()), "mpn_preprocess_u8_nchw")
+    stats["launches"] += 1
+    return out
+
+
+def stem_pack_input_u8(img_u8, fmt):
+    """uint8 [N,H,W,3] BGR image -> the tensor-core stem operand with resnet_preprocess fused in."""
+    assert img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[3] == 3
+    img_u8 = img_u8.contiguous()
+    N, H, W, _ = img_u8.shape
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    a = Act(fmt, N, H2 + 3, W2, 64, img_u8.device, cstride=16, wpitch=W2 + 3, k_overlap=1)
+    check(_lib.lib().mpn_stem_pack_input_u8(_ptr(img_u8), _ptr(a.hi), _ptr(a.lo), N, H, W, fmt, _stream()), "mpn_stem_pack_input_u8")
+    stats["launches"] += 1
+    return a
+
+
 def pack_stem_filter(weight, bn, fmt):
     L = _lib.lib()
     w = weight.detach().contiguous()

@@ -90,6 +90,13 @@ def main():
     d = torch.from_numpy(rng.standard_normal((2, a.shape[1], 4), dtype=np.float32) * 2)
     boxes = ClipBoxes()(BBoxTransform()(a, d), torch.zeros(2, 3, 64, 96))
     np.savez_compressed(os.path.join(OUT, "decode.npz"), anchors=a.numpy(), deltas=d.numpy(), boxes=boxes.numpy())
+    # image normalisation straight from the reference function (datasets/coco_data/preprocessing.py:15-26)
+    from datasets.coco_data.preprocessing import resnet_preprocess
+    prng = np.random.Generator(np.random.PCG64(21))
+    pimg = prng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    pfull = np.arange(256, dtype=np.uint8).repeat(3).reshape(16, 16, 3)  # every byte value in every channel
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), img=pimg, out=resnet_preprocess(pimg), full=pfull,
+                        out_full=resnet_preprocess(pfull))
     # network forwards
     runs = [("r50_cond_64x96_b2", 50, "conditioned", (64, 96), 2, 11, True),
             ("r50_refinit_64x96_b1", 50, "refinit", (64, 96), 1, 12, True),

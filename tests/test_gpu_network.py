@@ -168,3 +168,25 @@ def test_prn_batched_vs_oracle(precision, tol):
     assert out.shape == (37, 28, 18, 17) and saved[0] is out
     assert nerr(out, want) <= tol
     assert torch.allclose(out.reshape(37, -1).sum(1), torch.ones(37, device="cuda"), atol=1e-4)
+
+
+def test_uint8_input_with_fused_resnet_preprocess(golden_dir):
+    """raw cv2-style images; the normalisation is bit-identical to the reference's numpy code."""
+    from gpu_util import image, load_model, nerr
+    from multiposenet.pytorch_b200 import ops
+    from oracle.preprocess_oracle import resnet_preprocess
+    g = np.load(os.path.join(golden_dir, "preprocess.npz"))
+    for a, b in (("img", "out"), ("full", "out_full")):
+        got = ops.resnet_preprocess_u8(torch.from_numpy(g[a])[None].cuda())[0].cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), g[b].view(np.uint32))
+    rng = np.random.Generator(np.random.PCG64(5))
+    u8 = rng.integers(0, 256, (2, 64, 96, 3), dtype=np.uint8)
+    x = torch.from_numpy(np.stack([resnet_preprocess(im) for im in u8])).cuda()
+    m, _ = load_model(50, "conditioned", "bf16x3")
+    with torch.no_grad():
+        h_ref, _ = m([x, "keypoint_subnet"])
+        h_u8, _ = m([torch.from_numpy(u8).cuda(), "keypoint_subnet"])
+        _, (cls_ref, _, _) = m([x, "detection_subnet"])
+        _, (cls_u8, _, anc) = m([torch.from_numpy(u8).cuda(), "detection_subnet"])
+    assert torch.equal(h_ref, h_u8) and torch.equal(cls_ref, cls_u8)   # same bits in, same bits out
+    assert anc.shape[1] == ops.anchors_for(64, 96, anc.device).shape[1]

@@ -119,3 +119,10 @@ def test_live_reference_keys_and_forward():
     h2, (s, c, b) = m((x, "both"))
     oh2, (os_, oc, ob), _ = po.forward(sd, 50, x, "both")
     assert torch.equal(h2, oh2) and torch.equal(s, os_) and torch.equal(b, ob)
+
+
+def test_resnet_preprocess_bit_exact(golden_dir):
+    from oracle.preprocess_oracle import resnet_preprocess
+    g = _load(golden_dir, "preprocess.npz")
+    for a, b in (("img", "out"), ("full", "out_full")):
+        assert np.array_equal(resnet_preprocess(g[a]).view(np.uint32), g[b].view(np.uint32))
