@@ -420,6 +420,13 @@ extern "C" int mpn_preprocess_u8_nchw(const unsigned char* img_nhwc_bgr, float* 
 // the same, fused into the tensor-core stem's space-to-depth packing (see mpn_stem_pack_input)
 __global__ void stem_pack_input_u8_kernel(const unsigned char* __restrict__ img, void* hi, void* lo, int N, int H, int W, int H2p,
                                           int W2p, int fmt) {
+  // a byte has 256 values: tabulate the exact (IEEE-division) result per channel once per CTA instead of dividing per pixel
+  __shared__ float lut[3][256];
+  for (int t = threadIdx.x; t < 768; t += blockDim.x) {
+    const unsigned char fake[3] = {(unsigned char)(t & 255), (unsigned char)(t & 255), (unsigned char)(t & 255)};
+    lut[t >> 8][t & 255] = resnet_preprocess_px(fake, t >> 8);
+  }
+  __syncthreads();
   long long total = (long long)N * H2p * W2p * 16;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int cc = (int)(i & 15);
@@ -432,7 +439,7 @@ __global__ void stem_pack_input_u8_kernel(const unsigned char* __restrict__ img,
     if (cc < 12) {
       int c = cc % 3, ph = (cc / 3) >> 1, pw = (cc / 3) & 1;
       int ih = 2 * (hp - 2) + ph, iw = 2 * (wp - 2) + pw;
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = resnet_preprocess_px(img + (((long long)n * H + ih) * W + iw) * 3, c);
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = lut[c][img[(((long long)n * H + ih) * W + iw) * 3 + (2 - c)]];
     }
     mpn_store_act(hi, lo, i, fmt, v);
   }
