@@ -37,8 +37,8 @@ CLS_BIAS_SHIFT = {101: -0.7387505}
 
 
 def load_weights_into(model, layers):
-    from oracle import weights  # seeded synthetic weights (test infrastructure: data only)
-    w = weights.make_weights(layers, "conditioned", seed=0)
+    from multiposenet.pytorch_b200 import synthetic  # seeded synthetic weights (data only)
+    w = synthetic.make_weights(layers, "conditioned", seed=0)
     sd = model.state_dict()
     for k in sd:
         if k in w:
@@ -197,7 +197,6 @@ def run_train(args, rank, world, local):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from multiposenet.pytorch_b200 import poseNet, shard
-    from oracle import posenet_oracle as po
     B = args.batch if args.batch != 32 else 16
     model = poseNet(args.layers, precision=args.precision)
     load_weights_into(model, args.layers)
@@ -244,7 +243,6 @@ def run_train(args, rank, world, local):
     value = shard.whole_job_rate(B * args.steps, ms, dev)
     ms = shard.max_over_ranks(ms, dev)
     nparam = sum(p.numel() for p in model.parameters() if p.requires_grad)
-    fwd_gflop = (po.conv_flops_entire(args.layers, H, W) - 0) / 1e9  # upper bound; the trainable sub-graph is 198.2 (R101)
     if rank == 0:
         pk, pk_src = peaks()
         alg = 3.0 * 198.23e9 if args.layers == 101 else 3.0 * 152.78e9  # fwd + dgrad + wgrad of the keypoint sub-graph
@@ -296,8 +294,7 @@ def main():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
 
-    from multiposenet.pytorch_b200 import ops, poseNet, shard
-    from oracle import posenet_oracle as po
+    from multiposenet.pytorch_b200 import ops, poseNet, shard, synthetic
 
     B = args.batch
     model = poseNet(args.layers, precision=args.precision)
@@ -310,7 +307,7 @@ def main():
     else:
         bias_shift = calibrate_cls_bias(model, dev)
     eng = model.engine()
-    flops_img = po.conv_flops_entire(args.layers, H, W)
+    flops_img = synthetic.conv_flops_entire(args.layers, H, W)
     import multiposenet.pytorch_b200.engine as engine_mod
     engine_mod.USE_GRAPHS = bool(args.graph)  # the public forward() replays a captured graph as well
     if args.streams is not None:

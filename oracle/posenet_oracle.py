@@ -255,45 +255,5 @@ def prn_forward(sd, x):
 
 
 def conv_flops_entire(layers, H=480, W=640):
-    """Algorithmic conv FLOPs/img of the entire_net graph (2*MAC), SURVEY.md 8(d)."""
-    from .weights import param_spec
-
-    spec = param_spec(layers)
-    total = 0.0
-    # spatial size of each conv's OUTPUT, derived from the graph
-    h4, w4 = H // 4, W // 4
-    def out_hw(name):
-        if name == "fpn.conv1":
-            return H // 2, W // 2
-        if name.startswith("fpn.layer"):
-            li = int(name[len("fpn.layer")])
-            b = int(name.split(".")[2])
-            s = (1, 2, 4, 8)[li - 1]
-            hh, ww = h4 // s, w4 // s
-            if li > 1 and b == 0 and name.endswith("conv1"):
-                return hh * 2, ww * 2  # stride sits on conv2 (fpn.py:16)
-            return hh, ww
-        m = {"fpn.conv6": 64, "fpn.conv7": 128, "fpn.latlayer1": 32, "fpn.latlayer2": 16, "fpn.latlayer3": 8,
-             "fpn.toplayer0": 32, "fpn.toplayer1": 16, "fpn.toplayer2": 8, "fpn.toplayer": 32,
-             "fpn.flatlayer1": 16, "fpn.flatlayer2": 8, "fpn.flatlayer3": 4, "fpn.smooth1": 16,
-             "fpn.smooth2": 8, "fpn.smooth3": 4, "convt1": 32, "convs1": 32, "convt2": 16, "convs2": 16,
-             "convt3": 8, "convs3": 8, "convt4": 4, "convs4": 4, "conv2": 4, "convfin": 4}
-        if name in m:
-            d = m[name]
-            return -(-H // d), -(-W // d)
-        return None
-    for k, shp in spec.items():
-        if not (k.endswith(".weight") and len(shp) == 4):
-            continue
-        name = k[:-len(".weight")]
-        if name.startswith("convfin_k"):
-            continue  # keypoint_subnet mode only
-        mac = shp[0] * shp[1] * shp[2] * shp[3]
-        if name.startswith(("regressionModel", "classificationModel")):
-            cells = sum((-(-H // d)) * (-(-W // d)) for d in (8, 16, 32, 64, 128))
-            total += 2.0 * mac * cells
-            continue
-        hw = out_hw(name)
-        assert hw is not None, name
-        total += 2.0 * mac * hw[0] * hw[1]
-    return total
+    from multiposenet.pytorch_b200.synthetic import conv_flops_entire as f
+    return f(layers, H, W)

@@ -1,184 +1,7 @@
-"""Parameter inventory and seeded synthetic weight sets (TEST INFRASTRUCTURE).
+"""Seeded synthetic weight sets and the parameter inventory (TEST INFRASTRUCTURE view).
 
-`param_spec(layers)` lists every state_dict entry of the reference's
-`poseNet(layers)` (network/posenet.py:154-211, network/fpn.py:9-82) in registration
-order.  It is written from the constructor code, not imported, so that it is
-available on the GPU box where /root/reference does not exist; the not-gpu test
-`tests/test_oracle_vs_reference.py` checks it key-by-key against the real module.
-
-Two weight sets (last row / section 8(d)):
-  * "refinit"     -- what the reference constructor produces: normal(std=0.01) convs,
-                     zero conv bias, cls output weight 0 / bias -log(99), reg output 0,
-                     default BN (posenet.py:205-218).  Drawn here from numpy PCG64 so
-                     it is reproducible without torch's RNG.
-  * "conditioned" -- He-normal convs, randomised BN gamma/beta/mean/var, non-zero head
-                     outputs with the cls bias placed so ~1-5 % of anchors pass 0.05.
-All arrays are float32 numpy (int64 for num_batches_tracked).
+The generator itself is plain data code shared with bench.py and lives in multiposenet/pytorch_b200/synthetic.py;
+tests/test_oracle.py pins `param_spec` against the live reference's state_dict.
 """
-import math
-from collections import OrderedDict
-
-import numpy as np
-
-BLOCKS = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
-CLS_OUT_GAIN = 0.65
-REG_OUT_GAIN = 0.7
-
-
-def _conv(spec, name, cout, cin, k, bias):
-    spec[name + ".weight"] = (cout, cin, k, k)
-    if bias:
-        spec[name + ".bias"] = (cout,)
-
-
-def _bn(spec, name, c):
-    spec[name + ".weight"] = (c,)
-    spec[name + ".bias"] = (c,)
-    spec[name + ".running_mean"] = (c,)
-    spec[name + ".running_var"] = (c,)
-    spec[name + ".num_batches_tracked"] = ()
-
-
-def fpn_spec(layers, prefix="fpn."):
-    """network/fpn.py:37-74 (FPN.__init__) and :9-26 (Bottleneck.__init__)."""
-    s = OrderedDict()
-    _conv(s, prefix + "conv1", 64, 3, 7, False)
-    _bn(s, prefix + "bn1", 64)
-    in_planes = 64
-    for li, (planes, nblk, stride) in enumerate(zip((64, 128, 256, 512), BLOCKS[layers], (1, 2, 2, 2)), start=1):
-        for b in range(nblk):
-            st = stride if b == 0 else 1
-            p = "%slayer%d.%d." % (prefix, li, b)
-            _conv(s, p + "conv1", planes, in_planes, 1, False)
-            _bn(s, p + "bn1", planes)
-            _conv(s, p + "conv2", planes, planes, 3, False)
-            _bn(s, p + "bn2", planes)
-            _conv(s, p + "conv3", planes * 4, planes, 1, False)
-            _bn(s, p + "bn3", planes * 4)
-            if st != 1 or in_planes != planes * 4:
-                _conv(s, p + "downsample.0", planes * 4, in_planes, 1, False)
-                _bn(s, p + "downsample.1", planes * 4)
-            in_planes = planes * 4
-    _conv(s, prefix + "conv6", 256, 2048, 3, True)
-    _conv(s, prefix + "conv7", 256, 256, 3, True)
-    _conv(s, prefix + "latlayer1", 256, 2048, 1, True)
-    _conv(s, prefix + "latlayer2", 256, 1024, 1, True)
-    _conv(s, prefix + "latlayer3", 256, 512, 1, True)
-    for n in ("toplayer0", "toplayer1", "toplayer2"):
-        _conv(s, prefix + n, 256, 256, 3, True)
-    _conv(s, prefix + "toplayer", 256, 2048, 1, True)
-    _conv(s, prefix + "flatlayer1", 256, 1024, 1, True)
-    _conv(s, prefix + "flatlayer2", 256, 512, 1, True)
-    _conv(s, prefix + "flatlayer3", 256, 256, 1, True)
-    for n in ("smooth1", "smooth2", "smooth3"):
-        _conv(s, prefix + n, 256, 256, 3, True)
-    return s
-
-
-def param_spec(layers, prn_node_count=1024, prn_coeff=2):
-    """network/posenet.py:155-199 (poseNet.__init__), registration order."""
-    s = fpn_spec(layers)
-    for n in ("convfin_k2", "convfin_k3", "convfin_k4", "convfin_k5"):
-        _conv(s, n, 19, 256, 1, True)
-    for n in ("convt1", "convt2", "convt3", "convt4"):
-        _conv(s, n, 128, 256, 3, True)
-    for n in ("convs1", "convs2", "convs3", "convs4"):
-        _conv(s, n, 128, 128, 3, True)
-    _conv(s, "conv2", 256, 512, 3, True)
-    _conv(s, "convfin", 18, 256, 1, True)
-    for head, cout in (("regressionModel", 36), ("classificationModel", 9)):
-        for n in ("conv1", "conv2", "conv3", "conv4"):
-            _conv(s, "%s.%s" % (head, n), 256, 256, 3, True)
-        _conv(s, head + ".output", cout, 256, 3, True)
-    hw17 = (prn_coeff * 28) * (prn_coeff * 18) * 17
-    s["prn.dens1.weight"] = (prn_node_count, hw17)
-    s["prn.dens1.bias"] = (prn_node_count,)
-    s["prn.bneck.weight"] = (prn_node_count, prn_node_count)
-    s["prn.bneck.bias"] = (prn_node_count,)
-    s["prn.dens2.weight"] = (hw17, prn_node_count)
-    s["prn.dens2.bias"] = (hw17,)
-    return s
-
-
-def _gain(name):
-    """He gain sqrt(2) for convs whose output feeds a ReLU, 1 for the linear ones (FPN necks,
-    convt/convs, convfin*, head outputs, downsample, bottleneck conv3)."""
-    if ".layer" in name:
-        return math.sqrt(2.0) if name.endswith(("conv1.weight", "conv2.weight")) else 1.0
-    if name == "fpn.conv1.weight" or name == "conv2.weight":
-        return math.sqrt(2.0)
-    if name.startswith(("regressionModel", "classificationModel")) and not name.endswith("output.weight"):
-        return math.sqrt(2.0)
-    if name.startswith(("fpn.latlayer", "fpn.flatlayer", "fpn.toplayer.", "fpn.conv6")):
-        return 0.35  # laterals see post-ReLU trunk features with E[x^2] >> 1
-    return 1.0
-
-
-def _is_conv_weight(name, shape):
-    return name.endswith(".weight") and len(shape) == 4
-
-
-def make_weights(layers, kind="conditioned", seed=0, include_prn=False):
-    """Return OrderedDict name -> numpy array for every entry of param_spec.
-
-    PRN matrices (285 MB) are skipped unless include_prn (they are off the conv path).
-    """
-    assert kind in ("refinit", "conditioned")
-    rng = np.random.Generator(np.random.PCG64(seed))
-    spec = param_spec(layers)
-    out = OrderedDict()
-    for name, shape in spec.items():
-        if name.startswith("prn.") and not include_prn:
-            continue
-        if name.endswith("num_batches_tracked"):
-            out[name] = np.zeros((), dtype=np.int64)
-            continue
-        is_bn = (".bn" in name or "downsample.1" in name or name == "fpn.bn1.weight")
-        if name.startswith("prn."):
-            fan_in = shape[-1] if len(shape) == 2 else 1
-            if len(shape) == 2:
-                out[name] = (rng.standard_normal(shape, dtype=np.float32) / np.float32(math.sqrt(fan_in)))
-            else:
-                out[name] = np.zeros(shape, dtype=np.float32)
-            continue
-        if kind == "refinit":
-            if _is_conv_weight(name, shape):
-                out[name] = rng.standard_normal(shape, dtype=np.float32) * np.float32(0.01)
-            elif is_bn and name.endswith((".weight", ".running_var")):
-                out[name] = np.ones(shape, dtype=np.float32)
-            else:  # conv bias, bn bias, running_mean
-                out[name] = np.zeros(shape, dtype=np.float32)
-        else:
-            if _is_conv_weight(name, shape):
-                fan_in = shape[1] * shape[2] * shape[3]
-                out[name] = rng.standard_normal(shape, dtype=np.float32) * np.float32(_gain(name) / math.sqrt(fan_in))
-            elif is_bn and name.endswith("bn3.weight"):
-                # small residual-branch gain keeps the trunk O(1) through 33 blocks
-                out[name] = rng.uniform(0.2, 0.4, shape).astype(np.float32)
-            elif is_bn and name.endswith(".weight"):
-                out[name] = rng.uniform(0.5, 1.5, shape).astype(np.float32)
-            elif is_bn and name.endswith(".running_var"):
-                out[name] = rng.uniform(0.5, 1.5, shape).astype(np.float32)
-            elif is_bn and name.endswith(".running_mean"):
-                out[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
-            else:  # biases (conv and bn)
-                out[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
-    if kind == "refinit":
-        # posenet.py:205-209
-        out["classificationModel.output.weight"][...] = 0
-        out["classificationModel.output.bias"][...] = -math.log((1.0 - 0.01) / 0.01)
-        out["regressionModel.output.weight"][...] = 0
-        out["regressionModel.output.bias"][...] = 0
-    else:
-        # Score head: logits ~ N(-5.0, ~1.3-1.5) -> a few % of anchors above logit(0.05) = -2.94;
-        # box head: deltas with std ~1 (x std .1/.2 in the decode -> mild box motion).
-        out["classificationModel.output.weight"] *= np.float32(CLS_OUT_GAIN)
-        out["classificationModel.output.bias"][...] = -5.0
-        out["regressionModel.output.weight"] *= np.float32(REG_OUT_GAIN)
-    return out
-
-
-def to_torch_state_dict(weights):
-    import torch
-
-    return OrderedDict((k, torch.from_numpy(np.ascontiguousarray(v))) for k, v in weights.items())
+from multiposenet.pytorch_b200.synthetic import (BLOCKS, CLS_OUT_GAIN, REG_OUT_GAIN, fpn_spec, make_weights,  # noqa: F401
+                                                 param_spec, to_torch_state_dict)
