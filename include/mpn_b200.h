@@ -94,6 +94,11 @@ int mpn_conv2d_fwd_f32in(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* s
 int mpn_pack_filter_f32(const float* w_oihw, float* dst, int Cout, int Cin, int R, int S, int CoutPad, void* stream);
 /* OIHW fp32 -> [Cout][R][S][Cin] bf16 hi (+ lo = bf16(w - hi) if dst_lo != NULL) */
 int mpn_pack_filter_bf16(const float* w_oihw, void* dst_hi, void* dst_lo, int Cout, int Cin, int R, int S, void* stream);
+/* same with the eval-mode BatchNorm scale folded into the filter (w * scale[cout], rounded once in fp32, before the
+ * hi/lo split): the epilogue then only adds the folded bias, and a residual (fpn.py:45-46: out += shortcut(x)) can be
+ * accumulated by the tensor core ahead of it.  scale == NULL: plain packing. */
+int mpn_pack_filter_bf16_scaled(const float* w_oihw, const float* scale, void* dst_hi, void* dst_lo, int Cout, int Cin, int R, int S,
+                                void* stream);
 /* BatchNorm (eval) fold: scale = gamma/sqrt(var+eps), bias = beta - mean*scale   (fpn.py:15-19,25,43) */
 int mpn_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                 float* scale, float* bias, int C, void* stream);

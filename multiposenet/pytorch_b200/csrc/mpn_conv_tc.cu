@@ -13,14 +13,19 @@
 //   warp 0 lane 0 : TMA producer           (mbarrier full/empty ring of STAGES stages)
 //   warp 1 lane 0 : tcgen05.mma issuer     (accumulators double-buffered in TMEM, 2 x BN columns)
 //   warp 2        : TMEM allocate / free
-//   warps 4..11   : epilogue (two warps per TMEM lane quarter): tcgen05.ld -> swizzled smem transpose -> BN-fold
-//                   scale/bias, residual, nearest-upsample add, ReLU/sigmoid -> bf16 (hi/lo) NHWC with
-//                   64-byte row segments per 4 lanes, or fp32 NHWC / NCHW heads, optionally replicated x2/x4/x8
+//   warps 4..11   : epilogue (two warps per TMEM lane quarter), three variants (template EPI):
+//                   EPI_TMA  tcgen05.ld (thread = pixel row) -> BN-fold scale/bias, residual, ReLU/sigmoid -> bf16 hi/lo
+//                            -> 64B-swizzled smem box -> cp.async.bulk.tensor store (no per-row address math, no LSU stores)
+//                   EPI_LSU  same math through a swizzled smem transpose and 64-byte row segments per 4 lanes; handles the
+//                            nearest-upsample add and x2/x4/x8 replicated outputs (FPN laterals, keypoint concat)
+//                   EPI_F32  fp32 NHWC / NCHW heads (Cout <= 64), thread-per-row stores
 // Precision modes: MPN_FMT_BF16   one bf16 plane per operand, one MMA per K step;
 //                  MPN_FMT_BF16X2 hi/lo bf16 planes (x = hi + lo to ~2^-17), three MMAs per K step
 //                  (hi*hi + lo*hi + hi*lo) accumulated in fp32 -> fp32-grade parity with the reference.
 #include <cuda.h>
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "mpn_common.cuh"
 #include "mpn_tc_ptx.cuh"
@@ -39,15 +44,23 @@ constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32 a
 struct Maps {
   CUtensorMap a[2][4];  // [plane hi/lo][phase hp*2+wp]
   CUtensorMap b[2];     // [plane]
-  CUtensorMap r[2];     // [plane] residual operand, used only for L2 prefetch (no swizzle)
+  CUtensorMap bs[2];    // [plane] filter map with a tail_bn-row box (tail sub-tiles)
+  CUtensorMap y[2];     // [plane] output tensor (EPI_TMA): box {32 ch, TW, TH, TN}, 64B swizzle
+  CUtensorMap r[2];     // [plane] residual tensor (res_mma): box {64 ch, TW, TH, TN}, 128B swizzle = MN-major B operand
+  CUtensorMap ident;    // 128 x 128 bf16 identity matrix (res_mma): box {64, 128}, K-major A operand
 };
 
 struct TcParams {
   int N, OH, OW, Cout;
   int TW, TH, TN, rows;
   int tiles_w, tiles_h, tiles_n, tiles_co, total_tiles;
+  // Tail balancing: tiles [0, main_tiles) are BN wide; every further BN-wide tile is cut into tail_split sub-tiles of
+  // tail_bn columns so that the last partial round of the persistent schedule is spread over all SMs.
+  int main_tiles, tail_split, tail_bn;
+  // res_mma: the residual tile is added by the tensor core: after the filter taps, one extra ring iteration per plane
+  // loads I (128x128) as the A operand and the residual box [BN ch x 128 pixels] as an MN-major B operand, D += I * R.
+  int res_mma;
   int R, S, stride, pad, kb_per_tap, Cin;
-  int res_prefetch;  // 1: maps.r[] describe the residual tensor -> producer prefetches its tiles into L2
   int phase_empty;  // bit p set: phase view p has no pixels (tiny maps) -> load an all-OOB box instead
   const float* scale;
   const float* bias;
@@ -63,26 +76,63 @@ struct TcParams {
   void* y_lo;
 };
 
+struct TileCoord {
+  int co0, ncols, tw_i, th_i, tn_i;
+};
+
+template <int BN>
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile) {
+  TileCoord c;
+  int t = tile, sub = 0;
+  c.ncols = BN;
+  if (tile >= P.main_tiles) {
+    const int j = tile - P.main_tiles;
+    t = P.main_tiles + j / P.tail_split;
+    sub = j - (j / P.tail_split) * P.tail_split;
+    c.ncols = P.tail_bn;
+  }
+  const int co_t = t % P.tiles_co;
+  int mt = t / P.tiles_co;
+  c.tw_i = mt % P.tiles_w;
+  mt /= P.tiles_w;
+  c.th_i = mt % P.tiles_h;
+  c.tn_i = mt / P.tiles_h;
+  c.co0 = co_t * BN + sub * c.ncols;
+  return c;
+}
+
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool SPLIT, int STAGES, bool F32OUT>
+enum { EPI_LSU = 0, EPI_F32 = 1, EPI_TMA = 2 };
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+template <int BN, bool SPLIT, int STAGES, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ Maps maps, const TcParams P) {
   constexpr int PLANES = SPLIT ? 2 : 1;
   constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
   constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + B_TILE_BYTES);
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_M >> 4) << 24);  // | (N >> 3) << 17
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
-  uint8_t* epi_stage = smem_gen + STAGES * STAGE_BYTES + BAR_BYTES;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * STAGES + 4));
+  uint8_t* epi_stage = smem_gen + STAGES * STAGE_BYTES;  // 1024-byte aligned (TMA-store swizzle pattern)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k_iters = P.R * P.S * P.kb_per_tap;
@@ -92,6 +142,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     for (int p = 0; p < PLANES; ++p) {
       prefetch_tmap(&maps.b[p]);
       prefetch_tmap(&maps.a[p][0]);
+      if (P.tail_split > 1) prefetch_tmap(&maps.bs[p]);
+      if (EPI == EPI_TMA) prefetch_tmap(&maps.y[p]);
+      if (EPI == EPI_TMA && P.res_mma) prefetch_tmap(&maps.r[p]);
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -102,6 +155,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       mbar_init(tempty_bar(a), NUM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (EPI == EPI_TMA && P.res_mma && P.rows < BLOCK_M) {
+    // rows >= P.rows of a residual box are never written by TMA but are read (times a zero of I) by the MMA:
+    // make sure no stale NaN/Inf bit pattern of an earlier kernel sits there
+    uint4* z = reinterpret_cast<uint4*>(smem_gen);
+    for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += NUM_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
@@ -114,35 +174,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
   if (warp == 0 && lane == 0) {
     // =============================== TMA producer ===============================
-    const uint32_t tx_bytes = (uint32_t)PLANES * (uint32_t)(P.rows * BLOCK_K * 2 + B_TILE_BYTES);
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int co_t = tile % P.tiles_co;
-      int mt = tile / P.tiles_co;
-      const int tw_i = mt % P.tiles_w;
-      mt /= P.tiles_w;
-      const int th_i = mt % P.tiles_h;
-      const int tn_i = mt / P.tiles_h;
-      const int ow0 = tw_i * P.TW, oh0 = th_i * P.TH, n0 = tn_i * P.TN, co0 = co_t * BN;
-      if (P.res_prefetch) {
-        // pull the residual tile the epilogue will add into L2: this tile's on the first round (short lead),
-        // then always the NEXT tile's, a whole tile time ahead of its epilogue
-        if (tile == (int)blockIdx.x) {
-#pragma unroll
-          for (int p = 0; p < PLANES; ++p) tma_prefetch_l2_4d(&maps.r[p], co0, ow0, oh0, n0);
-        }
-        const int nt = tile + gridDim.x;
-        if (nt < P.total_tiles) {
-          const int nco = nt % P.tiles_co;
-          int nm = nt / P.tiles_co;
-          const int ntw = nm % P.tiles_w;
-          nm /= P.tiles_w;
-          const int nth = nm % P.tiles_h, ntn = nm / P.tiles_h;
-#pragma unroll
-          for (int p = 0; p < PLANES; ++p) tma_prefetch_l2_4d(&maps.r[p], nco * BN, ntw * P.TW, nth * P.TH, ntn * P.TN);
-        }
-      }
+      const TileCoord tc = decode_tile<BN>(P, tile);
+      const bool tail = tc.ncols != BN;
+      const uint32_t tx_bytes = (uint32_t)PLANES * (uint32_t)((P.rows + tc.ncols) * BLOCK_K * 2);
+      const int ow0 = tc.tw_i * P.TW, oh0 = tc.th_i * P.TH, n0 = tc.tn_i * P.TN, co0 = tc.co0;
       for (int tap = 0; tap < P.R * P.S; ++tap) {
         const int r = tap / P.S, s = tap - r * P.S;
         const int dh = r - P.pad, dw = s - P.pad;
@@ -169,8 +207,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
           for (int p = 0; p < PLANES; ++p) {
             tma_load_4d(sa + p * A_TILE_BYTES, &maps.a[p][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
-            tma_load_2d(sb + p * B_TILE_BYTES, &maps.b[p], full_bar(stage), kcol, co0);
+            tma_load_2d(sb + p * B_TILE_BYTES, tail ? &maps.bs[p] : &maps.b[p], full_bar(stage), kcol, co0);
           }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (EPI == EPI_TMA && P.res_mma) {
+#pragma unroll 1
+        for (int p = 0; p < PLANES; ++p) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), (uint32_t)(2 * A_TILE_BYTES + (tc.ncols / 64) * P.rows * 128));
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + PLANES * A_TILE_BYTES;
+          tma_load_2d(sa, &maps.ident, full_bar(stage), 0, 0);
+          tma_load_2d(sa + A_TILE_BYTES, &maps.ident, full_bar(stage), 64, 0);
+          for (int j = 0; j < tc.ncols / 64; ++j)
+            tma_load_4d(sb + j * (BLOCK_M * 128), &maps.r[p], full_bar(stage), co0 + 64 * j, ow0, oh0, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -186,6 +238,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const int ncols = decode_tile<BN>(P, tile).ncols;
+      const uint32_t IDESC = IDESC_BASE | ((uint32_t)(ncols >> 3) << 17);
+      const bool res_mma = EPI == EPI_TMA && P.res_mma;
       for (int ki = 0; ki < num_k_iters; ++ki) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
@@ -203,9 +258,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             umma_bf16(d_tmem, a_hi, b_lo, IDESC, 1u);
           }
         }
-        umma_commit(empty_bar(stage));                       // frees the smem stage when the MMAs retire
-        if (ki == num_k_iters - 1) umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        umma_commit(empty_bar(stage));                                        // frees the smem stage when the MMAs retire
+        if (ki == num_k_iters - 1 && !res_mma) umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (res_mma) {
+        // D += I(128x128, K-major) * R(128 pixels x ncols channels, MN-major: 64-channel blocks 16 KB apart)
+        const uint32_t idesc_mn = IDESC | (1u << 16);
+#pragma unroll 1
+        for (int p = 0; p < PLANES; ++p) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + PLANES * A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_M / 16; ++k) {
+            const uint64_t a_id = make_sdesc(sa + (k >> 2) * A_TILE_BYTES + (k & 3) * 32);
+            const uint64_t b_rs = make_sdesc_mn(sb + k * 2048, BLOCK_M * 128, 1024);
+            umma_bf16(d_tmem, a_id, b_rs, idesc_mn, 1u);
+          }
+          umma_commit(empty_bar(stage));
+          if (p == PLANES - 1) umma_commit(tfull_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp >= 4) {
@@ -218,17 +293,112 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const long long nstride = P.out_nstride > 0 ? P.out_nstride
                               : (P.out_mode == MPN_OUT_F32_NCHW ? (long long)P.Cout * OHr * OWr : (long long)OHr * OWr * P.out_cstride);
     int it = 0;
+    bool store_pending = false;  // EPI_TMA: a bulk store of this half may still be reading its staging box
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int co_t = tile % P.tiles_co;
-      int mt = tile / P.tiles_co;
-      const int tw_i = mt % P.tiles_w;
-      mt /= P.tiles_w;
-      const int th_i = mt % P.tiles_h;
-      const int tn_i = mt / P.tiles_h;
-      const int co0 = co_t * BN;
-      if constexpr (!F32OUT) {
+      const TileCoord tc = decode_tile<BN>(P, tile);
+      const int tw_i = tc.tw_i, th_i = tc.th_i, tn_i = tc.tn_i, co0 = tc.co0, ncols = tc.ncols;
+      if constexpr (EPI == EPI_TMA) {
+        // ---- thread = pixel row (the TMEM lane): 32 channels per step -> bf16 hi/lo -> 64B-swizzled box in smem -> TMA store.
+        // The two halves (4 warps each) own separate 16 KB staging boxes and alternate over the 32-channel blocks.
+        const int row = q * 32 + lane;
+        uint8_t* stg = epi_stage + half * (4 * EPI_STAGE_BYTES);       // [hi: rows x 64 B][lo: rows x 64 B] at +8192
+        const uint32_t stg_u32 = smem_base + STAGES * STAGE_BYTES + half * (4 * EPI_STAGE_BYTES);
+        const int sw = (row >> 1) & 3;                                 // CU_TENSOR_MAP_SWIZZLE_64B: chunk ^= (byte >> 7) & 3
+        const bool issuer = (q == 0 && lane == 0);
+        const int ow0 = tw_i * P.TW, oh0 = th_i * P.TH, n0 = tn_i * P.TN;
+        long long res_off = 0;
+        const bool res_lsu = P.res_cstride > 0 && !P.res_mma;
+        if (res_lsu) {
+          const int tw2 = row % P.TW, th2 = (row / P.TW) % P.TH, tn2 = row / (P.TW * P.TH);
+          const int ow2 = ow0 + tw2, oh2 = oh0 + th2, n2 = n0 + tn2;
+          const bool ok = row < P.rows && ow2 < P.OW && oh2 < P.OH && n2 < P.N;
+          res_off = ok ? ((long long)(n2 * P.OH + oh2) * P.OW + ow2) * P.res_cstride : 0;  // invalid rows read pixel 0 (never stored)
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+          const int cbase = co0 + c0;
+          if (cbase >= P.Cout) break;  // uniform over the half
+          uint32_t raw[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+          TMEM_LD_32x32b_X32(taddr, raw);
+          uint4 rh[4], rl[4];
+          if (res_lsu) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              rh[i] = __ldg(reinterpret_cast<const uint4*>(P.res_hi + res_off + cbase) + i);
+              if (SPLIT) rl[i] = __ldg(reinterpret_cast<const uint4*>(P.res_lo + res_off + cbase) + i);
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (P.scale) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(P.scale + cbase) + j);
+              v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
+            }
+          }
+          if (P.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(P.bias + cbase) + j);
+              v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
+          }
+          if (res_lsu) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              add_bf16x8_reg(v + 8 * i, rh[i]);
+              if (SPLIT) add_bf16x8_reg(v + 8 * i, rl[i]);
+            }
+          }
+          if (P.flags & MPN_EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (P.flags & MPN_EPI_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+          }
+          uint4 hi4[4], lo4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float* w = v + 8 * i;
+            hi4[i].x = pack_bf16(w[0], w[1]); hi4[i].y = pack_bf16(w[2], w[3]);
+            hi4[i].z = pack_bf16(w[4], w[5]); hi4[i].w = pack_bf16(w[6], w[7]);
+            if (SPLIT) {
+              lo4[i].x = pack_bf16(w[0] - bf16_lo_f(hi4[i].x), w[1] - bf16_hi_f(hi4[i].x));
+              lo4[i].y = pack_bf16(w[2] - bf16_lo_f(hi4[i].y), w[3] - bf16_hi_f(hi4[i].y));
+              lo4[i].z = pack_bf16(w[4] - bf16_lo_f(hi4[i].z), w[5] - bf16_hi_f(hi4[i].z));
+              lo4[i].w = pack_bf16(w[6] - bf16_lo_f(hi4[i].w), w[7] - bf16_hi_f(hi4[i].w));
+            }
+          }
+          // the previous store of this half must have finished READING the staging box before it is overwritten
+          if (store_pending) {
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            named_bar_sync(1 + half, 128);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            *reinterpret_cast<uint4*>(stg + row * 64 + ((i ^ sw) << 4)) = hi4[i];
+            if (SPLIT) *reinterpret_cast<uint4*>(stg + 8192 + row * 64 + ((i ^ sw) << 4)) = lo4[i];
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          named_bar_sync(1 + half, 128);
+          if (issuer) {
+            tma_store_4d(&maps.y[0], stg_u32, cbase, ow0, oh0, n0);
+            if (SPLIT) tma_store_4d(&maps.y[1], stg_u32 + 8192, cbase, ow0, oh0, n0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          store_pending = true;
+        }
+      } else if constexpr (EPI == EPI_LSU) {
         // ---- per-tile row bookkeeping for the coalesced phase: lane serves rows (lane>>2) + 8*i, i = 0..3
         long long obase[4];  // destination element offset of (n, oh*rep, ow*rep, out_coffset)
         int pixv[4];         // flat output pixel index, or -1 if the row is outside the tensor
@@ -250,7 +420,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         float* stg = reinterpret_cast<float*>(epi_stage + (warp - 4) * EPI_STAGE_BYTES);
         const int g = lane & 3;  // 8-channel group of this lane in the coalesced phase
 #pragma unroll 1
-        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        for (int c0 = half * 32; c0 < ncols; c0 += 64) {
           const int cbase = co0 + c0;
           if (cbase >= P.Cout) break;  // warp-uniform
           uint32_t raw[32];
@@ -345,7 +515,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = half * 16; c0 < BN; c0 += 32) {
+        for (int c0 = half * 16; c0 < ncols; c0 += 32) {
           const int cbase = co0 + c0;
           if (cbase >= P.Cout) break;  // warp-uniform
           uint32_t raw[16];
@@ -385,6 +555,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
+    if (EPI == EPI_TMA && store_pending && (warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   // =============================== teardown ===============================
   tc_fence_before();
@@ -393,6 +564,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 128 x 128 bf16 identity matrix in device memory (one per device, written once): the A operand of the residual MMA.
+__device__ __nv_bfloat16 g_identity[BLOCK_M * BLOCK_M];
+
+__global__ void init_identity_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < BLOCK_M * BLOCK_M) g_identity[i] = __float2bfloat16_rn((i / BLOCK_M) == (i % BLOCK_M) ? 1.f : 0.f);
+}
+
+int identity_matrix(const void** ptr, cudaStream_t st) {
+  static std::mutex mu;
+  static bool ready[64] = {};
+  static const void* addr[64] = {};
+  int dev = 0;
+  MPN_CUDA_OK(cudaGetDevice(&dev));
+  MPN_CHECK_ARG(dev >= 0 && dev < 64, "conv(tcgen05): device index out of range");
+  std::lock_guard<std::mutex> lock(mu);
+  if (!addr[dev]) {
+    void* a = nullptr;
+    MPN_CUDA_OK(cudaGetSymbolAddress(&a, g_identity));
+    addr[dev] = a;
+  }
+  if (!ready[dev]) {
+    // stream-ordered before the convolution that needs it; inside a stream capture the launch becomes a graph node and
+    // the matrix is not marked ready (an eager call later writes it for good)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    MPN_CUDA_OK(cudaStreamIsCapturing(st, &cs));
+    init_identity_kernel<<<BLOCK_M * BLOCK_M / 256, 256, 0, st>>>();
+    MPN_LAUNCH_OK();
+    if (cs == cudaStreamCaptureStatusNone) ready[dev] = true;
+  }
+  *ptr = addr[dev];
+  return MPN_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -418,8 +624,8 @@ void choose_tile(int N, int OH, int OW, int* TW, int* TH, int* TN) {
   *TW = bw; *TH = bh; *TN = bn;
 }
 
-template <int BN, bool SPLIT, bool F32OUT>
-int launch(const Maps& maps, const TcParams& P, cudaStream_t st) {
+template <int BN, bool SPLIT, int EPI>
+int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
   constexpr int PLANES = SPLIT ? 2 : 1;
   constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + BN * BLOCK_K * 2);
   constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - NUM_EPI_WARPS * EPI_STAGE_BYTES) / STAGE_BYTES;
@@ -427,11 +633,8 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st) {
   static_assert(STAGES >= 2, "not enough shared memory for a 2-stage ring");
   static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier area too small");
   const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
-  auto kern = conv_tc_kernel<BN, SPLIT, STAGES, F32OUT>;
+  auto kern = conv_tc_kernel<BN, SPLIT, STAGES, EPI>;
   MPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  int dev = 0, sms = 148;
-  MPN_CUDA_OK(cudaGetDevice(&dev));
-  MPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int grid = P.total_tiles < sms ? P.total_tiles : sms;
   kern<<<grid, NUM_THREADS, smem, st>>>(maps, P);
   MPN_LAUNCH_OK();
@@ -465,20 +668,66 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   P.tiles_w = mpn_divup(d->OW, P.TW);
   P.tiles_h = mpn_divup(d->OH, P.TH);
   P.tiles_n = mpn_divup(d->N, P.TN);
-  int BN = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
-  // Split mode: 256-wide tiles (2-stage ring, 96 B/cycle of smem operand traffic per MMA instead of 128) win
-  // whenever the 128-wide tiling needs more than one round of CTAs (measured r01c: 3x3 convs 435 -> 525 TFLOP/s);
-  // launches that fit in one round keep BN = 128 for twice the CTAs.  MPN_SPLIT_BN256 = 0/1 forces either.
+  // ---- tile plan.  A persistent launch runs `rounds` full rounds of G = min(tiles, SMs) tiles plus a partial round of
+  // `rem` tiles that would leave most SMs idle; the plan cuts those rem tiles into s sub-tiles of BN/s columns (>= 32)
+  // so the tail costs one narrow tile instead of one full tile.  Relative tile cost ~ (columns + 64): the fixed part is
+  // the 128-row activation window every tile loads regardless of its width (fitted on r01c/r01d: 256-wide tiles take
+  // 1.66x a 128-wide tile).  BN in {256, 128} (when Cout > 128) and s are chosen to minimise the makespan.  MPN_SPLIT_BN256 = 0/1 forces the width, MPN_TAIL_SPLIT = 0 disables the tail cut.
+  int sms = 148;
+  {
+    int dev = 0;
+    MPN_CUDA_OK(cudaGetDevice(&dev));
+    MPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   static const int split256 = getenv("MPN_SPLIT_BN256") ? atoi(getenv("MPN_SPLIT_BN256")) : -1;
-  if (split && BN == 256) {
-    const long long tiles128 = (long long)P.tiles_w * P.tiles_h * P.tiles_n * mpn_divup(d->Cout, 128);
-    const bool use256 = split256 >= 0 ? split256 != 0 : tiles128 > 148;
-    if (!use256) BN = 128;
+  static const int tail_on = getenv("MPN_TAIL_SPLIT") ? atoi(getenv("MPN_TAIL_SPLIT")) : 1;
+  const long long m_tiles = (long long)P.tiles_w * P.tiles_h * P.tiles_n;
+  const bool f32out = d->out_mode != MPN_OUT_ACT;
+  // Activation outputs without upsample-add / replication go through the TMA-store epilogue (MPN_EPI_TMA=0 forces the LSU
+  // one); there a split-format residual without an epilogue scale is added by the tensor core (MPN_RES_MMA=0: by the LSU).
+  static const int epi_tma_on = getenv("MPN_EPI_TMA") ? atoi(getenv("MPN_EPI_TMA")) : 1;
+  static const int res_mma_on = getenv("MPN_RES_MMA") ? atoi(getenv("MPN_RES_MMA")) : 1;
+  const bool epi_tma = epi_tma_on && !f32out && d->out_rep == 1 && d->up_cstride == 0;
+  const bool res_mma = res_mma_on && epi_tma && split && d->res_cstride > 0 && !p->scale && d->Cout % 64 == 0;
+  const int min_tail_bn = res_mma ? 64 : 32;
+  int BN = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
+  int tail_s = 1;
+  {
+    int cand[2] = {BN, 0};
+    if (BN == 256) {
+      if (split256 == 0) cand[0] = 128;
+      else if (split256 < 0) cand[1] = 128;
+    }
+    double best = 1e30;
+    for (int ci = 0; ci < 2 && cand[ci]; ++ci) {
+      const int bn = cand[ci];
+      const long long T = m_tiles * mpn_divup(d->Cout, bn);
+      const long long G = T < sms ? T : sms;
+      const long long rounds = T / G, rem = T % G;
+      const double c_full = bn + 64.0;
+      double cost = (double)(rounds + (rem > 0)) * c_full;
+      int s_best = 1;
+      if (tail_on && !f32out && rem > 0) {
+        for (int sdiv = 2; bn / sdiv >= min_tail_bn && rem * sdiv <= G; sdiv *= 2) {
+          const double c = (double)rounds * c_full + (bn / sdiv + 64.0);
+          if (c < cost) { cost = c; s_best = sdiv; }
+        }
+      }
+      if (cost < best) { best = cost; BN = bn; tail_s = s_best; }
+    }
   }
   P.tiles_co = mpn_divup(d->Cout, BN);
-  long long total = (long long)P.tiles_w * P.tiles_h * P.tiles_n * P.tiles_co;
-  MPN_CHECK_ARG(total < (1LL << 31), "conv(tcgen05): too many tiles");
-  P.total_tiles = (int)total;
+  {
+    const long long T = m_tiles * P.tiles_co;
+    MPN_CHECK_ARG(T < (1LL << 27), "conv(tcgen05): too many tiles");
+    const long long G = T < sms ? T : sms;
+    const long long rem = tail_s > 1 ? T % G : 0;
+    P.main_tiles = (int)(T - rem);
+    P.tail_split = tail_s;
+    P.tail_bn = BN / tail_s;
+    P.total_tiles = (int)(T - rem + rem * tail_s);
+  }
+  P.res_mma = res_mma ? 1 : 0;
   P.R = d->R; P.S = d->S; P.stride = d->stride; P.pad = d->pad; P.Cin = d->Cin; P.kb_per_tap = d->Cin / BLOCK_K;
   P.scale = p->scale; P.bias = p->bias;
   P.res_hi = (const __nv_bfloat16*)p->res_hi; P.res_lo = (const __nv_bfloat16*)p->res_lo; P.res_cstride = d->res_cstride;
@@ -523,37 +772,59 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
     cuuint32_t wbox[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN};
     int rc = encode(fn, &maps.b[pl], pl == 0 ? p->w_hi : p->w_lo, 2, wdims, wstrides, wbox);
     if (rc) return rc;
+    if (P.tail_split > 1) {
+      cuuint32_t sbox[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)P.tail_bn};
+      rc = encode(fn, &maps.bs[pl], pl == 0 ? p->w_hi : p->w_lo, 2, wdims, wstrides, sbox);
+      if (rc) return rc;
+    }
   }
-  if (d->res_cstride > 0 && d->out_mode == MPN_OUT_ACT) {
+  if (epi_tma) {
+    const long long nstride = d->out_nstride > 0 ? d->out_nstride : (long long)d->OH * d->OW * d->out_cstride;
+    for (int pl = 0; pl < planes; ++pl) {
+      cuuint64_t ydims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->OW, (cuuint64_t)d->OH, (cuuint64_t)d->N};
+      cuuint64_t ystr[3] = {(cuuint64_t)d->out_cstride * 2ULL, (cuuint64_t)d->OW * d->out_cstride * 2ULL, (cuuint64_t)nstride * 2ULL};
+      cuuint32_t ybox[4] = {32u, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
+      const char* yb = (const char*)(pl == 0 ? p->y_hi : p->y_lo) + (long long)d->out_coffset * 2LL;
+      int rc = encode(fn, &maps.y[pl], yb, 4, ydims, ystr, ybox, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+  }
+  if (res_mma) {
+    const void* ident = nullptr;
+    int rc = identity_matrix(&ident, (cudaStream_t)stream);
+    if (rc) return rc;
+    cuuint64_t idims[2] = {128, 128};
+    cuuint64_t istr[1] = {256};
+    cuuint32_t ibox[2] = {64, 128};
+    rc = encode(fn, &maps.ident, ident, 2, idims, istr, ibox);
+    if (rc) return rc;
     for (int pl = 0; pl < planes; ++pl) {
       cuuint64_t rdims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->OW, (cuuint64_t)d->OH, (cuuint64_t)d->N};
       cuuint64_t rstr[3] = {(cuuint64_t)d->res_cstride * 2ULL, (cuuint64_t)d->OW * d->res_cstride * 2ULL,
                             (cuuint64_t)d->OH * d->OW * d->res_cstride * 2ULL};
-      cuuint32_t rbox[4] = {(cuuint32_t)(BN < d->Cout ? BN : d->Cout), (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
-      int rc = encode(fn, &maps.r[pl], pl == 0 ? p->res_hi : p->res_lo, 4, rdims, rstr, rbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+      cuuint32_t rbox[4] = {64u, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
+      rc = encode(fn, &maps.r[pl], pl == 0 ? p->res_hi : p->res_lo, 4, rdims, rstr, rbox);
       if (rc) return rc;
     }
-    P.res_prefetch = 1;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const bool f32out = d->out_mode != MPN_OUT_ACT;
   if (f32out) {  // head outputs (18/19/36/9 channels): the thread-per-row fp32 store path, small-N tiles only
     MPN_CHECK_ARG(BN <= 64, "conv(tcgen05): fp32 outputs are built for Cout <= 64 (got %d)", d->Cout);
-    if (split) return BN == 64 ? launch<64, true, true>(maps, P, s) : launch<32, true, true>(maps, P, s);
-    return BN == 64 ? launch<64, false, true>(maps, P, s) : launch<32, false, true>(maps, P, s);
+    if (split) return BN == 64 ? launch<64, true, EPI_F32>(maps, P, s, sms) : launch<32, true, EPI_F32>(maps, P, s, sms);
+    return BN == 64 ? launch<64, false, EPI_F32>(maps, P, s, sms) : launch<32, false, EPI_F32>(maps, P, s, sms);
+  }
+#define MPN_TC_DISPATCH(SPLIT_, EPI_)                                     \
+  switch (BN) {                                                            \
+    case 256: return launch<256, SPLIT_, EPI_>(maps, P, s, sms);           \
+    case 128: return launch<128, SPLIT_, EPI_>(maps, P, s, sms);           \
+    case 64: return launch<64, SPLIT_, EPI_>(maps, P, s, sms);             \
+    default: return launch<32, SPLIT_, EPI_>(maps, P, s, sms);             \
   }
   if (split) {
-    switch (BN) {
-      case 256: return launch<256, true, false>(maps, P, s);
-      case 128: return launch<128, true, false>(maps, P, s);
-      case 64: return launch<64, true, false>(maps, P, s);
-      default: return launch<32, true, false>(maps, P, s);
-    }
+    if (epi_tma) { MPN_TC_DISPATCH(true, EPI_TMA) }
+    MPN_TC_DISPATCH(true, EPI_LSU)
   }
-  switch (BN) {
-    case 256: return launch<256, false, false>(maps, P, s);
-    case 128: return launch<128, false, false>(maps, P, s);
-    case 64: return launch<64, false, false>(maps, P, s);
-    default: return launch<32, false, false>(maps, P, s);
-  }
+  if (epi_tma) { MPN_TC_DISPATCH(false, EPI_TMA) }
+  MPN_TC_DISPATCH(false, EPI_LSU)
+#undef MPN_TC_DISPATCH
 }

@@ -53,7 +53,7 @@ extern "C" int mpn_pack_filter_f32(const float* w, float* dst, int Cout, int Cin
   return MPN_OK;
 }
 
-__global__ void pack_filter_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+__global__ void pack_filter_bf16_kernel(const float* __restrict__ w, const float* __restrict__ scale, __nv_bfloat16* __restrict__ hi,
                                         __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int R, int S) {
   long long total = (long long)Cout * R * S * Cin;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -64,6 +64,7 @@ __global__ void pack_filter_bf16_kernel(const float* __restrict__ w, __nv_bfloat
     int r = (int)(t % R);
     int co = (int)(t / R);
     float v = w[(((long long)co * Cin + ci) * R + r) * S + s];
+    if (scale) v = __fmul_rn(v, scale[co]);
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     hi[i] = h;
     if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -71,9 +72,14 @@ __global__ void pack_filter_bf16_kernel(const float* __restrict__ w, __nv_bfloat
 }
 
 extern "C" int mpn_pack_filter_bf16(const float* w, void* hi, void* lo, int Cout, int Cin, int R, int S, void* stream) {
+  return mpn_pack_filter_bf16_scaled(w, nullptr, hi, lo, Cout, Cin, R, S, stream);
+}
+
+extern "C" int mpn_pack_filter_bf16_scaled(const float* w, const float* scale, void* hi, void* lo, int Cout, int Cin, int R, int S,
+                                           void* stream) {
   MPN_CHECK_ARG(w && hi && Cout > 0 && Cin > 0 && R > 0 && S > 0, "mpn_pack_filter_bf16: bad argument");
   long long total = (long long)Cout * R * S * Cin;
-  pack_filter_bf16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+  pack_filter_bf16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, scale, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
                                                                                  Cout, Cin, R, S);
   MPN_LAUNCH_OK();
   return MPN_OK;

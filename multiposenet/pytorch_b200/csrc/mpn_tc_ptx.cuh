@@ -81,6 +81,17 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   return d;
 }
 
+// MN-major operand, 128-byte swizzle: 64-element MN blocks LBO bytes apart, 8-row K groups SBO bytes apart
+__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 #define TMEM_LD_32x32b_X32(taddr, v)                                                                                     \
   asm volatile(                                                                                                          \
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \

@@ -41,17 +41,6 @@ struct WParams {
   float* dw;
 };
 
-// MN-major operand, 128-byte swizzle: 64-element MN blocks LBO bytes apart, 8-row K groups SBO bytes apart
-__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(lbo_bytes >> 4) << 16;
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
 template <int BN, bool SPLIT, int STAGES>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WParams P) {
   constexpr int PLANES = SPLIT ? 2 : 1;

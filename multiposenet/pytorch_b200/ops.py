@@ -65,8 +65,12 @@ class PackedConv(object):
     __slots__ = ("Cout", "Cin", "R", "S", "fmt", "w_hi", "w_lo", "cout_pad", "scale", "bias")
 
 
-def pack_conv(weight, bias, bn, fmt):
-    """weight OIHW fp32 cuda; bias fp32 or None; bn = (gamma, beta, mean, var, eps) or None."""
+def pack_conv(weight, bias, bn, fmt, fold_scale=True):
+    """weight OIHW fp32 cuda; bias fp32 or None; bn = (gamma, beta, mean, var, eps) or None.
+
+    fold_scale (bf16 formats): the eval-mode BN scale is multiplied into the filter before the hi/lo split, so the
+    epilogue adds only the folded bias (and a residual can be accumulated on the tensor core); False keeps scale in
+    the epilogue."""
     L = _lib.lib()
     w = weight.detach().contiguous()
     assert w.is_cuda and w.dtype == torch.float32
@@ -74,17 +78,8 @@ def pack_conv(weight, bias, bn, fmt):
     pc.Cout, pc.Cin, pc.R, pc.S = w.shape
     pc.fmt = fmt
     dev = w.device
-    if fmt == FMT_F32:
-        pc.cout_pad = (pc.Cout + 63) // 64 * 64
-        pc.w_hi = torch.empty((pc.R, pc.S, pc.Cin, pc.cout_pad), dtype=torch.float32, device=dev)
-        pc.w_lo = None
-        check(L.mpn_pack_filter_f32(_ptr(w), _ptr(pc.w_hi), pc.Cout, pc.Cin, pc.R, pc.S, pc.cout_pad, _stream()), "mpn_pack_filter_f32")
-    else:
-        pc.cout_pad = pc.Cout
-        pc.w_hi = torch.empty((pc.Cout, pc.R, pc.S, pc.Cin), dtype=torch.bfloat16, device=dev)
-        pc.w_lo = torch.empty_like(pc.w_hi) if fmt == FMT_BF16X2 else None
-        check(L.mpn_pack_filter_bf16(_ptr(w), _ptr(pc.w_hi), _ptr(pc.w_lo), pc.Cout, pc.Cin, pc.R, pc.S, _stream()), "mpn_pack_filter_bf16")
     npad = (pc.Cout + 63) // 64 * 64
+    pc.scale = pc.bias = None
     if bn is not None:
         gamma, beta, mean, var, eps = bn
         pc.scale = torch.zeros(npad, dtype=torch.float32, device=dev)
@@ -92,13 +87,23 @@ def pack_conv(weight, bias, bn, fmt):
         check(L.mpn_fold_bn(_ptr(gamma.detach().contiguous()), _ptr(beta.detach().contiguous()), _ptr(mean.contiguous()),
                             _ptr(var.contiguous()), float(eps), _ptr(pc.scale), _ptr(pc.bias), pc.Cout, _stream()), "mpn_fold_bn")
         assert bias is None
+    elif bias is not None:
+        pc.bias = torch.zeros(npad, dtype=torch.float32, device=dev)
+        pc.bias[: pc.Cout].copy_(bias.detach())
+    if fmt == FMT_F32:
+        pc.cout_pad = npad
+        pc.w_hi = torch.empty((pc.R, pc.S, pc.Cin, pc.cout_pad), dtype=torch.float32, device=dev)
+        pc.w_lo = None
+        check(L.mpn_pack_filter_f32(_ptr(w), _ptr(pc.w_hi), pc.Cout, pc.Cin, pc.R, pc.S, pc.cout_pad, _stream()), "mpn_pack_filter_f32")
     else:
-        pc.scale = None
-        if bias is not None:
-            pc.bias = torch.zeros(npad, dtype=torch.float32, device=dev)
-            pc.bias[: pc.Cout].copy_(bias.detach())
-        else:
-            pc.bias = None
+        pc.cout_pad = pc.Cout
+        pc.w_hi = torch.empty((pc.Cout, pc.R, pc.S, pc.Cin), dtype=torch.bfloat16, device=dev)
+        pc.w_lo = torch.empty_like(pc.w_hi) if fmt == FMT_BF16X2 else None
+        fold = fold_scale and pc.scale is not None
+        check(L.mpn_pack_filter_bf16_scaled(_ptr(w), _ptr(pc.scale) if fold else None, _ptr(pc.w_hi), _ptr(pc.w_lo), pc.Cout, pc.Cin,
+                                            pc.R, pc.S, _stream()), "mpn_pack_filter_bf16_scaled")
+        if fold:
+            pc.scale = None
     return pc
 
 
