@@ -171,6 +171,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
+  // previous kernel in the stream; its results are visible after the wait.  The next kernel may start its own prologue
+  // as soon as every CTA of this grid got here.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0 && lane == 0) {
     // =============================== TMA producer ===============================
@@ -636,7 +641,19 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
   auto kern = conv_tc_kernel<BN, SPLIT, STAGES, EPI>;
   MPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = P.total_tiles < sms ? P.total_tiles : sms;
-  kern<<<grid, NUM_THREADS, smem, st>>>(maps, P);
+  static const int pdl = getenv("MPN_PDL") ? atoi(getenv("MPN_PDL")) : 0;  // opt-in: no step-time gain inside a CUDA graph (r01l)
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  MPN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, P));
   MPN_LAUNCH_OK();
   return MPN_OK;
 }

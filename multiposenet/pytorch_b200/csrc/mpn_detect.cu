@@ -125,18 +125,6 @@ __global__ void gather_sorted_kernel(const float* __restrict__ boxes, int box_st
   }
 }
 
-__device__ __forceinline__ float dev_iou(const float* a, const float* b) {
-  // nms_kernel.cu:16-24, operation for operation
-  float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
-  float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
-  float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
-  float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
-  float interS = __fmul_rn(width, height);
-  float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a[2], a[0]), 1.f), __fadd_rn(__fsub_rn(a[3], a[1]), 1.f));
-  float Sb = __fmul_rn(__fadd_rn(__fsub_rn(b[2], b[0]), 1.f), __fadd_rn(__fsub_rn(b[3], b[1]), 1.f));
-  return __fdiv_rn(interS, __fsub_rn(__fadd_rn(Sa, Sb), interS));
-}
-
 // grid (upper-triangle block pair, 1, image): only col_block >= row_block exists (the reduction never
 // reads the lower triangle, nms_cuda.c:52).  64 threads: thread t owns row box row_block*64+t.
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sdets, const int32_t* __restrict__ cand_cnt,
@@ -155,10 +143,14 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   if (row_start * 64 >= n || col_start * 64 >= n) return;
   const int row_size = min(n - row_start * 64, 64), col_size = min(n - col_start * 64, 64);
   const float* dets = sdets + (long long)b * max_cand * 5;
-  __shared__ float block_boxes[64 * 5];
+  __shared__ float block_boxes[64 * 5];  // x1 y1 x2 y2 area  (area = (x2-x1+1)*(y2-y1+1), nms_kernel.cu:22-23)
   if (threadIdx.x < col_size) {
+    float bx[4];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) block_boxes[threadIdx.x * 5 + k] = dets[(long long)(64 * col_start + threadIdx.x) * 5 + k];
+    for (int k = 0; k < 4; ++k) bx[k] = dets[(long long)(64 * col_start + threadIdx.x) * 5 + k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) block_boxes[threadIdx.x * 5 + k] = bx[k];
+    block_boxes[threadIdx.x * 5 + 4] = __fmul_rn(__fadd_rn(__fsub_rn(bx[2], bx[0]), 1.f), __fadd_rn(__fsub_rn(bx[3], bx[1]), 1.f));
   }
   __syncthreads();
   if (threadIdx.x < row_size) {
@@ -166,59 +158,85 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
     float cb[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) cb[k] = dets[(long long)cur * 5 + k];
+    const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(cb[2], cb[0]), 1.f), __fadd_rn(__fsub_rn(cb[3], cb[1]), 1.f));
     unsigned long long t = 0;
     int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
-    const bool fast_ok = thr > 1e-3f;  // the shortcuts below assume a positive threshold
+    // The shortcuts assume a positive finite threshold.  (1) disjoint boxes: interS == 0 exactly -> IoU is 0 (or NaN for a
+    // 0/0 union), never above the threshold.  (2) interS vs thr*union with a 1e-6 relative guard band (8 ulps, the
+    // products carry < 1 ulp of rounding): outside the band the correctly rounded quotient of nms_kernel.cu:24 is
+    // certainly above / below thr, so the division is only evaluated inside the band.
+    const bool fast_ok = thr > 1e-3f && thr < 1e3f;
     for (int i = start; i < col_size; ++i) {
       const float* bb = block_boxes + i * 5;
-      if (fast_ok) {
-        // disjoint boxes: interS == 0 exactly -> IoU is 0 (or NaN for a 0/0 union): never above a positive threshold
-        float w = __fadd_rn(__fsub_rn(fminf(cb[2], bb[2]), fmaxf(cb[0], bb[0])), 1.f);
-        float h = __fadd_rn(__fsub_rn(fminf(cb[3], bb[3]), fmaxf(cb[1], bb[1])), 1.f);
-        if (!(w > 0.f) || !(h > 0.f)) continue;
+      const float w = __fadd_rn(__fsub_rn(fminf(cb[2], bb[2]), fmaxf(cb[0], bb[0])), 1.f);
+      const float h = __fadd_rn(__fsub_rn(fminf(cb[3], bb[3]), fmaxf(cb[1], bb[1])), 1.f);
+      if (fast_ok && (!(w > 0.f) || !(h > 0.f))) continue;
+      const float interS = __fmul_rn(fmaxf(w, 0.f), fmaxf(h, 0.f));
+      const float uni = __fsub_rn(__fadd_rn(Sa, bb[4]), interS);
+      bool over;
+      const float pth = __fmul_rn(thr, uni);
+      if (fast_ok && uni > 0.f && interS > __fmul_rn(pth, 1.000001f)) {
+        over = true;
+      } else if (fast_ok && uni > 0.f && interS < __fmul_rn(pth, 0.999999f)) {
+        over = false;
+      } else {
+        const float v = __fdiv_rn(interS, uni);
+        over = ge ? (v >= thr) : (v > thr);
       }
-      float v = dev_iou(cb, bb);
-      if (ge ? (v >= thr) : (v > thr)) t |= 1ULL << i;
+      if (over) t |= 1ULL << i;
     }
     mask[((long long)b * max_cand + cur) * cb_stride + col_start] = t;
   }
 }
 
-// One CTA per image: the serial host loop of nms_cuda.c:46-58, 64 boxes at a time.
+// One CTA per image: the serial host loop of nms_cuda.c:46-58, 64 boxes at a time.  Per 64-box block the critical path is
+// (a) resolving the block against its own diagonal mask word by word -- only over the still-alive boxes -- and (b) OR-ing
+// the rows of the boxes it keeps into the later column blocks; the next block's diagonal words are prefetched meanwhile,
+// and the kept boxes are written out in parallel after the scan.
 __global__ void __launch_bounds__(128) nms_reduce_kernel(const unsigned long long* __restrict__ mask,
                                                         const int32_t* __restrict__ cand_cnt, int max_cand, int cb_stride,
                                                         const int32_t* __restrict__ ranks_sorted,
                                                         const float* __restrict__ sdets, int64_t* __restrict__ keep_idx,
                                                         int32_t* __restrict__ keep_cnt, float* __restrict__ out_scores,
                                                         float* __restrict__ out_boxes) {
-  extern __shared__ unsigned long long remv[];  // cb_stride words
-  __shared__ unsigned long long diag[64];
-  __shared__ unsigned long long keepbits_s;
-  __shared__ int kept_total;
+  extern __shared__ unsigned long long dyn[];  // remv[cb_stride] | keepbits[cb_stride] | prefix[cb_stride + 1] (as int)
+  unsigned long long* remv = dyn;
+  unsigned long long* keepbits = dyn + cb_stride;
+  int* prefix = reinterpret_cast<int*>(dyn + 2 * cb_stride);
+  __shared__ unsigned long long diag[2][64];
   const int b = blockIdx.x, tid = threadIdx.x;
   int n = cand_cnt[b];
   n = n < max_cand ? n : max_cand;
   const int col_blocks = (n + 63) / 64;
-  for (int j = tid; j < cb_stride; j += blockDim.x) remv[j] = 0ULL;
-  if (tid == 0) kept_total = 0;
-  __syncthreads();
+  for (int j = tid; j < cb_stride; j += blockDim.x) { remv[j] = 0ULL; keepbits[j] = 0ULL; }
   const unsigned long long* m = mask + (long long)b * max_cand * cb_stride;
+  if (tid < 64 && col_blocks > 0) diag[0][tid] = tid < min(n, 64) ? m[(long long)tid * cb_stride] : 0ULL;
+  __syncthreads();
   for (int rb = 0; rb < col_blocks; ++rb) {
     const int rows = min(n - rb * 64, 64);
-    if (tid < 64) diag[tid] = tid < rows ? m[(long long)(rb * 64 + tid) * cb_stride + rb] : 0ULL;
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long cur = remv[rb], kb = 0ULL;
-      for (int t = 0; t < rows; ++t) {
-        if (!((cur >> t) & 1ULL)) {
-          kb |= 1ULL << t;
-          cur |= diag[t];
-        }
-      }
-      keepbits_s = kb;
+    const unsigned long long* dg = diag[rb & 1];
+    // prefetch the next block's diagonal words (independent of the scan state)
+    unsigned long long nd = 0ULL;
+    if (tid >= 64 && rb + 1 < col_blocks) {
+      const int r = tid - 64, nrows = min(n - (rb + 1) * 64, 64);
+      if (r < nrows) nd = m[(long long)((rb + 1) * 64 + r) * cb_stride + rb + 1];
     }
+    if (tid == 0) {
+      const unsigned long long valid = rows == 64 ? ~0ULL : ((1ULL << rows) - 1ULL);
+      unsigned long long cur = remv[rb], kb = 0ULL;
+      unsigned long long alive = ~cur & valid;
+      while (alive) {  // boxes are visited in score order; diag[t] only has bits above t
+        const int t = __ffsll((long long)alive) - 1;
+        kb |= 1ULL << t;
+        cur |= dg[t];
+        alive &= ~cur;
+        alive &= ~((2ULL << t) - 1ULL);
+      }
+      keepbits[rb] = kb;
+    }
+    if (tid >= 64 && rb + 1 < col_blocks) diag[(rb + 1) & 1][tid - 64] = nd;
     __syncthreads();
-    const unsigned long long kb = keepbits_s;
+    const unsigned long long kb = keepbits[rb];
     // later column blocks: OR in the rows of every kept box of this block
     for (int j = rb + 1 + tid; j < col_blocks; j += blockDim.x) {
       unsigned long long acc = remv[j];
@@ -230,23 +248,29 @@ __global__ void __launch_bounds__(128) nms_reduce_kernel(const unsigned long lon
       }
       remv[j] = acc;
     }
-    // emit the kept boxes of this block in order
-    if (tid < 64 && ((kb >> tid) & 1ULL)) {
-      int pos = kept_total + __popcll(kb & ((1ULL << tid) - 1ULL));
-      long long o = (long long)b * max_cand;
-      int srt = rb * 64 + tid;  // position in the sorted list
-      keep_idx[o + pos] = (int64_t)ranks_sorted[o + srt];
-      if (out_scores) out_scores[o + pos] = sdets[(o + srt) * 5 + 4];
-      if (out_boxes) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) out_boxes[(o + pos) * 4 + k] = sdets[(o + srt) * 5 + k];
-      }
-    }
-    __syncthreads();
-    if (tid == 0) kept_total += __popcll(kb);
     __syncthreads();
   }
-  if (tid == 0) keep_cnt[b] = kept_total;
+  // exclusive prefix of the per-block keep counts (col_blocks <= a few hundred: one thread)
+  if (tid == 0) {
+    int run = 0;
+    for (int j = 0; j < col_blocks; ++j) { prefix[j] = run; run += __popcll(keepbits[j]); }
+    prefix[col_blocks] = run;
+    keep_cnt[b] = run;
+  }
+  __syncthreads();
+  const long long o = (long long)b * max_cand;
+  for (int srt = tid; srt < n; srt += blockDim.x) {
+    const int rb = srt >> 6, t = srt & 63;
+    const unsigned long long kb = keepbits[rb];
+    if (!((kb >> t) & 1ULL)) continue;
+    const int pos = prefix[rb] + __popcll(kb & ((1ULL << t) - 1ULL));
+    keep_idx[o + pos] = (int64_t)ranks_sorted[o + srt];
+    if (out_scores) out_scores[o + pos] = sdets[(o + srt) * 5 + 4];
+    if (out_boxes) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) out_boxes[(o + pos) * 4 + k] = sdets[(o + srt) * 5 + k];
+    }
+  }
 }
 
 struct Workspace {
@@ -314,8 +338,11 @@ int run_core(const float* boxes, int box_stride, long long box_image_stride, int
   dim3 mg(cb * (cb + 1) / 2, 1, B);
   nms_mask_kernel<<<mg, 64, 0, st>>>(w.sdets, cand_cnt, 0, max_cand, cb, cb, iou_thr, ge, w.mask);
   MPN_LAUNCH_OK();
-  nms_reduce_kernel<<<B, 128, cb * sizeof(unsigned long long), st>>>(w.mask, cand_cnt, max_cand, cb, w.ranks_out, w.sdets,
-                                                                     keep_idx, keep_cnt, out_scores, out_boxes);
+  const size_t red_smem = (size_t)(2 * cb + (cb + 2) / 2) * sizeof(unsigned long long);
+  MPN_CHECK_ARG(red_smem <= 200 * 1024, "nms: too many candidates for the on-device reduction (%d)", max_cand);
+  if (red_smem > 48 * 1024) MPN_CUDA_OK(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+  nms_reduce_kernel<<<B, 128, red_smem, st>>>(w.mask, cand_cnt, max_cand, cb, w.ranks_out, w.sdets, keep_idx, keep_cnt, out_scores,
+                                              out_boxes);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
