@@ -185,7 +185,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const TileCoord tc = decode_tile<BN>(P, tile);
       const bool tail = tc.ncols != BN;
       const uint32_t tx_bytes = (uint32_t)PLANES * (uint32_t)((P.rows + tc.ncols) * BLOCK_K * 2);
+      // narrow tail tiles are latency-bound on the ring: pack as many K blocks as fit into one stage (sub-blocks of
+      // [A planes][B planes], the B planes ncols*128 bytes apart) so that twice the bytes are in flight
+      const uint32_t bplane = tail ? (uint32_t)tc.ncols * 128u : (uint32_t)B_TILE_BYTES;
+      const uint32_t sub_bytes = (uint32_t)PLANES * ((uint32_t)A_TILE_BYTES + bplane);
+      const int kpack = tail ? (int)(STAGE_BYTES / sub_bytes) : 1;
       const int ow0 = tc.tw_i * P.TW, oh0 = tc.th_i * P.TH, n0 = tc.tn_i * P.TN, co0 = tc.co0;
+      int u = 0, ki = 0;
       for (int tap = 0; tap < P.R * P.S; ++tap) {
         const int r = tap / P.S, s = tap - r * P.S;
         const int dh = r - P.pad, dw = s - P.pad;
@@ -204,17 +210,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           hc = 1 << 24;
         }
         for (int kb = 0; kb < P.kb_per_tap; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), tx_bytes);
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          if (u == 0) {
+            const int group = min(kpack, num_k_iters - ki);
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), tx_bytes * (uint32_t)group);
+          }
+          const uint32_t sa = smem_base + stage * STAGE_BYTES + u * sub_bytes;
           const uint32_t sb = sa + PLANES * A_TILE_BYTES;
           const int kcol = tap * P.Cin + kb * BLOCK_K;
 #pragma unroll
           for (int p = 0; p < PLANES; ++p) {
             tma_load_4d(sa + p * A_TILE_BYTES, &maps.a[p][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
-            tma_load_2d(sb + p * B_TILE_BYTES, tail ? &maps.bs[p] : &maps.b[p], full_bar(stage), kcol, co0);
+            tma_load_2d(sb + p * bplane, tail ? &maps.bs[p] : &maps.b[p], full_bar(stage), kcol, co0);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          ++ki;
+          if (++u == kpack || ki == num_k_iters) {
+            u = 0;
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
       }
       if (EPI == EPI_TMA && P.res_mma) {
@@ -246,25 +259,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const int ncols = decode_tile<BN>(P, tile).ncols;
       const uint32_t IDESC = IDESC_BASE | ((uint32_t)(ncols >> 3) << 17);
       const bool res_mma = EPI == EPI_TMA && P.res_mma;
-      for (int ki = 0; ki < num_k_iters; ++ki) {
+      const bool tail = ncols != BN;
+      const uint32_t bplane = tail ? (uint32_t)ncols * 128u : (uint32_t)B_TILE_BYTES;
+      const uint32_t sub_bytes = (uint32_t)PLANES * ((uint32_t)A_TILE_BYTES + bplane);
+      const int kpack = tail ? (int)(STAGE_BYTES / sub_bytes) : 1;
+      for (int ki = 0; ki < num_k_iters;) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-        const uint32_t sb = sa + PLANES * A_TILE_BYTES;
+        const int group = min(kpack, num_k_iters - ki);
+        for (int u = 0; u < group; ++u, ++ki) {
+          const uint32_t sa = smem_base + stage * STAGE_BYTES + u * sub_bytes;
+          const uint32_t sb = sa + PLANES * A_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          const uint64_t a_hi = make_sdesc(sa + k * 32);
-          const uint64_t b_hi = make_sdesc(sb + k * 32);
-          umma_bf16(d_tmem, a_hi, b_hi, IDESC, (ki > 0 || k > 0) ? 1u : 0u);
-          if (SPLIT) {
-            const uint64_t a_lo = make_sdesc(sa + A_TILE_BYTES + k * 32);
-            const uint64_t b_lo = make_sdesc(sb + B_TILE_BYTES + k * 32);
-            umma_bf16(d_tmem, a_lo, b_hi, IDESC, 1u);
-            umma_bf16(d_tmem, a_hi, b_lo, IDESC, 1u);
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t a_hi = make_sdesc(sa + k * 32);
+            const uint64_t b_hi = make_sdesc(sb + k * 32);
+            umma_bf16(d_tmem, a_hi, b_hi, IDESC, (ki > 0 || k > 0) ? 1u : 0u);
+            if (SPLIT) {
+              const uint64_t a_lo = make_sdesc(sa + A_TILE_BYTES + k * 32);
+              const uint64_t b_lo = make_sdesc(sb + bplane + k * 32);
+              umma_bf16(d_tmem, a_lo, b_hi, IDESC, 1u);
+              umma_bf16(d_tmem, a_hi, b_lo, IDESC, 1u);
+            }
           }
         }
-        umma_commit(empty_bar(stage));                                        // frees the smem stage when the MMAs retire
-        if (ki == num_k_iters - 1 && !res_mma) umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        umma_commit(empty_bar(stage));                                    // frees the smem stage when the MMAs retire
+        if (ki == num_k_iters && !res_mma) umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       if (res_mma) {
@@ -710,13 +730,13 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   int BN = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
   int tail_s = 1;
   {
-    int cand[2] = {BN, 0};
+    int cand[3] = {BN, 0, 0};
     if (BN == 256) {
       if (split256 == 0) cand[0] = 128;
       else if (split256 < 0) cand[1] = 128;
     }
     double best = 1e30;
-    for (int ci = 0; ci < 2 && cand[ci]; ++ci) {
+    for (int ci = 0; ci < 3 && cand[ci]; ++ci) {
       const int bn = cand[ci];
       const long long T = m_tiles * mpn_divup(d->Cout, bn);
       const long long G = T < sms ? T : sms;
