@@ -466,7 +466,11 @@ def main():
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (%d launches/step)" % nconv, "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": pk_src + " (sustained cuBLAS bf16)",
                 "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / (elapsed_ms / args.steps),
-                "note": "algorithmic conv FLOPs (2*MAC, fp32-equivalent); bf16x3 issues 3 MMAs per algorithmic MAC"}
+                "mma_passes": 3 if args.precision == "bf16x3" else 1,
+                "tensor_pipe_frac": (3 if args.precision == "bf16x3" else 1) * achieved / peak,
+                "note": "achieved = algorithmic conv FLOPs (2*MAC, fp32-equivalent) / conv kernel time; bf16x3 issues 3 MMAs per "
+                        "algorithmic MAC (hi*hi + lo*hi + hi*lo), so tensor_pipe_frac = 3*frac is the share of the tensor peak the "
+                        "issued MMAs occupy"}
 
     # ---- optional: single-pass bf16 throughput (not the parity mode; reported beside the headline)
     fast = None

@@ -36,6 +36,15 @@ TC_CASES = [
     (3, 1, 2, 256, 256, 3, 2, 1, dict()),                                           # conv7: empty phase views
     (2, 60, 80, 64, 256, 1, 1, 0, dict(bn=True, relu=True, bias=False)),            # many tiles / persistence
     (1, 24, 32, 512, 256, 3, 1, 1, dict(relu=True)),                                # long K loop (72 k-iters)
+    # tile-plan / epilogue variants of the persistent kernel
+    (16, 30, 40, 64, 256, 3, 1, 1, dict(bn=True, relu=True, bias=False)),           # 160 tiles: tail cut into 32-col sub-tiles, 2 K blocks/stage
+    (8, 30, 40, 64, 256, 3, 1, 1, dict(bn=True, relu=True, bias=False)),            # 128-wide plan with a 32-col tail
+    (16, 30, 40, 64, 256, 1, 1, 0, dict(bn=True, residual=True, relu=True, bias=False)),  # tensor-core residual, 120-row boxes, 64-col tail
+    (4, 16, 32, 128, 512, 1, 1, 0, dict(bn=True, residual=True, relu=True, bias=False)),  # tensor-core residual, two channel tiles
+    (2, 8, 8, 128, 320, 1, 1, 0, dict(bn=True, residual=True, bias=False)),         # residual box partly beyond Cout
+    (2, 8, 8, 128, 96, 1, 1, 0, dict(bn=True, residual=True, relu=True, bias=False)),     # Cout % 64 != 0: residual through the LSU
+    (2, 8, 8, 128, 128, 1, 1, 0, dict(residual=True)),                              # residual without BN / bias (data-gradient accumulation)
+    (1, 10, 12, 128, 128, 3, 1, 1, dict(coffset=128, ctotal=512)),                  # TMA store into a channel slice of a wider tensor
 ]
 
 
