@@ -203,6 +203,19 @@ int mpn_nms(const float* dets, int n, float iou_thresh, int ge, int64_t* keep, i
 /* mask stage alone on already-sorted dets (== _nms() of nms_kernel.cu:73): mask [n, ceil(n/64)] u64 */
 int mpn_nms_mask(const float* sorted_dets, int n, float iou_thresh, int ge, uint64_t* mask, void* stream);
 
+/* ---- heat-map peak extraction (the step after the path)
+ * network/joint_utils.py:19-32 (find_peaks: 3x3-cross maximum == value and value > thre1), :61-138 (NMS: every peak's
+ * <=5x5 patch upsampled x factor with cv2.INTER_CUBIC, first arg-max = refined location and score, ids counting up over
+ * the joint types) and :141-152 (get_joint_list rows), as called by evaluate/tester.py:215-221 with factor = 480/120.
+ *   heat  : fp32 [B][C][H][W] (image_stride elements between images, >= C*H*W: pass the 18 used channels of a 19-channel map)
+ *   peaks : fp32 [B][max_peaks][5] rows (x, y, score, id, joint_type) in the reference's order (joint type, then row-major);
+ *           x, y are integers in the factor-times-upsampled grid (the caller multiplies by its image scale, :146-147)
+ *   count : int32 [B] number of peaks found (rows beyond max_peaks are counted, not written)
+ * The bicubic arithmetic is OpenCV's (Keys A = -0.75, half-pixel centres, clamped taps) in unfused fp32. */
+size_t mpn_heatmap_peaks_workspace_bytes(int B, int C);
+int mpn_heatmap_peaks(const float* heat, int B, int C, int H, int W, long long image_stride, float thre1, int factor,
+                      float* peaks, int max_peaks, int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,9 @@ _SIGS = {
     "mpn_nms_workspace_bytes": (c_size_t, [c_int]),
     "mpn_nms": (c_int, [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mpn_nms_mask": (c_int, [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "mpn_heatmap_peaks_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mpn_heatmap_peaks": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_ll, c_float, c_int, c_void_p, c_int, c_void_p,
+                                  c_void_p, c_size_t, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS.keys())

@@ -328,3 +328,23 @@ def nms_mask(sorted_dets, thresh, ge=False):
     mask = torch.zeros((n, cb), dtype=torch.int64, device=sorted_dets.device)
     check(_lib.lib().mpn_nms_mask(_ptr(sorted_dets.contiguous()), n, float(thresh), int(bool(ge)), _ptr(mask), _stream()), "mpn_nms_mask")
     return mask
+
+
+def heatmap_peaks(heat, thre1=0.1, factor=4, max_peaks=1024, channels=18):
+    """joint_utils.NMS + get_joint_list on the device (network/joint_utils.py:61-152, tester.py:215-221).
+
+    heat: CUDA fp32 [B, C>=channels, H, W] heat maps.  Returns (rows fp32 [B, max_peaks, 5] = (x, y, score, id, joint_type)
+    in the reference's order, count int32 [B]); coordinates are in the factor-times-upsampled grid (multiply by the
+    caller's image scale, joint_utils.py:146-147)."""
+    assert heat.is_cuda and heat.dtype == torch.float32 and heat.dim() == 4 and heat.shape[1] >= channels
+    heat = heat.contiguous()
+    B, C, H, W = heat.shape
+    L = _lib.lib()
+    rows = torch.zeros((B, max_peaks, 5), dtype=torch.float32, device=heat.device)
+    count = torch.zeros((B,), dtype=torch.int32, device=heat.device)
+    wsb = L.mpn_heatmap_peaks_workspace_bytes(B, channels)
+    ws = torch.empty((max(wsb, 4),), dtype=torch.uint8, device=heat.device)
+    check(L.mpn_heatmap_peaks(_ptr(heat), B, channels, H, W, C * H * W, float(thre1), int(factor), _ptr(rows), max_peaks, _ptr(count),
+                              _ptr(ws), wsb, _stream()), "mpn_heatmap_peaks")
+    stats["launches"] += 2
+    return rows, count

@@ -119,6 +119,20 @@ def main():
             nm["%s_keep_gt_%g" % (k, thr)] = kg
             nm["%s_keep_ge_%g" % (k, thr)] = kc
     np.savez_compressed(os.path.join(OUT, "nms.npz"), **nm)
+    # heat-map peaks: the reference's own get_joint_list (scipy maximum_filter + cv2.resize INTER_CUBIC of this container)
+    from network.joint_utils import get_joint_list
+    from . import peaks_oracle
+    pk = {"cv2": np.array(__import__("cv2").__version__)}
+    small = peaks_oracle.synthetic_heatmaps(5, C=18, H=24, W=32, persons=2)
+    pk["small_heat"] = small
+    pk["small_rows"] = get_joint_list(np.zeros((96, 128, 3), np.float32), {"thre1": 0.1}, np.ascontiguousarray(small.transpose(1, 2, 0)), 1.0)
+    pk["small_rows_f2"] = get_joint_list(np.zeros((48, 64, 3), np.float32), {"thre1": 0.1}, np.ascontiguousarray(small.transpose(1, 2, 0)), 1.0)
+    for seed in (1, 2):  # full-size maps are regenerated from the seed (peaks_oracle.synthetic_heatmaps); checksum pins them
+        hm = peaks_oracle.synthetic_heatmaps(seed)
+        pk["seed%d_sum" % seed] = np.array(hm.astype(np.float64).sum())
+        pk["seed%d_rows" % seed] = get_joint_list(np.zeros((480, 640, 3), np.float32), {"thre1": 0.1},
+                                                  np.ascontiguousarray(hm.transpose(1, 2, 0)), 1.0)
+    np.savez_compressed(os.path.join(OUT, "peaks.npz"), **pk)
     print("wrote", sorted(os.listdir(OUT)))
 
 

@@ -126,3 +126,52 @@ def test_resnet_preprocess_bit_exact(golden_dir):
     g = _load(golden_dir, "preprocess.npz")
     for a, b in (("img", "out"), ("full", "out_full")):
         assert np.array_equal(resnet_preprocess(g[a]).view(np.uint32), g[b].view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------
+# heat-map peak extraction (joint_utils.py:19-32, 61-152)
+def _check_rows(mine, gold, score_tol=1e-6):
+    assert mine.shape == gold.shape
+    assert np.array_equal(mine[:, [0, 1, 3, 4]], gold[:, [0, 1, 3, 4]])   # x, y, id, joint type: exact
+    assert np.abs(mine[:, 2] - gold[:, 2]).max() <= score_tol            # cv2's SIMD build vs unfused float32
+
+
+def test_peaks_oracle_vs_reference_goldens(golden_dir):
+    from oracle import peaks_oracle
+    g = _load(golden_dir, "peaks.npz")
+    _check_rows(peaks_oracle.joint_list(g["small_heat"], 0.1, 4), g["small_rows"])
+    _check_rows(peaks_oracle.joint_list(g["small_heat"], 0.1, 2), g["small_rows_f2"])
+    hm = peaks_oracle.synthetic_heatmaps(1)
+    assert abs(float(hm.astype(np.float64).sum()) - float(g["seed1_sum"])) < 1e-3   # the seeded maps are the golden's maps
+    _check_rows(peaks_oracle.joint_list(hm, 0.1, 4), g["seed1_rows"])
+
+
+def test_peaks_oracle_edge_cases():
+    from oracle import peaks_oracle
+    H, W = 24, 32
+    hm = peaks_oracle.synthetic_heatmaps(5, C=6, H=H, W=W, persons=1)
+    as_set = lambda a: {tuple(int(v) for v in r) for r in a}
+    assert (0, 0) in as_set(peaks_oracle.find_peaks(hm[0], 0.1))                                 # corner
+    assert (7, H - 1) in as_set(peaks_oracle.find_peaks(hm[1], 0.1))                             # bottom edge
+    assert {(W // 3, H // 3), (W // 3 + 1, H // 3)} <= as_set(peaks_oracle.find_peaks(hm[2], 0.1))  # both plateau pixels
+    assert (W - 1, H // 2) in as_set(peaks_oracle.find_peaks(hm[3], 0.1))                        # right edge
+    assert (10, 10) not in as_set(peaks_oracle.find_peaks(hm[4], 0.1))                           # == thre1 is not a peak
+    rows = peaks_oracle.joint_list(hm, 0.1, 4)
+    assert np.array_equal(rows[:, 3], np.arange(len(rows)))                                      # ids count up over joint types
+    assert (np.diff(rows[:, 4]) >= 0).all()                                                      # grouped by joint type
+    assert len(peaks_oracle.joint_list(np.zeros((3, 8, 8), np.float32), 0.1, 4)) == 0            # empty maps
+
+
+def test_peaks_oracle_vs_live_reference():
+    pytest.importorskip("cv2")
+    from oracle import peaks_oracle, refshim
+    if not os.path.isdir(refshim.REF_ROOT):
+        pytest.skip("reference checkout not present (GPU box)")
+    refshim.import_reference()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from network.joint_utils import get_joint_list
+    hm = peaks_oracle.synthetic_heatmaps(9, C=18, H=40, W=56, persons=3)
+    gold = get_joint_list(np.zeros((160, 224, 3), np.float32), {"thre1": 0.1}, np.ascontiguousarray(hm.transpose(1, 2, 0)), 1.0)
+    _check_rows(peaks_oracle.joint_list(hm, 0.1, 4), gold)
