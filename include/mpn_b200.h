@@ -216,6 +216,30 @@ size_t mpn_heatmap_peaks_workspace_bytes(int B, int C);
 int mpn_heatmap_peaks(const float* heat, int B, int C, int H, int W, long long image_stride, float thre1, int factor,
                       float* peaks, int max_peaks, int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- PRN assignment: evaluate/tester.py:333-513 (Tester.prn_process) for every person box of a
+ * batch of images.  Peaks are the joint-list rows of the images regrouped by (image, joint type) in their original order
+ * (:337-350, the neck row dropped by the caller, tester.py:224-229); a peak's id is its index in that order.
+ *   peak_xy        f64 [n_peaks][2]   peak_type i32 [n_peaks] (0..16)   peak_img_start i32 [B+1]
+ *   joint_start    i32 [B][18]  first peak of joint type t of image b (entry 17 = end of the image's peaks)
+ *   boxes_xywh     f64 [P][4]   (x1, y1, x2-x1, y2-y1) (:356-358), boxes sorted by image
+ *   box_img        i32 [P]      box_img_start i32 [B+1]
+ *   gauss_w_host   f64 [5]      HOST: scipy's normalised sigma=1 weights, index = distance from the centre
+ *   owner          i32 [P][17][gh][gw]  id of the peak in each grid cell (-1 = none), written by build_inputs
+ *   inp / output   f32 [P][gh][gw][17]  PRN input (gaussian-blurred one-hots, :396-403) / PRN output (posenet.py:337-350)
+ *   bbox_keypoints f64 [P][17][3]       (x, y, 1) of the assigned peak, (x, y, 0) of the arg-max fallback, else zeros (:451-483)
+ * kmax >= the largest number of peaks of one image.  workspace is shared by the two calls (build_inputs leaves the
+ * per-plane occupancy there for assign).  Index decisions use unfused float64 / float32 arithmetic in the reference's
+ * operation order (scipy's correlate1d, numpy's pairwise float32 sum). */
+size_t mpn_prn_workspace_bytes(int P, int n_peaks, int kmax);
+int mpn_prn_build_inputs(const double* peak_xy, const int32_t* peak_type, const int32_t* peak_img_start, int n_peaks,
+                         const double* boxes_xywh, const int32_t* box_img, int P, int gh, int gw, double in_thres,
+                         const double* gauss_w_host, int32_t* owner, float* inp, void* workspace, size_t workspace_bytes,
+                         int kmax, void* stream);
+int mpn_prn_assign(const double* peak_xy, const int32_t* peak_img_start, const int32_t* joint_start, int n_peaks,
+                   const double* boxes_xywh, const int32_t* box_img, const int32_t* box_img_start, int P, int B, int gh, int gw,
+                   const int32_t* owner, const float* output, double* bbox_keypoints, void* workspace,
+                   size_t workspace_bytes, int kmax, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

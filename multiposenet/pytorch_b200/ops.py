@@ -348,3 +348,44 @@ def heatmap_peaks(heat, thre1=0.1, factor=4, max_peaks=1024, channels=18):
                               _ptr(ws), wsb, _stream()), "mpn_heatmap_peaks")
     stats["launches"] += 2
     return rows, count
+
+
+# ------------------------------------------------------------------ PRN assignment (evaluate/tester.py:333-513)
+def prn_workspace(P, n_peaks, kmax, device):
+    wsb = _lib.lib().mpn_prn_workspace_bytes(P, n_peaks, kmax)
+    return torch.empty((max(int(wsb), 8),), dtype=torch.uint8, device=device), int(wsb)
+
+
+def prn_build_inputs(peak_xy, peak_type, peak_img_start, boxes_xywh, box_img, grid_hw, in_thres, gauss_w, kmax, workspace):
+    """tester.py:363-403 on the device for every box of the batch.  peak_xy f64 [n,2], peak_type i32 [n], peak_img_start
+    i32 [B+1], boxes_xywh f64 [P,4], box_img i32 [P] (CUDA tensors); gauss_w: 5 host doubles.  Returns (owner i32
+    [P,17,h,w], inp fp32 [P,h,w,17])."""
+    gh, gw = grid_hw
+    P, n = boxes_xywh.shape[0], peak_type.shape[0]
+    assert boxes_xywh.is_cuda and boxes_xywh.dtype == torch.float64 and box_img.dtype == torch.int32
+    assert peak_xy.dtype == torch.float64 and peak_type.dtype == torch.int32 and peak_img_start.dtype == torch.int32
+    owner = torch.empty((P, 17, gh, gw), dtype=torch.int32, device=boxes_xywh.device)
+    inp = torch.empty((P, gh, gw, 17), dtype=torch.float32, device=boxes_xywh.device)
+    gw_arr = (ctypes.c_double * 5)(*[float(v) for v in gauss_w])
+    ws, wsb = workspace
+    check(_lib.lib().mpn_prn_build_inputs(_ptr(peak_xy), _ptr(peak_type), _ptr(peak_img_start), n, _ptr(boxes_xywh), _ptr(box_img), P,
+                                          gh, gw, float(in_thres), ctypes.cast(gw_arr, ctypes.c_void_p), _ptr(owner), _ptr(inp), _ptr(ws), wsb,
+                                          int(kmax), _stream()), "mpn_prn_build_inputs")
+    stats["launches"] += 2
+    return owner, inp
+
+
+def prn_assign(peak_xy, peak_img_start, joint_start, boxes_xywh, box_img, box_img_start, owner, output, kmax, workspace):
+    """tester.py:412-483 on the device.  output: fp32 [P,h,w,17] PRN output.  Returns bbox_keypoints f64 [P,17,3]."""
+    P, _, gh, gw = owner.shape
+    B = box_img_start.shape[0] - 1
+    assert output.is_cuda and output.dtype == torch.float32 and tuple(output.shape) == (P, gh, gw, 17)
+    assert joint_start.dtype == torch.int32 and tuple(joint_start.shape) == (B, 18) and box_img_start.dtype == torch.int32
+    output = output.contiguous()
+    res = torch.empty((P, 17, 3), dtype=torch.float64, device=owner.device)
+    ws, wsb = workspace
+    check(_lib.lib().mpn_prn_assign(_ptr(peak_xy), _ptr(peak_img_start), _ptr(joint_start), peak_xy.shape[0], _ptr(boxes_xywh), _ptr(box_img),
+                                    _ptr(box_img_start), P, B, gh, gw, _ptr(owner), _ptr(output), _ptr(res), _ptr(ws), wsb, int(kmax),
+                                    _stream()), "mpn_prn_assign")
+    stats["launches"] += 3
+    return res

@@ -71,6 +71,68 @@ def nms_cases():
     return cases
 
 
+PRN_CASES = [(0, {}), (1, dict(persons=8)), (2, dict(drop_joint=3)), (3, dict(persons=1, extra_boxes=0)),
+             (4, dict(persons=12, noise_peaks=30)), (5, dict(persons=3, drop_joint=0, extra_boxes=2)),
+             (6, dict(persons=0, extra_boxes=2, noise_peaks=0)), (7, dict(persons=4, hw=(200, 160), noise_peaks=40))]
+
+
+def import_reference_tester():
+    """evaluate/tester.py imports pycocotools and (through datasets/coco_data/prn_gaussian.py:2) skimage, neither installed
+    here.  pycocotools is only used by Tester.val/coco_eval -> empty stub.  skimage.filters.gaussian(image) with the
+    defaults prn_process uses is a one-line call of scipy.ndimage.gaussian_filter (skimage/filters/_gaussian.py of the
+    pinned 0.13.1: image = img_as_float(image); return ndi.gaussian_filter(image, sigma, output=output, mode=mode,
+    cval=cval, truncate=truncate)) -> shimmed with exactly that call."""
+    import types
+    import scipy.ndimage as ndi
+    refshim.import_reference()
+
+    def gaussian(image, sigma=1, output=None, mode="nearest", cval=0, multichannel=None, preserve_range=False, truncate=4.0):
+        return ndi.gaussian_filter(np.asarray(image, dtype=np.float64), sigma, output=output, mode=mode, cval=cval, truncate=truncate)
+
+    sk, skf = types.ModuleType("skimage"), types.ModuleType("skimage.filters")
+    skf.gaussian, sk.filters = gaussian, skf
+    sys.modules.setdefault("skimage", sk)
+    sys.modules.setdefault("skimage.filters", skf)
+    for n in ("pycocotools", "pycocotools.coco", "pycocotools.cocoeval"):
+        sys.modules.setdefault(n, types.ModuleType(n))
+    sys.modules["pycocotools.coco"].COCO = object
+    sys.modules["pycocotools.cocoeval"].COCOeval = object
+    sys.modules["lib"].__path__ = [os.path.join(refshim.REF_ROOT, "lib")]      # lib.utils.* from the checkout
+    for k in [k for k in sys.modules if k == "evaluate" or k.startswith("evaluate.")]:
+        if not (getattr(sys.modules[k], "__file__", "") or "").startswith(refshim.REF_ROOT):
+            del sys.modules[k]
+    import evaluate.tester as tester
+    assert tester.__file__.startswith(refshim.REF_ROOT)
+    return tester
+
+
+def prn_goldens():
+    """tests/golden/prn_assign.npz: Tester.prn_process of the reference (evaluate/tester.py:333-513) on seeded cases, with
+    the PRN replaced by prn_oracle.synthetic_prn (so the records do not depend on 285 MB of weights)."""
+    from . import prn_oracle
+    tester = import_reference_tester()
+
+    class Params(object):
+        coeff, in_thres = 2, 0.21
+
+    class Self(object):
+        params = Params()
+
+    g = {}
+    for seed, kw in PRN_CASES:
+        kps, boxes = prn_oracle.synthetic_case(seed, **kw)
+        fn = prn_oracle.synthetic_prn(seed)
+        me = Self()
+        me.model = lambda args, fn=fn: (torch.from_numpy(fn(args[0].cpu().numpy())), None)
+        rec = tester.Tester.prn_process(me, [list(k) for k in kps], [list(b) for b in boxes], "img%d" % seed, seed)
+        g["case%d_keypoints" % seed] = np.array([r["keypoints"] for r in rec], dtype=np.float64).reshape(len(rec), 51)
+        g["case%d_score" % seed] = np.array([r["score"] for r in rec], dtype=np.float64)
+        g["case%d_bbox" % seed] = np.array([r["bbox"] for r in rec], dtype=np.float64).reshape(len(rec), 4)
+    g["cases"] = np.array(json.dumps(PRN_CASES))
+    g["versions"] = np.array(json.dumps({"numpy": np.__version__, "scipy": __import__("scipy").__version__}))
+    np.savez_compressed(os.path.join(OUT, "prn_assign.npz"), **g)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     meta = {"torch": torch.__version__, "numpy": np.__version__, "reference": refshim.REF_ROOT,
@@ -133,8 +195,11 @@ def main():
         pk["seed%d_rows" % seed] = get_joint_list(np.zeros((480, 640, 3), np.float32), {"thre1": 0.1},
                                                   np.ascontiguousarray(hm.transpose(1, 2, 0)), 1.0)
     np.savez_compressed(os.path.join(OUT, "peaks.npz"), **pk)
+    prn_goldens()
     print("wrote", sorted(os.listdir(OUT)))
 
 
 if __name__ == "__main__":
+    if "prn" in sys.argv[1:]:   # only the PRN-assignment vectors
+        sys.exit(prn_goldens())
     sys.exit(main())
