@@ -228,3 +228,33 @@ def conv_flops_entire(layers, H=480, W=640):
         assert hw is not None, name
         total += 2.0 * mac * hw[0] * hw[1]
     return total
+
+
+def calibrate_output_bias(model, x, what, per_image, threshold):
+    """Synthetic-weight construction for random-weight benchmarks / tests: shift ONE bias so that about `per_image`
+    outputs per image exceed `threshold` on the probe batch x (CUDA fp32 [B,3,H,W]).
+      what == 'cls'  : class-head output bias, sigmoid scores (posenet.py:262-279 score filter / tester.py:236 box filter)
+      what == 'heat' : convfin bias, the 18 supervised heat-map channels (joint_utils.py:19-32 thre1)
+    Returns the shift that was added."""
+    import math
+    import torch
+    with torch.no_grad():
+        if what == "cls":
+            _, (cls, _, _) = model((x, "detection_subnet"))
+            p = cls[:, :, 0].double().clamp(1e-12, 1 - 1e-12)
+            v = torch.log(p / (1 - p))
+            thr = math.log(threshold / (1.0 - threshold))
+            bias = model.classificationModel.output.bias
+        elif what == "heat":
+            heat, _ = model((x, "keypoint_subnet"))
+            v = heat[:, :18].double().flatten(1)
+            thr = float(threshold)
+            bias = model.convfin.bias
+        else:
+            raise ValueError(what)
+        flat = v.flatten()
+        k = max(1, min(flat.numel() - 1, int(round(per_image * v.shape[0]))))
+        cut = float(torch.topk(flat, k + 1).values[-1])          # the (k+1)-th largest value lands exactly on the threshold
+        shift = thr - cut
+        bias += shift
+    return shift
