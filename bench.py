@@ -55,6 +55,17 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def conv_traffic_record():
+    """roofline.traffic: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per conv_tc_kernel launch, averaged over
+    the launches of one forward step, from the newest committed ncu pass (scripts/ncu_conv_step.py + summarise_ncu_csv.py)."""
+    import glob
+    recs = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_conv_traffic.json")))
+    if not recs:
+        return None, None
+    d = json.load(open(recs[-1]))
+    return d.get("traffic_bytes_per_launch"), "profiles/%s (%d launches under ncu)" % (os.path.basename(recs[-1]), d.get("launches", 0))
+
+
 class ClockSampler(object):
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -262,6 +273,73 @@ def run_train(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def run_full(args, rank, world, local):
+    """BASELINE config 5: full inference incl. heat-map peaks and PRN assignment (the body of Tester._process,
+    evaluate/tester.py:200-243) for a batch of 64 images per GPU, through evaluate.process_batch with HOST images in and
+    per-person records out.  Synthetic-weight construction: the class-head and convfin biases are shifted once so that
+    about `--persons` boxes per image pass the 0.5 box filter and ~170 heat-map peaks per image pass thre1."""
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from multiposenet.pytorch_b200 import ops, poseNet, shard, synthetic
+    from multiposenet.pytorch_b200.evaluate import process_batch
+    B = args.batch if args.batch != 32 else 64
+    model = poseNet(args.layers, precision=args.precision)
+    load_weights_into(model, args.layers)
+    model = model.to(dev).eval()
+    rng = np.random.Generator(np.random.PCG64(777 + rank))
+    host = [torch.from_numpy(rng.standard_normal((B, 3, H, W), dtype=np.float32)).pin_memory() for _ in range(2)]
+    probe = host[0][:4].to(dev)
+    shifts = {"cls": synthetic.calibrate_output_bias(model, probe, "cls", per_image=4 * args.persons, threshold=0.5),
+              "heat": synthetic.calibrate_output_bias(model, probe, "heat", per_image=600, threshold=0.1)}
+    scales = [1.0] * B
+    stats = {}
+
+    def step(i):
+        x = host[i % 2].to(dev, non_blocking=True)
+        recs, heat, det = process_batch(model, x, scales, max_persons=args.persons)
+        stats["persons"] = sum(len(r) for r in recs) / float(B)
+        stats["assigned"] = sum(1 for r in recs for q in r for v in q["keypoints"][2::3] if v > 0) / float(B)
+        return recs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    l0 = ops.stats["launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    value = shard.whole_job_rate(B * args.steps, ms, dev)
+    ms = shard.max_over_ranks(ms, dev)
+    if rank == 0:
+        print(json.dumps({
+            "mode": "full", "metric": "images/sec (3x480x640) full inference incl. peaks + PRN assignment, host images in, records out",
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+            "data": "synthetic",
+            "config": {"workload": "R%d entire_net + NMS + heat-map peaks + PRN assignment, batch %d/GPU, 3x480x640" % (args.layers, B),
+                       "global_batch": B * world, "persons_per_image": stats.get("persons"), "assigned_joints_per_image": stats.get("assigned"),
+                       "max_persons": args.persons, "bias_shifts": shifts, "parallelism": "dp%d (image shards, no collective)" % world},
+            "gpu_launches": ops.stats["launches"] - l0, "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -273,7 +351,9 @@ def main():
     ap.add_argument("--layers", type=int, default=LAYERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true")
-    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train = BASELINE config 4 (extra line, not the headline)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "full"],
+                    help="train = BASELINE config 4, full = config 5 incl. peaks + PRN assignment (extra lines, not the headline)")
+    ap.add_argument("--persons", type=int, default=20, help="--mode full: person boxes per image fed to the PRN")
     ap.add_argument("--streams", type=int, default=None, help="branch-level side streams (default: engine default = on)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (0 = eager launches)")
     args = ap.parse_args()
@@ -284,6 +364,8 @@ def main():
         return run_reference(args, rank, world)
     if args.mode == "train":
         return run_train(args, rank, world, local)
+    if args.mode == "full":
+        return run_full(args, rank, world, local)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
@@ -460,11 +542,13 @@ def main():
         conv_ms = sum(t for t, _ in tc) / nprof
         nconv = len(tc) // nprof
         stem_flops = 2.0 * 64 * 3 * 49 * (H // 2) * (W // 2)
-        alg = (flops_img - stem_flops) * B  # the stem runs on the CUDA-core kernel
+        on_cuda_cores = any(simt for _, _, _, simt in evs)  # fp32 mode / MPN_TC_STEM=0: the stem is not a tensor-core launch
+        alg = (flops_img - (stem_flops if on_cuda_cores else 0.0)) * B
+        traffic, traffic_src = conv_traffic_record()
         achieved = alg / (conv_ms / 1e3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (%d launches/step)" % nconv, "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": pk_src + " (sustained cuBLAS bf16)",
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_src + " (sustained cuBLAS bf16)",
                 "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / (elapsed_ms / args.steps),
                 "mma_passes": 3 if args.precision == "bf16x3" else 1,
                 "tensor_pipe_frac": (3 if args.precision == "bf16x3" else 1) * achieved / peak,

@@ -1,0 +1,42 @@
+"""Target for the ncu passes: pack the weights (one forward), then ONE eager forward step whose launches are profiled.
+
+    ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \\
+        --clock-control none -k regex:conv_tc_kernel -s <launches of the first forward> -c <launches of one step> \\
+        --csv --log-file gpurun_out/conv_traffic.csv python scripts/ncu_conv_step.py
+The number of conv_tc_kernel launches per forward is printed (179 for R101 entire_net)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+from multiposenet.pytorch_b200 import ops, poseNet
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--precision", default="bf16x3")
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--layers", type=int, default=101)
+    ap.add_argument("--steps", type=int, default=2)
+    a = ap.parse_args()
+    dev = torch.device("cuda")
+    m = poseNet(a.layers, precision=a.precision)
+    bench.load_weights_into(m, a.layers)
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        m.classificationModel.output.bias += bench.CLS_BIAS_SHIFT.get(a.layers, 0.0)
+    eng = m.engine()
+    x = torch.randn(a.batch, 3, bench.H, bench.W, device=dev)
+    for i in range(a.steps):
+        ops.stats["conv_events"] = evs = []
+        eng.entire_forward_device(x, max_cand=4096)
+        torch.cuda.synchronize()
+        print("forward %d: %d conv launches" % (i, len(evs)))
+    ops.stats["conv_events"] = None
+
+
+if __name__ == "__main__":
+    main()
