@@ -298,7 +298,9 @@ extern "C" int mpn_prn_build_inputs(const double* peak_xy, const int32_t* peak_t
   for (int i = 0; i < 5; ++i) g.w[i] = gauss_w_host[i];
   int32_t* plane_has = (int32_t*)((char*)workspace + prn_align8((size_t)P * (size_t)(kmax > 0 ? kmax : 1) * sizeof(double)) +
                                   prn_align8((size_t)(n_peaks + 1) * sizeof(int32_t)));
-  prn_blur_kernel<<<P * NJ, PRN_THREADS, 2 * gh * gw * sizeof(double), st>>>(owner, gh, gw, g, inp, plane_has);
+  const size_t blur_smem = 2 * (size_t)gh * gw * sizeof(double);
+  if (blur_smem > 48 * 1024) MPN_CUDA_OK(cudaFuncSetAttribute(prn_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem));
+  prn_blur_kernel<<<P * NJ, PRN_THREADS, blur_smem, st>>>(owner, gh, gw, g, inp, plane_has);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
