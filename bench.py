@@ -550,11 +550,11 @@ def main():
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (%d launches/step)" % nconv, "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_src + " (sustained cuBLAS bf16)",
                 "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / (elapsed_ms / args.steps),
-                "mma_passes": 3 if args.precision == "bf16x3" else 1,
-                "tensor_pipe_frac": (3 if args.precision == "bf16x3" else 1) * achieved / peak,
+                "mma_passes": {"bf16x3": 3, "f16f8": 2}.get(args.precision, 1),
+                "tensor_pipe_frac": {"bf16x3": 3, "f16f8": 2}.get(args.precision, 1) * achieved / peak,
                 "note": "achieved = algorithmic conv FLOPs (2*MAC, fp32-equivalent) / conv kernel time; bf16x3 issues 3 MMAs per "
                         "algorithmic MAC (hi*hi + lo*hi + hi*lo), so tensor_pipe_frac = 3*frac is the share of the tensor peak the "
-                        "issued MMAs occupy"}
+                        "issued MMAs occupy; f16f8 issues 1 fp16 MMA + 2 fp8 MMAs at twice the rate = 2 bf16-equivalent passes"}
 
     # ---- optional: single-pass bf16 throughput (not the parity mode; reported beside the headline)
     fast = None
@@ -594,7 +594,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16x3": "bf16x3 (hi/lo split, fp32 accumulate)", "bf16": "bf16", "fp32": "f32"}[args.precision],
+            "dtype": {"bf16x3": "bf16x3 (hi/lo split, fp32 accumulate)", "bf16": "bf16", "fp32": "f32",
+                      "f16f8": "f16f8 (fp16 hi*hi + two fp8 cross terms, fp32 accumulate)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "R%d-FPN entire_net fwd (keypoint + RetinaNet heads) + decode/filter/NMS, batch %d/GPU, 3x480x640"
                                    % (args.layers, B), "global_batch": B * world, "parallelism": "dp%d (image shards, no collective)" % world,

@@ -35,6 +35,12 @@ extern "C" {
 #define MPN_FMT_F32 0    /* one fp32 plane                    -> CUDA-core fp32 path           */
 #define MPN_FMT_BF16 1   /* one bf16 plane                    -> tcgen05 single-pass bf16      */
 #define MPN_FMT_BF16X2 2 /* bf16 hi plane + bf16 lo plane     -> tcgen05 3-pass split (~fp32)  */
+#define MPN_FMT_F16F8 3  /* fp16 hi plane + two fp8 byte planes -> tcgen05 1 f16 + 2 half-cost fp8 passes (~fp32, |x| < 65504):
+                            x = hi + 2^-12 * lo8, lo8 = e5m2((x - hi) * 2^12), h8 = e5m2(x).  Every `*_lo` pointer of this
+                            format addresses the two byte planes back to back: [lo8 : E elements][h8 : E elements], E = the
+                            element count of the hi plane.  Filters: hi = fp16(w'), lo8 = e4m3(w' - hi), h8 = e4m3(w' * 2^-12)
+                            with w' = w * 2^k (one power of two per filter, mpn_conv_desc.acc_scale = 2^-k), so that
+                            x*w*2^k = xhi*whi (kind::f16) + xlo8*wh8 + xh8*wlo8 (kind::f8f6f4) lands in ONE accumulator.   */
 
 /* Output modes of a conv epilogue. */
 #define MPN_OUT_ACT 0      /* activation format `fmt`, NHWC                                   */
@@ -67,6 +73,8 @@ typedef struct mpn_conv_desc {
   int in_hpitch;             /* rows per input image in memory (0 = H); tcgen05 path only     */
   int k_overlap;             /* 1: in_cstride < Cin is intended -- each "pixel" of Cin channels is a window of
                                 Cin/in_cstride neighbouring pixels (stem as a space-to-depth conv) */
+  float acc_scale;           /* MPN_FMT_F16F8: the accumulator is multiplied by this (2^-k of the filter packing) before
+                                scale/bias; 0 is read as 1 */
 } mpn_conv_desc;
 
 typedef struct mpn_conv_ptrs {
@@ -99,6 +107,12 @@ int mpn_pack_filter_bf16(const float* w_oihw, void* dst_hi, void* dst_lo, int Co
  * accumulated by the tensor core ahead of it.  scale == NULL: plain packing. */
 int mpn_pack_filter_bf16_scaled(const float* w_oihw, const float* scale, void* dst_hi, void* dst_lo, int Cout, int Cin, int R, int S,
                                 void* stream);
+/* MPN_FMT_F16F8 filters: max|w * scale| (device scalar, *amax must be zeroed by the caller) -> the host picks k with
+ * max|w * scale| * 2^k in [2^14, 2^15) -> [Cout][R][S][Cin] fp16 hi, e4m3 lo8 / h8 byte planes (dst_lo8h8 = the two planes back
+ * to back).  stem = 1: the [64][4][64] space-to-depth layout of mpn_stem_pack_filter (Cin = 3, R = S = 7). */
+int mpn_filter_absmax(const float* w_oihw, const float* scale, int Cout, int per_cout, float* amax, void* stream);
+int mpn_pack_filter_f16f8(const float* w_oihw, const float* scale, float wscale, void* dst_hi, void* dst_lo8h8, int Cout, int Cin,
+                          int R, int S, int stem, void* stream);
 /* BatchNorm (eval) fold: scale = gamma/sqrt(var+eps), bias = beta - mean*scale   (fpn.py:15-19,25,43) */
 int mpn_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                 float* scale, float* bias, int C, void* stream);

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmpn_b200.so")
 
-FMT_F32, FMT_BF16, FMT_BF16X2 = 0, 1, 2
+FMT_F32, FMT_BF16, FMT_BF16X2, FMT_F16F8 = 0, 1, 2, 3
 OUT_ACT, OUT_F32_NHWC, OUT_F32_NCHW = 0, 1, 2
 EPI_RELU, EPI_SIGMOID = 1, 2
 
@@ -19,7 +19,8 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [(n, c_int) for n in (
         "N", "H", "W", "Cin", "Cout", "R", "S", "stride", "pad", "OH", "OW", "fmt", "in_cstride", "flags",
         "res_cstride", "up_h", "up_w", "up_cstride", "out_mode", "out_cstride", "out_coffset", "out_rep")] + [
-        ("out_nstride", c_ll), ("w_cout_pad", c_int), ("in_wpitch", c_int), ("in_hpitch", c_int), ("k_overlap", c_int)]
+        ("out_nstride", c_ll), ("w_cout_pad", c_int), ("in_wpitch", c_int), ("in_hpitch", c_int), ("k_overlap", c_int),
+        ("acc_scale", c_float)]
 
 
 class ConvPtrs(ctypes.Structure):
@@ -42,6 +43,8 @@ _SIGS = {
     "mpn_pack_filter_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_pack_filter_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_pack_filter_bf16_scaled": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_filter_absmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "mpn_pack_filter_f16f8": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_fold_bn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "mpn_stem_pack_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_stem_pack_filter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

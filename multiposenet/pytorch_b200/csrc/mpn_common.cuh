@@ -1,6 +1,8 @@
 // Shared helpers for libmpn_b200.so (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -33,16 +35,32 @@ static inline int mpn_divup(long long a, long long b) { return (int)((a + b - 1)
 // ---- activation element access shared by the CUDA-core kernels ---------------------------------
 __device__ __forceinline__ float mpn_bf16_bits_to_float(unsigned short b) { return __uint_as_float(((unsigned)b) << 16); }
 
+// ---- MPN_FMT_F16F8: x = fp16 hi + 2^-12 * e5m2 lo (+ an e5m2 copy of x for the tensor core's cross term).  The `lo`
+// pointer of that format addresses TWO consecutive byte planes: [lo8 : plane elements][h8 : plane elements].
+#define MPN_F8_LO_SCALE 4096.f
+#define MPN_F8_LO_INV (1.f / 4096.f)
+__device__ __forceinline__ float mpn_e5m2_to_float(unsigned char b) { return __half2float(__ushort_as_half((unsigned short)((unsigned short)b << 8))); }
+__device__ __forceinline__ unsigned char mpn_float_to_e5m2(float v) { return (unsigned char)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2); }
+__device__ __forceinline__ unsigned char mpn_float_to_e4m3(float v) { return (unsigned char)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+
 __device__ __forceinline__ float mpn_load_act(const void* hi, const void* lo, long long idx, int fmt) {
   if (fmt == MPN_FMT_F32) return ((const float*)hi)[idx];
+  if (fmt == MPN_FMT_F16F8)
+    return __half2float(((const __half*)hi)[idx]) + mpn_e5m2_to_float(((const unsigned char*)lo)[idx]) * MPN_F8_LO_INV;
   float v = __bfloat162float(((const __nv_bfloat16*)hi)[idx]);
   if (fmt == MPN_FMT_BF16X2) v += __bfloat162float(((const __nv_bfloat16*)lo)[idx]);
   return v;
 }
 
-__device__ __forceinline__ void mpn_store_act(void* hi, void* lo, long long idx, int fmt, float v) {
+// plane = number of elements of one plane of the destination tensor (needed by MPN_FMT_F16F8 to find the h8 plane)
+__device__ __forceinline__ void mpn_store_act(void* hi, void* lo, long long idx, int fmt, float v, long long plane = 0) {
   if (fmt == MPN_FMT_F32) {
     ((float*)hi)[idx] = v;
+  } else if (fmt == MPN_FMT_F16F8) {
+    const __half h = __float2half_rn(v);
+    ((__half*)hi)[idx] = h;
+    ((unsigned char*)lo)[idx] = mpn_float_to_e5m2((v - __half2float(h)) * MPN_F8_LO_SCALE);
+    ((unsigned char*)lo)[plane + idx] = mpn_float_to_e5m2(v);
   } else {
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     ((__nv_bfloat16*)hi)[idx] = h;

@@ -163,7 +163,7 @@ int check_desc(const mpn_conv_desc* d, const mpn_conv_ptrs* p) {
   MPN_CHECK_ARG(p->x_hi && p->w_hi && p->y_hi, "conv: null x/w/y");
   MPN_CHECK_ARG(d->res_cstride == 0 || p->res_hi, "conv: residual pointer missing");
   MPN_CHECK_ARG(d->up_cstride == 0 || (p->up_hi && d->up_h > 0 && d->up_w > 0), "conv: upsample source missing");
-  if (d->fmt == MPN_FMT_BF16X2) {
+  if (d->fmt == MPN_FMT_BF16X2 || d->fmt == MPN_FMT_F16F8) {
     MPN_CHECK_ARG(d->out_mode != MPN_OUT_ACT || p->y_lo, "conv: BF16X2 output needs y_lo");
     MPN_CHECK_ARG(d->res_cstride == 0 || p->res_lo, "conv: BF16X2 residual needs res_lo");
     MPN_CHECK_ARG(d->up_cstride == 0 || p->up_lo, "conv: BF16X2 upsample source needs up_lo");
@@ -200,7 +200,7 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
 extern "C" int mpn_conv2d_fwd(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream) {
   MPN_CHECK_ARG(d, "conv: null descriptor");
   if (d->fmt == MPN_FMT_F32) return launch_simt(d, p, MPN_FMT_F32, stream);
-  if (d->fmt == MPN_FMT_BF16 || d->fmt == MPN_FMT_BF16X2) {
+  if (d->fmt == MPN_FMT_BF16 || d->fmt == MPN_FMT_BF16X2 || d->fmt == MPN_FMT_F16F8) {
     int rc = check_desc(d, p);
     if (rc) return rc;
     return mpn_conv_tc_launch(d, p, stream);
@@ -211,5 +211,6 @@ extern "C" int mpn_conv2d_fwd(const mpn_conv_desc* d, const mpn_conv_ptrs* p, vo
 
 extern "C" int mpn_conv2d_fwd_f32in(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream) {
   MPN_CHECK_ARG(d, "conv: null descriptor");
+  MPN_CHECK_ARG(d->fmt != MPN_FMT_F16F8, "conv(fp32 input): F16F8 outputs come from the tensor-core stem only (MPN_TC_STEM=1)");
   return launch_simt(d, p, MPN_FMT_F32, stream);
 }

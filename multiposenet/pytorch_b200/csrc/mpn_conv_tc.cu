@@ -22,6 +22,10 @@
 // Precision modes: MPN_FMT_BF16   one bf16 plane per operand, one MMA per K step;
 //                  MPN_FMT_BF16X2 hi/lo bf16 planes (x = hi + lo to ~2^-17), three MMAs per K step
 //                  (hi*hi + lo*hi + hi*lo) accumulated in fp32 -> fp32-grade parity with the reference.
+//                  MPN_FMT_F16F8  fp16 hi plane + two fp8 byte planes (lo8 = e5m2((x - hi) * 2^12), h8 = e5m2(x)); filters
+//                  prescaled by 2^k: fp16 hi, lo8 = e4m3(w' - hi), h8 = e4m3(w' * 2^-12).  Per 64-channel K block:
+//                  4 kind::f16 MMAs (hi*hi) + 2 + 2 kind::f8f6f4 MMAs of K = 32 (xlo8*wh8, xh8*wlo8) into the SAME fp32
+//                  accumulator = 8 MMA slots instead of 12, product error ~2^-15 (scripts/precision_study.py).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -42,10 +46,10 @@ constexpr int BAR_BYTES = 256;
 constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32 accumulators, 16B chunks XOR-swizzled
 
 struct Maps {
-  CUtensorMap a[2][4];  // [plane hi/lo][phase hp*2+wp]
-  CUtensorMap b[2];     // [plane]
-  CUtensorMap bs[2];    // [plane] filter map with a tail_bn-row box (tail sub-tiles)
-  CUtensorMap y[2];     // [plane] output tensor (EPI_TMA): box {32 ch, TW, TH, TN}, 64B swizzle
+  CUtensorMap a[3][4];  // [plane hi/lo(/h8)][phase hp*2+wp]; F16F8: planes 1, 2 are byte tensors, 64B swizzle
+  CUtensorMap b[3];     // [plane]
+  CUtensorMap bs[3];    // [plane] filter map with a tail_bn-row box (tail sub-tiles)
+  CUtensorMap y[3];     // [plane] output tensor (EPI_TMA): box {32 ch, TW, TH, TN}, 64B swizzle (F16F8 byte planes: none)
   CUtensorMap r[2];     // [plane] residual tensor (res_mma): box {64 ch, TW, TH, TN}, 128B swizzle = MN-major B operand
   CUtensorMap ident;    // 128 x 128 bf16 identity matrix (res_mma): box {64, 128}, K-major A operand
 };
@@ -74,6 +78,8 @@ struct TcParams {
   long long out_nstride;
   void* y_hi;
   void* y_lo;
+  long long y_plane;  // F16F8: elements of one output plane (the h8 plane starts y_plane bytes after y_lo)
+  float acc_scale;    // F16F8: 2^-k of the filter prescale, applied to the accumulator first
 };
 
 struct TileCoord {
@@ -113,13 +119,67 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                : "memory");
 }
 
-template <int BN, bool SPLIT, int STAGES, int EPI>
+enum { MODE_BF16 = 0, MODE_BF16X2 = 1, MODE_F16F8 = 2 };
+
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major byte operand, 64-byte rows, 64-byte swizzle, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t make_sdesc64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float f16_lo_f(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xFFFFu))); }
+__device__ __forceinline__ float f16_hi_f(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
+__device__ __forceinline__ uint32_t e5m2x2(float a, float b) {  // a in the low byte
+  return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
+}
+__device__ __forceinline__ uint32_t e5m2x4(float a, float b, float c, float d) { return e5m2x2(a, b) | (e5m2x2(c, d) << 16); }
+// v[0..7] += 8 fp16 values (hi plane) ; v[0..3] += 2^-12 * 4 e5m2 bytes (lo8 plane)
+__device__ __forceinline__ void add_f16x8_reg(float* v, const uint4& t) {
+  v[0] += f16_lo_f(t.x); v[1] += f16_hi_f(t.x); v[2] += f16_lo_f(t.y); v[3] += f16_hi_f(t.y);
+  v[4] += f16_lo_f(t.z); v[5] += f16_hi_f(t.z); v[6] += f16_lo_f(t.w); v[7] += f16_hi_f(t.w);
+}
+__device__ __forceinline__ void add_e5m2x4_reg(float* v, uint32_t w) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] += mpn_e5m2_to_float((unsigned char)(w >> (8 * j))) * MPN_F8_LO_INV;
+}
+// 8 floats -> fp16 hi (uint4), lo8 = e5m2((v - hi) * 2^12) (uint2), h8 = e5m2(v) (uint2)
+__device__ __forceinline__ void split_f16f8x8(const float* w, uint4& hi, uint2& lo8, uint2& h8) {
+  hi.x = pack_f16(w[0], w[1]); hi.y = pack_f16(w[2], w[3]); hi.z = pack_f16(w[4], w[5]); hi.w = pack_f16(w[6], w[7]);
+  lo8.x = e5m2x4((w[0] - f16_lo_f(hi.x)) * MPN_F8_LO_SCALE, (w[1] - f16_hi_f(hi.x)) * MPN_F8_LO_SCALE,
+                 (w[2] - f16_lo_f(hi.y)) * MPN_F8_LO_SCALE, (w[3] - f16_hi_f(hi.y)) * MPN_F8_LO_SCALE);
+  lo8.y = e5m2x4((w[4] - f16_lo_f(hi.z)) * MPN_F8_LO_SCALE, (w[5] - f16_hi_f(hi.z)) * MPN_F8_LO_SCALE,
+                 (w[6] - f16_lo_f(hi.w)) * MPN_F8_LO_SCALE, (w[7] - f16_hi_f(hi.w)) * MPN_F8_LO_SCALE);
+  h8.x = e5m2x4(w[0], w[1], w[2], w[3]);
+  h8.y = e5m2x4(w[4], w[5], w[6], w[7]);
+}
+
+template <int BN, int MODE, int STAGES, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ Maps maps, const TcParams P) {
-  constexpr int PLANES = SPLIT ? 2 : 1;
+  constexpr bool SPLIT = MODE == MODE_BF16X2;
+  constexpr bool F8 = MODE == MODE_F16F8;
+  // "plane units" of 128 bytes per row and K block: BF16X2 = hi + lo; F16F8 = hi (128 B) + lo8 (64 B) + h8 (64 B)
+  constexpr int PLANES = MODE == MODE_BF16 ? 1 : 2;
+  constexpr int NMAPS = F8 ? 3 : PLANES;
   constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
   constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + B_TILE_BYTES);
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_M >> 4) << 24);  // | (N >> 3) << 17
+  // c = F32; a, b = BF16 (1) or, for F16F8, F16 (0);  | (N >> 3) << 17 per tile
+  constexpr uint32_t IDESC_BASE = (1u << 4) | (F8 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  constexpr uint32_t IDESC_F8 = (1u << 4) | (1u << 7) | ((uint32_t)(BLOCK_M >> 4) << 24);  // a = E5M2 (1), b = E4M3 (0)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -139,12 +199,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int p = 0; p < PLANES; ++p) {
+    for (int p = 0; p < NMAPS; ++p) {
       prefetch_tmap(&maps.b[p]);
       prefetch_tmap(&maps.a[p][0]);
       if (P.tail_split > 1) prefetch_tmap(&maps.bs[p]);
       if (EPI == EPI_TMA) prefetch_tmap(&maps.y[p]);
-      if (EPI == EPI_TMA && P.res_mma) prefetch_tmap(&maps.r[p]);
+      if (EPI == EPI_TMA && P.res_mma && p < 2) prefetch_tmap(&maps.r[p]);
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -218,10 +278,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           const uint32_t sa = smem_base + stage * STAGE_BYTES + u * sub_bytes;
           const uint32_t sb = sa + PLANES * A_TILE_BYTES;
           const int kcol = tap * P.Cin + kb * BLOCK_K;
+          if constexpr (F8) {
+            // A: [hi 16 KB][lo8 8 KB][h8 8 KB]; B: [hi ncols*128][lo8 ncols*64][h8 ncols*64]
+            tma_load_4d(sa, &maps.a[0][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
+            tma_load_4d(sa + A_TILE_BYTES, &maps.a[1][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
+            tma_load_4d(sa + A_TILE_BYTES + A_TILE_BYTES / 2, &maps.a[2][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
+            tma_load_2d(sb, tail ? &maps.bs[0] : &maps.b[0], full_bar(stage), kcol, co0);
+            tma_load_2d(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], full_bar(stage), kcol, co0);
+            tma_load_2d(sb + bplane + bplane / 2, tail ? &maps.bs[2] : &maps.b[2], full_bar(stage), kcol, co0);
+          } else {
 #pragma unroll
-          for (int p = 0; p < PLANES; ++p) {
-            tma_load_4d(sa + p * A_TILE_BYTES, &maps.a[p][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
-            tma_load_2d(sb + p * bplane, tail ? &maps.bs[p] : &maps.b[p], full_bar(stage), kcol, co0);
+            for (int p = 0; p < PLANES; ++p) {
+              tma_load_4d(sa + p * A_TILE_BYTES, &maps.a[p][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
+              tma_load_2d(sb + p * bplane, tail ? &maps.bs[p] : &maps.b[p], full_bar(stage), kcol, co0);
+            }
           }
           ++ki;
           if (++u == kpack || ki == num_k_iters) {
@@ -270,16 +340,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         for (int u = 0; u < group; ++u, ++ki) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES + u * sub_bytes;
           const uint32_t sb = sa + PLANES * A_TILE_BYTES;
+          if constexpr (F8) {
+            const uint32_t idesc8 = IDESC_F8 | ((uint32_t)(ncols >> 3) << 17);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t a_hi = make_sdesc(sa + k * 32);
-            const uint64_t b_hi = make_sdesc(sb + k * 32);
-            umma_bf16(d_tmem, a_hi, b_hi, IDESC, (ki > 0 || k > 0) ? 1u : 0u);
-            if (SPLIT) {
-              const uint64_t a_lo = make_sdesc(sa + A_TILE_BYTES + k * 32);
-              const uint64_t b_lo = make_sdesc(sb + bplane + k * 32);
-              umma_bf16(d_tmem, a_lo, b_hi, IDESC, 1u);
-              umma_bf16(d_tmem, a_hi, b_lo, IDESC, 1u);
+            for (int k = 0; k < BLOCK_K / 16; ++k)  // fp16 hi * fp16 hi, K = 16 per instruction
+              umma_bf16(d_tmem, make_sdesc(sa + k * 32), make_sdesc(sb + k * 32), IDESC, (ki > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 32; ++k) {  // fp8 cross terms, K = 32 per instruction
+              umma_f8(d_tmem, make_sdesc64(sa + A_TILE_BYTES + k * 32), make_sdesc64(sb + bplane + bplane / 2 + k * 32), idesc8, 1u);  // xlo8 * wh8
+              umma_f8(d_tmem, make_sdesc64(sa + A_TILE_BYTES + A_TILE_BYTES / 2 + k * 32), make_sdesc64(sb + bplane + k * 32), idesc8, 1u);  // xh8 * wlo8
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t a_hi = make_sdesc(sa + k * 32);
+              const uint64_t b_hi = make_sdesc(sb + k * 32);
+              umma_bf16(d_tmem, a_hi, b_hi, IDESC, (ki > 0 || k > 0) ? 1u : 0u);
+              if (SPLIT) {
+                const uint64_t a_lo = make_sdesc(sa + A_TILE_BYTES + k * 32);
+                const uint64_t b_lo = make_sdesc(sb + bplane + k * 32);
+                umma_bf16(d_tmem, a_lo, b_hi, IDESC, 1u);
+                umma_bf16(d_tmem, a_hi, b_lo, IDESC, 1u);
+              }
             }
           }
         }
@@ -356,12 +438,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             for (int i = 0; i < 4; ++i) {
               rh[i] = __ldg(reinterpret_cast<const uint4*>(P.res_hi + res_off + cbase) + i);
               if (SPLIT) rl[i] = __ldg(reinterpret_cast<const uint4*>(P.res_lo + res_off + cbase) + i);
+              if (F8 && i < 2) rl[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(P.res_lo) + res_off + cbase) + i);
             }
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (F8) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= P.acc_scale;
+          }
           if (P.scale) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -377,10 +464,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
           }
           if (res_lsu) {
+            if constexpr (F8) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              add_bf16x8_reg(v + 8 * i, rh[i]);
-              if (SPLIT) add_bf16x8_reg(v + 8 * i, rl[i]);
+              for (int i = 0; i < 4; ++i) add_f16x8_reg(v + 8 * i, rh[i]);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                add_e5m2x4_reg(v + 16 * i, rl[i].x); add_e5m2x4_reg(v + 16 * i + 4, rl[i].y);
+                add_e5m2x4_reg(v + 16 * i + 8, rl[i].z); add_e5m2x4_reg(v + 16 * i + 12, rl[i].w);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                add_bf16x8_reg(v + 8 * i, rh[i]);
+                if (SPLIT) add_bf16x8_reg(v + 8 * i, rl[i]);
+              }
             }
           }
           if (P.flags & MPN_EPI_RELU) {
@@ -392,6 +489,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
           }
           uint4 hi4[4], lo4[4];
+          uint2 l8[4], h8[4];
+          if constexpr (F8) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_f16f8x8(v + 8 * i, hi4[i], l8[i], h8[i]);
+          } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float* w = v + 8 * i;
@@ -404,6 +506,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               lo4[i].w = pack_bf16(w[6] - bf16_lo_f(hi4[i].w), w[7] - bf16_hi_f(hi4[i].w));
             }
           }
+          }
           // the previous store of this half must have finished READING the staging box before it is overwritten
           if (store_pending) {
             if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -414,11 +517,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             *reinterpret_cast<uint4*>(stg + row * 64 + ((i ^ sw) << 4)) = hi4[i];
             if (SPLIT) *reinterpret_cast<uint4*>(stg + 8192 + row * 64 + ((i ^ sw) << 4)) = lo4[i];
           }
+          if constexpr (F8) {  // byte planes: [lo8: rows x 32 B] at +8192, [h8: rows x 32 B] at +12288, unswizzled boxes
+            *reinterpret_cast<uint4*>(stg + 8192 + row * 32) = make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y);
+            *reinterpret_cast<uint4*>(stg + 8192 + row * 32 + 16) = make_uint4(l8[2].x, l8[2].y, l8[3].x, l8[3].y);
+            *reinterpret_cast<uint4*>(stg + 12288 + row * 32) = make_uint4(h8[0].x, h8[0].y, h8[1].x, h8[1].y);
+            *reinterpret_cast<uint4*>(stg + 12288 + row * 32 + 16) = make_uint4(h8[2].x, h8[2].y, h8[3].x, h8[3].y);
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           named_bar_sync(1 + half, 128);
           if (issuer) {
             tma_store_4d(&maps.y[0], stg_u32, cbase, ow0, oh0, n0);
             if (SPLIT) tma_store_4d(&maps.y[1], stg_u32 + 8192, cbase, ow0, oh0, n0);
+            if (F8) {
+              tma_store_4d(&maps.y[1], stg_u32 + 8192, cbase, ow0, oh0, n0);
+              tma_store_4d(&maps.y[2], stg_u32 + 12288, cbase, ow0, oh0, n0);
+            }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           store_pending = true;
@@ -460,6 +573,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               const long long o = (long long)(pixv[i] < 0 ? 0 : pixv[i]) * P.res_cstride + ch;
               rh[i] = __ldg(reinterpret_cast<const uint4*>(P.res_hi + o));
               if (SPLIT) rl[i] = __ldg(reinterpret_cast<const uint4*>(P.res_lo + o));
+              if (F8) {
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(P.res_lo) + o));
+                rl[i].x = t.x; rl[i].y = t.y;
+              }
             }
           }
           if (P.up_cstride > 0) {
@@ -468,6 +585,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               const long long o = (long long)upv[i] * P.up_cstride + ch;
               uh[i] = __ldg(reinterpret_cast<const uint4*>(P.up_hi + o));
               if (SPLIT) ul[i] = __ldg(reinterpret_cast<const uint4*>(P.up_lo + o));
+              if (F8) {
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(P.up_lo) + o));
+                ul[i].x = t.x; ul[i].y = t.y;
+              }
             }
           }
           float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, bi0 = make_float4(0.f, 0.f, 0.f, 0.f), bi1 = bi0;
@@ -489,15 +610,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const uint4 f1 = *reinterpret_cast<const uint4*>(stg + rr * 32 + (((2 * g + 1) ^ (rr & 7)) << 2));
             float v[8] = {__uint_as_float(f0.x), __uint_as_float(f0.y), __uint_as_float(f0.z), __uint_as_float(f0.w),
                           __uint_as_float(f1.x), __uint_as_float(f1.y), __uint_as_float(f1.z), __uint_as_float(f1.w)};
+            if (F8) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] *= P.acc_scale;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], scv[j], biv[j]);
-            if (P.res_cstride > 0) {
-              add_bf16x8_reg(v, rh[i]);
-              if (SPLIT) add_bf16x8_reg(v, rl[i]);
-            }
-            if (P.up_cstride > 0) {
-              add_bf16x8_reg(v, uh[i]);
-              if (SPLIT) add_bf16x8_reg(v, ul[i]);
+            if constexpr (F8) {
+              if (P.res_cstride > 0) { add_f16x8_reg(v, rh[i]); add_e5m2x4_reg(v, rl[i].x); add_e5m2x4_reg(v + 4, rl[i].y); }
+              if (P.up_cstride > 0) { add_f16x8_reg(v, uh[i]); add_e5m2x4_reg(v, ul[i].x); add_e5m2x4_reg(v + 4, ul[i].y); }
+            } else {
+              if (P.res_cstride > 0) {
+                add_bf16x8_reg(v, rh[i]);
+                if (SPLIT) add_bf16x8_reg(v, rl[i]);
+              }
+              if (P.up_cstride > 0) {
+                add_bf16x8_reg(v, uh[i]);
+                if (SPLIT) add_bf16x8_reg(v, ul[i]);
+              }
             }
             if (P.flags & MPN_EPI_RELU) {
 #pragma unroll
@@ -508,6 +638,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               for (int j = 0; j < 8; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
             }
             uint4 hi4, lo4;
+            uint2 l8, h8;
+            if constexpr (F8) {
+              split_f16f8x8(v, hi4, l8, h8);
+              if (pixv[i] >= 0) {
+                unsigned char* ylo = reinterpret_cast<unsigned char*>(P.y_lo);
+                for (int ry = 0; ry < rep; ++ry)
+                  for (int rx = 0; rx < rep; ++rx) {
+                    const long long o = obase[i] + ((long long)ry * OWr + rx) * P.out_cstride + ch;
+                    *reinterpret_cast<uint4*>((__half*)P.y_hi + o) = hi4;
+                    *reinterpret_cast<uint2*>(ylo + o) = l8;
+                    *reinterpret_cast<uint2*>(ylo + P.y_plane + o) = h8;
+                  }
+              }
+              continue;
+            }
             hi4.x = pack_bf16(v[0], v[1]); hi4.y = pack_bf16(v[2], v[3]); hi4.z = pack_bf16(v[4], v[5]); hi4.w = pack_bf16(v[6], v[7]);
             if (SPLIT) {
               lo4.x = pack_bf16(v[0] - bf16_lo_f(hi4.x), v[1] - bf16_hi_f(hi4.x));
@@ -553,6 +698,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             v[j] = __uint_as_float(raw[j]);
+            if (F8) v[j] *= P.acc_scale;
             if (j < nc) {
               if (P.scale) v[j] *= __ldg(P.scale + cbase + j);
               if (P.bias) v[j] += __ldg(P.bias + cbase + j);
@@ -649,16 +795,16 @@ void choose_tile(int N, int OH, int OW, int* TW, int* TH, int* TN) {
   *TW = bw; *TH = bh; *TN = bn;
 }
 
-template <int BN, bool SPLIT, int EPI>
+template <int BN, int MODE, int EPI>
 int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
-  constexpr int PLANES = SPLIT ? 2 : 1;
+  constexpr int PLANES = MODE == MODE_BF16 ? 1 : 2;
   constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + BN * BLOCK_K * 2);
   constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - NUM_EPI_WARPS * EPI_STAGE_BYTES) / STAGE_BYTES;
   constexpr int STAGES = MAXS > 8 ? 8 : MAXS;
   static_assert(STAGES >= 2, "not enough shared memory for a 2-stage ring");
   static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier area too small");
   const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
-  auto kern = conv_tc_kernel<BN, SPLIT, STAGES, EPI>;
+  auto kern = conv_tc_kernel<BN, MODE, STAGES, EPI>;
   MPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = P.total_tiles < sms ? P.total_tiles : sms;
   static const int pdl = getenv("MPN_PDL") ? atoi(getenv("MPN_PDL")) : 0;  // opt-in: no step-time gain inside a CUDA graph (r01l)
@@ -682,6 +828,11 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
 
 int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream) {
   const bool split = d->fmt == MPN_FMT_BF16X2;
+  const bool f8 = d->fmt == MPN_FMT_F16F8;
+  MPN_CHECK_ARG(!f8 || (p->x_lo && p->w_lo), "conv(tcgen05): F16F8 needs the byte planes of x and w");
+  MPN_CHECK_ARG(!f8 || (d->in_cstride % 16 == 0 && d->res_cstride % 16 == 0 && d->up_cstride % 16 == 0 &&
+                        (d->out_mode != MPN_OUT_ACT || (d->out_cstride % 16 == 0 && d->out_coffset % 16 == 0))),
+                "conv(tcgen05): F16F8 byte planes need channel strides / offsets that are multiples of 16");
   MPN_CHECK_ARG(d->stride == 1 || d->stride == 2, "conv(tcgen05): stride must be 1 or 2");
   MPN_CHECK_ARG(d->Cin % BLOCK_K == 0, "conv(tcgen05): Cin must be a multiple of 64 (got %d)", d->Cin);
   MPN_CHECK_ARG(d->in_cstride % 8 == 0, "conv(tcgen05): in_cstride must be a multiple of 8");
@@ -773,10 +924,16 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   P.flags = d->flags; P.out_mode = d->out_mode; P.out_cstride = d->out_cstride; P.out_coffset = d->out_coffset;
   P.out_rep = d->out_rep; P.out_nstride = d->out_nstride;
   P.y_hi = p->y_hi; P.y_lo = p->y_lo;
+  P.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
+  {
+    const long long rep2 = (long long)d->out_rep * d->out_rep;
+    const long long ns = d->out_nstride > 0 ? d->out_nstride : (long long)d->OH * d->OW * rep2 * d->out_cstride;
+    P.y_plane = (long long)d->N * ns;
+  }
 
   alignas(64) Maps maps;
   memset(&maps, 0, sizeof(maps));
-  const int planes = split ? 2 : 1;
+  const int planes = f8 ? 3 : split ? 2 : 1;
   const int st = d->stride;
   const int nphase = st == 1 ? 1 : 4;
   const long long wpitch = d->in_wpitch > 0 ? d->in_wpitch : d->W;   // pixels per row in memory
@@ -785,8 +942,15 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   MPN_CHECK_ARG(!d->k_overlap || (st == 1 && d->Cin == BLOCK_K && d->in_cstride % 8 == 0 &&
                                   wpitch >= d->W + d->Cin / d->in_cstride - 1),
                 "conv(tcgen05): k_overlap needs stride 1, Cin == 64 and a row pitch covering the window");
+  const long long x_plane = (long long)d->N * hpitch * wpitch * d->in_cstride;   // F16F8: h8 plane = lo8 plane + x_plane bytes
+  const long long w_plane = (long long)d->Cout * d->R * d->S * d->Cin;
   for (int pl = 0; pl < planes; ++pl) {
-    const char* xb = (const char*)(pl == 0 ? p->x_hi : p->x_lo);
+    const bool bytes = f8 && pl > 0;                 // byte planes: 1-byte elements, 64-byte swizzle
+    const unsigned long long es = bytes ? 1ULL : 2ULL;
+    const CUtensorMapSwizzle swz = bytes ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapDataType dt = bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const char* xb = (const char*)(pl == 0 ? p->x_hi : p->x_lo) + (f8 && pl == 2 ? x_plane : 0);
+    const char* wb = (const char*)(pl == 0 ? p->w_hi : p->w_lo) + (f8 && pl == 2 ? w_plane : 0);
     for (int ph = 0; ph < nphase; ++ph) {
       const int hp = ph >> 1, wp = ph & 1;
       const int Hp = (d->H - hp + st - 1) / st, Wp = (d->W - wp + st - 1) / st;
@@ -795,34 +959,37 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
         continue;
       }
       cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)d->N};
-      cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * st * 2ULL, (cuuint64_t)wpitch * d->in_cstride * st * 2ULL,
-                               (cuuint64_t)hpitch * wpitch * d->in_cstride * 2ULL};
+      cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * st * es, (cuuint64_t)wpitch * d->in_cstride * st * es,
+                               (cuuint64_t)hpitch * wpitch * d->in_cstride * es};
       cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
-      const char* base = xb + ((long long)hp * wpitch + wp) * d->in_cstride * 2LL;
-      int rc = encode(fn, &maps.a[pl][ph], base, 4, dims, strides, box);
+      const char* base = xb + ((long long)hp * wpitch + wp) * d->in_cstride * (long long)es;
+      int rc = encode(fn, &maps.a[pl][ph], base, 4, dims, strides, box, swz, dt);
       if (rc) return rc;
     }
     MPN_CHECK_ARG(!(P.phase_empty & 1), "conv(tcgen05): empty input");
     const cuuint64_t K = (cuuint64_t)d->R * d->S * d->Cin;
     cuuint64_t wdims[2] = {K, (cuuint64_t)d->Cout};
-    cuuint64_t wstrides[1] = {K * 2ULL};
+    cuuint64_t wstrides[1] = {K * es};
     cuuint32_t wbox[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN};
-    int rc = encode(fn, &maps.b[pl], pl == 0 ? p->w_hi : p->w_lo, 2, wdims, wstrides, wbox);
+    int rc = encode(fn, &maps.b[pl], wb, 2, wdims, wstrides, wbox, swz, dt);
     if (rc) return rc;
     if (P.tail_split > 1) {
       cuuint32_t sbox[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)P.tail_bn};
-      rc = encode(fn, &maps.bs[pl], pl == 0 ? p->w_hi : p->w_lo, 2, wdims, wstrides, sbox);
+      rc = encode(fn, &maps.bs[pl], wb, 2, wdims, wstrides, sbox, swz, dt);
       if (rc) return rc;
     }
   }
   if (epi_tma) {
     const long long nstride = d->out_nstride > 0 ? d->out_nstride : (long long)d->OH * d->OW * d->out_cstride;
     for (int pl = 0; pl < planes; ++pl) {
+      const bool bytes = f8 && pl > 0;
+      const unsigned long long es = bytes ? 1ULL : 2ULL;
       cuuint64_t ydims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->OW, (cuuint64_t)d->OH, (cuuint64_t)d->N};
-      cuuint64_t ystr[3] = {(cuuint64_t)d->out_cstride * 2ULL, (cuuint64_t)d->OW * d->out_cstride * 2ULL, (cuuint64_t)nstride * 2ULL};
+      cuuint64_t ystr[3] = {(cuuint64_t)d->out_cstride * es, (cuuint64_t)d->OW * d->out_cstride * es, (cuuint64_t)nstride * es};
       cuuint32_t ybox[4] = {32u, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
-      const char* yb = (const char*)(pl == 0 ? p->y_hi : p->y_lo) + (long long)d->out_coffset * 2LL;
-      int rc = encode(fn, &maps.y[pl], yb, 4, ydims, ystr, ybox, CU_TENSOR_MAP_SWIZZLE_64B);
+      const char* yb = (const char*)(pl == 0 ? p->y_hi : p->y_lo) + (f8 && pl == 2 ? P.y_plane : 0) + (long long)d->out_coffset * (long long)es;
+      int rc = encode(fn, &maps.y[pl], yb, 4, ydims, ystr, ybox, bytes ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B,
+                      bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
       if (rc) return rc;
     }
   }
@@ -835,7 +1002,7 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
     cuuint32_t ibox[2] = {64, 128};
     rc = encode(fn, &maps.ident, ident, 2, idims, istr, ibox);
     if (rc) return rc;
-    for (int pl = 0; pl < planes; ++pl) {
+    for (int pl = 0; pl < 2; ++pl) {
       cuuint64_t rdims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->OW, (cuuint64_t)d->OH, (cuuint64_t)d->N};
       cuuint64_t rstr[3] = {(cuuint64_t)d->res_cstride * 2ULL, (cuuint64_t)d->OW * d->res_cstride * 2ULL,
                             (cuuint64_t)d->OH * d->OW * d->res_cstride * 2ULL};
@@ -847,8 +1014,9 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   cudaStream_t s = (cudaStream_t)stream;
   if (f32out) {  // head outputs (18/19/36/9 channels): the thread-per-row fp32 store path, small-N tiles only
     MPN_CHECK_ARG(BN <= 64, "conv(tcgen05): fp32 outputs are built for Cout <= 64 (got %d)", d->Cout);
-    if (split) return BN == 64 ? launch<64, true, EPI_F32>(maps, P, s, sms) : launch<32, true, EPI_F32>(maps, P, s, sms);
-    return BN == 64 ? launch<64, false, EPI_F32>(maps, P, s, sms) : launch<32, false, EPI_F32>(maps, P, s, sms);
+    if (f8) return BN == 64 ? launch<64, MODE_F16F8, EPI_F32>(maps, P, s, sms) : launch<32, MODE_F16F8, EPI_F32>(maps, P, s, sms);
+    if (split) return BN == 64 ? launch<64, MODE_BF16X2, EPI_F32>(maps, P, s, sms) : launch<32, MODE_BF16X2, EPI_F32>(maps, P, s, sms);
+    return BN == 64 ? launch<64, MODE_BF16, EPI_F32>(maps, P, s, sms) : launch<32, MODE_BF16, EPI_F32>(maps, P, s, sms);
   }
 #define MPN_TC_DISPATCH(SPLIT_, EPI_)                                     \
   switch (BN) {                                                            \
@@ -857,11 +1025,15 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
     case 64: return launch<64, SPLIT_, EPI_>(maps, P, s, sms);             \
     default: return launch<32, SPLIT_, EPI_>(maps, P, s, sms);             \
   }
-  if (split) {
-    if (epi_tma) { MPN_TC_DISPATCH(true, EPI_TMA) }
-    MPN_TC_DISPATCH(true, EPI_LSU)
+  if (f8) {
+    if (epi_tma) { MPN_TC_DISPATCH(MODE_F16F8, EPI_TMA) }
+    MPN_TC_DISPATCH(MODE_F16F8, EPI_LSU)
   }
-  if (epi_tma) { MPN_TC_DISPATCH(false, EPI_TMA) }
-  MPN_TC_DISPATCH(false, EPI_LSU)
+  if (split) {
+    if (epi_tma) { MPN_TC_DISPATCH(MODE_BF16X2, EPI_TMA) }
+    MPN_TC_DISPATCH(MODE_BF16X2, EPI_LSU)
+  }
+  if (epi_tma) { MPN_TC_DISPATCH(MODE_BF16, EPI_TMA) }
+  MPN_TC_DISPATCH(MODE_BF16, EPI_LSU)
 #undef MPN_TC_DISPATCH
 }

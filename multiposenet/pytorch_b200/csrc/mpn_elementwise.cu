@@ -85,6 +85,73 @@ extern "C" int mpn_pack_filter_bf16_scaled(const float* w, const float* scale, v
   return MPN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// MPN_FMT_F16F8 filters (see mpn_b200.h).  amax: max |w * scale[co]| over the filter (non-negative floats order like their bits).
+__global__ void filter_absmax_kernel(const float* __restrict__ w, const float* __restrict__ scale, long long total, int per_cout,
+                                     float* amax) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v = w[i];
+    if (scale) v = __fmul_rn(v, scale[i / per_cout]);
+    m = fmaxf(m, fabsf(v));
+  }
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));
+}
+
+extern "C" int mpn_filter_absmax(const float* w, const float* scale, int Cout, int per_cout, float* amax, void* stream) {
+  MPN_CHECK_ARG(w && amax && Cout > 0 && per_cout > 0, "mpn_filter_absmax: bad argument");
+  const long long total = (long long)Cout * per_cout;
+  filter_absmax_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, scale, total, per_cout, amax);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+__global__ void pack_filter_f16f8_kernel(const float* __restrict__ w, const float* __restrict__ scale, float wscale, __half* __restrict__ hi,
+                                         unsigned char* __restrict__ lo8, unsigned char* __restrict__ h8, int Cout, int Cin, int R, int S,
+                                         int stem) {
+  const long long total = stem ? (long long)Cout * 256 : (long long)Cout * R * S * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    int co;
+    if (stem) {  // [co][r2][k], k = s2*16 + cc (stem_pack_filter_kernel)
+      const int k = (int)(i & 63), r2 = (int)((i >> 6) & 3);
+      co = (int)(i >> 8);
+      const int s2 = k >> 4, cc = k & 15;
+      if (cc < 12) {
+        const int c = cc % 3, ph = (cc / 3) >> 1, pw = (cc / 3) & 1;
+        const int r = 2 * r2 + ph - 1, s = 2 * s2 + pw - 1;
+        if (r >= 0 && r < 7 && s >= 0 && s < 7) v = w[((co * 3 + c) * 7 + r) * 7 + s];
+      }
+    } else {
+      const int ci = (int)(i % Cin);
+      long long t = i / Cin;
+      const int s = (int)(t % S);
+      t /= S;
+      const int r = (int)(t % R);
+      co = (int)(t / R);
+      v = w[(((long long)co * Cin + ci) * R + r) * S + s];
+    }
+    if (scale) v = __fmul_rn(v, scale[co]);
+    v = __fmul_rn(v, wscale);  // a power of two: exact
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo8[i] = mpn_float_to_e4m3(v - __half2float(h));   // pairs with the activations' e5m2 copy
+    h8[i] = mpn_float_to_e4m3(v * MPN_F8_LO_INV);      // pairs with the activations' lo8 = e5m2((x - hi) * 2^12)
+  }
+}
+
+extern "C" int mpn_pack_filter_f16f8(const float* w, const float* scale, float wscale, void* hi, void* lo8h8, int Cout, int Cin, int R,
+                                     int S, int stem, void* stream) {
+  MPN_CHECK_ARG(w && hi && lo8h8 && Cout > 0 && Cin > 0 && R > 0 && S > 0 && wscale > 0.f, "mpn_pack_filter_f16f8: bad argument");
+  MPN_CHECK_ARG(!stem || (Cin == 3 && R == 7 && S == 7), "mpn_pack_filter_f16f8: the stem layout is for a [Cout,3,7,7] filter");
+  const long long total = stem ? (long long)Cout * 256 : (long long)Cout * R * S * Cin;
+  pack_filter_f16f8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, scale, wscale, (__half*)hi, (unsigned char*)lo8h8,
+                                                                                  (unsigned char*)lo8h8 + total, Cout, Cin, R, S, stem);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
 __global__ void fold_bn_kernel(const float* g, const float* b, const float* m, const float* v, float eps, float* scale,
                                float* bias, int C) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,14 +185,14 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* hi, voi
     int h = (int)(q % H);
     int n = (int)(q / H);
     float v = c < C ? src[(((long long)n * C + c) * H + h) * W + w] : 0.f;
-    mpn_store_act(hi, lo, i, fmt, v);
+    mpn_store_act(hi, lo, i, fmt, v, total);
   }
 }
 
 extern "C" int mpn_nchw_to_nhwc(const float* src, void* hi, void* lo, int N, int C, int H, int W, int cstride, int fmt,
                                 void* stream) {
   MPN_CHECK_ARG(src && hi && N > 0 && C > 0 && H > 0 && W > 0 && cstride >= C, "mpn_nchw_to_nhwc: bad argument");
-  MPN_CHECK_ARG(fmt != MPN_FMT_BF16X2 || lo, "mpn_nchw_to_nhwc: BF16X2 needs a lo plane");
+  MPN_CHECK_ARG((fmt != MPN_FMT_BF16X2 && fmt != MPN_FMT_F16F8) || lo, "mpn_nchw_to_nhwc: split formats need a lo plane");
   long long total = (long long)N * H * W * cstride;
   nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, hi, lo, N, C, H, W, cstride, fmt);
   MPN_LAUNCH_OK();
@@ -186,7 +253,7 @@ __global__ void maxpool3x3s2_kernel(const void* __restrict__ xhi, const void* __
         m = fmaxf(m, mpn_load_act(xhi, xlo, (((long long)n * H + ih) * W + iw) * C + c, fmt));
       }
     }
-    mpn_store_act(yhi, ylo, i, fmt, m);
+    mpn_store_act(yhi, ylo, i, fmt, m, total);
   }
 }
 
@@ -256,7 +323,7 @@ extern "C" int mpn_maxpool3x3s2(const void* xhi, const void* xlo, void* yhi, voi
   MPN_CHECK_ARG(xhi && yhi && N > 0 && H > 0 && W > 0 && C > 0, "mpn_maxpool3x3s2: bad argument");
   int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   long long total = (long long)N * OH * OW * C;
-  if (fmt != MPN_FMT_F32 && C % 8 == 0) {
+  if ((fmt == MPN_FMT_BF16 || fmt == MPN_FMT_BF16X2) && C % 8 == 0) {
     long long t8 = total / 8;
     if (fmt == MPN_FMT_BF16X2)
       maxpool3x3s2_bf16_kernel<true><<<grid_for(t8, 256), 256, 0, (cudaStream_t)stream>>>(
@@ -274,7 +341,7 @@ extern "C" int mpn_maxpool3x3s2(const void* xhi, const void* xlo, void* yhi, voi
 
 __global__ void relu_kernel(const void* xhi, const void* xlo, void* yhi, void* ylo, long long n, int fmt) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    mpn_store_act(yhi, ylo, i, fmt, fmaxf(mpn_load_act(xhi, xlo, i, fmt), 0.f));
+    mpn_store_act(yhi, ylo, i, fmt, fmaxf(mpn_load_act(xhi, xlo, i, fmt), 0.f), n);
 }
 
 extern "C" int mpn_relu(const void* xhi, const void* xlo, void* yhi, void* ylo, long long n, int fmt, void* stream) {
@@ -302,13 +369,13 @@ __global__ void stem_pack_input_kernel(const float* __restrict__ img, void* hi, 
       int ih = 2 * (hp - 2) + ph, iw = 2 * (wp - 2) + pw;
       if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = img[(((long long)n * 3 + c) * H + ih) * W + iw];
     }
-    mpn_store_act(hi, lo, i, fmt, v);
+    mpn_store_act(hi, lo, i, fmt, v, total);
   }
 }
 
 extern "C" int mpn_stem_pack_input(const float* img, void* hi, void* lo, int N, int H, int W, int fmt, void* stream) {
   MPN_CHECK_ARG(img && hi && N > 0 && H > 0 && W > 0, "mpn_stem_pack_input: bad argument");
-  MPN_CHECK_ARG(fmt == MPN_FMT_BF16 || (fmt == MPN_FMT_BF16X2 && lo), "mpn_stem_pack_input: fmt must be BF16 or BF16X2 (with lo)");
+  MPN_CHECK_ARG(fmt == MPN_FMT_BF16 || ((fmt == MPN_FMT_BF16X2 || fmt == MPN_FMT_F16F8) && lo), "mpn_stem_pack_input: fmt must be BF16, BF16X2 or F16F8 (with lo)");
   int H2p = (H + 1) / 2 + 3, W2p = (W + 1) / 2 + 3;
   long long total = (long long)N * H2p * W2p * 16;
   stem_pack_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, hi, lo, N, H, W, H2p, W2p, fmt);
@@ -385,7 +452,7 @@ __global__ void __launch_bounds__(512) add_softmax_rows_kernel(const void* __res
 extern "C" int mpn_add_softmax_rows(const void* ahi, const void* alo, const float* res, float* out, int P, int D, int a_stride,
                                     int fmt, void* stream) {
   MPN_CHECK_ARG(ahi && res && out && P > 0 && D > 0 && a_stride >= D, "mpn_add_softmax_rows: bad argument");
-  MPN_CHECK_ARG(fmt != MPN_FMT_BF16X2 || alo, "mpn_add_softmax_rows: BF16X2 needs a lo plane");
+  MPN_CHECK_ARG((fmt != MPN_FMT_BF16X2 && fmt != MPN_FMT_F16F8) || alo, "mpn_add_softmax_rows: split formats need a lo plane");
   add_softmax_rows_kernel<<<P, 512, 0, (cudaStream_t)stream>>>(ahi, alo, res, out, D, a_stride, fmt);
   MPN_LAUNCH_OK();
   return MPN_OK;
@@ -447,14 +514,14 @@ __global__ void stem_pack_input_u8_kernel(const unsigned char* __restrict__ img,
       int ih = 2 * (hp - 2) + ph, iw = 2 * (wp - 2) + pw;
       if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = lut[c][img[(((long long)n * H + ih) * W + iw) * 3 + (2 - c)]];
     }
-    mpn_store_act(hi, lo, i, fmt, v);
+    mpn_store_act(hi, lo, i, fmt, v, total);
   }
 }
 
 extern "C" int mpn_stem_pack_input_u8(const unsigned char* img_nhwc_bgr, void* hi, void* lo, int N, int H, int W, int fmt,
                                       void* stream) {
   MPN_CHECK_ARG(img_nhwc_bgr && hi && N > 0 && H > 0 && W > 0, "mpn_stem_pack_input_u8: bad argument");
-  MPN_CHECK_ARG(fmt == MPN_FMT_BF16 || (fmt == MPN_FMT_BF16X2 && lo), "mpn_stem_pack_input_u8: fmt must be BF16 or BF16X2 (with lo)");
+  MPN_CHECK_ARG(fmt == MPN_FMT_BF16 || ((fmt == MPN_FMT_BF16X2 || fmt == MPN_FMT_F16F8) && lo), "mpn_stem_pack_input_u8: fmt must be BF16, BF16X2 or F16F8 (with lo)");
   int H2p = (H + 1) / 2 + 3, W2p = (W + 1) / 2 + 3;
   long long total = (long long)N * H2p * W2p * 16;
   stem_pack_input_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img_nhwc_bgr, hi, lo, N, H, W, H2p, W2p, fmt);

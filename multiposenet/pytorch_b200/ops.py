@@ -7,10 +7,12 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (EPI_RELU, EPI_SIGMOID, FMT_BF16, FMT_BF16X2, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_NHWC, ConvDesc,
+import math
+
+from ._lib import (EPI_RELU, EPI_SIGMOID, FMT_BF16, FMT_BF16X2, FMT_F16F8, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_NHWC, ConvDesc,
                    ConvPtrs, check)
 
-PRECISIONS = {"fp32": FMT_F32, "bf16": FMT_BF16, "bf16x3": FMT_BF16X2}
+PRECISIONS = {"fp32": FMT_F32, "bf16": FMT_BF16, "bf16x3": FMT_BF16X2, "f16f8": FMT_F16F8}
 
 # Launch accounting for bench.py: `launches` counts kernels launched through this module; when
 # `conv_events` is a list, every tensor-core / CUDA-core conv launch is bracketed by CUDA events.
@@ -26,11 +28,12 @@ def _ptr(t):
 
 
 def _dtype(fmt):
-    return torch.float32 if fmt == FMT_F32 else torch.bfloat16
+    return torch.float32 if fmt == FMT_F32 else torch.float16 if fmt == FMT_F16F8 else torch.bfloat16
 
 
 class Act(object):
-    """NHWC activation: `hi` (and `lo` for the split format) are [N,H,W,cstride] tensors."""
+    """NHWC activation: `hi` (and `lo` for the split formats) are [N,H,W,cstride] tensors; FMT_F16F8: hi fp16, lo = uint8
+    [2,N,H,W,cstride] (the e5m2 residual plane and the e5m2 copy plane back to back, see mpn_b200.h)."""
     __slots__ = ("fmt", "N", "H", "W", "C", "cstride", "hi", "lo", "wpitch", "k_overlap")
 
     def __init__(self, fmt, N, H, W, C, device, cstride=None, zero=False, wpitch=0, k_overlap=0):
@@ -40,7 +43,12 @@ class Act(object):
         mk = torch.zeros if zero else torch.empty
         shape = (N, H, wpitch if wpitch else W, self.cstride)
         self.hi = mk(shape, dtype=_dtype(fmt), device=device)
-        self.lo = mk(shape, dtype=torch.bfloat16, device=device) if fmt == FMT_BF16X2 else None
+        if fmt == FMT_F16F8:
+            if self.cstride % 16:
+                raise ValueError("FMT_F16F8 activations need a channel stride that is a multiple of 16 (got %d)" % self.cstride)
+            self.lo = mk((2,) + shape, dtype=torch.uint8, device=device)
+        else:
+            self.lo = mk(shape, dtype=torch.bfloat16, device=device) if fmt == FMT_BF16X2 else None
 
     def to_nchw(self):
         out = torch.empty((self.N, self.C, self.H, self.W), dtype=torch.float32, device=self.hi.device)
@@ -62,7 +70,7 @@ def act_from_nchw(x, fmt, cstride=None):
 
 class PackedConv(object):
     """Filter + per-channel epilogue constants of one nn.Conv2d (+ folded eval-mode BatchNorm2d)."""
-    __slots__ = ("Cout", "Cin", "R", "S", "fmt", "w_hi", "w_lo", "cout_pad", "scale", "bias")
+    __slots__ = ("Cout", "Cin", "R", "S", "fmt", "w_hi", "w_lo", "cout_pad", "scale", "bias", "acc_scale")
 
 
 def pack_conv(weight, bias, bn, fmt, fold_scale=True):
@@ -90,11 +98,18 @@ def pack_conv(weight, bias, bn, fmt, fold_scale=True):
     elif bias is not None:
         pc.bias = torch.zeros(npad, dtype=torch.float32, device=dev)
         pc.bias[: pc.Cout].copy_(bias.detach())
+    pc.acc_scale = 0.0
     if fmt == FMT_F32:
         pc.cout_pad = npad
         pc.w_hi = torch.empty((pc.R, pc.S, pc.Cin, pc.cout_pad), dtype=torch.float32, device=dev)
         pc.w_lo = None
         check(L.mpn_pack_filter_f32(_ptr(w), _ptr(pc.w_hi), pc.Cout, pc.Cin, pc.R, pc.S, pc.cout_pad, _stream()), "mpn_pack_filter_f32")
+    elif fmt == FMT_F16F8:
+        pc.cout_pad = pc.Cout
+        fold = fold_scale and pc.scale is not None
+        _pack_f16f8(pc, w, pc.scale if fold else None, stem=False)
+        if fold:
+            pc.scale = None
     else:
         pc.cout_pad = pc.Cout
         pc.w_hi = torch.empty((pc.Cout, pc.R, pc.S, pc.Cin), dtype=torch.bfloat16, device=dev)
@@ -105,6 +120,26 @@ def pack_conv(weight, bias, bn, fmt, fold_scale=True):
         if fold:
             pc.scale = None
     return pc
+
+
+def _pack_f16f8(pc, w, scale, stem):
+    """FMT_F16F8 filter planes: the filter (times the folded BN scale) is prescaled by the power of two 2^k that brings its
+    largest magnitude into [2^14, 2^15) -- exact, undone by acc_scale = 2^-k in the epilogue -- so that the fp16 hi plane,
+    the e4m3 residual plane and the e4m3 copy (times 2^-12, pairing with the activations' 2^12-scaled residual) all sit
+    in range and the three products share one accumulator."""
+    L = _lib.lib()
+    amax = torch.zeros(1, dtype=torch.float32, device=w.device)
+    per = w[0].numel()
+    check(L.mpn_filter_absmax(_ptr(w), _ptr(scale), pc.Cout, per, _ptr(amax), _stream()), "mpn_filter_absmax")
+    a = float(amax.item())
+    k = 0 if not (a > 0.0 and math.isfinite(a)) else max(-100, min(100, 14 - math.frexp(a)[1] + 1))   # a * 2^k in [2^14, 2^15)
+    shape = (pc.Cout, 4, 1, 64) if stem else (pc.Cout, pc.R, pc.S, pc.Cin)
+    pc.w_hi = torch.empty(shape, dtype=torch.float16, device=w.device)
+    pc.w_lo = torch.empty((2,) + shape, dtype=torch.uint8, device=w.device)
+    Cout, Cin, R, S = w.shape
+    check(L.mpn_pack_filter_f16f8(_ptr(w), _ptr(scale), float(2.0 ** k), _ptr(pc.w_hi), _ptr(pc.w_lo), Cout, Cin, R, S, int(stem), _stream()),
+          "mpn_pack_filter_f16f8")
+    pc.acc_scale = float(2.0 ** -k)
 
 
 def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=None, out=None, out_mode=OUT_ACT,
@@ -129,6 +164,7 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
     d.flags = (EPI_RELU if relu else 0) | (EPI_SIGMOID if sigmoid else 0)
     d.out_mode, d.out_rep, d.out_coffset = out_mode, out_rep, out_coffset
     d.w_cout_pad = pc.cout_pad
+    d.acc_scale = getattr(pc, "acc_scale", 0.0)
     p = ConvPtrs()
     p.x_hi, p.x_lo = _ptr(x.hi), _ptr(x.lo)
     p.w_hi, p.w_lo = _ptr(pc.w_hi), _ptr(pc.w_lo)
@@ -214,9 +250,13 @@ def pack_stem_filter(weight, bn, fmt):
     assert tuple(w.shape[1:]) == (3, 7, 7)
     pc = PackedConv()
     pc.Cout, pc.Cin, pc.R, pc.S, pc.fmt, pc.cout_pad = w.shape[0], 64, 4, 1, fmt, w.shape[0]
-    pc.w_hi = torch.empty((pc.Cout, 4, 1, 64), dtype=torch.bfloat16, device=w.device)
-    pc.w_lo = torch.empty_like(pc.w_hi) if fmt == FMT_BF16X2 else None
-    check(L.mpn_stem_pack_filter(_ptr(w), _ptr(pc.w_hi), _ptr(pc.w_lo), pc.Cout, _stream()), "mpn_stem_pack_filter")
+    pc.acc_scale = 0.0
+    if fmt == FMT_F16F8:
+        _pack_f16f8(pc, w, None, stem=True)   # the BN scale stays in the epilogue, as for the bf16 stem
+    else:
+        pc.w_hi = torch.empty((pc.Cout, 4, 1, 64), dtype=torch.bfloat16, device=w.device)
+        pc.w_lo = torch.empty_like(pc.w_hi) if fmt == FMT_BF16X2 else None
+        check(L.mpn_stem_pack_filter(_ptr(w), _ptr(pc.w_hi), _ptr(pc.w_lo), pc.Cout, _stream()), "mpn_stem_pack_filter")
     gamma, beta, mean, var, eps = bn
     npad = (pc.Cout + 63) // 64 * 64
     pc.scale = torch.zeros(npad, dtype=torch.float32, device=w.device)

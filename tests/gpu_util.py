@@ -4,7 +4,7 @@ import torch
 import torch.nn.functional as F
 
 from multiposenet.pytorch_b200 import ops
-from multiposenet.pytorch_b200._lib import FMT_BF16, FMT_BF16X2, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_NHWC
+from multiposenet.pytorch_b200._lib import FMT_BF16, FMT_BF16X2, FMT_F16F8, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_NHWC
 
 
 def no_tf32():

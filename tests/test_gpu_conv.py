@@ -77,7 +77,13 @@ def test_conv_tcgen05_bf16(case):
     _check(1, case, 6e-3, 3e-2)
 
 
-@pytest.mark.parametrize("fmt,tol", [(2, 1e-4), (1, 2e-2)])
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_f16f8(case):
+    # fp16 hi*hi on kind::f16 + the two fp8 cross terms on kind::f8f6f4: product error ~2^-15, output re-split 2^-15
+    _check(3, case, 2e-4, 2e-4)
+
+
+@pytest.mark.parametrize("fmt,tol", [(2, 1e-4), (1, 2e-2), (3, 2e-4)])
 @pytest.mark.parametrize("shape", [(2, 64, 96), (1, 50, 70), (2, 33, 47)])
 def test_tensor_core_stem_vs_torch(fmt, tol, shape):
     """fpn.py:99: 7x7/2 conv + BN + ReLU as a tcgen05 conv over the space-to-depth image."""

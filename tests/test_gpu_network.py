@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 # max|a-b|/max|b| per output tensor (north_star: 1e-3 vs the fp32 reference)
-TOL = {"fp32": 1e-4, "bf16x3": 1e-3}
+TOL = {"fp32": 1e-4, "bf16x3": 1e-3, "f16f8": 1e-3}
 
 
 def _run_all(m, x):
@@ -21,7 +21,7 @@ def _run_all(m, x):
     return heat, saved, cls, reg, anc, heat2, sc, cl, bx
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
 @pytest.mark.parametrize("name", ["r50_cond_64x96_b2", "r50_refinit_64x96_b1", "r101_cond_64x96_b1"])
 def test_network_vs_reference_golden(golden_dir, name, precision):
     from gpu_util import image, load_model, nerr
