@@ -58,6 +58,7 @@ struct TcParams {
   int N, OH, OW, Cout;
   int TW, TH, TN, rows;
   int tiles_w, tiles_h, tiles_n, tiles_co, total_tiles;
+  int m_tiles;  // tiles_w * tiles_h * tiles_n; CTA-pair kernels: a "tile" is a pair of consecutive M tiles x one Cout block
   // Tail balancing: tiles [0, main_tiles) are BN wide; every further BN-wide tile is cut into tail_split sub-tiles of
   // tail_bn columns so that the last partial round of the persistent schedule is spread over all SMs.
   int main_tiles, tail_split, tail_bn;
@@ -86,8 +87,8 @@ struct TileCoord {
   int co0, ncols, tw_i, th_i, tn_i;
 };
 
-template <int BN>
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile) {
+template <int BN, bool PAIR = false>
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, int rank = 0) {
   TileCoord c;
   int t = tile, sub = 0;
   c.ncols = BN;
@@ -99,11 +100,19 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile) {
   }
   const int co_t = t % P.tiles_co;
   int mt = t / P.tiles_co;
+  c.co0 = co_t * BN + sub * c.ncols;
+  if (PAIR) {
+    mt = 2 * mt + rank;
+    if (mt >= P.m_tiles) {  // odd tile count: the pair's second half is a box beyond the last image (zero loads, clipped stores)
+      c.tw_i = c.th_i = 0;
+      c.tn_i = P.tiles_n;
+      return c;
+    }
+  }
   c.tw_i = mt % P.tiles_w;
   mt /= P.tiles_w;
   c.th_i = mt % P.tiles_h;
   c.tn_i = mt / P.tiles_h;
-  c.co0 = co_t * BN + sub * c.ncols;
   return c;
 }
 
@@ -167,19 +176,25 @@ __device__ __forceinline__ void split_f16f8x8(const float* w, uint4& hi, uint2& 
   h8.y = e5m2x4(w[4], w[5], w[6], w[7]);
 }
 
-template <int BN, int MODE, int STAGES, int EPI>
+// PAIR: the kernel runs as 2-CTA clusters (one TPC).  The two CTAs take two consecutive M tiles of the same Cout block; each
+// loads its own activation box and HALF of the filter rows, the leader (cluster rank 0) issues one M = 256
+// tcgen05.mma.cta_group::2 per K step for both, so every SM reads half the B operand from shared memory and fills half of
+// it by TMA -- the single-CTA kernel is bound by shared-memory bandwidth (96 B/clk of MMA operand reads + the TMA fill
+// against 128 B/clk), not by the tensor pipe.
+template <int BN, int MODE, int STAGES, int EPI, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ Maps maps, const TcParams P) {
   constexpr bool SPLIT = MODE == MODE_BF16X2;
   constexpr bool F8 = MODE == MODE_F16F8;
   // "plane units" of 128 bytes per row and K block: BF16X2 = hi + lo; F16F8 = hi (128 B) + lo8 (64 B) + h8 (64 B)
   constexpr int PLANES = MODE == MODE_BF16 ? 1 : 2;
   constexpr int NMAPS = F8 ? 3 : PLANES;
-  constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
+  constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BLOCK_K * 2;  // filter rows held by THIS CTA
   constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + B_TILE_BYTES);
+  constexpr int MMA_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   // c = F32; a, b = BF16 (1) or, for F16F8, F16 (0);  | (N >> 3) << 17 per tile
-  constexpr uint32_t IDESC_BASE = (1u << 4) | (F8 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BLOCK_M >> 4) << 24);
-  constexpr uint32_t IDESC_F8 = (1u << 4) | (1u << 7) | ((uint32_t)(BLOCK_M >> 4) << 24);  // a = E5M2 (1), b = E4M3 (0)
+  constexpr uint32_t IDESC_BASE = (1u << 4) | (F8 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(MMA_M >> 4) << 24);
+  constexpr uint32_t IDESC_F8 = (1u << 4) | (1u << 7) | ((uint32_t)(MMA_M >> 4) << 24);  // a = E5M2 (1), b = E4M3 (0)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -196,6 +211,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k_iters = P.R * P.S * P.kb_per_tap;
+  const int cta_rank = PAIR ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // first (pair) tile of this CTA / cluster
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -212,7 +231,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), NUM_EPI_WARPS);
+      mbar_init(tempty_bar(a), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // pair: the epilogue warps of both CTAs release the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -224,11 +243,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything is signalled across the pair
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
@@ -241,16 +266,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // =============================== TMA producer ===============================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile<BN>(P, tile);
+    const uint32_t lead_full0 = PAIR ? mapa_shared(full_bar(0), 0) : 0u;  // the leader's full barriers, as cluster addresses
+    for (int tile = tile0; tile < P.total_tiles; tile += tile_step) {
+      const TileCoord tc = decode_tile<BN, PAIR>(P, tile, cta_rank);
       const bool tail = tc.ncols != BN;
-      const uint32_t tx_bytes = (uint32_t)PLANES * (uint32_t)((P.rows + tc.ncols) * BLOCK_K * 2);
+      const int brows = PAIR ? tc.ncols / 2 : tc.ncols;                     // filter rows this CTA loads
+      // bytes of one K block landing in this CTA; the leader's barrier of a pair expects both CTAs' bytes
+      const uint32_t tx_bytes = (uint32_t)PLANES * (uint32_t)((P.rows + brows) * BLOCK_K * 2) * (PAIR ? 2u : 1u);
       // narrow tail tiles are latency-bound on the ring: pack as many K blocks as fit into one stage (sub-blocks of
       // [A planes][B planes], the B planes ncols*128 bytes apart) so that twice the bytes are in flight
-      const uint32_t bplane = tail ? (uint32_t)tc.ncols * 128u : (uint32_t)B_TILE_BYTES;
+      const uint32_t bplane = tail ? (uint32_t)brows * 128u : (uint32_t)B_TILE_BYTES;
       const uint32_t sub_bytes = (uint32_t)PLANES * ((uint32_t)A_TILE_BYTES + bplane);
-      const int kpack = tail ? (int)(STAGE_BYTES / sub_bytes) : 1;
-      const int ow0 = tc.tw_i * P.TW, oh0 = tc.th_i * P.TH, n0 = tc.tn_i * P.TN, co0 = tc.co0;
+      const int kpack = (tail && !PAIR) ? (int)(STAGE_BYTES / sub_bytes) : 1;
+      const int ow0 = tc.tw_i * P.TW, oh0 = tc.th_i * P.TH, n0 = tc.tn_i * P.TN, co0 = tc.co0 + cta_rank * brows;
       int u = 0, ki = 0;
       for (int tap = 0; tap < P.R * P.S; ++tap) {
         const int r = tap / P.S, s = tap - r * P.S;
@@ -273,12 +301,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           if (u == 0) {
             const int group = min(kpack, num_k_iters - ki);
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), tx_bytes * (uint32_t)group);
+            if (leader) mbar_expect_tx(full_bar(stage), tx_bytes * (uint32_t)group);
           }
           const uint32_t sa = smem_base + stage * STAGE_BYTES + u * sub_bytes;
           const uint32_t sb = sa + PLANES * A_TILE_BYTES;
           const int kcol = tap * P.Cin + kb * BLOCK_K;
-          if constexpr (F8) {
+          if constexpr (PAIR) {
+            const uint32_t lb = lead_full0 + 8u * stage;
+            if constexpr (F8) {
+              tma_load_4d_pair(sa, &maps.a[0][ph], lb, kb * BLOCK_K, wc, hc, n0);
+              tma_load_4d_pair(sa + A_TILE_BYTES, &maps.a[1][ph], lb, kb * BLOCK_K, wc, hc, n0);
+              tma_load_4d_pair(sa + A_TILE_BYTES + A_TILE_BYTES / 2, &maps.a[2][ph], lb, kb * BLOCK_K, wc, hc, n0);
+              tma_load_2d_pair(sb, tail ? &maps.bs[0] : &maps.b[0], lb, kcol, co0);
+              tma_load_2d_pair(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], lb, kcol, co0);
+              tma_load_2d_pair(sb + bplane + bplane / 2, tail ? &maps.bs[2] : &maps.b[2], lb, kcol, co0);
+            } else {
+#pragma unroll
+              for (int p = 0; p < PLANES; ++p) {
+                tma_load_4d_pair(sa + p * A_TILE_BYTES, &maps.a[p][ph], lb, kb * BLOCK_K, wc, hc, n0);
+                tma_load_2d_pair(sb + p * bplane, tail ? &maps.bs[p] : &maps.b[p], lb, kcol, co0);
+              }
+            }
+          } else if constexpr (F8) {
             // A: [hi 16 KB][lo8 8 KB][h8 8 KB]; B: [hi ncols*128][lo8 ncols*64][h8 ncols*64]
             tma_load_4d(sa, &maps.a[0][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
             tma_load_4d(sa + A_TILE_BYTES, &maps.a[1][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
@@ -300,7 +344,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           }
         }
       }
-      if (EPI == EPI_TMA && P.res_mma) {
+      if (EPI == EPI_TMA && !PAIR && P.res_mma) {
 #pragma unroll 1
         for (int p = 0; p < PLANES; ++p) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -315,24 +359,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // =============================== MMA issuer ===============================
+  } else if (warp == 1 && lane == 0 && leader) {
+    // =============================== MMA issuer (pair: the leader CTA only) ===============================
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < P.total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      const int ncols = decode_tile<BN>(P, tile).ncols;
+      const int ncols = decode_tile<BN, PAIR>(P, tile, 0).ncols;
       const uint32_t IDESC = IDESC_BASE | ((uint32_t)(ncols >> 3) << 17);
-      const bool res_mma = EPI == EPI_TMA && P.res_mma;
+      const bool res_mma = EPI == EPI_TMA && !PAIR && P.res_mma;
       const bool tail = ncols != BN;
-      const uint32_t bplane = tail ? (uint32_t)ncols * 128u : (uint32_t)B_TILE_BYTES;
+      const uint32_t bplane = tail ? (uint32_t)(PAIR ? ncols / 2 : ncols) * 128u : (uint32_t)B_TILE_BYTES;
       const uint32_t sub_bytes = (uint32_t)PLANES * ((uint32_t)A_TILE_BYTES + bplane);
-      const int kpack = tail ? (int)(STAGE_BYTES / sub_bytes) : 1;
+      const int kpack = (tail && !PAIR) ? (int)(STAGE_BYTES / sub_bytes) : 1;
       for (int ki = 0; ki < num_k_iters;) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
@@ -340,33 +384,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         for (int u = 0; u < group; ++u, ++ki) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES + u * sub_bytes;
           const uint32_t sb = sa + PLANES * A_TILE_BYTES;
+          auto mma16 = [&](uint64_t a, uint64_t b, uint32_t accum) {
+            if (PAIR) umma_f16_pair(d_tmem, a, b, IDESC, accum);
+            else umma_bf16(d_tmem, a, b, IDESC, accum);
+          };
           if constexpr (F8) {
             const uint32_t idesc8 = IDESC_F8 | ((uint32_t)(ncols >> 3) << 17);
+            auto mma8 = [&](uint64_t a, uint64_t b) {
+              if (PAIR) umma_f8_pair(d_tmem, a, b, idesc8, 1u);
+              else umma_f8(d_tmem, a, b, idesc8, 1u);
+            };
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k)  // fp16 hi * fp16 hi, K = 16 per instruction
-              umma_bf16(d_tmem, make_sdesc(sa + k * 32), make_sdesc(sb + k * 32), IDESC, (ki > 0 || k > 0) ? 1u : 0u);
+              mma16(make_sdesc(sa + k * 32), make_sdesc(sb + k * 32), (ki > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 32; ++k) {  // fp8 cross terms, K = 32 per instruction
-              umma_f8(d_tmem, make_sdesc64(sa + A_TILE_BYTES + k * 32), make_sdesc64(sb + bplane + bplane / 2 + k * 32), idesc8, 1u);  // xlo8 * wh8
-              umma_f8(d_tmem, make_sdesc64(sa + A_TILE_BYTES + A_TILE_BYTES / 2 + k * 32), make_sdesc64(sb + bplane + k * 32), idesc8, 1u);  // xh8 * wlo8
+              mma8(make_sdesc64(sa + A_TILE_BYTES + k * 32), make_sdesc64(sb + bplane + bplane / 2 + k * 32));  // xlo8 * wh8
+              mma8(make_sdesc64(sa + A_TILE_BYTES + A_TILE_BYTES / 2 + k * 32), make_sdesc64(sb + bplane + k * 32));  // xh8 * wlo8
             }
           } else {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
               const uint64_t a_hi = make_sdesc(sa + k * 32);
               const uint64_t b_hi = make_sdesc(sb + k * 32);
-              umma_bf16(d_tmem, a_hi, b_hi, IDESC, (ki > 0 || k > 0) ? 1u : 0u);
+              mma16(a_hi, b_hi, (ki > 0 || k > 0) ? 1u : 0u);
               if (SPLIT) {
                 const uint64_t a_lo = make_sdesc(sa + A_TILE_BYTES + k * 32);
                 const uint64_t b_lo = make_sdesc(sb + bplane + k * 32);
-                umma_bf16(d_tmem, a_lo, b_hi, IDESC, 1u);
-                umma_bf16(d_tmem, a_hi, b_lo, IDESC, 1u);
+                mma16(a_lo, b_hi, 1u);
+                mma16(a_hi, b_lo, 1u);
               }
             }
           }
         }
-        umma_commit(empty_bar(stage));                                    // frees the smem stage when the MMAs retire
-        if (ki == num_k_iters && !res_mma) umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        if (PAIR) {  // multicast: the barrier at the same offset in both CTAs of the pair
+          umma_commit_pair(empty_bar(stage));
+          if (ki == num_k_iters) umma_commit_pair(tfull_bar(acc));
+        } else {
+          umma_commit(empty_bar(stage));                                    // frees the smem stage when the MMAs retire
+          if (ki == num_k_iters && !res_mma) umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       if (res_mma) {
@@ -401,10 +458,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                               : (P.out_mode == MPN_OUT_F32_NCHW ? (long long)P.Cout * OHr * OWr : (long long)OHr * OWr * P.out_cstride);
     int it = 0;
     bool store_pending = false;  // EPI_TMA: a bulk store of this half may still be reading its staging box
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+    const uint32_t lead_tempty0 = PAIR ? mapa_shared(tempty_bar(0), 0) : 0u;
+    for (int tile = tile0; tile < P.total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const TileCoord tc = decode_tile<BN>(P, tile);
+      const TileCoord tc = decode_tile<BN, PAIR>(P, tile, cta_rank);
       const int tw_i = tc.tw_i, th_i = tc.th_i, tn_i = tc.tn_i, co0 = tc.co0, ncols = tc.ncols;
       if constexpr (EPI == EPI_TMA) {
         // ---- thread = pixel row (the TMEM lane): 32 channels per step -> bf16 hi/lo -> 64B-swizzled box in smem -> TMA store.
@@ -724,16 +782,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(lead_tempty0 + 8u * acc);  // the leader's MMA issuer waits for both CTAs' epilogues
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
     if (EPI == EPI_TMA && store_pending && (warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   // =============================== teardown ===============================
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // no CTA of the pair frees TMEM / exits while the other may still signal or read it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -795,18 +858,19 @@ void choose_tile(int N, int OH, int OW, int* TW, int* TH, int* TN) {
   *TW = bw; *TH = bh; *TN = bn;
 }
 
-template <int BN, int MODE, int EPI>
+template <int BN, int MODE, int EPI, bool PAIR = false>
 int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
   constexpr int PLANES = MODE == MODE_BF16 ? 1 : 2;
-  constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + BN * BLOCK_K * 2);
+  constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BLOCK_K * 2);
   constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - NUM_EPI_WARPS * EPI_STAGE_BYTES) / STAGE_BYTES;
   constexpr int STAGES = MAXS > 8 ? 8 : MAXS;
   static_assert(STAGES >= 2, "not enough shared memory for a 2-stage ring");
   static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier area too small");
   const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
-  auto kern = conv_tc_kernel<BN, MODE, STAGES, EPI>;
+  auto kern = conv_tc_kernel<BN, MODE, STAGES, EPI, PAIR>;
   MPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = P.total_tiles < sms ? P.total_tiles : sms;
+  if (PAIR) grid = 2 * (P.total_tiles < sms / 2 ? P.total_tiles : sms / 2);  // one 2-CTA cluster per pair tile, <= SMs/2 clusters
   static const int pdl = getenv("MPN_PDL") ? atoi(getenv("MPN_PDL")) : 0;  // opt-in: no step-time gain inside a CUDA graph (r01l)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -814,11 +878,22 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   MPN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, P));
   MPN_LAUNCH_OK();
   return MPN_OK;
@@ -877,9 +952,15 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   static const int res_mma_on = getenv("MPN_RES_MMA") ? atoi(getenv("MPN_RES_MMA")) : 1;
   const bool epi_tma = epi_tma_on && !f32out && d->out_rep == 1 && d->up_cstride == 0;
   const bool res_mma = res_mma_on && epi_tma && split && d->res_cstride > 0 && !p->scale && d->Cout % 64 == 0;
-  const int min_tail_bn = res_mma ? 64 : 32;
+  // CTA-pair kernel (MPN_PAIR=0 disables): activation outputs of >= 128 channels, no residual (the tensor-core residual add
+  // stays on the single-CTA kernel), enough M tiles to form pairs.  A pair tile = two consecutive M tiles x one Cout block.
+  static const int pair_on = getenv("MPN_PAIR") ? atoi(getenv("MPN_PAIR")) : 1;
+  const bool pair = pair_on && !f32out && d->res_cstride == 0 && d->Cout >= 128 && m_tiles >= 2 && sms >= 2;
+  const int min_tail_bn = pair ? 64 : res_mma ? 64 : 32;
   int BN = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
   int tail_s = 1;
+  const long long sched_m = pair ? (m_tiles + 1) / 2 : m_tiles;   // schedulable M units
+  const int sched_sms = pair ? sms / 2 : sms;                      // ... and the units that run at once
   {
     int cand[3] = {BN, 0, 0};
     if (BN == 256) {
@@ -889,8 +970,8 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
     double best = 1e30;
     for (int ci = 0; ci < 3 && cand[ci]; ++ci) {
       const int bn = cand[ci];
-      const long long T = m_tiles * mpn_divup(d->Cout, bn);
-      const long long G = T < sms ? T : sms;
+      const long long T = sched_m * mpn_divup(d->Cout, bn);
+      const long long G = T < sched_sms ? T : sched_sms;
       const long long rounds = T / G, rem = T % G;
       const double c_full = bn + 64.0;
       double cost = (double)(rounds + (rem > 0)) * c_full;
@@ -906,9 +987,10 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   }
   P.tiles_co = mpn_divup(d->Cout, BN);
   {
-    const long long T = m_tiles * P.tiles_co;
+    const long long T = sched_m * P.tiles_co;
     MPN_CHECK_ARG(T < (1LL << 27), "conv(tcgen05): too many tiles");
-    const long long G = T < sms ? T : sms;
+    const long long G = T < sched_sms ? T : sched_sms;
+    P.m_tiles = (int)m_tiles;
     const long long rem = tail_s > 1 ? T % G : 0;
     P.main_tiles = (int)(T - rem);
     P.tail_split = tail_s;
@@ -970,11 +1052,11 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
     const cuuint64_t K = (cuuint64_t)d->R * d->S * d->Cin;
     cuuint64_t wdims[2] = {K, (cuuint64_t)d->Cout};
     cuuint64_t wstrides[1] = {K * es};
-    cuuint32_t wbox[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN};
+    cuuint32_t wbox[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(pair ? BN / 2 : BN)};   // pair: each CTA loads half of the filter rows
     int rc = encode(fn, &maps.b[pl], wb, 2, wdims, wstrides, wbox, swz, dt);
     if (rc) return rc;
     if (P.tail_split > 1) {
-      cuuint32_t sbox[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)P.tail_bn};
+      cuuint32_t sbox[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(pair ? P.tail_bn / 2 : P.tail_bn)};
       rc = encode(fn, &maps.bs[pl], wb, 2, wdims, wstrides, sbox, swz, dt);
       if (rc) return rc;
     }
@@ -1019,6 +1101,10 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
     return BN == 64 ? launch<64, MODE_BF16, EPI_F32>(maps, P, s, sms) : launch<32, MODE_BF16, EPI_F32>(maps, P, s, sms);
   }
 #define MPN_TC_DISPATCH(SPLIT_, EPI_)                                     \
+  if (pair) {                                                              \
+    if (BN == 256) return launch<256, SPLIT_, EPI_, true>(maps, P, s, sms); \
+    return launch<128, SPLIT_, EPI_, true>(maps, P, s, sms);               \
+  }                                                                        \
   switch (BN) {                                                            \
     case 256: return launch<256, SPLIT_, EPI_>(maps, P, s, sms);           \
     case 128: return launch<128, SPLIT_, EPI_>(maps, P, s, sms);           \
