@@ -117,7 +117,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, in
 }
 
 // ---------------------------------------------------------------------------------------------
-enum { EPI_LSU = 0, EPI_F32 = 1, EPI_TMA = 2 };
+// EPI_TMA_RES = EPI_TMA with the shortcut tensor brought in by TMA as well (32-channel boxes, double-buffered per epilogue half)
+enum { EPI_LSU = 0, EPI_F32 = 1, EPI_TMA = 2, EPI_TMA_RES = 3 };
+constexpr int RES_STAGE_BYTES = 16384;  // per (half, buffer): [hi: rows x 64 B, 64B swizzle][lo: rows x 64 B | lo8: rows x 32 B]
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -191,6 +193,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BLOCK_K * 2;  // filter rows held by THIS CTA
   constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + B_TILE_BYTES);
   constexpr int MMA_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
+  constexpr bool TMAEPI = EPI == EPI_TMA || EPI == EPI_TMA_RES;
+  constexpr bool RESLD = EPI == EPI_TMA_RES;
+  constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES + (RESLD ? 4 * RES_STAGE_BYTES : 0);
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   // c = F32; a, b = BF16 (1) or, for F16F8, F16 (0);  | (N >> 3) << 17 per tile
   constexpr uint32_t IDESC_BASE = (1u << 4) | (F8 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(MMA_M >> 4) << 24);
@@ -198,15 +203,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES + EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto res_full_bar = [&](int h, int b) { return bar_base + 8u * (2 * STAGES + 5 + 2 * h + b); };
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + EPI_BYTES + 8 * (2 * STAGES + 4));
   uint8_t* epi_stage = smem_gen + STAGES * STAGE_BYTES;  // 1024-byte aligned (TMA-store swizzle pattern)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -222,8 +228,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       prefetch_tmap(&maps.b[p]);
       prefetch_tmap(&maps.a[p][0]);
       if (P.tail_split > 1) prefetch_tmap(&maps.bs[p]);
-      if (EPI == EPI_TMA) prefetch_tmap(&maps.y[p]);
-      if (EPI == EPI_TMA && P.res_mma && p < 2) prefetch_tmap(&maps.r[p]);
+      if (TMAEPI) prefetch_tmap(&maps.y[p]);
+      if (TMAEPI && (P.res_mma || RESLD) && p < 2) prefetch_tmap(&maps.r[p]);
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -233,9 +239,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // pair: the epilogue warps of both CTAs release the leader
     }
+    if (RESLD) {
+      for (int i = 0; i < 4; ++i) mbar_init(res_full_bar(i >> 1, i & 1), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (EPI == EPI_TMA && P.res_mma && P.rows < BLOCK_M) {
+  if (TMAEPI && P.res_mma && P.rows < BLOCK_M) {
     // rows >= P.rows of a residual box are never written by TMA but are read (times a zero of I) by the MMA:
     // make sure no stale NaN/Inf bit pattern of an earlier kernel sits there
     uint4* z = reinterpret_cast<uint4*>(smem_gen);
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           }
         }
       }
-      if (EPI == EPI_TMA && !PAIR && P.res_mma) {
+      if (TMAEPI && !PAIR && P.res_mma) {
 #pragma unroll 1
         for (int p = 0; p < PLANES; ++p) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       const int ncols = decode_tile<BN, PAIR>(P, tile, 0).ncols;
       const uint32_t IDESC = IDESC_BASE | ((uint32_t)(ncols >> 3) << 17);
-      const bool res_mma = EPI == EPI_TMA && !PAIR && P.res_mma;
+      const bool res_mma = TMAEPI && !PAIR && P.res_mma;
       const bool tail = ncols != BN;
       const uint32_t bplane = tail ? (uint32_t)(PAIR ? ncols / 2 : ncols) * 128u : (uint32_t)B_TILE_BYTES;
       const uint32_t sub_bytes = (uint32_t)PLANES * ((uint32_t)A_TILE_BYTES + bplane);
@@ -459,12 +468,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     int it = 0;
     bool store_pending = false;  // EPI_TMA: a bulk store of this half may still be reading its staging box
     const uint32_t lead_tempty0 = PAIR ? mapa_shared(tempty_bar(0), 0) : 0u;
+    // RESLD: the shortcut box of 32-channel chunk n + 1 of this half (next chunk of the tile, or the first one of the CTA's next
+    // tile) is requested by TMA when chunk n starts, into the buffer chunk n - 1 was read from (every thread of the half has
+    // passed that chunk's barriers), so a whole chunk period covers the load latency and no LSU load touches the shortcut.
+    uint32_t res_n = 0;  // chunks of this half consumed so far: buffer = res_n & 1, mbarrier parity = (res_n >> 1) & 1
+    const uint32_t res_bytes = (uint32_t)P.rows * (SPLIT ? 128u : F8 ? 96u : 64u);
+    auto res_issue = [&](uint32_t n, int cb, int w0, int h0, int i0) {
+      const uint32_t bar = res_full_bar(half, (int)(n & 1u));
+      const uint32_t dst = smem_base + STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + (uint32_t)(half * 2 + (int)(n & 1u)) * RES_STAGE_BYTES;
+      mbar_expect_tx(bar, res_bytes);
+      tma_load_4d(dst, &maps.r[0], bar, cb, w0, h0, i0);
+      if (SPLIT || F8) tma_load_4d(dst + 8192, &maps.r[1], bar, cb, w0, h0, i0);
+    };
+    if (RESLD && q == 0 && lane == 0 && tile0 < P.total_tiles) {
+      const TileCoord t0 = decode_tile<BN, PAIR>(P, tile0, cta_rank);
+      res_issue(0u, t0.co0 + half * 32, t0.tw_i * P.TW, t0.th_i * P.TH, t0.tn_i * P.TN);
+    }
     for (int tile = tile0; tile < P.total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const TileCoord tc = decode_tile<BN, PAIR>(P, tile, cta_rank);
       const int tw_i = tc.tw_i, th_i = tc.th_i, tn_i = tc.tn_i, co0 = tc.co0, ncols = tc.ncols;
-      if constexpr (EPI == EPI_TMA) {
+      if constexpr (TMAEPI) {
         // ---- thread = pixel row (the TMEM lane): 32 channels per step -> bf16 hi/lo -> 64B-swizzled box in smem -> TMA store.
         // The two halves (4 warps each) own separate 16 KB staging boxes and alternate over the 32-channel blocks.
         const int row = q * 32 + lane;
@@ -474,13 +499,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const bool issuer = (q == 0 && lane == 0);
         const int ow0 = tw_i * P.TW, oh0 = th_i * P.TH, n0 = tn_i * P.TN;
         long long res_off = 0;
-        const bool res_lsu = P.res_cstride > 0 && !P.res_mma;
+        const bool res_lsu = !RESLD && P.res_cstride > 0 && !P.res_mma;
         if (res_lsu) {
           const int tw2 = row % P.TW, th2 = (row / P.TW) % P.TH, tn2 = row / (P.TW * P.TH);
           const int ow2 = ow0 + tw2, oh2 = oh0 + th2, n2 = n0 + tn2;
           const bool ok = row < P.rows && ow2 < P.OW && oh2 < P.OH && n2 < P.N;
           res_off = ok ? ((long long)(n2 * P.OH + oh2) * P.OW + ow2) * P.res_cstride : 0;  // invalid rows read pixel 0 (never stored)
         }
+        // The shortcut operand does not depend on the accumulator: the 64 (+64 / +32) bytes of a row's next 32-channel chunk are
+        // requested one chunk ahead -- the first one before the accumulator is even complete -- so the global-load latency
+        // hides behind the previous chunk's convert / stage / store instead of stalling every chunk (4 per tile and warp).
+        uint4 nh[4], nl[4];
+        auto load_res = [&](int cb) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            nh[i] = __ldg(reinterpret_cast<const uint4*>(P.res_hi + res_off + cb) + i);
+            if (SPLIT) nl[i] = __ldg(reinterpret_cast<const uint4*>(P.res_lo + res_off + cb) + i);
+            if (F8 && i < 2) nl[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(P.res_lo) + res_off + cb) + i);
+          }
+        };
+        if (res_lsu && half * 32 < ncols && co0 + half * 32 < P.Cout) load_res(co0 + half * 32);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
 #pragma unroll 1
@@ -493,11 +531,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           uint4 rh[4], rl[4];
           if (res_lsu) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              rh[i] = __ldg(reinterpret_cast<const uint4*>(P.res_hi + res_off + cbase) + i);
-              if (SPLIT) rl[i] = __ldg(reinterpret_cast<const uint4*>(P.res_lo + res_off + cbase) + i);
-              if (F8 && i < 2) rl[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(P.res_lo) + res_off + cbase) + i);
+            for (int i = 0; i < 4; ++i) { rh[i] = nh[i]; rl[i] = nl[i]; }
+            if (c0 + 64 < ncols && cbase + 64 < P.Cout) load_res(cbase + 64);
+          }
+          if constexpr (RESLD) {
+            if (issuer) {
+              if (c0 + 64 < ncols && cbase + 64 < P.Cout) {
+                res_issue(res_n + 1u, cbase + 64, ow0, oh0, n0);
+              } else if (tile + tile_step < P.total_tiles) {
+                const TileCoord t2 = decode_tile<BN, PAIR>(P, tile + tile_step, cta_rank);
+                res_issue(res_n + 1u, t2.co0 + half * 32, t2.tw_i * P.TW, t2.th_i * P.TH, t2.tn_i * P.TN);
+              }
             }
+            mbar_wait(res_full_bar(half, (int)(res_n & 1u)), (res_n >> 1) & 1u);
+            const uint8_t* rs = epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES + (half * 2 + (int)(res_n & 1u)) * RES_STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              rh[i] = *reinterpret_cast<const uint4*>(rs + row * 64 + ((i ^ sw) << 4));
+              if (SPLIT) rl[i] = *reinterpret_cast<const uint4*>(rs + 8192 + row * 64 + ((i ^ sw) << 4));
+              if (F8 && i < 2) rl[i] = *reinterpret_cast<const uint4*>(rs + 8192 + row * 32 + (i << 4));
+            }
+            ++res_n;
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           float v[32];
@@ -521,7 +575,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
             }
           }
-          if (res_lsu) {
+          if (res_lsu || RESLD) {
             if constexpr (F8) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) add_f16x8_reg(v + 8 * i, rh[i]);
@@ -787,7 +841,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         else mbar_arrive(tempty_bar(acc));
       }
     }
-    if (EPI == EPI_TMA && store_pending && (warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (TMAEPI && store_pending && (warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   // =============================== teardown ===============================
   tc_fence_before();
@@ -862,11 +916,12 @@ template <int BN, int MODE, int EPI, bool PAIR = false>
 int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
   constexpr int PLANES = MODE == MODE_BF16 ? 1 : 2;
   constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BLOCK_K * 2);
-  constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - NUM_EPI_WARPS * EPI_STAGE_BYTES) / STAGE_BYTES;
+  constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES + (EPI == EPI_TMA_RES ? 4 * RES_STAGE_BYTES : 0);
+  constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
   constexpr int STAGES = MAXS > 8 ? 8 : MAXS;
   static_assert(STAGES >= 2, "not enough shared memory for a 2-stage ring");
-  static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier area too small");
-  const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+  static_assert(8 * (2 * STAGES + 9) <= BAR_BYTES, "barrier area too small");
+  const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EPI_BYTES;
   auto kern = conv_tc_kernel<BN, MODE, STAGES, EPI, PAIR>;
   MPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = P.total_tiles < sms ? P.total_tiles : sms;
@@ -955,7 +1010,10 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   // CTA-pair kernel (MPN_PAIR=0 disables): activation outputs of >= 128 channels, no residual (the tensor-core residual add
   // stays on the single-CTA kernel), enough M tiles to form pairs.  A pair tile = two consecutive M tiles x one Cout block.
   static const int pair_on = getenv("MPN_PAIR") ? atoi(getenv("MPN_PAIR")) : 1;
-  const bool pair = pair_on && !f32out && d->res_cstride == 0 && d->Cout >= 128 && m_tiles >= 2 && sms >= 2;
+  const bool pair = pair_on && !f32out && !res_mma && d->Cout >= 128 && m_tiles >= 2 && sms >= 2;
+  // ... and there the shortcut of a residual conv comes in by TMA (MPN_RES_TMA=0: per-thread global loads in the epilogue)
+  static const int res_tma_on = getenv("MPN_RES_TMA") ? atoi(getenv("MPN_RES_TMA")) : 1;
+  const bool res_tma = res_tma_on && pair && epi_tma && d->res_cstride > 0 && d->Cout % 64 == 0;
   const int min_tail_bn = pair ? 64 : res_mma ? 64 : 32;
   int BN = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
   int tail_s = 1;
@@ -1093,6 +1151,20 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
       if (rc) return rc;
     }
   }
+  if (res_tma) {  // shortcut boxes in the geometry of the output boxes: 32 channels x the tile's pixels
+    for (int pl = 0; pl < (f8 || split ? 2 : 1); ++pl) {
+      const bool bytes = f8 && pl > 0;
+      const unsigned long long es = bytes ? 1ULL : 2ULL;
+      cuuint64_t rdims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->OW, (cuuint64_t)d->OH, (cuuint64_t)d->N};
+      cuuint64_t rstr[3] = {(cuuint64_t)d->res_cstride * es, (cuuint64_t)d->OW * d->res_cstride * es,
+                            (cuuint64_t)d->OH * d->OW * d->res_cstride * es};
+      cuuint32_t rbox[4] = {32u, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
+      int rc = encode(fn, &maps.r[pl], pl == 0 ? p->res_hi : p->res_lo, 4, rdims, rstr, rbox,
+                      bytes ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B,
+                      bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+      if (rc) return rc;
+    }
+  }
   cudaStream_t s = (cudaStream_t)stream;
   if (f32out) {  // head outputs (18/19/36/9 channels): the thread-per-row fp32 store path, small-N tiles only
     MPN_CHECK_ARG(BN <= 64, "conv(tcgen05): fp32 outputs are built for Cout <= 64 (got %d)", d->Cout);
@@ -1111,15 +1183,24 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
     case 64: return launch<64, SPLIT_, EPI_>(maps, P, s, sms);             \
     default: return launch<32, SPLIT_, EPI_>(maps, P, s, sms);             \
   }
+#define MPN_TC_DISPATCH_RES(SPLIT_)                                                  \
+  if (res_tma) {                                                                      \
+    if (BN == 256) return launch<256, SPLIT_, EPI_TMA_RES, true>(maps, P, s, sms);    \
+    return launch<128, SPLIT_, EPI_TMA_RES, true>(maps, P, s, sms);                   \
+  }
   if (f8) {
+    MPN_TC_DISPATCH_RES(MODE_F16F8)
     if (epi_tma) { MPN_TC_DISPATCH(MODE_F16F8, EPI_TMA) }
     MPN_TC_DISPATCH(MODE_F16F8, EPI_LSU)
   }
   if (split) {
+    MPN_TC_DISPATCH_RES(MODE_BF16X2)
     if (epi_tma) { MPN_TC_DISPATCH(MODE_BF16X2, EPI_TMA) }
     MPN_TC_DISPATCH(MODE_BF16X2, EPI_LSU)
   }
+  MPN_TC_DISPATCH_RES(MODE_BF16)
   if (epi_tma) { MPN_TC_DISPATCH(MODE_BF16, EPI_TMA) }
   MPN_TC_DISPATCH(MODE_BF16, EPI_LSU)
 #undef MPN_TC_DISPATCH
+#undef MPN_TC_DISPATCH_RES
 }

@@ -42,8 +42,8 @@ def main():
     ap.add_argument("--once", action="store_true", help="one launch per shape, no timing loop (ncu target)")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    fmt = {"bf16x3": _lib.FMT_BF16X2, "bf16": _lib.FMT_BF16}[a.precision]
-    tol = 2e-4 if a.precision == "bf16x3" else 3e-2
+    fmt = {"bf16x3": _lib.FMT_BF16X2, "bf16": _lib.FMT_BF16, "f16f8": _lib.FMT_F16F8}[a.precision]
+    tol = {"bf16x3": 2e-4, "f16f8": 4e-4}.get(a.precision, 3e-2)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device("cuda")
@@ -53,7 +53,7 @@ def main():
              "%-40s %9s %9s %9s %9s" % ("shape", "us", "TFLOP/s", "us(L2cold)", "relerr")]
     bad = 0
     for name, H, W, Cin, Cout, k, stride, res in SHAPES:
-        if a.only and a.only not in name:
+        if a.only and not any(t in name for t in a.only.split(",")):
             continue
         B = a.batch
         x = torch.randn(B, Cin, H, W, device=dev, generator=g)

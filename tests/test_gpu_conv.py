@@ -45,6 +45,11 @@ TC_CASES = [
     (2, 8, 8, 128, 96, 1, 1, 0, dict(bn=True, residual=True, relu=True, bias=False)),     # Cout % 64 != 0: residual through the LSU
     (2, 8, 8, 128, 128, 1, 1, 0, dict(residual=True)),                              # residual without BN / bias (data-gradient accumulation)
     (1, 10, 12, 128, 128, 3, 1, 1, dict(coffset=128, ctotal=512)),                  # TMA store into a channel slice of a wider tensor
+    # CTA-pair kernel with the shortcut loaded by TMA (f16f8 / bf16; bf16x3 under MPN_RES_MMA=0)
+    (3, 30, 40, 64, 320, 1, 1, 0, dict(bn=True, residual=True, relu=True, bias=False)),   # 30 M tiles, last channel tile 64 of 256 wide
+    (5, 15, 20, 128, 256, 1, 1, 0, dict(bn=True, residual=True, relu=True, bias=False)),  # 15 M tiles: the last pair has a phantom half
+    (2, 30, 40, 128, 128, 3, 1, 1, dict(residual=True, relu=True)),                       # 128-wide pair tiles, 3x3 taps
+    (32, 30, 40, 64, 1024, 1, 1, 0, dict(bn=True, residual=True, relu=True, bias=False)), # layer3 expansion shape: many tiles per CTA
 ]
 
 
