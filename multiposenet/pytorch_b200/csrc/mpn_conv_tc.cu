@@ -164,8 +164,13 @@ __device__ __forceinline__ void add_f16x8_reg(float* v, const uint4& t) {
   v[4] += f16_lo_f(t.z); v[5] += f16_hi_f(t.z); v[6] += f16_lo_f(t.w); v[7] += f16_hi_f(t.w);
 }
 __device__ __forceinline__ void add_e5m2x4_reg(float* v, uint32_t w) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) v[j] += mpn_e5m2_to_float((unsigned char)(w >> (8 * j))) * MPN_F8_LO_INV;
+  // an e5m2 byte is the upper byte of an fp16: one PRMT turns two bytes into a half2 (the products with 2^-12 are exact, so
+  // the FMA equals multiply-then-add)
+  const uint32_t p01 = __byte_perm(w, 0u, 0x1404), p23 = __byte_perm(w, 0u, 0x3424);
+  v[0] = fmaf(f16_lo_f(p01), MPN_F8_LO_INV, v[0]);
+  v[1] = fmaf(f16_hi_f(p01), MPN_F8_LO_INV, v[1]);
+  v[2] = fmaf(f16_lo_f(p23), MPN_F8_LO_INV, v[2]);
+  v[3] = fmaf(f16_hi_f(p23), MPN_F8_LO_INV, v[3]);
 }
 // 8 floats -> fp16 hi (uint4), lo8 = e5m2((v - hi) * 2^12) (uint2), h8 = e5m2(v) (uint2)
 __device__ __forceinline__ void split_f16f8x8(const float* w, uint4& hi, uint2& lo8, uint2& h8) {
@@ -557,7 +562,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (F8) {
+          // F16F8: the accumulator carries the filter prescale 2^k; acc_scale = 2^-k is exact, so folding it into the bias add
+          // (one FMA) gives the same bits as multiply-then-add
+          const bool fused_bias = F8 && P.bias && !P.scale;
+          if (F8 && !fused_bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= P.acc_scale;
           }
@@ -568,7 +576,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
             }
           }
-          if (P.bias) {
+          if (fused_bias) {
+            const float as = P.acc_scale;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(P.bias + cbase) + j);
+              v[4 * j] = fmaf(v[4 * j], as, t.x); v[4 * j + 1] = fmaf(v[4 * j + 1], as, t.y);
+              v[4 * j + 2] = fmaf(v[4 * j + 2], as, t.z); v[4 * j + 3] = fmaf(v[4 * j + 3], as, t.w);
+            }
+          } else if (P.bias) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 t = __ldg(reinterpret_cast<const float4*>(P.bias + cbase) + j);

@@ -318,6 +318,60 @@ __global__ void maxpool3x3s2_bf16_kernel(const uint4* __restrict__ xhi, const ui
   }
 }
 
+// MPN_FMT_F16F8 planes, 8 channels per thread (16 B of fp16 hi + 8 B of e5m2 lo8): same arithmetic as the generic kernel
+// (value = hi + 2^-12 * lo8, maximum, re-split into hi / lo8 / h8), vector loads and stores.
+__global__ void maxpool3x3s2_f16f8_kernel(const uint4* __restrict__ xhi, const uint2* __restrict__ xlo, uint4* __restrict__ yhi,
+                                          uint2* __restrict__ ylo, uint2* __restrict__ yh8, int N, int H, int W, int C8, int OH, int OW) {
+  long long total = (long long)N * OH * OW * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C8);
+    long long p = i / C8;
+    int ow = (int)(p % OW);
+    long long q = p / OW;
+    int oh = (int)(q % OH);
+    int n = (int)(q / OH);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= W) continue;
+        long long o = (((long long)n * H + ih) * W + iw) * C8 + c;
+        const uint4 h = __ldg(xhi + o);
+        const uint2 l = __ldg(xlo + o);
+        const unsigned hv[4] = {h.x, h.y, h.z, h.w};
+        const unsigned lv[2] = {l.x, l.y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hv[j]));
+          const unsigned b0 = (lv[j >> 1] >> (16 * (j & 1))) & 0xFFu, b1 = (lv[j >> 1] >> (16 * (j & 1) + 8)) & 0xFFu;
+          m[2 * j] = fmaxf(m[2 * j], f.x + mpn_e5m2_to_float((unsigned char)b0) * MPN_F8_LO_INV);
+          m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y + mpn_e5m2_to_float((unsigned char)b1) * MPN_F8_LO_INV);
+        }
+      }
+    }
+    unsigned oh4[4], ol2[2] = {0u, 0u}, og2[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 t = __floats2half2_rn(m[2 * j], m[2 * j + 1]);
+      oh4[j] = *reinterpret_cast<const unsigned*>(&t);
+      const float2 f = __half22float2(t);
+      const unsigned l0 = mpn_float_to_e5m2((m[2 * j] - f.x) * MPN_F8_LO_SCALE), l1 = mpn_float_to_e5m2((m[2 * j + 1] - f.y) * MPN_F8_LO_SCALE);
+      const unsigned g0 = mpn_float_to_e5m2(m[2 * j]), g1 = mpn_float_to_e5m2(m[2 * j + 1]);
+      ol2[j >> 1] |= (l0 | (l1 << 8)) << (16 * (j & 1));
+      og2[j >> 1] |= (g0 | (g1 << 8)) << (16 * (j & 1));
+    }
+    yhi[i] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
+    ylo[i] = make_uint2(ol2[0], ol2[1]);
+    yh8[i] = make_uint2(og2[0], og2[1]);
+  }
+}
+
 extern "C" int mpn_maxpool3x3s2(const void* xhi, const void* xlo, void* yhi, void* ylo, int N, int H, int W, int C, int fmt,
                                 void* stream) {
   MPN_CHECK_ARG(xhi && yhi && N > 0 && H > 0 && W > 0 && C > 0, "mpn_maxpool3x3s2: bad argument");
@@ -331,6 +385,12 @@ extern "C" int mpn_maxpool3x3s2(const void* xhi, const void* xlo, void* yhi, voi
     else
       maxpool3x3s2_bf16_kernel<false><<<grid_for(t8, 256), 256, 0, (cudaStream_t)stream>>>(
           (const uint4*)xhi, nullptr, (uint4*)yhi, nullptr, N, H, W, C / 8, OH, OW);
+    MPN_LAUNCH_OK();
+    return MPN_OK;
+  }
+  if (fmt == MPN_FMT_F16F8 && C % 8 == 0) {
+    maxpool3x3s2_f16f8_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)xhi, (const uint2*)xlo, (uint4*)yhi, (uint2*)ylo, (uint2*)((unsigned char*)ylo + total), N, H, W, C / 8, OH, OW);
     MPN_LAUNCH_OK();
     return MPN_OK;
   }

@@ -177,6 +177,8 @@ class poseNet(nn.Module):
     def train_engine(self, precision=None):
         from ..train_engine import TrainEngine
         precision = precision or self._precision or _engine.DEFAULT_PRECISION
+        if precision == "f16f8":  # inference-only format: the weight-gradient kernel reads bf16 planes
+            precision = "bf16x3"
         engines = self.__dict__.setdefault("_engines", {})
         key = ("train", precision, id(self))
         e = engines.get(key)

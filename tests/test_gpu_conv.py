@@ -107,3 +107,22 @@ def test_tensor_core_stem_vs_torch(fmt, tol, shape):
     y = ops.conv2d(ops.stem_pack_input(x, fmt), pc, relu=True).to_nchw()
     assert y.shape == ref.shape
     assert nerr(y, ref) <= tol
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [(2, 64, 17, 23), (1, 8, 6, 6), (2, 4, 9, 8), (3, 64, 32, 40)])
+def test_maxpool3x3s2_vs_torch(fmt, shape):
+    """fpn.py:100 max_pool2d(3, 2, 1): the maximum of representable values is representable, so every format is exact
+    (C % 8 == 0 takes the vectorised bf16 / f16f8 kernels, C = 4 the generic one)."""
+    import torch.nn.functional as F
+    from multiposenet.pytorch_b200 import ops
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, C, H, W, generator=g)
+    x = torch.where(x.abs() < 1e-2, torch.full_like(x, 0.5), x).cuda()  # keep clear of the fp16 / e5m2 subnormal range
+    xa = ops.act_from_nchw(x, fmt)
+    xr = xa.to_nchw()  # the values the format actually holds
+    y = ops.maxpool3x3s2(xa).to_nchw()
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    assert y.shape == ref.shape
+    assert torch.equal(y, ref)

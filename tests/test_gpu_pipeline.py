@@ -8,21 +8,22 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _model():
+def _model(precision="bf16x3"):
     from gpu_util import image, load_model
     from multiposenet.pytorch_b200 import synthetic
-    m, _ = load_model(50, "conditioned", "bf16x3")
+    m, _ = load_model(50, "conditioned", precision)
     x = image(7, (3, 3, 96, 128))
     synthetic.calibrate_output_bias(m, x, "cls", per_image=40, threshold=0.5)     # ~40 anchors/image above the box filter
     synthetic.calibrate_output_bias(m, x, "heat", per_image=150, threshold=0.1)   # ~150 heat-map pixels/image above thre1
     return m, x
 
 
-def test_pipeline_batch_equals_per_image_and_oracle():
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_pipeline_batch_equals_per_image_and_oracle(precision):
     from multiposenet.pytorch_b200.evaluate import pipeline, prn_process, process_batch
     from multiposenet.pytorch_b200.network.joint_utils import get_joint_list
     from oracle import peaks_oracle, prn_oracle as po
-    m, x = _model()
+    m, x = _model(precision)
     scales = [1.5, 2.0, 1.0]
     names, ids = ["a", "b", "c"], [5, 6, 7]
     recs, heat, det = process_batch(m, x, scales, names, ids)

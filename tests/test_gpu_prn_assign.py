@@ -105,13 +105,14 @@ def test_prn_scatter_quirks_and_window_sums():
     assert np.array_equal(kp, po.assign(xy, ty, boxes, want_owner, out))
 
 
-def test_prn_process_with_the_real_prn():
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_prn_process_with_the_real_prn(precision):
     """End to end through poseNet's batched tcgen05 PRN: records equal the oracle's when it is fed the same PRN outputs."""
     from multiposenet.pytorch_b200 import poseNet
     from multiposenet.pytorch_b200.evaluate import prn_process
     from oracle import prn_oracle as po
     torch.manual_seed(0)
-    m = poseNet(50, prn_node_count=128, prn_coeff=2, precision="bf16x3").cuda().eval()
+    m = poseNet(50, prn_node_count=128, prn_coeff=2, precision=precision).cuda().eval()
     kps, boxes = po.synthetic_case(21, persons=5)
     rec = prn_process(m, kps, boxes, "x", 3)
 
