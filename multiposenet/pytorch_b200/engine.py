@@ -26,7 +26,10 @@ import torch
 from . import ops
 from ._lib import FMT_BF16, FMT_BF16X2, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_NHWC
 
-DEFAULT_PRECISION = os.environ.get("MPN_PRECISION", "bf16x3")
+# Inference default: f16f8 (fp16 hi plane + two fp8 cross-term planes, 8 MMA slots per K block) -- within 3.3e-4 of the fp32
+# reference on every output (profiles/r01s_parity_margin.txt; the bar is 1e-3) and ~15 % faster than bf16x3, which has the
+# same error.  Training (train_engine) runs on bf16x3 / bf16 planes.
+DEFAULT_PRECISION = os.environ.get("MPN_PRECISION", "f16f8")
 USE_GRAPHS = os.environ.get("MPN_CUDA_GRAPH", "0") == "1"
 TC_STEM = os.environ.get("MPN_TC_STEM", "1") == "1"
 USE_STREAMS = os.environ.get("MPN_STREAMS", "0") == "1"  # measured: no gain on B200 (r01c), kept as an option
@@ -63,9 +66,21 @@ class Engine(object):
 
     # ------------------------------------------------------------------ weights
     def _signature(self):
+        """(storage address, version counter) of every parameter and buffer: in-place updates (optimizer.step,
+        load_state_dict), .to()/.cuda() and replaced Parameter objects all change it.  The (owner dict, name) slots are
+        collected once -- walking the module tree costs ~4 ms for R101, which a synchronous caller pays as GPU idle time
+        in front of every graph replay; reading 708 slots costs ~0.3 ms."""
+        slots = self.__dict__.get("_slots")
+        if slots is None:
+            slots = []
+            for mod in self.model.modules():
+                slots.extend((mod._parameters, n) for n, t in mod._parameters.items() if t is not None)
+                slots.extend((mod._buffers, n) for n, t in mod._buffers.items() if t is not None)
+            self._slots = slots
         sig = []
-        for t in list(self.model.parameters()) + list(self.model.buffers()):
-            sig.append((t.data_ptr(), t._version))
+        for d, n in slots:
+            t = d.get(n)
+            sig.append((t.data_ptr(), t._version) if t is not None else None)
         return tuple(sig)
 
     def _ensure_packed(self):

@@ -117,6 +117,8 @@ def test_maxpool3x3s2_vs_torch(fmt, shape):
     import torch.nn.functional as F
     from multiposenet.pytorch_b200 import ops
     N, C, H, W = shape
+    if fmt == 3 and C % 16:
+        C = 16  # f16f8 byte planes need 16-channel rows
     g = torch.Generator().manual_seed(11)
     x = torch.randn(N, C, H, W, generator=g)
     x = torch.where(x.abs() < 1e-2, torch.full_like(x, 0.5), x).cuda()  # keep clear of the fp16 / e5m2 subnormal range
