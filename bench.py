@@ -536,12 +536,14 @@ def main():
         pk, pk_src = peaks()
         nprof = 2
         engine_mod.USE_STREAMS = False  # serial launches: clean per-kernel durations
+        level_default, engine_mod.LEVEL_STREAMS = engine_mod.LEVEL_STREAMS, False
         ops.stats["conv_events"] = evs = []
         for i in range(nprof):
             eng.entire_forward_device(devin[i % len(devin)], max_cand=MAXC)  # eager: events around each launch
         torch.cuda.synchronize()
         ops.stats["conv_events"] = None
         engine_mod.USE_STREAMS = streams_default
+        engine_mod.LEVEL_STREAMS = level_default
         tc = [(a.elapsed_time(b), f) for a, b, f, simt in evs if not simt]
         conv_ms = sum(t for t, _ in tc) / nprof
         nconv = len(tc) // nprof
@@ -606,7 +608,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "R%d-FPN entire_net fwd (keypoint + RetinaNet heads) + decode/filter/NMS, batch %d/GPU, 3x480x640"
                                    % (args.layers, B), "global_batch": B * world, "parallelism": "dp%d (image shards, no collective)" % world,
-                       "precision": args.precision, "candidates_per_image": n_s, "kept_per_image": n_k, "max_cand": MAXC, "cuda_graph": bool(args.graph), "branch_streams": streams_default,
+                       "precision": args.precision, "candidates_per_image": n_s, "kept_per_image": n_k, "max_cand": MAXC, "cuda_graph": bool(args.graph), "branch_streams": streams_default, "level_streams": engine_mod.LEVEL_STREAMS,
                        "cls_bias_shift": bias_shift,
                        "l2": "2 rotating input batches; activations >5 GB/step >> 126 MB L2, no explicit flush",
                        "gflop_per_image": flops_img / 1e9},

@@ -33,6 +33,8 @@ DEFAULT_PRECISION = os.environ.get("MPN_PRECISION", "f16f8")
 USE_GRAPHS = os.environ.get("MPN_CUDA_GRAPH", "0") == "1"
 TC_STEM = os.environ.get("MPN_TC_STEM", "1") == "1"
 USE_STREAMS = os.environ.get("MPN_STREAMS", "0") == "1"  # measured: no gain on B200 (r01c), kept as an option
+LEVEL_STREAMS = os.environ.get("MPN_LEVEL_STREAMS", "1") == "1"  # small pyramid levels of the RetinaNet towers side by side
+SMALL_LEVEL_PIXELS = 120 * 80  # batch x H x W of a level that cannot fill the GPU (<= 40 CTA pairs of 2 x 120 pixels)
 
 
 def _bn_tuple(bn):
@@ -204,16 +206,20 @@ class Engine(object):
             outs.append(ops.conv2d(src, self._pc(name, getattr(m, name)), out_mode=OUT_F32_NCHW, out_rep=rep))
         return outs
 
-    def _tower(self, head, hname, feats, out, per, sigmoid):
+    def _tower_level(self, head, hname, f, off, A, out, per, sigmoid):
+        o = f
+        for n in ("conv1", "conv2", "conv3", "conv4"):
+            o = ops.conv2d(o, self._pc("%s.%s" % (hname, n), getattr(head, n)), pad=1, relu=True)
+        ops.conv2d(o, self._pc(hname + ".output", head.output), pad=1, sigmoid=sigmoid, out_mode=OUT_F32_NHWC,
+                   out_tensor=out, out_elem_offset=off * per, out_cstride=9 * per, out_nstride=A * per)
+
+    def _tower(self, head, hname, feats, out, per, sigmoid, levels=None):
         cells = [f.H * f.W for f in feats]
         A = 9 * sum(cells)
         off = 0
-        for f, ncell in zip(feats, cells):
-            o = f
-            for n in ("conv1", "conv2", "conv3", "conv4"):
-                o = ops.conv2d(o, self._pc("%s.%s" % (hname, n), getattr(head, n)), pad=1, relu=True)
-            ops.conv2d(o, self._pc(hname + ".output", head.output), pad=1, sigmoid=sigmoid, out_mode=OUT_F32_NHWC,
-                       out_tensor=out, out_elem_offset=off * per, out_cstride=9 * per, out_nstride=A * per)
+        for i, (f, ncell) in enumerate(zip(feats, cells)):
+            if levels is None or i in levels:
+                self._tower_level(head, hname, f, off, A, out, per, sigmoid)
             off += ncell * 9
 
     def detection_heads(self, feats):
@@ -224,7 +230,30 @@ class Engine(object):
         dev = feats[0].hi.device
         cls = torch.empty((B, A, 1), dtype=torch.float32, device=dev)
         reg = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
-        if USE_STREAMS:
+        small = [i for i, f in enumerate(feats) if f.N * f.H * f.W <= SMALL_LEVEL_PIXELS]
+        if LEVEL_STREAMS and small and len(small) < len(feats):
+            # The five convs of a small pyramid level (P5-P7: at most 40 CTA pairs, a serial K loop per CTA) are latency
+            # bound and leave most SMs idle.  The large levels run first on the current stream (their persistent kernels
+            # want every SM); then the small-level chains of both towers run side by side, one stream per (tower, level).
+            big = [i for i in range(len(feats)) if i not in small]
+            self._tower(m.regressionModel, "regressionModel", feats, reg, 4, False, levels=big)
+            self._tower(m.classificationModel, "classificationModel", feats, cls, 1, True, levels=big)
+            cur = torch.cuda.current_stream()
+            sides = []
+            for ti, (head, hname, out, per, sig) in enumerate(((m.regressionModel, "regressionModel", reg, 4, False),
+                                                               (m.classificationModel, "classificationModel", cls, 1, True))):
+                for li in small:
+                    if ti == 0 and li == small[0]:
+                        continue  # the first chain stays on the current stream (below)
+                    side = self._side(10 + ti * 8 + li, dev)
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        self._tower(head, hname, feats, out, per, sig, levels=[li])
+                    sides.append(side)
+            self._tower(m.regressionModel, "regressionModel", feats, reg, 4, False, levels=[small[0]])
+            for side in sides:
+                cur.wait_stream(side)
+        elif USE_STREAMS:
             cur, side = torch.cuda.current_stream(), self._side(1, dev)
             side.wait_stream(cur)
             with torch.cuda.stream(side):

@@ -28,6 +28,8 @@ def main():
     m = m.to(dev).eval()
     with torch.no_grad():
         m.classificationModel.output.bias += bench.CLS_BIAS_SHIFT.get(a.layers, 0.0)
+    import multiposenet.pytorch_b200.engine as E
+    E.LEVEL_STREAMS = False  # serial launches
     eng = m.engine()
     x = torch.randn(a.batch, 3, bench.H, bench.W, device=dev)
     for i in range(a.steps):

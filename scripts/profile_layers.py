@@ -19,7 +19,8 @@ def main():
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import multiposenet.pytorch_b200.engine as E
-    E.USE_STREAMS = False  # serial launches: clean per-kernel durations
+    E.USE_STREAMS = False
+    E.LEVEL_STREAMS = False  # serial launches: clean per-kernel durations
     dev = torch.device("cuda")
     m = poseNet(a.layers, precision=a.precision)
     bench.load_weights_into(m, a.layers)
