@@ -276,8 +276,9 @@ def run_train(args, rank, world, local):
 def run_full(args, rank, world, local):
     """BASELINE config 5: full inference incl. heat-map peaks and PRN assignment (the body of Tester._process,
     evaluate/tester.py:200-243) for a batch of 64 images per GPU, through evaluate.process_batch with HOST images in and
-    per-person records out.  Synthetic-weight construction: the class-head and convfin biases are shifted once so that
-    about `--persons` boxes per image pass the 0.5 box filter and ~170 heat-map peaks per image pass thre1."""
+    per-person records out.  Synthetic-weight construction: the class-head bias of the headline bench (~3700 candidates per
+    image), the best `--persons` NMS survivors per image as person boxes, and a convfin bias shift that lets ~170 heat-map
+    peaks per image pass thre1."""
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -292,14 +293,38 @@ def run_full(args, rank, world, local):
     rng = np.random.Generator(np.random.PCG64(777 + rank))
     host = [torch.from_numpy(rng.standard_normal((B, 3, H, W), dtype=np.float32)).pin_memory() for _ in range(2)]
     probe = host[0][:4].to(dev)
-    shifts = {"cls": synthetic.calibrate_output_bias(model, probe, "cls", per_image=4 * args.persons, threshold=0.5),
+    # Detection load = the headline bench's (cfg3 regime: ~3700 anchors per image above the 0.05 filter, ~490 kept by NMS);
+    # the best `--persons` kept boxes per image go to the PRN (random weights have no meaningful 0.5 score level, and a
+    # bias that lifts 80 anchors above 0.5 lifts > 20000 above 0.05, i.e. benchmarks a 20000-box NMS: r01p/r01t, 420 img/s).
+    if args.layers in CLS_BIAS_SHIFT:
+        cls_shift = CLS_BIAS_SHIFT[args.layers]
+        with torch.no_grad():
+            model.classificationModel.output.bias += cls_shift
+    else:
+        cls_shift = calibrate_cls_bias(model, dev)
+    shifts = {"cls": cls_shift,
               "heat": synthetic.calibrate_output_bias(model, probe, "heat", per_image=600, threshold=0.1)}
     scales = [1.0] * B
     stats = {}
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    pending = {}
+
+    def prefetch(i):
+        """H2D of batch i from pinned host memory on a copy stream: overlaps the previous batch's kernels and host work."""
+        with torch.cuda.stream(copy_stream):
+            xb = host[i % 2].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return xb, ev
+
     def step(i):
-        x = host[i % 2].to(dev, non_blocking=True)
-        recs, heat, det = process_batch(model, x, scales, max_persons=args.persons)
+        x, ev = pending.pop(i, None) or prefetch(i)
+        torch.cuda.current_stream().wait_event(ev)
+        x.record_stream(torch.cuda.current_stream())
+        pending[i + 1] = prefetch(i + 1)
+        recs, heat, det = process_batch(model, x, scales, max_persons=args.persons, box_score_thresh=0.05)
+        stats["candidates"] = float(det.cand_cnt.float().mean())
         stats["persons"] = sum(len(r) for r in recs) / float(B)
         stats["assigned"] = sum(1 for r in recs for q in r for v in q["keypoints"][2::3] if v > 0) / float(B)
         return recs
@@ -312,6 +337,7 @@ def run_full(args, rank, world, local):
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
+    pending.clear()  # every timed step uploads its own batch inside the timed region
     l0 = ops.stats["launches"]
     sampler = ClockSampler(local)
     if rank == 0:
@@ -334,6 +360,7 @@ def run_full(args, rank, world, local):
             "data": "synthetic",
             "config": {"workload": "R%d entire_net + NMS + heat-map peaks + PRN assignment, batch %d/GPU, 3x480x640" % (args.layers, B),
                        "global_batch": B * world, "persons_per_image": stats.get("persons"), "assigned_joints_per_image": stats.get("assigned"),
+                       "candidates_per_image": stats.get("candidates"), "box_score_thresh": 0.05,
                        "max_persons": args.persons, "bias_shifts": shifts, "parallelism": "dp%d (image shards, no collective)" % world},
             "gpu_launches": ops.stats["launches"] - l0, "clocks": clocks}))
     if world > 1:

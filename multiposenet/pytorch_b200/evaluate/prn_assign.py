@@ -77,16 +77,17 @@ def prn_process_batch(model, kps_per_image, bboxes_per_image, file_names=None, i
     with torch.no_grad():
         output, _ = model([inp, "prn_subnet"])                                   # :400-408, all persons in one batch
     kp = ops.prn_assign(peak_xy, pstart_t, jstart_t, boxes, box_img_t, bstart_t, owner, output.float(), kmax, ws).cpu().numpy()
+    kpl = kp.reshape(-1, 3 * NUM_JOINTS).tolist()                                # python floats: the same IEEE doubles
     for li, b in enumerate(live):                                                # :485-511
-        bx = box_l[li]
-        for i in range(len(bx)):
-            k = kp[bstart[li] + i].reshape(51)
+        bxl = box_l[li].tolist()
+        for i in range(len(bxl)):
+            k = kpl[bstart[li] + i]
             pose_score = 0
-            for f in range(NUM_JOINTS):
-                pose_score += k[3 * f + 2]
+            for v in k[2::3]:                                                    # sequential sum over the 17 joints (:497-499)
+                pose_score += v
             pose_score /= 17.0
             results[b].append({"image_id": image_ids[b], "file_name": file_names[b], "category_id": 1,
-                               "bbox": [float(v) for v in bx[i]], "score": float(pose_score), "keypoints": k.tolist()})
+                               "bbox": bxl[i], "score": float(pose_score), "keypoints": k})
     return results
 
 
