@@ -79,11 +79,12 @@ class Engine(object):
                 slots.extend((mod._parameters, n) for n, t in mod._parameters.items() if t is not None)
                 slots.extend((mod._buffers, n) for n, t in mod._buffers.items() if t is not None)
             self._slots = slots
-        sig = []
-        for d, n in slots:
-            t = d.get(n)
-            sig.append((t.data_ptr(), t._version) if t is not None else None)
-        return tuple(sig)
+        try:
+            ts = [d[n] for d, n in slots]
+            return (tuple(map(torch.Tensor.data_ptr, ts)), tuple([t._version for t in ts]))   # ~0.1-0.4 ms for 708 tensors
+        except (KeyError, TypeError, AttributeError):  # a parameter / buffer was removed or set to None: recollect the slots
+            self._slots = None
+            return (object(),)
 
     def _ensure_packed(self):
         sig = self._signature()
