@@ -43,6 +43,7 @@ constexpr int NUM_THREADS = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spar
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 256;
+constexpr int BIAS_BYTES = 1024;  // EPI_TMA: the tile's folded-BN bias, 2 halves x 4 chunks x 32 channels (behind the barriers)
 constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32 accumulators, 16B chunks XOR-swizzled
 
 struct Maps {
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + EPI_BYTES + 8 * (2 * STAGES + 4));
   uint8_t* epi_stage = smem_gen + STAGES * STAGE_BYTES;  // 1024-byte aligned (TMA-store swizzle pattern)
+  float* bias_smem = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k_iters = P.R * P.S * P.kb_per_tap;
@@ -524,6 +526,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           }
         };
         if (res_lsu && half * 32 < ncols && co0 + half * 32 < P.Cout) load_res(co0 + half * 32);
+        // The bias of the tile's columns goes through shared memory once per tile: with ~30 KB of L1 left beside the 225 KB
+        // carve-out the per-chunk __ldg of 128 bytes missed to L2 every time (ncu r01v: 4-8 % of the epilogue warps' samples
+        // on the dependent FMA).  Each half keeps the 4 x 32 values of its own chunks, so the halves stay independent; every
+        // thread of the half is past the barriers of the previous tile's last chunk, i.e. done reading the old values.
+        float* bias_h = bias_smem + half * 128;
+        const bool bias_staged = P.bias != nullptr && BN <= 256;
+        if (bias_staged) {
+            const int tq = q * 32 + lane;                       // 0..127 within the half
+            const int col = half * 32 + 64 * (tq >> 5) + (tq & 31);
+            bias_h[tq] = (col < ncols && co0 + col < P.Cout) ? __ldg(P.bias + co0 + col) : 0.f;
+            named_bar_sync(1 + half, 128);
+        }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
 #pragma unroll 1
@@ -576,18 +590,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
               v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
             }
           }
+          const float4* bias4 = reinterpret_cast<const float4*>(bias_h + (c0 >> 6) * 32);  // chunk (c0 - half*32) / 64 of this half
           if (fused_bias) {
             const float as = P.acc_scale;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(P.bias + cbase) + j);
+              const float4 t = bias4[j];
               v[4 * j] = fmaf(v[4 * j], as, t.x); v[4 * j + 1] = fmaf(v[4 * j + 1], as, t.y);
               v[4 * j + 2] = fmaf(v[4 * j + 2], as, t.z); v[4 * j + 3] = fmaf(v[4 * j + 3], as, t.w);
             }
           } else if (P.bias) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(P.bias + cbase) + j);
+              const float4 t = bias4[j];
               v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
             }
           }
@@ -933,11 +948,12 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
   constexpr int PLANES = MODE == MODE_BF16 ? 1 : 2;
   constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BLOCK_K * 2);
   constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES + (EPI == EPI_TMA_RES ? 4 * RES_STAGE_BYTES : 0);
-  constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
+  constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - BIAS_BYTES - EPI_BYTES) / STAGE_BYTES;
   constexpr int STAGES = MAXS > 8 ? 8 : MAXS;
   static_assert(STAGES >= 2, "not enough shared memory for a 2-stage ring");
   static_assert(8 * (2 * STAGES + 9) <= BAR_BYTES, "barrier area too small");
-  const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EPI_BYTES;
+  const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BIAS_BYTES + EPI_BYTES;
+  static_assert(STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BIAS_BYTES + EPI_BYTES <= SMEM_LIMIT, "shared memory budget");
   auto kern = conv_tc_kernel<BN, MODE, STAGES, EPI, PAIR>;
   MPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = P.total_tiles < sms ? P.total_tiles : sms;

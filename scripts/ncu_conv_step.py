@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--layers", type=int, default=101)
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--names-out", default=None, help="write the layer shape of every conv launch of one step, in launch order")
     a = ap.parse_args()
     dev = torch.device("cuda")
     m = poseNet(a.layers, precision=a.precision)
@@ -32,12 +33,26 @@ def main():
     E.LEVEL_STREAMS = False  # serial launches
     eng = m.engine()
     x = torch.randn(a.batch, 3, bench.H, bench.W, device=dev)
+    names, real = [], ops.conv2d
+
+    def named(xa, pc, **kw):  # launch order -> layer shape, to label the rows of the ncu CSV (scripts/summarise_ncu_csv.py --names)
+        names.append("%dx%d c%d->%d k%d s%d%s%s%s" % (xa.H, xa.W, pc.Cin, pc.Cout, pc.R, kw.get("stride", 1),
+                                                      " res" if kw.get("residual") is not None else "",
+                                                      " up" if kw.get("up") is not None else "",
+                                                      " rep%d" % kw["out_rep"] if kw.get("out_rep", 1) > 1 else ""))
+        return real(xa, pc, **kw)
+
+    if a.names_out:
+        ops.conv2d = named
     for i in range(a.steps):
         ops.stats["conv_events"] = evs = []
         eng.entire_forward_device(x, max_cand=4096)
         torch.cuda.synchronize()
         print("forward %d: %d conv launches" % (i, len(evs)))
     ops.stats["conv_events"] = None
+    if a.names_out:
+        per = len(names) // a.steps
+        open(a.names_out, "w").write("\n".join(names[-per:]) + "\n")
 
 
 if __name__ == "__main__":

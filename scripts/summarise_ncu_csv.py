@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--kernel", default="conv_tc_kernel")
     ap.add_argument("--out", default=None)
     ap.add_argument("--note", default="")
+    ap.add_argument("--names", default=None, help="layer shape per launch, in launch order (scripts/ncu_conv_step.py --names-out)")
+    ap.add_argument("--table", default=None, help="with --names: per-shape table (count, us, DRAM GB/s, %% of HBM peak, tensor-pipe %%)")
+    ap.add_argument("--hbm-gbs", type=float, default=6556.2, help="measured HBM peak (MEASURED_PEAKS.json)")
     a = ap.parse_args()
     launches = {}
     for r in read_rows(a.csv):
@@ -51,6 +54,25 @@ def main():
     print(json.dumps(rec, indent=1))
     if a.out:
         json.dump(rec, open(a.out, "w"), indent=1)
+    if a.names:
+        names = [l.strip() for l in open(a.names) if l.strip()]
+        ids = sorted(launches, key=lambda k: int(k))
+        if len(names) != len(ids):
+            raise SystemExit("--names has %d rows, the CSV %d launches of %s" % (len(names), len(ids), a.kernel))
+        agg = {}
+        for nm, i in zip(names, ids):
+            d = launches[i]
+            g = agg.setdefault(nm, [0, 0.0, 0.0, 0.0])
+            tt = d.get("gpu__time_duration.sum", 0.0)
+            g[0] += 1; g[1] += tt; g[2] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0); g[3] += d.get(key, 0.0) * tt
+        lines = ["%-38s %5s %10s %9s %10s %9s %9s" % ("launch (under ncu: serialised, cold L2)", "count", "us total", "us each", "DRAM GB/s", "of HBM", "tensor %")]
+        for nm, g in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            gbs = g[2] / g[1] / 1e9 if g[1] else 0.0
+            lines.append("%-38s %5d %10.1f %9.1f %10.0f %8.1f%% %8.1f%%" % (nm, g[0], g[1] * 1e6, g[1] * 1e6 / g[0], gbs, 100.0 * gbs / a.hbm_gbs, g[3] / g[1] if g[1] else 0.0))
+        txt = "\n".join(lines)
+        print(txt)
+        if a.table:
+            open(a.table, "w").write(txt + "\n")
 
 
 if __name__ == "__main__":
