@@ -363,7 +363,17 @@ class Engine(object):
         """Run `kind` ('entire', 'keypoint', 'detection') through a captured CUDA graph of its launch
         sequence (captured on first use per input shape; ~250 launches replayed with one driver call).
         The returned tensors are the graph's static outputs: they are overwritten by the next replay."""
-        key = (kind, tuple(img.shape), str(img.device), tuple(sorted(kw.items())))
+        key = (kind, tuple(img.shape), str(img.device), str(img.dtype), tuple(sorted(kw.items())))
+        g = self._graphs.get(key) if self._sig is not None and self._graph_sig == self._sig else None
+        if g is not None:
+            # Fast path: replay first, then validate the weights while the GPU runs -- the signature walk (~0.4 ms) would
+            # otherwise be GPU idle time in front of every replay of a synchronous caller.  If the weights did change
+            # since the capture, this replay's outputs are discarded and the slow path below repacks, recaptures and reruns.
+            graph, static_in, out = g
+            static_in.copy_(img, non_blocking=True)
+            graph.replay()
+            if self._signature() == self._sig:
+                return out
         self._ensure_packed()
         if getattr(self, "_graph_sig", None) != self._sig:
             self._graphs, self._graph_sig = {}, self._sig  # weights changed -> recapture

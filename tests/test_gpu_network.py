@@ -131,6 +131,29 @@ def test_cuda_graph_replay_matches_eager():
         assert torch.equal(det_g.keep_idx[0, :k], keep_e[0, :k])
 
 
+def test_cuda_graph_follows_weight_updates():
+    """graphed() replays first and validates the weights while the GPU runs: after an in-place update, a load_state_dict
+    or a dtype round trip the stale replay must be discarded and the result must be the eager result of the NEW weights."""
+    from gpu_util import image, load_model
+    m, _ = load_model(50, "conditioned", "f16f8")
+    eng = m.engine()
+    x = image(23, (2, 3, 96, 128))
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    h0 = eng.graphed("keypoint", x)[0].clone()
+    assert torch.equal(eng.graphed("keypoint", x)[0], h0)          # fast path, unchanged weights
+    with torch.no_grad():
+        m.convfin.bias.add_(0.25)
+    h1 = eng.graphed("keypoint", x)[0].clone()
+    assert torch.equal(h1, eng.keypoint_forward(x)[0])
+    assert float((h1 - h0).abs().min()) > 0.2                       # every heat-map value moved with the bias
+    m.load_state_dict(sd0)                                          # the original weights, bit for bit
+    h2 = eng.graphed("keypoint", x)[0].clone()
+    assert torch.equal(h2, h0)
+    m.double().float()                                              # new storages, same values
+    assert torch.equal(eng.graphed("keypoint", x)[0], h0)
+    assert torch.equal(eng.graphed("keypoint", x)[0], h0)
+
+
 @pytest.mark.parametrize("hw", [(100, 130), (75, 50)])
 def test_detection_subnet_ragged_sizes_vs_oracle(hw):
     """Odd image sizes: ceil-shaped pyramid levels, non-2x nearest upsample-add (fpn.py:84-95), 1x1 P7."""
