@@ -25,7 +25,7 @@
 //                  MPN_FMT_F16F8  fp16 hi plane + two fp8 byte planes (lo8 = e5m2((x - hi) * 2^12), h8 = e5m2(x)); filters
 //                  prescaled by 2^k: fp16 hi, lo8 = e4m3(w' - hi), h8 = e4m3(w' * 2^-12).  Per 64-channel K block:
 //                  4 kind::f16 MMAs (hi*hi) + 2 + 2 kind::f8f6f4 MMAs of K = 32 (xlo8*wh8, xh8*wlo8) into the SAME fp32
-//                  accumulator = 8 MMA slots instead of 12, product error ~2^-15 (scripts/precision_study.py).
+//                  accumulator = 8 MMA slots instead of 12, product error ~2^-15 (tests/tools/precision_study.py).
 #include <cuda.h>
 #include <stdlib.h>
 
