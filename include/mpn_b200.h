@@ -88,6 +88,10 @@ typedef struct mpn_conv_ptrs {
 
 const char* mpn_last_error(void);
 int mpn_version(void);
+/* sizeof(mpn_conv_desc) / sizeof(mpn_conv_ptrs) as compiled into the library: a foreign-language binding (ctypes, cgo, JNI)
+ * compares them with its own struct layout when it loads the library. */
+int mpn_sizeof_conv_desc(void);
+int mpn_sizeof_conv_ptrs(void);
 /* 1 if the current device can run the tcgen05 kernels (compute capability 10.x). */
 int mpn_device_supports_tcgen05(void);
 

@@ -37,6 +37,8 @@ _lib = None
 _SIGS = {
     "mpn_last_error": (ctypes.c_char_p, []),
     "mpn_version": (c_int, []),
+    "mpn_sizeof_conv_desc": (c_int, []),
+    "mpn_sizeof_conv_ptrs": (c_int, []),
     "mpn_device_supports_tcgen05": (c_int, []),
     "mpn_conv2d_fwd": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvPtrs), c_void_p]),
     "mpn_conv2d_fwd_f32in": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvPtrs), c_void_p]),
@@ -107,6 +109,10 @@ def lib():
             fn = getattr(l, name)  # AttributeError if a declared symbol is not exported
             fn.restype = res
             fn.argtypes = args
+        for struct, size in ((ConvDesc, l.mpn_sizeof_conv_desc()), (ConvPtrs, l.mpn_sizeof_conv_ptrs())):
+            if ctypes.sizeof(struct) != size:
+                raise MpnError("%s is %d bytes here but %d in libmpn_b200.so: rebuild the library (include/mpn_b200.h changed)"
+                               % (struct.__name__, ctypes.sizeof(struct), size))
         _lib = l
     return _lib
 

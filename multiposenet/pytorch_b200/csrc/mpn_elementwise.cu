@@ -16,6 +16,9 @@ void mpn_set_error(const char* fmt, ...) {
 
 extern "C" const char* mpn_last_error(void) { return g_err; }
 extern "C" int mpn_version(void) { return 100; }
+// sizeof of the two structs that cross the boundary by pointer: a binding checks its own layout against these at load time
+extern "C" int mpn_sizeof_conv_desc(void) { return (int)sizeof(mpn_conv_desc); }
+extern "C" int mpn_sizeof_conv_ptrs(void) { return (int)sizeof(mpn_conv_ptrs); }
 
 extern "C" int mpn_device_supports_tcgen05(void) {
   int dev = 0, major = 0;

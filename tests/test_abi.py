@@ -28,6 +28,9 @@ def test_header_symbols_exported():
     L = _lib.lib()
     assert L.mpn_version() >= 100
     assert L.mpn_num_anchors(480, 640) == 57600
+    # the two by-pointer structs have the layout the library was compiled with (also checked at every load)
+    assert ctypes.sizeof(_lib.ConvDesc) == L.mpn_sizeof_conv_desc()
+    assert ctypes.sizeof(_lib.ConvPtrs) == L.mpn_sizeof_conv_ptrs()
 
 
 def test_host_side_entry_points_and_errors():
