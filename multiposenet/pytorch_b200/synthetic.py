@@ -7,7 +7,7 @@ oracle/weights.py, by the tests.
 `poseNet(layers)` (network/posenet.py:154-211, network/fpn.py:9-82) in registration
 order.  It is written from the constructor code, not imported, so that it is
 available on the GPU box where /root/reference does not exist; the not-gpu test
-`tests/test_oracle_vs_reference.py` checks it key-by-key against the real module.
+`tests/test_oracle.py` checks it key-by-key against the real module.
 
 Two weight sets (last row / section 8(d)):
   * "refinit"     -- what the reference constructor produces: normal(std=0.01) convs,
