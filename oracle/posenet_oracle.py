@@ -6,7 +6,7 @@ torch is used here only as the fp32 array library the reference itself calls
 (conv2d / batch_norm / max_pool2d are the third-party arithmetic, see oracle/__init__).
 
 Pinned against the real reference modules by oracle/make_goldens.py (container-side) and
-tests/test_oracle_vs_reference.py; tests/golden/*.npz hold the reference's outputs.
+tests/test_oracle.py; tests/golden/*.npz hold the reference's outputs.
 """
 import math
 
