@@ -62,3 +62,23 @@ def test_precision_defaults():
     assert m.train_engine().precision == "bf16x3"
     assert poseNet(50, precision="bf16").train_engine().precision == "bf16"
     assert poseNet(50, precision="bf16x3").engine().precision == "bf16x3"
+
+
+def test_joints_for_prn_and_regroup():
+    """tester.py:222-229 drops the neck rows (type 1) and shifts later joint types down by one; prn_process regroups the
+    rows by joint type in their original order (tester.py:337-350)."""
+    from multiposenet.pytorch_b200.evaluate.pipeline import joints_for_prn
+    from multiposenet.pytorch_b200.evaluate.prn_assign import _regroup
+    rows = np.array([[10, 11, 0.9, 0, 0], [20, 21, 0.8, 1, 1], [30, 31, 0.7, 2, 2], [40, 41, 0.6, 3, 17], [50, 51, 0.5, 4, 2],
+                     [60, 61, 0.4, 5, 0]], dtype=np.float64)
+    out = joints_for_prn(rows)
+    assert out[:, 4].tolist() == [0, 1, 16, 1, 0]                 # neck gone, types 2.. shifted down, type 0 kept
+    assert out[:, 0].tolist() == [10, 30, 40, 50, 60] and out.dtype == np.float64
+    assert joints_for_prn(np.zeros((0, 5))).shape == (0, 5)
+    xy, ty = _regroup(out)
+    assert ty.tolist() == [0, 0, 1, 1, 16] and ty.dtype == np.int32
+    assert xy[:, 0].tolist() == [10, 60, 30, 50, 40]              # stable within a joint type
+    xy0, ty0 = _regroup([])
+    assert xy0.shape == (0, 2) and ty0.shape == (0,)
+    xy1, ty1 = _regroup(np.array([[1, 2, 0.5, 0, 17], [3, 4, 0.5, 1, 3]], dtype=np.float64))   # types outside 0..16 are ignored
+    assert ty1.tolist() == [3] and xy1.tolist() == [[3.0, 4.0]]
