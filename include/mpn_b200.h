@@ -212,6 +212,13 @@ size_t mpn_detect_workspace_bytes(int B, int A, int max_cand);
 int mpn_filter_sort_nms(const float* cls, const float* boxes, int B, int A, float score_thresh, float iou_thresh, int ge,
                         int max_cand, int32_t* cand_idx, int32_t* cand_cnt, int64_t* keep_idx, int32_t* keep_cnt,
                         float* out_scores, float* out_boxes, void* workspace, size_t workspace_bytes, void* stream);
+/* Profiling twin of mpn_filter_sort_nms (bench.py roofline_aux): same work and outputs, plus CUDA events between the stages on
+ * `stream`; BLOCKS until the last stage finished and writes stage_ms[5] (host) = filter/compact, segment sort, gather, IoU
+ * bit-mask, greedy reduction. */
+int mpn_filter_sort_nms_profile(const float* cls, const float* boxes, int B, int A, float score_thresh, float iou_thresh, int ge,
+                                int max_cand, int32_t* cand_idx, int32_t* cand_cnt, int64_t* keep_idx, int32_t* keep_cnt,
+                                float* out_scores, float* out_boxes, void* workspace, size_t workspace_bytes, void* stream,
+                                float* stage_ms);
 /* pth_nms equivalents on raw device memory.  dets [n,5] (x1,y1,x2,y2,score), any order.
  * keep [n] int64 (device), num_out [1] int32 (device). Mirrors gpu_nms (ge=0) / cpu_nms (ge=1) + the
  * sort/gather of pth_nms.py:25-44. workspace: mpn_nms_workspace_bytes(n). */

@@ -81,6 +81,8 @@ _SIGS = {
     "mpn_detect_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mpn_filter_sort_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mpn_filter_sort_nms_profile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "mpn_nms_workspace_bytes": (c_size_t, [c_int]),
     "mpn_nms": (c_int, [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mpn_nms_mask": (c_int, [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p]),

@@ -43,6 +43,17 @@ __device__ __forceinline__ float mpn_e5m2_to_float(unsigned char b) { return __h
 __device__ __forceinline__ unsigned char mpn_float_to_e5m2(float v) { return (unsigned char)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2); }
 __device__ __forceinline__ unsigned char mpn_float_to_e4m3(float v) { return (unsigned char)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
 
+// fp32 -> fp16 with saturation to +-65504 (one F2FP.SATFINITE instruction): an activation beyond the fp16 range is clamped
+// instead of becoming inf (and NaN once the e5m2 residual plane is added back) -- the overflow guard of MPN_FMT_F16F8.
+__device__ __forceinline__ uint32_t mpn_pack_f16x2_sat(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ __half mpn_f16_sat(float v) {
+  return __ushort_as_half((unsigned short)(mpn_pack_f16x2_sat(v, 0.f) & 0xFFFFu));
+}
+
 __device__ __forceinline__ float mpn_load_act(const void* hi, const void* lo, long long idx, int fmt) {
   if (fmt == MPN_FMT_F32) return ((const float*)hi)[idx];
   if (fmt == MPN_FMT_F16F8)
@@ -57,7 +68,7 @@ __device__ __forceinline__ void mpn_store_act(void* hi, void* lo, long long idx,
   if (fmt == MPN_FMT_F32) {
     ((float*)hi)[idx] = v;
   } else if (fmt == MPN_FMT_F16F8) {
-    const __half h = __float2half_rn(v);
+    const __half h = mpn_f16_sat(v);
     ((__half*)hi)[idx] = h;
     ((unsigned char*)lo)[idx] = mpn_float_to_e5m2((v - __half2float(h)) * MPN_F8_LO_SCALE);
     ((unsigned char*)lo)[plane + idx] = mpn_float_to_e5m2(v);

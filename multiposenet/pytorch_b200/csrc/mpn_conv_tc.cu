@@ -149,10 +149,7 @@ __device__ __forceinline__ uint64_t make_sdesc64(uint32_t saddr) {
   d |= (uint64_t)4 << 61;  // SWIZZLE_64B
   return d;
 }
-__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
-  __half2 t = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) { return mpn_pack_f16x2_sat(a, b); }  // saturating: no inf planes
 __device__ __forceinline__ float f16_lo_f(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xFFFFu))); }
 __device__ __forceinline__ float f16_hi_f(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
 __device__ __forceinline__ uint32_t e5m2x2(float a, float b) {  // a in the low byte

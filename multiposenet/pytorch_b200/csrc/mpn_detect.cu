@@ -10,6 +10,7 @@
 // operation order (no FMA contraction is possible in devIoU either).
 #include <cub/cub.cuh>
 #include <math.h>
+#include <stdlib.h>
 
 #include "mpn_common.cuh"
 
@@ -189,6 +190,85 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   }
 }
 
+// The IoU test of one (row box, column box) pair, in the reference's operation order (nms_kernel.cu:16-24) with explicit
+// round-to-nearest intrinsics.  Shortcuts (positive finite threshold only): (1) disjoint boxes: interS == 0 exactly -> IoU is
+// 0 (or NaN for a 0/0 union), never above the threshold; (2) interS vs thr*union with a 1e-6 relative guard band (8 ulps, the
+// products carry < 1 ulp of rounding): outside the band the correctly rounded quotient is certainly above / below thr, so the
+// division is only evaluated inside the band.
+__device__ __forceinline__ bool nms_pair_over(const float4& a, float Sa, const float4& bb, float Sb, float thr, int ge, bool fast_ok) {
+  const float w = __fadd_rn(__fsub_rn(fminf(a.z, bb.z), fmaxf(a.x, bb.x)), 1.f);
+  const float h = __fadd_rn(__fsub_rn(fminf(a.w, bb.w), fmaxf(a.y, bb.y)), 1.f);
+  if (fast_ok && (!(w > 0.f) || !(h > 0.f))) return false;
+  const float interS = __fmul_rn(fmaxf(w, 0.f), fmaxf(h, 0.f));
+  const float uni = __fsub_rn(__fadd_rn(Sa, Sb), interS);
+  const float pth = __fmul_rn(thr, uni);
+  if (fast_ok && uni > 0.f && interS > __fmul_rn(pth, 1.000001f)) return true;
+  if (fast_ok && uni > 0.f && interS < __fmul_rn(pth, 0.999999f)) return false;
+  const float v = __fdiv_rn(interS, uni);
+  return ge ? (v >= thr) : (v > thr);
+}
+
+// Second-generation mask kernel.  grid (row block, column group, image); a CTA of 128 threads owns one 64-box row block and
+// up to NMS_CG consecutive column blocks of the upper triangle (first group starts at the diagonal).  Thread t: row box
+// t & 63, column half t >> 6 (warp-uniform) -> one 32-bit half of every mask word.  The column boxes of block j + 1 are
+// fetched from global memory into registers while block j is evaluated from shared memory (double buffer, one barrier
+// per block), so a CTA pays the global-load latency once instead of once per 64 x 64 pairs, and the row box is loaded once
+// per NMS_CG blocks.  Same bits as nms_mask_kernel (same pair function).
+constexpr int NMS_CG = 8;
+__global__ void __launch_bounds__(128) nms_mask_kernel_v2(const float* __restrict__ sdets, const int32_t* __restrict__ cand_cnt,
+                                                         int n_fixed, int max_cand, int cb_stride, float thr, int ge,
+                                                         unsigned long long* __restrict__ mask) {
+  const int b = blockIdx.z;
+  int n = cand_cnt ? cand_cnt[b] : n_fixed;
+  n = n < max_cand ? n : max_cand;
+  const int row_start = blockIdx.x;
+  const int col_first = row_start + blockIdx.y * NMS_CG;
+  if (row_start * 64 >= n || col_first * 64 >= n) return;
+  const int col_blocks = (n + 63) >> 6;
+  const int nblk = min(NMS_CG, col_blocks - col_first);
+  const float* dets = sdets + (long long)b * max_cand * 5;
+  __shared__ float4 cbox[2][64];
+  __shared__ float carea[2][64];
+  const int tid = threadIdx.x, r = tid & 63, half = tid >> 6;
+  const int cur = 64 * row_start + r;
+  const bool row_ok = cur < n;
+  float4 rbx = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row_ok) rbx = make_float4(dets[(long long)cur * 5], dets[(long long)cur * 5 + 1], dets[(long long)cur * 5 + 2], dets[(long long)cur * 5 + 3]);
+  const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(rbx.z, rbx.x), 1.f), __fadd_rn(__fsub_rn(rbx.w, rbx.y), 1.f));
+  const bool fast_ok = thr > 1e-3f && thr < 1e3f;
+  // threads 0..63 stage column box `tid` of a block (boxes beyond n: zeros, never tested)
+  auto fetch = [&](int cblk, float4& v) {
+    const int c = 64 * cblk + tid;
+    v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < 64 && c < n) v = make_float4(dets[(long long)c * 5], dets[(long long)c * 5 + 1], dets[(long long)c * 5 + 2], dets[(long long)c * 5 + 3]);
+  };
+  auto stage = [&](int buf, const float4& v) {
+    if (tid < 64) {
+      cbox[buf][tid] = v;
+      carea[buf][tid] = __fmul_rn(__fadd_rn(__fsub_rn(v.z, v.x), 1.f), __fadd_rn(__fsub_rn(v.w, v.y), 1.f));
+    }
+  };
+  float4 nxt;
+  fetch(col_first, nxt);
+  stage(0, nxt);
+  __syncthreads();
+  unsigned int* mask32 = reinterpret_cast<unsigned int*>(mask + ((long long)b * max_cand + cur) * cb_stride);
+  for (int j = 0; j < nblk; ++j) {
+    const int cblk = col_first + j, buf = j & 1;
+    if (j + 1 < nblk) fetch(cblk + 1, nxt);
+    if (row_ok) {
+      const int col_size = min(n - cblk * 64, 64);
+      const int lo = max(32 * half, cblk == row_start ? r + 1 : 0), hi = min(32 * half + 32, col_size);
+      unsigned int t = 0u;
+      for (int i = lo; i < hi; ++i)
+        if (nms_pair_over(rbx, Sa, cbox[buf][i], carea[buf][i], thr, ge, fast_ok)) t |= 1u << (i & 31);
+      mask32[2 * cblk + half] = t;   // little endian: half 0 = columns 0..31 of the 64-bit word
+    }
+    if (j + 1 < nblk) stage(buf ^ 1, nxt);
+    __syncthreads();
+  }
+}
+
 // One CTA per image: the serial host loop of nms_cuda.c:46-58, 64 boxes at a time.  Per 64-box block the critical path is
 // (a) resolving the block against its own diagonal mask word by word -- only over the still-alive boxes -- and (b) OR-ing
 // the rows of the boxes it keeps into the later column blocks; the next block's diagonal words are prefetched meanwhile,
@@ -273,6 +353,111 @@ __global__ void __launch_bounds__(128) nms_reduce_kernel(const unsigned long lon
   }
 }
 
+// Second-generation reduction: same serial semantics, but the mask rows of a 64-box block (words rb .. col_blocks) are staged
+// in shared memory by cp.async two blocks ahead, so neither the resolve of the diagonal words nor the OR of the kept rows
+// waits on an L2 round trip inside the serial chain.  Dynamic smem: remv | keepbits | prefix | 2 x [64][cbs] words.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__global__ void __launch_bounds__(128) nms_reduce_kernel_v2(const unsigned long long* __restrict__ mask,
+                                                           const int32_t* __restrict__ cand_cnt, int max_cand, int cb_stride,
+                                                           const int32_t* __restrict__ ranks_sorted,
+                                                           const float* __restrict__ sdets, int64_t* __restrict__ keep_idx,
+                                                           int32_t* __restrict__ keep_cnt, float* __restrict__ out_scores,
+                                                           float* __restrict__ out_boxes) {
+  extern __shared__ __align__(16) unsigned long long dyn2[];
+  const int cbs = (cb_stride + 1) & ~1;   // row pitch of the staged blocks in words (16-byte chunks)
+  unsigned long long* remv = dyn2;
+  unsigned long long* keepbits = dyn2 + cbs;
+  int* prefix = reinterpret_cast<int*>(dyn2 + 2 * cbs);
+  unsigned long long* stg = dyn2 + 2 * cbs + (((cbs + 2) / 2 + 1) & ~1);   // 16-byte aligned
+  const int b = blockIdx.x, tid = threadIdx.x;
+  int n = cand_cnt[b];
+  n = n < max_cand ? n : max_cand;
+  const int col_blocks = (n + 63) / 64;
+  for (int j = tid; j < cbs; j += blockDim.x) { remv[j] = 0ULL; keepbits[j] = 0ULL; }
+  const unsigned long long* m = mask + (long long)b * max_cand * cb_stride;
+  // stage block rb: rows rb*64 .. +63 (those < n), words (rb & ~1) .. col_blocks-1 rounded up to a pair; cb_stride is even or
+  // the row start may be 8-byte aligned only -> fall back to 8-byte copies when the pitch is odd
+  const bool pair_ok = (cb_stride & 1) == 0;
+  auto prefetch = [&](int rb) {
+    if (rb < col_blocks) {
+      unsigned long long* dst = stg + (size_t)(rb & 1) * 64 * cbs;
+      const int rows = min(n - rb * 64, 64);
+      if (pair_ok) {
+        const int w0 = rb & ~1, nch = (col_blocks - w0 + 1) >> 1;   // 16-byte chunks per row
+        for (int i = tid; i < rows * nch; i += blockDim.x) {
+          const int rr = i / nch, c = w0 + 2 * (i - rr * nch);
+          cp_async16(dst + rr * cbs + c, m + (long long)(rb * 64 + rr) * cb_stride + c);
+        }
+      } else {
+        const int nw = col_blocks - rb;
+        for (int i = tid; i < rows * nw; i += blockDim.x) {
+          const int rr = i / nw, c = rb + (i - rr * nw);
+          dst[rr * cbs + c] = m[(long long)(rb * 64 + rr) * cb_stride + c];
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(0);
+  prefetch(1);
+  for (int rb = 0; rb < col_blocks; ++rb) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the newest group (block rb + 1) has landed
+    __syncthreads();
+    const unsigned long long* blk = stg + (size_t)(rb & 1) * 64 * cbs;
+    const int rows = min(n - rb * 64, 64);
+    if (tid == 0) {
+      const unsigned long long valid = rows == 64 ? ~0ULL : ((1ULL << rows) - 1ULL);
+      unsigned long long cur = remv[rb], kb = 0ULL;
+      unsigned long long alive = ~cur & valid;
+      while (alive) {  // boxes are visited in score order; the diagonal word of box t only has bits above t
+        const int t = __ffsll((long long)alive) - 1;
+        kb |= 1ULL << t;
+        cur |= blk[t * cbs + rb];
+        alive &= ~cur;
+        alive &= ~((2ULL << t) - 1ULL);
+      }
+      keepbits[rb] = kb;
+    }
+    __syncthreads();
+    const unsigned long long kb = keepbits[rb];
+    for (int j = rb + 1 + tid; j < col_blocks; j += blockDim.x) {
+      unsigned long long acc = remv[j];
+      unsigned long long bits = kb;
+      while (bits) {
+        const int t = __ffsll((long long)bits) - 1;
+        bits &= bits - 1;
+        acc |= blk[t * cbs + j];
+      }
+      remv[j] = acc;
+    }
+    __syncthreads();   // every thread is done with this staging buffer: refill it with block rb + 2
+    prefetch(rb + 2);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (tid == 0) {
+    int run = 0;
+    for (int j = 0; j < col_blocks; ++j) { prefix[j] = run; run += __popcll(keepbits[j]); }
+    prefix[col_blocks] = run;
+    keep_cnt[b] = run;
+  }
+  __syncthreads();
+  const long long o = (long long)b * max_cand;
+  for (int srt = tid; srt < n; srt += blockDim.x) {
+    const int rb = srt >> 6, t = srt & 63;
+    const unsigned long long kb = keepbits[rb];
+    if (!((kb >> t) & 1ULL)) continue;
+    const int pos = prefix[rb] + __popcll(kb & ((1ULL << t) - 1ULL));
+    keep_idx[o + pos] = (int64_t)ranks_sorted[o + srt];
+    if (out_scores) out_scores[o + pos] = sdets[(o + srt) * 5 + 4];
+    if (out_boxes) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) out_boxes[(o + pos) * 4 + k] = sdets[(o + srt) * 5 + k];
+    }
+  }
+}
+
 struct Workspace {
   float* keys_in;
   float* keys_out;
@@ -322,28 +507,65 @@ Workspace carve(void* base, int B, int max_cand) {
   return w;
 }
 
+// MPN_NMS_V2=0 selects the first-generation mask / reduce kernels (kept as the A/B reference)
+int nms_v2_enabled() {
+  static const int on = getenv("MPN_NMS_V2") ? atoi(getenv("MPN_NMS_V2")) : 1;
+  return on;
+}
+
+size_t reduce_v2_smem(int cb) {
+  const int cbs = (cb + 1) & ~1;
+  return (size_t)(2 * cbs + (((cbs + 2) / 2 + 1) & ~1) + 2 * 64 * cbs) * sizeof(unsigned long long);
+}
+
+int launch_mask(const float* sdets, const int32_t* cand_cnt, int n_fixed, int max_cand, int B, float iou_thr, int ge,
+                unsigned long long* mask, cudaStream_t st) {
+  const int cb = (max_cand + 63) / 64;
+  if (nms_v2_enabled() && cb <= 65535) {
+    dim3 mg(cb, mpn_divup(cb, NMS_CG), B);
+    nms_mask_kernel_v2<<<mg, 128, 0, st>>>(sdets, cand_cnt, n_fixed, max_cand, cb, iou_thr, ge, mask);
+  } else {
+    dim3 mg(cb * (cb + 1) / 2, 1, B);
+    nms_mask_kernel<<<mg, 64, 0, st>>>(sdets, cand_cnt, n_fixed, max_cand, cb, cb, iou_thr, ge, mask);
+  }
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+// ev (optional): 5 events recorded after sort, gather, mask, reduce (ev[0] is recorded by the caller before the filter,
+// ev[1] after it) -- mpn_filter_sort_nms_profile
 int run_core(const float* boxes, int box_stride, long long box_image_stride, int B, int max_cand, float iou_thr, int ge,
              const int32_t* cand_idx, const int32_t* cand_cnt, int64_t* keep_idx, int32_t* keep_cnt, float* out_scores,
-             float* out_boxes, Workspace& w, cudaStream_t st) {
+             float* out_boxes, Workspace& w, cudaStream_t st, cudaEvent_t* ev = nullptr) {
   segments_kernel<<<mpn_divup(B, 128), 128, 0, st>>>(cand_cnt, B, max_cand, w.seg_begin, w.seg_end);
   MPN_LAUNCH_OK();
   size_t tb = w.cub_bytes;
   MPN_CUDA_OK(cub::DeviceSegmentedRadixSort::SortPairsDescending(w.cub_temp, tb, w.keys_in, w.keys_out, w.ranks_in, w.ranks_out,
                                                                  B * max_cand, B, w.seg_begin, w.seg_end, 0, 32, st));
+  if (ev) MPN_CUDA_OK(cudaEventRecord(ev[2], st));
   dim3 gg(mpn_divup(max_cand, 256), B);
   gather_sorted_kernel<<<gg, 256, 0, st>>>(boxes, box_stride, box_image_stride, cand_idx, cand_cnt, w.keys_out, w.ranks_out,
                                            max_cand, w.sdets);
   MPN_LAUNCH_OK();
+  if (ev) MPN_CUDA_OK(cudaEventRecord(ev[3], st));
   const int cb = (max_cand + 63) / 64;
-  dim3 mg(cb * (cb + 1) / 2, 1, B);
-  nms_mask_kernel<<<mg, 64, 0, st>>>(w.sdets, cand_cnt, 0, max_cand, cb, cb, iou_thr, ge, w.mask);
+  int rc = launch_mask(w.sdets, cand_cnt, 0, max_cand, B, iou_thr, ge, w.mask, st);
+  if (rc) return rc;
+  if (ev) MPN_CUDA_OK(cudaEventRecord(ev[4], st));
+  const size_t v2_smem = reduce_v2_smem(cb);
+  if (nms_v2_enabled() && v2_smem <= 200 * 1024) {
+    if (v2_smem > 48 * 1024) MPN_CUDA_OK(cudaFuncSetAttribute(nms_reduce_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2_smem));
+    nms_reduce_kernel_v2<<<B, 128, v2_smem, st>>>(w.mask, cand_cnt, max_cand, cb, w.ranks_out, w.sdets, keep_idx, keep_cnt, out_scores,
+                                                   out_boxes);
+  } else {
+    const size_t red_smem = (size_t)(2 * cb + (cb + 2) / 2) * sizeof(unsigned long long);
+    MPN_CHECK_ARG(red_smem <= 200 * 1024, "nms: too many candidates for the on-device reduction (%d)", max_cand);
+    if (red_smem > 48 * 1024) MPN_CUDA_OK(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+    nms_reduce_kernel<<<B, 128, red_smem, st>>>(w.mask, cand_cnt, max_cand, cb, w.ranks_out, w.sdets, keep_idx, keep_cnt, out_scores,
+                                                out_boxes);
+  }
   MPN_LAUNCH_OK();
-  const size_t red_smem = (size_t)(2 * cb + (cb + 2) / 2) * sizeof(unsigned long long);
-  MPN_CHECK_ARG(red_smem <= 200 * 1024, "nms: too many candidates for the on-device reduction (%d)", max_cand);
-  if (red_smem > 48 * 1024) MPN_CUDA_OK(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
-  nms_reduce_kernel<<<B, 128, red_smem, st>>>(w.mask, cand_cnt, max_cand, cb, w.ranks_out, w.sdets, keep_idx, keep_cnt, out_scores,
-                                              out_boxes);
-  MPN_LAUNCH_OK();
+  if (ev) MPN_CUDA_OK(cudaEventRecord(ev[5], st));
   return MPN_OK;
 }
 
@@ -426,6 +648,31 @@ extern "C" int mpn_filter_sort_nms(const float* cls, const float* boxes, int B, 
                   out_boxes, w, st);
 }
 
+extern "C" int mpn_filter_sort_nms_profile(const float* cls, const float* boxes, int B, int A, float score_thresh, float iou_thresh,
+                                           int ge, int max_cand, int32_t* cand_idx, int32_t* cand_cnt, int64_t* keep_idx,
+                                           int32_t* keep_cnt, float* out_scores, float* out_boxes, void* workspace,
+                                           size_t workspace_bytes, void* stream, float* stage_ms) {
+  MPN_CHECK_ARG(cls && boxes && B > 0 && A > 0 && max_cand > 0 && stage_ms, "mpn_filter_sort_nms_profile: bad argument");
+  MPN_CHECK_ARG(cand_idx && cand_cnt && keep_idx && keep_cnt && workspace, "mpn_filter_sort_nms_profile: null output/workspace");
+  Workspace w = carve(workspace, B, max_cand);
+  MPN_CHECK_ARG(workspace_bytes >= w.total, "mpn_filter_sort_nms_profile: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t ev[6];
+  for (int i = 0; i < 6; ++i) MPN_CUDA_OK(cudaEventCreate(&ev[i]));
+  MPN_CUDA_OK(cudaEventRecord(ev[0], st));
+  filter_compact_kernel<<<B, 1024, 0, st>>>(cls, A, score_thresh, max_cand, cand_idx, cand_cnt, w.keys_in, w.ranks_in);
+  MPN_LAUNCH_OK();
+  MPN_CUDA_OK(cudaEventRecord(ev[1], st));
+  int rc = run_core(boxes, 4, (long long)A * 4, B, max_cand, iou_thresh, ge, cand_idx, cand_cnt, keep_idx, keep_cnt, out_scores,
+                    out_boxes, w, st, ev);
+  if (rc == MPN_OK) {
+    MPN_CUDA_OK(cudaEventSynchronize(ev[5]));
+    for (int i = 0; i < 5; ++i) MPN_CUDA_OK(cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
+  }
+  for (int i = 0; i < 6; ++i) cudaEventDestroy(ev[i]);
+  return rc;
+}
+
 extern "C" size_t mpn_nms_workspace_bytes(int n) {
   if (n <= 0) return 256;
   // extra: cand_idx[n] + cand_cnt[1]
@@ -452,10 +699,5 @@ extern "C" int mpn_nms(const float* dets, int n, float iou_thresh, int ge, int64
 
 extern "C" int mpn_nms_mask(const float* sorted_dets, int n, float iou_thresh, int ge, uint64_t* mask, void* stream) {
   MPN_CHECK_ARG(sorted_dets && mask && n > 0, "mpn_nms_mask: bad argument");
-  const int cb = (n + 63) / 64;
-  dim3 mg(cb * (cb + 1) / 2, 1, 1);
-  nms_mask_kernel<<<mg, 64, 0, (cudaStream_t)stream>>>(sorted_dets, nullptr, n, n, cb, cb, iou_thresh, ge,
-                                                      (unsigned long long*)mask);
-  MPN_LAUNCH_OK();
-  return MPN_OK;
+  return launch_mask(sorted_dets, nullptr, n, n, 1, iou_thresh, ge, (unsigned long long*)mask, (cudaStream_t)stream);
 }

@@ -361,8 +361,8 @@ __global__ void maxpool3x3s2_f16f8_kernel(const uint4* __restrict__ xhi, const u
     unsigned oh4[4], ol2[2] = {0u, 0u}, og2[2] = {0u, 0u};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const __half2 t = __floats2half2_rn(m[2 * j], m[2 * j + 1]);
-      oh4[j] = *reinterpret_cast<const unsigned*>(&t);
+      oh4[j] = mpn_pack_f16x2_sat(m[2 * j], m[2 * j + 1]);
+      const __half2 t = *reinterpret_cast<const __half2*>(&oh4[j]);
       const float2 f = __half22float2(t);
       const unsigned l0 = mpn_float_to_e5m2((m[2 * j] - f.x) * MPN_F8_LO_SCALE), l1 = mpn_float_to_e5m2((m[2 * j + 1] - f.y) * MPN_F8_LO_SCALE);
       const unsigned g0 = mpn_float_to_e5m2(m[2 * j]), g1 = mpn_float_to_e5m2(m[2 * j + 1]);

@@ -15,7 +15,9 @@ libmpn_b200 launches on NHWC activations:
   post     : decode+clip, filter, radix sort, bit-mask NMS, gather -- all on the device
 
 Precision modes (env MPN_PRECISION or Engine(precision=...)):
-  "bf16x3" (default) tcgen05, hi/lo bf16 split, 3 MMAs / K-step: fp32-grade parity (<1e-3)
+  "f16f8" (default)  tcgen05, fp16 plane + two fp8 cross-term planes, 8 MMA slots / K block: fp32-grade parity (<1e-3);
+                     activations saturate at +-65504 (Engine.check_range / MPN_RANGE_CHECK=1 reports a clamped layer)
+  "bf16x3"           tcgen05, hi/lo bf16 split, 3 MMAs / K-step: fp32-grade parity (<1e-3), full fp32 range
   "bf16"             tcgen05, single bf16 plane: fastest, ~1e-2 relative error after 100 layers
   "fp32"             CUDA-core fp32 FMA kernel: exact-mode reference on the device
 """
@@ -30,7 +32,11 @@ from ._lib import FMT_BF16, FMT_BF16X2, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_
 # reference on every output (profiles/r01s_parity_margin.txt; the bar is 1e-3) and ~15 % faster than bf16x3, which has the
 # same error.  Training (train_engine) runs on bf16x3 / bf16 planes.
 DEFAULT_PRECISION = os.environ.get("MPN_PRECISION", "f16f8")
-USE_GRAPHS = os.environ.get("MPN_CUDA_GRAPH", "0") == "1"
+# The public forward() replays a captured CUDA graph from the SECOND call with the same (mode, shape, dtype, device) on
+# (the first call runs eagerly: a caller that never repeats a shape -- multi-scale TTA -- never pays a capture); at most
+# MAX_GRAPHS captured graphs are kept per engine (least recently used evicted: each holds its own activation pool).
+USE_GRAPHS = os.environ.get("MPN_CUDA_GRAPH", "1") == "1"
+MAX_GRAPHS = int(os.environ.get("MPN_MAX_GRAPHS", "4"))
 TC_STEM = os.environ.get("MPN_TC_STEM", "1") == "1"
 USE_STREAMS = os.environ.get("MPN_STREAMS", "0") == "1"  # measured: no gain on B200 (r01c), kept as an option
 LEVEL_STREAMS = os.environ.get("MPN_LEVEL_STREAMS", "1") == "1"  # small pyramid levels of the RetinaNet towers side by side
@@ -67,22 +73,41 @@ class Engine(object):
         return st
 
     # ------------------------------------------------------------------ weights
+    def _collect_slots(self):
+        """One walk over the module tree (~4 ms for R101): the (owner dict, name) slot of every parameter and buffer, the
+        (parent._modules, name, child) link of every submodule and the BatchNorm modules (their eps is part of the fold)."""
+        slots, links, bns = [], [], []
+        for mod in self.model.modules():
+            slots.extend((mod._parameters, n) for n, t in mod._parameters.items() if t is not None)
+            slots.extend((mod._buffers, n) for n, t in mod._buffers.items() if t is not None)
+            links.extend((mod._modules, n, c) for n, c in mod._modules.items() if c is not None)
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                bns.append(mod)
+        self._slots, self._links, self._bns = slots, links, bns
+
+    def invalidate(self):
+        """Forget the packed filters, the captured graphs and the cached module walk.  Needed after edits the signature
+        cannot see: in-place writes through `.data` / `.detach()` views (`p.data.mul_()`, `p.data.fill_()` -- those do not
+        bump the version counter of `p`).  poseNet.load_state_dict / _apply (.to, .cuda, .half ...) call it themselves."""
+        self._packed, self._sig = {}, None
+        self._graphs, self._graph_sig = {}, None
+        self._slots = None
+
     def _signature(self):
-        """(storage address, version counter) of every parameter and buffer: in-place updates (optimizer.step,
-        load_state_dict), .to()/.cuda() and replaced Parameter objects all change it.  The (owner dict, name) slots are
-        collected once -- walking the module tree costs ~4 ms for R101, which a synchronous caller pays as GPU idle time
-        in front of every graph replay; reading 708 slots costs ~0.3 ms."""
-        slots = self.__dict__.get("_slots")
-        if slots is None:
-            slots = []
-            for mod in self.model.modules():
-                slots.extend((mod._parameters, n) for n, t in mod._parameters.items() if t is not None)
-                slots.extend((mod._buffers, n) for n, t in mod._buffers.items() if t is not None)
-            self._slots = slots
+        """(storage address, version counter) of every parameter and buffer, the identity of every submodule link and every
+        BatchNorm eps: in-place updates (optimizer.step, load_state_dict), .to()/.cuda(), replaced Parameter objects,
+        replaced submodules (`m.convfin = nn.Conv2d(...)`) and a changed `bn.eps` all change it.  The slots are collected
+        once -- walking the module tree costs ~4 ms for R101, which a synchronous caller pays as GPU idle time in front of
+        every graph replay; reading them costs ~0.3 ms.  NOT seen: writes through `.data` views -> call invalidate()."""
+        if self.__dict__.get("_slots") is None:
+            self._collect_slots()
         try:
-            ts = [d[n] for d, n in slots]
-            return (tuple(map(torch.Tensor.data_ptr, ts)), tuple([t._version for t in ts]))   # ~0.1-0.4 ms for 708 tensors
-        except (KeyError, TypeError, AttributeError):  # a parameter / buffer was removed or set to None: recollect the slots
+            for d, n, c in self._links:
+                if d[n] is not c:       # a submodule was replaced: the cached walk is stale
+                    raise KeyError(n)
+            ts = [d[n] for d, n in self._slots]
+            return (tuple(map(torch.Tensor.data_ptr, ts)), tuple([t._version for t in ts]), tuple([b.eps for b in self._bns]))
+        except (KeyError, TypeError, AttributeError):  # something was removed, replaced or set to None: walk again next time
             self._slots = None
             return (object(),)
 
@@ -334,7 +359,7 @@ class Engine(object):
         res = x.reshape(P, -1).contiguous()
         D = res.shape[1]
         if self.fmt == FMT_F32:
-            raise NotImplementedError("PRN runs on the tcgen05 path (precision bf16x3 or bf16)")
+            raise NotImplementedError("PRN runs on the tcgen05 path (precision f16f8, bf16x3 or bf16), not in the fp32 CUDA-core mode")
         Dp = (D + 63) // 64 * 64
 
         def pc(name, lin, cin_pad, cout_pad=None):
@@ -363,9 +388,10 @@ class Engine(object):
         """Run `kind` ('entire', 'keypoint', 'detection') through a captured CUDA graph of its launch
         sequence (captured on first use per input shape; ~250 launches replayed with one driver call).
         The returned tensors are the graph's static outputs: they are overwritten by the next replay."""
-        key = (kind, tuple(img.shape), str(img.device), str(img.dtype), tuple(sorted(kw.items())))
+        key = self._graph_key(kind, img, kw)
         g = self._graphs.get(key) if self._sig is not None and self._graph_sig == self._sig else None
         if g is not None:
+            self._graphs[key] = self._graphs.pop(key)  # most recently used last
             # Fast path: replay first, then validate the weights while the GPU runs -- the signature walk (~0.4 ms) would
             # otherwise be GPU idle time in front of every replay of a synchronous caller.  If the weights did change
             # since the capture, this replay's outputs are discarded and the slow path below repacks, recaptures and reruns.
@@ -375,7 +401,7 @@ class Engine(object):
             if self._signature() == self._sig:
                 return out
         self._ensure_packed()
-        if getattr(self, "_graph_sig", None) != self._sig:
+        if self._graph_sig != self._sig:
             self._graphs, self._graph_sig = {}, self._sig  # weights changed -> recapture
         g = self._graphs.get(key)
         fn = {"entire": self.entire_forward_device, "keypoint": self.keypoint_forward, "detection": self.detection_forward}[kind]
@@ -393,17 +419,48 @@ class Engine(object):
             with torch.cuda.graph(graph):
                 out = fn(static_in, **kw)
             g = (graph, static_in, out)
+            while len(self._graphs) >= max(1, MAX_GRAPHS):
+                self._graphs.pop(next(iter(self._graphs)))  # least recently used
             self._graphs[key] = g
         graph, static_in, out = g
         static_in.copy_(img, non_blocking=True)
         graph.replay()
         return out
 
+    @staticmethod
+    def _graph_key(kind, img, kw):
+        return (kind, tuple(img.shape), str(img.device), str(img.dtype), tuple(sorted(kw.items())))
+
+    def _wants_graph(self, kind, img, **kw):
+        """Graph replay for the public calls: on from the second call with the same key (see USE_GRAPHS)."""
+        if not USE_GRAPHS or (img.is_cuda and torch.cuda.is_current_stream_capturing()):
+            return False
+        key = self._graph_key(kind, img, kw)
+        if key in self._graphs:
+            return True
+        seen = self.__dict__.setdefault("_seen", {})
+        if len(seen) > 256:
+            seen.clear()
+        seen[key] = seen.get(key, 0) + 1
+        return seen[key] >= 2
+
+    def check_range(self, img, kind="entire"):
+        """Overflow guard of the f16f8 format (fp16 planes saturate at +-65504): runs one eager forward that reads back the
+        largest magnitude of every activation tensor and raises MpnError naming the first clamped layer.  Debug aid for a
+        new checkpoint; MPN_RANGE_CHECK=1 does the same on every eager conv call."""
+        fn = {"entire": self.entire_forward_device, "keypoint": self.keypoint_forward, "detection": self.detection_forward}[kind]
+        prev, ops.stats["range_check"] = ops.stats.get("range_check"), True
+        try:
+            fn(img)
+        finally:
+            ops.stats["range_check"] = prev
+        return True
+
     @torch.no_grad()
     def entire_forward(self, img, max_cand=4096):
         """posenet.py:236-285: (heat, [nms_scores, nms_class, boxes]) for image 0, like the reference;
         the per-image results of the whole batch stay in self.last_detections."""
-        if USE_GRAPHS:
+        if self._wants_graph("entire", img, max_cand=max_cand):
             heat, cls, reg, boxes, det = self.graphed("entire", img, max_cand=max_cand)
             heat = heat.clone()  # static graph output -> caller-owned
         else:

@@ -36,25 +36,50 @@ def _regroup(kps):
     return np.ascontiguousarray(kps[order, :2]), np.ascontiguousarray(ty[order])
 
 
-def prn_process_batch(model, kps_per_image, bboxes_per_image, file_names=None, image_ids=None, coeff=2, in_thres=0.21):
+def _reference_would_divide_by_zero(xy, ty, bx, in_thres):
+    """tester.py:371-372 / :476-477 divide by ceil(box width / height).  A box with width or height <= 0 contains no peak
+    (the strict inside test :366-369 cannot hold), so the first division is never reached for it; the second one sits in the
+    fallback branch (:473), taken when some joint type has no peak inside ANY box of the image, and runs over ALL boxes:
+    it raises ZeroDivisionError exactly when that branch is reached and some box has ceil(w) == 0 or ceil(h) == 0."""
+    if not (np.ceil(bx[:, 2:]) == 0).any():
+        return False
+    inside = ((xy[:, None, 0] > bx[None, :, 0] - bx[None, :, 2] * in_thres) & (xy[:, None, 1] > bx[None, :, 1] - bx[None, :, 3] * in_thres) &
+              (xy[:, None, 0] < bx[None, :, 0] + bx[None, :, 2] * (1.0 + in_thres)) & (xy[:, None, 1] < bx[None, :, 1] + bx[None, :, 3] * (1.0 + in_thres)))
+    hit = inside.any(axis=1)
+    return any(not hit[ty == j].any() for j in range(NUM_JOINTS))
+
+
+def prn_process_batch(model, kps_per_image, bboxes_per_image, file_names=None, image_ids=None, coeff=2, in_thres=0.21, strict=True):
     """kps_per_image[b]: joint rows (x, y, score, id, joint_type 0..16) of image b (tester.py:219-229);
     bboxes_per_image[b]: person boxes (x1, y1, x2, y2) (tester.py:232-240).  Returns one list of records per image, each
-    list identical to Tester.prn_process(kps, bbox_list, file_name, image_id)."""
+    list identical to Tester.prn_process(kps, bbox_list, file_name, image_id).
+
+    Degenerate boxes (ClipBoxes can leave x2 < x1): handled per box like the reference -- they contain no peaks.  Only where
+    the reference itself raises ZeroDivisionError for an image (see _reference_would_divide_by_zero) does this function
+    raise (strict=True, after nothing was launched) or return [] for that image alone (strict=False)."""
     nimg = len(kps_per_image)
     assert len(bboxes_per_image) == nimg
     file_names = file_names if file_names is not None else [""] * nimg
     image_ids = image_ids if image_ids is not None else [0] * nimg
     gh, gw = int(28 * coeff), int(18 * coeff)                                    # :353-354
     results = [[] for _ in range(nimg)]
-    live = [b for b in range(nimg) if len(bboxes_per_image[b]) > 0]              # :360 (an image without boxes yields [])
+    cand = [b for b in range(nimg) if len(bboxes_per_image[b]) > 0]              # :360 (an image without boxes yields [])
+    prep, live = {}, []
+    for b in cand:
+        xy, ty = _regroup(kps_per_image[b])
+        bx = np.array([[bb[0], bb[1], bb[2] - bb[0], bb[3] - bb[1]] for bb in bboxes_per_image[b]], dtype=np.float64)   # :356-358
+        if _reference_would_divide_by_zero(xy, ty, bx, in_thres):
+            if strict:
+                raise ZeroDivisionError("prn_process: image %d reaches the fallback branch with a box whose ceil(width) or "
+                                        "ceil(height) is 0 (tester.py:476-477 divides by it)" % b)
+            continue
+        prep[b] = (xy, ty, bx)
+        live.append(b)
     if not live:
         return results
     xy_l, ty_l, box_l, box_img, pstart, bstart, jstart = [], [], [], [], [0], [0], []
     for li, b in enumerate(live):
-        xy, ty = _regroup(kps_per_image[b])
-        bx = np.array([[bb[0], bb[1], bb[2] - bb[0], bb[3] - bb[1]] for bb in bboxes_per_image[b]], dtype=np.float64)   # :356-358
-        if not (np.ceil(bx[:, 2:]) > 0).all():
-            raise ZeroDivisionError("prn_process: a box with ceil(width) or ceil(height) <= 0 (tester.py:371-372 divides by it)")
+        xy, ty, bx = prep[b]
         jstart.append(pstart[-1] + np.searchsorted(ty, np.arange(NUM_JOINTS + 1), side="left"))
         xy_l.append(xy); ty_l.append(ty); box_l.append(bx)
         box_img += [li] * len(bx)

@@ -161,6 +161,39 @@ class poseNet(nn.Module):
             if isinstance(m, nn.BatchNorm2d):
                 m.eval()
 
+    # -- engine cache: packed filters, streams and CUDA graphs live OUTSIDE the module state ------------------------
+    def invalidate_engines(self):
+        """Drop packed filters / captured graphs of every engine of this module.  Called by load_state_dict and _apply;
+        call it yourself after in-place edits through `.data` views (`p.data.mul_()`), which no version counter records."""
+        for e in self.__dict__.get("_engines", {}).values():
+            inv = getattr(e, "invalidate", None)
+            if inv is not None:
+                inv()
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_engines()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_engines()
+        return out
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_engines"] = {}  # torch.save(model) / pickling: engines hold streams, graphs and packed device buffers
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_engines" else copy.deepcopy(v, memo)
+        return new
+
     def engine(self, precision=None):
         precision = precision or self._precision or _engine.DEFAULT_PRECISION
         # nn.DataParallel replicas share this dict (shallow __dict__ copy): key by module identity
@@ -168,8 +201,9 @@ class poseNet(nn.Module):
         key = (precision, id(self))
         e = engines.get(key)
         if e is None or e.model is not self:
-            if len(engines) > 32:
-                engines.clear()
+            if len(engines) > 32:  # nn.DataParallel makes fresh replicas every call: drop the engines of dead replicas only
+                for k in [k for k, v in engines.items() if v.model is not self and k[0] != "train"][:16]:
+                    del engines[k]
             e = _engine.Engine(self, precision)
             engines[key] = e
         return e
@@ -231,11 +265,13 @@ class poseNet(nn.Module):
         return self.forward((img_batch, "detection_subnet"))
 
     def prn_forward(self, img_batch):
-        if img_batch.is_cuda and not (torch.is_grad_enabled() and self.training):
-            with torch.cuda.device(img_batch.device):
-                out = self.engine().prn_forward(img_batch)  # batched, tensor cores
+        if img_batch.is_cuda and not self.training:
+            with torch.cuda.device(img_batch.device), torch.no_grad():
+                out = self.engine().prn_forward(img_batch)  # batched, tensor cores (eval: dropout is the identity)
         else:
-            out = self.prn(img_batch)  # training of the PRN (nn.Linear library calls), SURVEY 8(f)
+            # model.train(): nn.Dropout is active in the reference (posenet.py:341-342) whether or not grad is enabled, and
+            # PRN training (multipose_prn_train.py) stays three nn.Linear library calls, SURVEY 8(f)
+            out = self.prn(img_batch)
         return out, [out]
 
     @staticmethod

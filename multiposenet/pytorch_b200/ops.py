@@ -16,7 +16,10 @@ PRECISIONS = {"fp32": FMT_F32, "bf16": FMT_BF16, "bf16x3": FMT_BF16X2, "f16f8": 
 
 # Launch accounting for bench.py: `launches` counts kernels launched through this module; when
 # `conv_events` is a list, every tensor-core / CUDA-core conv launch is bracketed by CUDA events.
-stats = {"launches": 0, "conv_events": None}
+import os
+
+stats = {"launches": 0, "conv_events": None, "range_check": os.environ.get("MPN_RANGE_CHECK", "0") == "1"}
+F16_MAX = 65504.0
 
 
 def _stream():
@@ -205,6 +208,12 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
         e1.record()
         ev.append((e0, e1, 2.0 * x.N * d.OH * d.OW * pc.Cout * pc.Cin * pc.R * pc.S, bool(f32_input or fmt == FMT_F32)))
     stats["launches"] += 1
+    if stats.get("range_check") and fmt == FMT_F16F8 and out_mode == OUT_ACT and not torch.cuda.is_current_stream_capturing():
+        amax = float(ret.hi.abs().max())  # debug mode: one reduction + host sync per conv
+        if not amax < F16_MAX:
+            raise _lib.MpnError("f16f8 range guard: a conv output (%dx%d, %d -> %d channels, %dx%d filter) reached |x| >= 65504 and was "
+                                "clamped by the saturating fp16 store; run this model with precision='bf16x3'"
+                                % (d.OH, d.OW, pc.Cin, pc.Cout, pc.R, pc.S))
     return ret
 
 
@@ -321,8 +330,10 @@ class Detections(object):
     __slots__ = ("cand_idx", "cand_cnt", "keep_idx", "keep_cnt", "scores", "boxes", "max_cand")
 
 
-def filter_sort_nms(cls, boxes, score_thresh=0.05, iou_thresh=0.5, ge=False, max_cand=4096):
-    """cls [B,A,1] or [B,A] fp32, boxes [B,A,4] fp32 -> Detections (device tensors, no host sync)."""
+def filter_sort_nms(cls, boxes, score_thresh=0.05, iou_thresh=0.5, ge=False, max_cand=4096, stage_ms=None):
+    """cls [B,A,1] or [B,A] fp32, boxes [B,A,4] fp32 -> Detections (device tensors, no host sync).
+    stage_ms: a list -> the blocking profiling twin runs instead and appends the five stage times (ms): filter, sort, gather,
+    mask, reduce (bench.py roofline_aux)."""
     L = _lib.lib()
     B, A = boxes.shape[0], boxes.shape[1]
     max_cand = int(min(max(64, max_cand), A))
@@ -337,10 +348,18 @@ def filter_sort_nms(cls, boxes, score_thresh=0.05, iou_thresh=0.5, ge=False, max
     det.boxes = torch.empty((B, max_cand, 4), dtype=torch.float32, device=dev)
     ws_bytes = L.mpn_detect_workspace_bytes(B, A, max_cand)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    check(L.mpn_filter_sort_nms(_ptr(cls.contiguous()), _ptr(boxes.contiguous()), B, A, float(score_thresh), float(iou_thresh),
-                                int(bool(ge)), max_cand, _ptr(det.cand_idx), _ptr(det.cand_cnt), _ptr(det.keep_idx),
-                                _ptr(det.keep_cnt), _ptr(det.scores), _ptr(det.boxes), _ptr(ws), ws_bytes, _stream()),
-          "mpn_filter_sort_nms")
+    if stage_ms is not None:
+        ms = (ctypes.c_float * 5)()
+        check(L.mpn_filter_sort_nms_profile(_ptr(cls.contiguous()), _ptr(boxes.contiguous()), B, A, float(score_thresh), float(iou_thresh),
+                                            int(bool(ge)), max_cand, _ptr(det.cand_idx), _ptr(det.cand_cnt), _ptr(det.keep_idx),
+                                            _ptr(det.keep_cnt), _ptr(det.scores), _ptr(det.boxes), _ptr(ws), ws_bytes, _stream(),
+                                            ctypes.cast(ms, ctypes.c_void_p)), "mpn_filter_sort_nms_profile")
+        stage_ms.append([float(v) for v in ms])
+    else:
+        check(L.mpn_filter_sort_nms(_ptr(cls.contiguous()), _ptr(boxes.contiguous()), B, A, float(score_thresh), float(iou_thresh),
+                                    int(bool(ge)), max_cand, _ptr(det.cand_idx), _ptr(det.cand_cnt), _ptr(det.keep_idx),
+                                    _ptr(det.keep_cnt), _ptr(det.scores), _ptr(det.boxes), _ptr(ws), ws_bytes, _stream()),
+              "mpn_filter_sort_nms")
     stats["launches"] += 6  # filter/compact, segments, radix sort (>=1), gather, mask, reduce
     return det
 

@@ -133,6 +133,107 @@ def prn_goldens():
     np.savez_compressed(os.path.join(OUT, "prn_assign.npz"), **g)
 
 
+TRAIN_GRAD_KEYS = ["fpn.conv1.weight", "fpn.bn1.weight", "fpn.bn1.bias", "fpn.layer1.0.conv1.weight", "fpn.layer1.0.bn3.weight",
+                   "fpn.layer2.0.downsample.0.weight", "fpn.layer3.2.conv2.weight", "fpn.layer4.2.conv3.weight", "fpn.layer4.2.bn3.bias",
+                   "fpn.toplayer.weight", "fpn.flatlayer2.weight", "fpn.smooth3.weight", "fpn.smooth3.bias", "convt1.weight", "convs4.bias",
+                   "conv2.weight", "conv2.bias", "convfin.weight", "convfin.bias", "convfin_k3.weight", "convfin_k5.bias"]
+TRAIN_STAT_KEYS = ["fpn.bn1.running_mean", "fpn.bn1.running_var", "fpn.layer3.1.bn2.running_mean", "fpn.layer4.2.bn3.running_var"]
+
+
+def sample_flat(a, limit=16384):
+    """Strided sample of a flattened array (keeps the golden file small); the same rule is applied by the tests."""
+    f = np.ascontiguousarray(a).reshape(-1)
+    return np.ascontiguousarray(f[:: max(1, -(-f.size // limit))])
+
+
+def train_case(hw=(64, 96), batch=2):
+    """The seeded training problem of tests/golden/train_step.npz (also rebuilt by the tests)."""
+    x = image(41, (batch, 3) + hw)
+    rng = np.random.Generator(np.random.PCG64(9))
+    gt = rng.random((batch, 18, hw[0] // 4, hw[1] // 4), dtype=np.float32)
+    wt = (rng.random((batch, 18, hw[0] // 4, hw[1] // 4)) > 0.2).astype(np.float32)
+    return x, gt, wt
+
+
+def train_golden():
+    """tests/golden/train_step.npz: the reference's own training forward + loss + autograd backward for the keypoint subnet:
+    model.train() (BatchNorm on batch statistics, trainer.py:170-174), model([img, 'keypoint_subnet']) (posenet.py:288-318),
+    poseNet.build_loss -> build_keypoint_loss (posenet.py:352-403), loss.backward() (trainer.py:245-259)."""
+    layers, hw, batch = 50, (64, 96), 2
+    w = weights.make_weights(layers, "conditioned", seed=0)
+    m = refshim.build_reference_model(layers, w)
+    m.train()
+    x, gt, wt = (torch.from_numpy(a) for a in train_case(hw, batch))
+    with torch.enable_grad():
+        out, saved = m([x, "keypoint_subnet"])
+        loss, log = m.build_loss(saved, "keypoint_subnet", gt, wt)
+        m.zero_grad()
+        loss.backward()
+    g = {"loss": np.array(float(loss), dtype=np.float64), "log_keys": np.array(json.dumps(list(log.keys()))),
+         "log_vals": np.array([float(v) for v in log.values()], dtype=np.float64)}
+    for i, s_ in enumerate(saved):
+        g["saved%d" % i] = s_.detach().numpy()
+    params = dict(m.named_parameters())
+    for k in TRAIN_GRAD_KEYS:
+        g["grad:" + k] = sample_flat(params[k].grad.numpy())
+    bufs = dict(m.named_buffers())
+    for k in TRAIN_STAT_KEYS:
+        g["stat:" + k] = bufs[k].numpy().copy()
+    g["meta"] = np.array(json.dumps({"layers": layers, "hw": hw, "batch": batch, "kind": "conditioned", "torch": torch.__version__,
+                                     "problem": "oracle.make_goldens.train_case", "mode": "model.train(): BN batch statistics"}))
+    np.savez_compressed(os.path.join(OUT, "train_step.npz"), **g)
+    print("train_step", float(loss), {k: v.shape for k, v in g.items() if k.startswith("grad:")})
+
+
+def prn_case(seed, persons, coeff):
+    """Seeded PRN input: per person a [28*coeff, 18*coeff, 17] stack of sparse, blurred peaks (tester.py:393-404 shape)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    h, w_ = 28 * coeff, 18 * coeff
+    x = np.zeros((persons, h, w_, 17), dtype=np.float32)
+    for p in range(persons):
+        for j in range(17):
+            for _ in range(int(rng.integers(0, 3))):
+                cy, cx = int(rng.integers(1, h - 1)), int(rng.integers(1, w_ - 1))
+                x[p, cy - 1:cy + 2, cx - 1:cx + 2, j] += np.array([[.06, .12, .06], [.12, .25, .12], [.06, .12, .06]], np.float32) * float(rng.uniform(1, 4))
+    return x
+
+
+def prn_weights(node_count, coeff, seed=5):
+    """Seeded PRN parameters (three Linear layers, posenet.py:130-141) in state_dict naming."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    d = 28 * coeff * 18 * coeff * 17
+    out = {}
+    for name, (o, i) in (("prn.dens1", (node_count, d)), ("prn.bneck", (node_count, node_count)), ("prn.dens2", (d, node_count))):
+        out[name + ".weight"] = rng.standard_normal((o, i), dtype=np.float32) * np.float32(1.0 / np.sqrt(i))
+        out[name + ".bias"] = rng.standard_normal((o,), dtype=np.float32) * np.float32(0.1)
+    return out
+
+
+def prn_forward_golden():
+    """tests/golden/prn_forward.npz: the reference's own PRN (posenet.py:130-152 PRN.forward and :337-350 prn_forward) in eval
+    mode, a small net (256 nodes, coeff 1) and the production shape (1024 nodes, coeff 2: 34272 -> 1024 -> 1024 -> 34272)."""
+    ref = refshim.import_reference()
+    g = {}
+    for tag, nodes, coeff, persons in (("small", 256, 1, 5), ("prod", 1024, 2, 3)):
+        pw = prn_weights(nodes, coeff)
+        prn = ref.PRN(nodes, coeff)
+        prn.load_state_dict({k[len("prn."):]: torch.from_numpy(v) for k, v in pw.items()})
+        prn.eval()
+        x = torch.from_numpy(prn_case(17, persons, coeff))
+        with torch.no_grad():
+            out = prn(x)
+            model = ref.poseNet(50, prn_node_count=nodes, prn_coeff=coeff)
+            model.prn.load_state_dict(prn.state_dict())
+            model.eval()
+            out2, saved = model([x, "prn_subnet"])
+        assert torch.equal(out, out2) and saved[0] is out2
+        g[tag + "_out"] = out.numpy()
+        g[tag + "_meta"] = np.array(json.dumps({"nodes": nodes, "coeff": coeff, "persons": persons, "input": "prn_case(17, persons, coeff)",
+                                                "weights": "prn_weights(nodes, coeff, seed=5)"}))
+    np.savez_compressed(os.path.join(OUT, "prn_forward.npz"), **g)
+    print("prn_forward", {k: v.shape for k, v in g.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     meta = {"torch": torch.__version__, "numpy": np.__version__, "reference": refshim.REF_ROOT,
@@ -196,10 +297,16 @@ def main():
                                                   np.ascontiguousarray(hm.transpose(1, 2, 0)), 1.0)
     np.savez_compressed(os.path.join(OUT, "peaks.npz"), **pk)
     prn_goldens()
+    train_golden()
+    prn_forward_golden()
     print("wrote", sorted(os.listdir(OUT)))
 
 
 if __name__ == "__main__":
     if "prn" in sys.argv[1:]:   # only the PRN-assignment vectors
         sys.exit(prn_goldens())
+    if "train" in sys.argv[1:]:   # only the training-step vectors
+        sys.exit(train_golden())
+    if "prn_forward" in sys.argv[1:]:
+        sys.exit(prn_forward_golden())
     sys.exit(main())

@@ -82,3 +82,80 @@ def test_joints_for_prn_and_regroup():
     assert xy0.shape == (0, 2) and ty0.shape == (0,)
     xy1, ty1 = _regroup(np.array([[1, 2, 0.5, 0, 17], [3, 4, 0.5, 1, 3]], dtype=np.float64))   # types outside 0..16 are ignored
     assert ty1.tolist() == [3] and xy1.tolist() == [[3.0, 4.0]]
+
+
+def test_signature_sees_module_replacement_and_bn_eps_and_invalidate():
+    """a replaced submodule (`m.convfin = nn.Conv2d(...)`) and a changed bn.eps must change the signature; writes
+    through `.data` views bump no version counter, so Engine.invalidate() / poseNet.invalidate_engines() is the contract."""
+    import copy
+    import pickle
+    from multiposenet.pytorch_b200 import poseNet
+    m = poseNet(50, precision="bf16x3")
+    e = m.engine()
+    s0 = e._signature()
+    m.convfin = torch.nn.Conv2d(256, 18, 1)
+    s1 = e._signature()                       # stale walk detected ...
+    s2, s3 = e._signature(), e._signature()   # ... re-collected, then stable
+    assert s1 != s0 and s2 == s3 and s2 != s0
+    m.fpn.layer1[0].bn1.eps = 1e-3
+    s4 = e._signature()
+    assert s4 != s3
+    m.fpn.layer2[1] = copy.deepcopy(m.fpn.layer2[1])   # a replaced block deep in the tree
+    assert e._signature() != s4
+    s5 = e._signature()
+    assert e._signature() == s5
+    # .data in-place edits are invisible to the signature (documented) -> explicit invalidation
+    e._sig, e._packed = s5, {"x": 1}
+    m.conv2.weight.data.mul_(2.0)
+    assert e._signature() == s5
+    m.invalidate_engines()
+    assert e._packed == {} and e._sig is None and e._graphs == {}
+    # load_state_dict and _apply invalidate by themselves
+    e._packed = {"x": 1}
+    m.load_state_dict(m.state_dict())
+    assert e._packed == {}
+    e._packed = {"x": 1}
+    m.float()
+    assert e._packed == {}
+    # engines stay out of copies and pickles (they hold streams, graphs and packed device buffers)
+    m2 = copy.deepcopy(m)
+    assert m2.__dict__["_engines"] == {} and m.__dict__["_engines"]
+    assert m2.engine() is not e and m2.engine().model is m2
+    m3 = pickle.loads(pickle.dumps(m))
+    assert m3.__dict__["_engines"] == {}
+    assert torch.equal(m3.conv2.weight, m.conv2.weight)
+
+
+def test_graph_policy_second_call_and_lru():
+    """The public forward replays a CUDA graph from the second call with the same key; captured graphs are LRU-capped."""
+    from multiposenet.pytorch_b200 import engine as E, poseNet
+    e = E.Engine(poseNet(50), "f16f8")
+    x = torch.zeros(2, 3, 64, 96)
+    if not E.USE_GRAPHS:
+        return
+    assert e._wants_graph("entire", x, max_cand=4096) is False     # first sight of this shape: eager
+    assert e._wants_graph("entire", x, max_cand=4096) is True      # second call: capture + replay
+    assert e._wants_graph("entire", torch.zeros(2, 3, 96, 96), max_cand=4096) is False
+    assert e._graph_key("entire", x, {"max_cand": 4096}) != e._graph_key("keypoint", x, {})
+
+
+def test_prn_degenerate_boxes_follow_the_reference():
+    """tester.py divides by ceil(w), ceil(h) only for boxes that contain a peak (impossible for w <= 0) or in the
+    fallback branch (some joint type without a peak inside any box), where ceil == 0 raises ZeroDivisionError."""
+    from multiposenet.pytorch_b200.evaluate.prn_assign import _reference_would_divide_by_zero as zdiv
+    xy = np.array([[50.0, 60.0]] * 17)
+    ty = np.arange(17, dtype=np.int32)
+    good = np.array([[10.0, 10.0, 100.0, 200.0]])
+    flat = np.array([[10.0, 10.0, -0.5, 50.0]])       # ceil(w) == 0
+    neg = np.array([[10.0, 10.0, -30.0, 50.0]])       # ceil(w) == -30: the reference divides happily
+    assert not zdiv(xy, ty, good, 0.21)
+    assert not zdiv(xy, ty, np.concatenate([good, flat]), 0.21)        # every type has a peak in `good`: fallback not reached
+    assert zdiv(xy[:16], ty[:16], np.concatenate([good, flat]), 0.21)  # type 16 has no peak -> fallback over ALL boxes -> 1/0
+    assert not zdiv(xy[:16], ty[:16], np.concatenate([good, neg]), 0.21)
+    assert zdiv(np.zeros((0, 2)), np.zeros((0,), np.int32), flat, 0.21)
+    # cross-check against the python restatement of the reference method
+    from oracle import prn_oracle
+    import pytest
+    kps = [[50.0, 60.0, 0.9, i, i] for i in range(16)]
+    with pytest.raises(ZeroDivisionError):
+        prn_oracle.prn_process(kps, [[10, 10, 110, 210], [10, 10, 9.5, 60]], prn_oracle.synthetic_prn(0))

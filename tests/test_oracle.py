@@ -175,3 +175,42 @@ def test_peaks_oracle_vs_live_reference():
     hm = peaks_oracle.synthetic_heatmaps(9, C=18, H=40, W=56, persons=3)
     gold = get_joint_list(np.zeros((160, 224, 3), np.float32), {"thre1": 0.1}, np.ascontiguousarray(hm.transpose(1, 2, 0)), 1.0)
     _check_rows(peaks_oracle.joint_list(hm, 0.1, 4), gold)
+
+
+# ---------------------------------------------------------------------------------------------
+# train-mode forward + loss + autograd backward and the PRN MLP (a16): the restatement against vectors made
+# by the live reference (oracle/make_goldens.py train_golden / prn_forward_golden)
+def test_train_mode_oracle_vs_reference_golden(golden_dir):
+    from oracle import make_goldens as mg
+    g = _load(golden_dir, "train_step.npz")
+    meta = json.loads(str(g["meta"]))
+    sd = weights.to_torch_state_dict(weights.make_weights(meta["layers"], meta["kind"], seed=0))
+    for k, v in sd.items():
+        if v.dtype == torch.float32 and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+    x, gt, wt = (torch.from_numpy(a) for a in mg.train_case(tuple(meta["hw"]), meta["batch"]))
+    with torch.enable_grad():
+        saved = po.forward_train_keypoint(sd, meta["layers"], x)
+        loss = po.keypoint_loss(saved, gt, wt)
+        loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    for i, s in enumerate(saved):
+        np.testing.assert_allclose(s.detach().numpy(), g["saved%d" % i], rtol=1e-4, atol=1e-5 * float(np.abs(g["saved%d" % i]).max()))
+    for k in mg.TRAIN_GRAD_KEYS:
+        want = g["grad:" + k]
+        got = mg.sample_flat(sd[k].grad.numpy())
+        assert got.shape == want.shape, k
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max(), k   # same graph, same torch: only summation order may differ
+
+
+def test_prn_forward_oracle_vs_reference_golden(golden_dir):
+    from oracle import make_goldens as mg
+    g = _load(golden_dir, "prn_forward.npz")
+    for tag in ("small", "prod"):
+        meta = json.loads(str(g[tag + "_meta"]))
+        sd = {k: torch.from_numpy(v) for k, v in mg.prn_weights(meta["nodes"], meta["coeff"]).items()}
+        x = torch.from_numpy(mg.prn_case(17, meta["persons"], meta["coeff"]))
+        out, saved = po.prn_forward(sd, x)
+        assert out.shape == g[tag + "_out"].shape and saved[0] is out
+        np.testing.assert_allclose(out.numpy(), g[tag + "_out"], rtol=2e-5, atol=1e-9)
+        assert abs(float(out.sum()) - meta["persons"]) < 1e-3
