@@ -11,6 +11,15 @@ One "step" = one forward of batch 32/GPU through poseNet's entire_net graph incl
   roofline      : conv_tc_kernel (all tcgen05 conv launches of a step): algorithmic conv FLOPs / summed duration
   cpu_baseline  : the oracle port of the reference graph on the host cores (bounded sample)
 --impl reference times that CPU port alone (the reference's Python cannot travel to the GPU box).
+
+The same JSON line also carries (unless --no-extras), so that the one command the driver runs measures every BASELINE config:
+  parity        : max|a-b|/max|b| of heat / cls / reg (and the kept-box count) of image 0 of the timed batch against the fp32
+                  CPU oracle output the cpu_baseline leg computes anyway; the run FAILS if one exceeds 1e-3
+  cpu_cfg1      : BASELINE configs[0]: R50 keypoint_subnet, batch 1, CPU oracle port (+ the same call on the GPU, host in/out)
+  roofline_aux  : decode / filter / sort / gather / IoU mask / greedy reduction (bench load and the cfg3 100-person feed) and the
+                  batched PRN forward: algorithmic bytes / CUDA-event time against the measured HBM copy bandwidth
+  train_step    : BASELINE configs[3]: keypoint-subnet training step, batch 16/GPU, NCCL gradient allreduce at N ranks
+  full_pipeline : BASELINE configs[4]: entire_net + NMS + heat-map peaks + PRN assignment, batch 64/GPU, host images in
 """
 import argparse
 import json
@@ -200,16 +209,14 @@ def freeze_for_keypoint_training(model):
                 p.requires_grad = False
 
 
-def run_train(args, rank, world, local):
-    """BASELINE config 4: keypoint-subnet training step (fwd + bwd + NCCL gradient allreduce + Adam), batch 16/GPU."""
-    import torch.distributed as dist
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+def train_leg(args, rank, world, local, steps, warmup, precision=None):
+    """BASELINE config 4: keypoint-subnet training step (fwd + bwd + NCCL gradient allreduce + Adam), batch 16/GPU.
+    Collective: every rank calls it; returns the record on rank 0 (None elsewhere)."""
     from multiposenet.pytorch_b200 import poseNet, shard
-    B = args.batch if args.batch != 32 else 16
-    model = poseNet(args.layers, precision=args.precision)
+    dev = torch.device("cuda", local)
+    precision = precision or ("bf16x3" if args.precision in (None, "f16f8", "fp32") else args.precision)
+    B = args.train_batch
+    model = poseNet(args.layers, precision=precision)
     load_weights_into(model, args.layers)
     model = model.to(dev).train()
     freeze_for_keypoint_training(model)
@@ -219,23 +226,28 @@ def run_train(args, rank, world, local):
     x = torch.from_numpy(rng.standard_normal((B, 3, H, W), dtype=np.float32)).to(dev)
     gt = torch.from_numpy(rng.random((B, 18, H // 4, W // 4), dtype=np.float32)).to(dev)
     wt = torch.from_numpy((rng.random((B, 18, H // 4, W // 4)) > 0.2).astype(np.float32)).to(dev)
+    comm_ms = []
 
     def step():
-        if args.graph:
-            loss, outs, grads = eng.graphed_forward_backward(x, gt, wt)  # one cudaGraphLaunch for fwd + bwd
+        if hasattr(eng, "train_step_overlapped") and args.graph and args.overlap:
+            loss = eng.train_step_overlapped(x, gt, wt, world)   # bucketed allreduce under the tail of the backward
         else:
-            loss, outs, grads = eng.forward_backward(x, gt, wt)
-        eng.assign_grads(grads, world)   # one NCCL allreduce over the flat fp32 gradient (no-op at world 1)
+            if args.graph:
+                loss, outs, grads = eng.graphed_forward_backward(x, gt, wt)  # one cudaGraphLaunch for fwd + bwd
+            else:
+                loss, outs, grads = eng.forward_backward(x, gt, wt)
+            eng.assign_grads(grads, world)   # one NCCL allreduce over the flat fp32 gradient (no-op at world 1)
         opt.step()
         return loss
 
     def barrier():
         if world > 1:
+            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
 
     losses = []
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         losses.append(step().clone())
     barrier()
     sampler = ClockSampler(local)
@@ -244,50 +256,80 @@ def run_train(args, rank, world, local):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         losses.append(step().clone())
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
-    value = shard.whole_job_rate(B * args.steps, ms, dev)
+    value = shard.whole_job_rate(B * steps, ms, dev)
     ms = shard.max_over_ranks(ms, dev)
     nparam = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    # the allreduce alone (same flat buffer size), timed after the step loop: what an un-overlapped collective costs
+    ar_ms = None
+    if world > 1:
+        import torch.distributed as dist
+        flat = torch.zeros(nparam, dtype=torch.float32, device=dev)
+        for _ in range(2):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            dist.all_reduce(flat)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_ms = shard.max_over_ranks(e0.elapsed_time(e1) / 5, dev)
+        del flat
+    rec = None
     if rank == 0:
         pk, pk_src = peaks()
         alg = 3.0 * 198.23e9 if args.layers == 101 else 3.0 * 152.78e9  # fwd + dgrad + wgrad of the keypoint sub-graph
-        ach = alg * B * world * args.steps / (ms / 1e3) / 1e12 / world
-        print(json.dumps({
+        ach = alg * B * world * steps / (ms / 1e3) / 1e12 / world
+        rec = {
             "mode": "train", "metric": "images/sec keypoint-subnet training step (fwd+bwd+allreduce+Adam), 3x480x640", "value": value,
-            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "wall_ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
+            "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms / steps,
+            "wall_ms_per_step": wall * 1e3 / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": precision, "data": "synthetic",
             "config": {"workload": "R%d keypoint_subnet train step, batch %d/GPU, BN train mode, Adam lr 1e-4" % (args.layers, B),
-                       "global_batch": B * world, "cuda_graph": bool(args.graph), "parallelism": "dp%d, one NCCL allreduce of %d fp32 gradients (%.1f MB) per step" % (
-                           world, nparam, nparam * 4 / 1e6)},
+                       "global_batch": B * world, "cuda_graph": bool(args.graph),
+                       "allreduce_overlapped": bool(hasattr(eng, "train_step_overlapped") and args.graph and args.overlap and world > 1),
+                       "parallelism": "dp%d, NCCL allreduce of %d fp32 gradients (%.1f MB) per step" % (world, nparam, nparam * 4 / 1e6)},
+            "allreduce_alone_ms": ar_ms, "allreduce_bytes": nparam * 4,
             "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk.get("bf16_tflops_sustained"), "unit": "TFLOP/s",
-                         "frac": ach / pk.get("bf16_tflops_sustained"), "note": "per-GPU algorithmic FLOPs = 3 x forward of the trainable graph"}}))
+                         "frac": ach / pk.get("bf16_tflops_sustained"), "note": "per-GPU algorithmic FLOPs = 3 x forward of the trainable graph"}}
+    del eng, opt, model
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_train(args, rank, world, local):
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.batch != 32:
+        args.train_batch = args.batch
+    rec = train_leg(args, rank, world, local, args.steps, args.warmup, precision=args.precision)
+    if rank == 0:
+        print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_full(args, rank, world, local):
+def full_leg(args, rank, world, local, steps, warmup, precision=None):
     """BASELINE config 5: full inference incl. heat-map peaks and PRN assignment (the body of Tester._process,
     evaluate/tester.py:200-243) for a batch of 64 images per GPU, through evaluate.process_batch with HOST images in and
     per-person records out.  Synthetic-weight construction: the class-head bias of the headline bench (~3700 candidates per
     image), the best `--persons` NMS survivors per image as person boxes, and a convfin bias shift that lets ~170 heat-map
-    peaks per image pass thre1."""
-    import torch.distributed as dist
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    peaks per image pass thre1.  Every rank calls it; the record comes back on rank 0."""
     from multiposenet.pytorch_b200 import ops, poseNet, shard, synthetic
     from multiposenet.pytorch_b200.evaluate import process_batch
-    B = args.batch if args.batch != 32 else 64
-    model = poseNet(args.layers, precision=args.precision)
+    dev = torch.device("cuda", local)
+    precision = precision or args.precision
+    B = args.full_batch
+    model = poseNet(args.layers, precision=precision)
     load_weights_into(model, args.layers)
     model = model.to(dev).eval()
     rng = np.random.Generator(np.random.PCG64(777 + rank))
@@ -331,10 +373,11 @@ def run_full(args, rank, world, local):
 
     def barrier():
         if world > 1:
+            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(warmup, 3)):
         step(i)
     barrier()
     pending.clear()  # every timed step uploads its own batch inside the timed region
@@ -344,27 +387,153 @@ def run_full(args, rank, world, local):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step(i)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
-    value = shard.whole_job_rate(B * args.steps, ms, dev)
+    value = shard.whole_job_rate(B * steps, ms, dev)
     ms = shard.max_over_ranks(ms, dev)
+    rec = None
     if rank == 0:
-        print(json.dumps({
+        rec = {
             "mode": "full", "metric": "images/sec (3x480x640) full inference incl. peaks + PRN assignment, host images in, records out",
-            "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision,
             "data": "synthetic",
             "config": {"workload": "R%d entire_net + NMS + heat-map peaks + PRN assignment, batch %d/GPU, 3x480x640" % (args.layers, B),
                        "global_batch": B * world, "persons_per_image": stats.get("persons"), "assigned_joints_per_image": stats.get("assigned"),
                        "candidates_per_image": stats.get("candidates"), "box_score_thresh": 0.05,
                        "max_persons": args.persons, "bias_shifts": shifts, "parallelism": "dp%d (image shards, no collective)" % world},
-            "gpu_launches": ops.stats["launches"] - l0, "clocks": clocks}))
+            "h2d_bytes_per_step": host[0].numel() * 4, "gpu_launches": ops.stats["launches"] - l0, "clocks": clocks}
+    pending.clear()
+    del model, host
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_full(args, rank, world, local):
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.batch != 32:
+        args.full_batch = args.batch
+    rec = full_leg(args, rank, world, local, args.steps, args.warmup)
+    if rank == 0:
+        print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_cfg1_leg(dev):
+    """BASELINE configs[0]: ResNet50-FPN keypoint subnet forward, batch 1, 3x480x640 on the host cores (the oracle port of the
+    evaluate/multipose_keypoint_val.py forward, seeded weights), and the same call through the public API on the GPU with the
+    host copies inside the timed region."""
+    from multiposenet.pytorch_b200 import poseNet
+    from oracle import posenet_oracle as po, weights   # checker-side: the CPU baseline leg
+    w = weights.make_weights(50, "conditioned", seed=0)
+    sd = weights.to_torch_state_dict(w)
+    x = torch.from_numpy(np.random.Generator(np.random.PCG64(50)).standard_normal((1, 3, H, W), dtype=np.float32))
+    with torch.no_grad():
+        ref_heat, _ = po.forward(sd, 50, x, "keypoint_subnet")
+        ts = []
+        t_start = time.perf_counter()
+        while len(ts) < 5 and time.perf_counter() - t_start < 15:
+            t0 = time.perf_counter(); po.forward(sd, 50, x, "keypoint_subnet"); ts.append(time.perf_counter() - t0)
+    cpu_ms = float(np.median(ts)) * 1e3
+    m = poseNet(50)
+    sdm = m.state_dict()
+    for k in sdm:
+        if k in w:
+            sdm[k] = torch.from_numpy(np.ascontiguousarray(w[k]))
+    m.load_state_dict(sdm)
+    m = m.to(dev).eval()
+    xp = x.pin_memory()
+    out_host = torch.empty((1, 18, H // 4, W // 4), dtype=torch.float32).pin_memory()
+
+    def once():
+        with torch.no_grad():
+            heat, saved = m((xp.to(dev, non_blocking=True), "keypoint_subnet"))
+        out_host.copy_(heat, non_blocking=True)
+        torch.cuda.synchronize()
+        return heat
+    for _ in range(3):
+        heat = once()
+    err = float((heat.cpu() - ref_heat).abs().max() / ref_heat.abs().max())
+    t0 = time.perf_counter()
+    for _ in range(20):
+        once()
+    gpu_ms = (time.perf_counter() - t0) / 20 * 1e3
+    del m
+    torch.cuda.empty_cache()
+    return {"workload": "R50 keypoint_subnet forward, batch 1, 3x480x640 (BASELINE configs[0])", "cpu_ms": cpu_ms,
+            "cpu_images_per_s": 1e3 / cpu_ms, "cpu_threads": torch.get_num_threads(), "cpu_kind": "port (oracle restatement, torch CPU fp32)",
+            "gpu_ms_e2e": gpu_ms, "gpu_images_per_s_e2e": 1e3 / gpu_ms, "gpu_precision": "f16f8",
+            "gpu_note": "public model((img,'keypoint_subnet')) call, pinned host image in, heat map back, wall clock incl. sync",
+            "heat_err_vs_cpu": err, "speedup_e2e": cpu_ms / gpu_ms}
+
+
+def aux_roofline_leg(model, eng, dev, cls, boxes, reg, n_s, n_k, B):
+    """HBM-bound kernels of the path against the measured copy bandwidth: algorithmic bytes / CUDA-event
+    time.  decode: its own launch; filter .. reduce: events between the stages (mpn_filter_sort_nms_profile); twice: the
+    bench's own detection load and the cfg3 feed (100 persons x 41 jittered candidates per image)."""
+    from multiposenet.pytorch_b200 import ops, synthetic
+    pk, pk_src = peaks()
+    hbm = pk.get("hbm_gbs")
+    A = boxes.shape[1]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    anchors = ops.anchors_for(H, W, dev)
+    for _ in range(2):
+        ops.decode_clip(anchors, reg, H, W)
+    e0.record()
+    for _ in range(10):
+        ops.decode_clip(anchors, reg, H, W)
+    e1.record()
+    torch.cuda.synchronize()
+    out = {"peak_gbs": hbm, "peak_source": pk_src, "unit": "GB/s", "kernels": []}
+
+    def add(regime, name, ms, nbytes, note):
+        out["kernels"].append({"regime": regime, "kernel": name, "ms": ms, "bytes": nbytes, "achieved": nbytes / (ms / 1e3) / 1e9 if ms > 0 else None,
+                               "frac": (nbytes / (ms / 1e3) / 1e9 / hbm) if (ms > 0 and hbm) else None, "bytes_model": note})
+    add("bench", "decode_clip_kernel", e0.elapsed_time(e1) / 10, B * A * 32.0, "16 B reg read + 16 B box written per anchor (anchors stay in L2)")
+
+    def stages(regime, c, bx, ns, nk, max_cand):
+        st = []
+        for _ in range(3):
+            ops.filter_sort_nms(c, bx, 0.05, 0.5, max_cand=max_cand, stage_ms=st)
+        ms = np.median(np.array(st), axis=0)
+        cb = (ns + 63) // 64
+        add(regime, "filter_compact_kernel", float(ms[0]), B * (A * 4.0 + ns * 12.0), "4 B score per anchor + 12 B per candidate written")
+        add(regime, "cub segmented radix sort (+segments)", float(ms[1]), B * ns * 16.0, "one ideal pass: 8 B key+rank read and written per candidate")
+        add(regime, "gather_sorted_kernel", float(ms[2]), B * ns * 48.0, "key, rank, index, 16 B box read, 20 B row written per candidate")
+        add(regime, "nms_mask_kernel", float(ms[3]), B * (ns * 20.0 + ns * cb * 8.0 / 2), "N_s*20 B read + upper triangle of N_s x ceil(N_s/64) u64 written")
+        add(regime, "nms_reduce_kernel", float(ms[4]), B * (ns * cb * 8.0 / 2 + nk * 36.0), "upper-triangle mask rows staged once + kept rows written")
+        return float(ms.sum())
+    tot_bench = stages("bench (~%d candidates, ~%d kept per image)" % (n_s, n_k), cls, boxes, int(n_s), int(n_k), 4096)
+    c3, b3 = synthetic.cfg3_detections(B, seed=3)
+    c3, b3 = torch.from_numpy(c3).to(dev), torch.from_numpy(b3).to(dev)
+    det3 = ops.filter_sort_nms(c3, b3, 0.05, 0.5, max_cand=4224)
+    ns3, nk3 = float(det3.cand_cnt.float().mean()), float(det3.keep_cnt.float().mean())
+    tot_cfg3 = stages("cfg3 (100 persons x 41 candidates: N_s %d, kept %.0f per image)" % (ns3, nk3), c3, b3, int(ns3), int(nk3), 4224)
+    out["post_process_ms"] = {"bench": tot_bench, "cfg3": tot_cfg3, "batch": B}
+    # batched PRN forward (weights are the traffic): 20 persons per image of the batch
+    P = 20 * B
+    xin = torch.rand(P, 56, 36, 17, device=dev) * 0.2
+    with torch.no_grad():
+        for _ in range(2):
+            eng.prn_forward(xin)
+        e0.record()
+        for _ in range(5):
+            eng.prn_forward(xin)
+        e1.record()
+    torch.cuda.synchronize()
+    nw = sum(p.numel() for p in model.prn.parameters())
+    wbytes = nw * (4.0 if eng.precision in ("f16f8", "bf16x3") else 2.0)
+    add("prn", "PRN forward (3 FCs on conv_tc_kernel + add_softmax_rows), %d persons" % P, e0.elapsed_time(e1) / 5,
+        wbytes + P * 34272 * 4.0 * 4, "packed weights read once (%d parameters) + input, FC3 output, residual and softmax output rows" % nw)
+    return out
 
 
 def main():
@@ -385,6 +554,11 @@ def main():
     ap.add_argument("--persons", type=int, default=20, help="--mode full: person boxes per image fed to the PRN")
     ap.add_argument("--streams", type=int, default=None, help="branch-level side streams (default: engine default = on)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (0 = eager launches)")
+    ap.add_argument("--overlap", type=int, default=1, help="training: bucketed allreduce under the backward (0 = one blocking allreduce)")
+    ap.add_argument("--no-extras", action="store_true", help="skip parity / cpu_cfg1 / roofline_aux / train_step / full_pipeline keys")
+    ap.add_argument("--train-batch", type=int, default=16)
+    ap.add_argument("--full-batch", type=int, default=64)
+    ap.add_argument("--extra-steps", type=int, default=5, help="timed steps of the train_step / full_pipeline legs of the default line")
     args = ap.parse_args()
     if args.precision is None:
         args.precision = os.environ.get("MPN_PRECISION") or ("bf16x3" if args.mode == "train" else "f16f8")
@@ -618,13 +792,61 @@ def main():
         sd["classificationModel.output.bias"] = model.classificationModel.output.bias.detach().cpu().clone()
         nthreads, navail = pick_cpu_threads(sd)
         x1 = host[0][:1].clone()
-        cpu_reference_step(sd, x1)
+        cpu_out = cpu_reference_step(sd, x1)
         ts = []
         t_start = time.perf_counter()
         while len(ts) < 5 and time.perf_counter() - t_start < 25:
             t0 = time.perf_counter(); cpu_reference_step(sd, x1); ts.append(time.perf_counter() - t0)
         cpu = {"value": 1.0 / float(np.median(ts)), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "%d timed forwards of 1 image (R%d entire_net + NMS) after 1 warm-up; full step is %d images; %d of %d host threads" % (len(ts), args.layers, B, nthreads, navail)}
+
+    # ---- parity of the timed configuration: image 0 of the timed batch against the fp32 CPU oracle (same weights, same image)
+    parity = None
+    if cpu is not None:
+        with torch.no_grad():
+            gheat, gcls, greg, gboxes, gdet = eng.entire_forward_device(devin[0], max_cand=MAXC)
+        torch.cuda.synchronize()
+        oheat, (osc, ocl, obx), oaux = cpu_out
+        nerr = lambda a_, b_: float((a_.double().cpu() - b_.double()).abs().max() / b_.double().abs().max())
+        parity = {"heat": nerr(gheat[:1], oheat), "cls": nerr(gcls[:1], oaux["cls"]), "reg": nerr(greg[:1], oaux["reg"]),
+                  "kept_boxes": [int(gdet.keep_cnt[0]), int(len(osc))], "bar": 1e-3, "metric": "max|a-b|/max|b| per output tensor",
+                  "against": "fp32 oracle port on the host (oracle/posenet_oracle.py), image 0 of the timed batch, R%d %s" % (args.layers, args.precision)}
+        parity["ok"] = bool(max(parity["heat"], parity["cls"], parity["reg"]) <= (1e-3 if args.precision != "bf16" else 1.0))
+
+    extras = {}
+    if not args.no_extras:
+        def guarded(name, fn):
+            try:
+                extras[name] = fn()
+            except Exception as e:  # an auxiliary leg must not lose the headline line
+                import traceback
+                extras[name] = {"error": "%s: %s" % (type(e).__name__, e), "trace": traceback.format_exc()[-1500:]}
+        if rank == 0:
+            guarded("roofline_aux", lambda: aux_roofline_leg(model, eng, dev, cls, boxes, reg, n_s, n_k, B))
+            if world == 1 and not args.no_cpu_baseline:
+                guarded("cpu_cfg1", lambda: cpu_cfg1_leg(dev))
+    # free the inference engines before the other configurations run
+    del out, heat, cls, reg, boxes, det
+    model.invalidate_engines()
+    model.__dict__["_engines"].clear()
+    del eng, model
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        barrier()
+        try:
+            extras["train_step"] = train_leg(args, rank, world, local, args.extra_steps, 3)
+        except Exception as e:
+            import traceback
+            extras["train_step"] = {"error": "%s: %s" % (type(e).__name__, e), "trace": traceback.format_exc()[-1500:]}
+        gc.collect(); torch.cuda.empty_cache()
+        barrier()
+        try:
+            extras["full_pipeline"] = full_leg(args, rank, world, local, args.extra_steps, 3)
+        except Exception as e:
+            import traceback
+            extras["full_pipeline"] = {"error": "%s: %s" % (type(e).__name__, e), "trace": traceback.format_exc()[-1500:]}
 
     if rank == 0:
         line = {
@@ -642,8 +864,12 @@ def main():
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "e2e_u8_input": e2e_u8, "roofline": roof, "cpu_baseline": cpu, "fast_mode": fast, "alt_parity_mode": alt,
+            "parity": parity,
         }
+        line.update(extras)
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            sys.exit("parity check failed: %s" % json.dumps(parity))
     if world > 1:
         dist.destroy_process_group()
 

@@ -258,3 +258,28 @@ def calibrate_output_bias(model, x, what, per_image, threshold):
         shift = thr - cut
         bias += shift
     return shift
+
+
+def cfg3_detections(batch, seed=0, H=480, W=640, persons=100, per_person=41, anchors=57600):
+    """SURVEY 8(d) cfg3 detection load, fed to the filter/sort/NMS stage directly: per image `persons` ground-truth boxes
+    (w ~ U(20,120), h ~ U(60,300), centres uniform in the image) x `per_person` jittered candidates (+-10 % centre / size) =
+    ~4100 candidates with DISTINCT scores in (0.05, 1) scattered over the `anchors` slots; every other slot scores 0.01.
+    Returns (cls [batch, anchors, 1] fp32, boxes [batch, anchors, 4] fp32) numpy arrays; expected kept boxes ~ persons."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = persons * per_person
+    cls = np.full((batch, anchors, 1), 0.01, dtype=np.float32)
+    boxes = np.zeros((batch, anchors, 4), dtype=np.float32)
+    boxes[:, :, 2:] = 1.0
+    for b in range(batch):
+        w = rng.uniform(20, 120, persons); h = rng.uniform(60, 300, persons)
+        cx = rng.uniform(0, W, persons); cy = rng.uniform(0, H, persons)
+        jw = (w[:, None] * rng.uniform(0.9, 1.1, (persons, per_person))).reshape(-1)
+        jh = (h[:, None] * rng.uniform(0.9, 1.1, (persons, per_person))).reshape(-1)
+        jx = (cx[:, None] + w[:, None] * rng.uniform(-0.1, 0.1, (persons, per_person))).reshape(-1)
+        jy = (cy[:, None] + h[:, None] * rng.uniform(-0.1, 0.1, (persons, per_person))).reshape(-1)
+        bx = np.stack([jx - jw / 2, jy - jh / 2, jx + jw / 2, jy + jh / 2], 1)
+        bx[:, 0::2] = np.clip(bx[:, 0::2], 0, W); bx[:, 1::2] = np.clip(bx[:, 1::2], 0, H)
+        slots = np.sort(rng.choice(anchors, n, replace=False))
+        boxes[b, slots] = bx.astype(np.float32)
+        cls[b, slots, 0] = rng.permutation(np.linspace(0.0501, 0.9999, n)).astype(np.float32)
+    return cls, boxes
