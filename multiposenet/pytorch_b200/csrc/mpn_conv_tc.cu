@@ -76,6 +76,7 @@ struct TcParams {
   const __nv_bfloat16* up_hi;
   const __nv_bfloat16* up_lo;
   int up_h, up_w, up_cstride;
+  int up_tma;  // EPI_TMA_RES brings in the 2x-nearest-upsample source (box {32 ch, TW/2, TH/2, TN}) instead of a shortcut tensor
   int flags, out_mode, out_cstride, out_coffset, out_rep;
   long long out_nstride;
   void* y_hi;
@@ -476,10 +477,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // tile) is requested by TMA when chunk n starts, into the buffer chunk n - 1 was read from (every thread of the half has
     // passed that chunk's barriers), so a whole chunk period covers the load latency and no LSU load touches the shortcut.
     uint32_t res_n = 0;  // chunks of this half consumed so far: buffer = res_n & 1, mbarrier parity = (res_n >> 1) & 1
-    const uint32_t res_bytes = (uint32_t)P.rows * (SPLIT ? 128u : F8 ? 96u : 64u);
+    // up_tma: the box holds the half-resolution source pixels of the tile (fpn.py:84-95, exact 2x nearest upsample): output
+    // pixel (th, tw) of the tile adds source row (th/2) * (TW/2) + tw/2 of the box (tile origins and sizes are even)
+    const int src_rows = P.up_tma ? (P.TW >> 1) * (P.TH >> 1) * P.TN : P.rows;
+    const uint32_t res_bytes = (uint32_t)src_rows * (SPLIT ? 128u : F8 ? 96u : 64u);
     auto res_issue = [&](uint32_t n, int cb, int w0, int h0, int i0) {
       const uint32_t bar = res_full_bar(half, (int)(n & 1u));
       const uint32_t dst = smem_base + STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + (uint32_t)(half * 2 + (int)(n & 1u)) * RES_STAGE_BYTES;
+      if (P.up_tma) { w0 >>= 1; h0 >>= 1; }
       mbar_expect_tx(bar, res_bytes);
       tma_load_4d(dst, &maps.r[0], bar, cb, w0, h0, i0);
       if (SPLIT || F8) tma_load_4d(dst + 8192, &maps.r[1], bar, cb, w0, h0, i0);
@@ -500,6 +505,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         uint8_t* stg = epi_stage + half * (4 * EPI_STAGE_BYTES);       // [hi: rows x 64 B][lo: rows x 64 B] at +8192
         const uint32_t stg_u32 = smem_base + STAGES * STAGE_BYTES + half * (4 * EPI_STAGE_BYTES);
         const int sw = (row >> 1) & 3;                                 // CU_TENSOR_MAP_SWIZZLE_64B: chunk ^= (byte >> 7) & 3
+        int rrow = row;                                                // row of the shortcut / upsample-source box this pixel adds
+        if (RESLD && P.up_tma) {
+          const int tw2 = row % P.TW, th2 = (row / P.TW) % P.TH, tn2 = row / (P.TW * P.TH);
+          rrow = row < P.rows ? (tn2 * (P.TH >> 1) + (th2 >> 1)) * (P.TW >> 1) + (tw2 >> 1) : 0;
+        }
+        const int rsw = (rrow >> 1) & 3;
         const bool issuer = (q == 0 && lane == 0);
         const int ow0 = tw_i * P.TW, oh0 = th_i * P.TH, n0 = tn_i * P.TN;
         long long res_off = 0;
@@ -563,9 +574,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const uint8_t* rs = epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES + (half * 2 + (int)(res_n & 1u)) * RES_STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              rh[i] = *reinterpret_cast<const uint4*>(rs + row * 64 + ((i ^ sw) << 4));
-              if (SPLIT) rl[i] = *reinterpret_cast<const uint4*>(rs + 8192 + row * 64 + ((i ^ sw) << 4));
-              if (F8 && i < 2) rl[i] = *reinterpret_cast<const uint4*>(rs + 8192 + row * 32 + (i << 4));
+              rh[i] = *reinterpret_cast<const uint4*>(rs + rrow * 64 + ((i ^ rsw) << 4));
+              if (SPLIT) rl[i] = *reinterpret_cast<const uint4*>(rs + 8192 + rrow * 64 + ((i ^ rsw) << 4));
+              if (F8 && i < 2) rl[i] = *reinterpret_cast<const uint4*>(rs + 8192 + rrow * 32 + (i << 4));
             }
             ++res_n;
           }
@@ -919,11 +930,13 @@ int identity_matrix(const void** ptr, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------------------------
 // Pick the pixel box (TW x TH x TN <= 128) that wastes the fewest MMA rows.
-void choose_tile(int N, int OH, int OW, int* TW, int* TH, int* TN) {
+// even: only boxes with even width and height (the 2x-upsample source of a tile is then one half-resolution box)
+void choose_tile(int N, int OH, int OW, int* TW, int* TH, int* TN, bool even = false) {
   double best = -1.0;
   int bw = 1, bh = 1, bn = 1;
   for (int tw = 1; tw <= 128 && tw <= OW; ++tw) {
     for (int th = 1; th * tw <= 128 && th <= OH; ++th) {
+      if (even && ((tw | th) & 1)) continue;
       int tn = 1;
       if (tw == OW && th == OH) {
         tn = 128 / (tw * th);
@@ -1010,7 +1023,11 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.N = d->N; P.OH = d->OH; P.OW = d->OW; P.Cout = d->Cout;
-  choose_tile(d->N, d->OH, d->OW, &P.TW, &P.TH, &P.TN);
+  {
+    static const int up_even = getenv("MPN_UP_TMA") ? atoi(getenv("MPN_UP_TMA")) : 1;
+    const bool up2x = up_even && d->up_cstride > 0 && d->OH == 2 * d->up_h && d->OW == 2 * d->up_w && d->OH >= 2 && d->OW >= 2;
+    choose_tile(d->N, d->OH, d->OW, &P.TW, &P.TH, &P.TN, up2x);
+  }
   P.rows = P.TW * P.TH * P.TN;
   P.tiles_w = mpn_divup(d->OW, P.TW);
   P.tiles_h = mpn_divup(d->OH, P.TH);
@@ -1034,7 +1051,15 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   // one); there a split-format residual without an epilogue scale is added by the tensor core (MPN_RES_MMA=0: by the LSU).
   static const int epi_tma_on = getenv("MPN_EPI_TMA") ? atoi(getenv("MPN_EPI_TMA")) : 1;
   static const int res_mma_on = getenv("MPN_RES_MMA") ? atoi(getenv("MPN_RES_MMA")) : 1;
-  const bool epi_tma = epi_tma_on && !f32out && d->out_rep == 1 && d->up_cstride == 0;
+  // ... and an exact-2x nearest-upsample add (FPN laterals, fpn.py:84-95) rides on the same TMA machinery as the shortcut
+  // (MPN_UP_TMA=0: the LSU epilogue): even tile sizes put every tile's source pixels in one half-resolution box
+  static const int up_tma_on = getenv("MPN_UP_TMA") ? atoi(getenv("MPN_UP_TMA")) : 1;
+  static const int pair_on_ = getenv("MPN_PAIR") ? atoi(getenv("MPN_PAIR")) : 1;
+  static const int res_tma_on_ = getenv("MPN_RES_TMA") ? atoi(getenv("MPN_RES_TMA")) : 1;
+  const bool up_tma = up_tma_on && epi_tma_on && pair_on_ && res_tma_on_ && !f32out && d->out_rep == 1 && d->up_cstride > 0 &&
+                      d->res_cstride == 0 && d->OH == 2 * d->up_h && d->OW == 2 * d->up_w && P.TW % 2 == 0 && P.TH % 2 == 0 &&
+                      d->Cout >= 128 && d->Cout % 64 == 0 && m_tiles >= 2 && sms >= 2;
+  const bool epi_tma = epi_tma_on && !f32out && d->out_rep == 1 && (d->up_cstride == 0 || up_tma);
   const bool res_mma = res_mma_on && epi_tma && split && d->res_cstride > 0 && !p->scale && d->Cout % 64 == 0;
   // CTA-pair kernel (MPN_PAIR=0 disables): activation outputs of >= 128 channels, no residual (the tensor-core residual add
   // stays on the single-CTA kernel), enough M tiles to form pairs.  A pair tile = two consecutive M tiles x one Cout block.
@@ -1042,7 +1067,7 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   const bool pair = pair_on && !f32out && !res_mma && d->Cout >= 128 && m_tiles >= 2 && sms >= 2;
   // ... and there the shortcut of a residual conv comes in by TMA (MPN_RES_TMA=0: per-thread global loads in the epilogue)
   static const int res_tma_on = getenv("MPN_RES_TMA") ? atoi(getenv("MPN_RES_TMA")) : 1;
-  const bool res_tma = res_tma_on && pair && epi_tma && d->res_cstride > 0 && d->Cout % 64 == 0;
+  const bool res_tma = res_tma_on && pair && epi_tma && (d->res_cstride > 0 || up_tma) && d->Cout % 64 == 0;
   const int min_tail_bn = pair ? 64 : res_mma ? 64 : 32;
   int BN = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
   int tail_s = 1;
@@ -1085,6 +1110,7 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
     P.total_tiles = (int)(T - rem + rem * tail_s);
   }
   P.res_mma = res_mma ? 1 : 0;
+  P.up_tma = up_tma ? 1 : 0;
   P.R = d->R; P.S = d->S; P.stride = d->stride; P.pad = d->pad; P.Cin = d->Cin; P.kb_per_tap = d->Cin / BLOCK_K;
   P.scale = p->scale; P.bias = p->bias;
   P.res_hi = (const __nv_bfloat16*)p->res_hi; P.res_lo = (const __nv_bfloat16*)p->res_lo; P.res_cstride = d->res_cstride;
@@ -1180,15 +1206,16 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
       if (rc) return rc;
     }
   }
-  if (res_tma) {  // shortcut boxes in the geometry of the output boxes: 32 channels x the tile's pixels
+  if (res_tma) {  // shortcut boxes in the geometry of the output boxes: 32 channels x the tile's pixels (up_tma: x its source pixels)
+    const int rw = up_tma ? d->up_w : d->OW, rh_ = up_tma ? d->up_h : d->OH, rcs = up_tma ? d->up_cstride : d->res_cstride;
     for (int pl = 0; pl < (f8 || split ? 2 : 1); ++pl) {
       const bool bytes = f8 && pl > 0;
       const unsigned long long es = bytes ? 1ULL : 2ULL;
-      cuuint64_t rdims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->OW, (cuuint64_t)d->OH, (cuuint64_t)d->N};
-      cuuint64_t rstr[3] = {(cuuint64_t)d->res_cstride * es, (cuuint64_t)d->OW * d->res_cstride * es,
-                            (cuuint64_t)d->OH * d->OW * d->res_cstride * es};
-      cuuint32_t rbox[4] = {32u, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
-      int rc = encode(fn, &maps.r[pl], pl == 0 ? p->res_hi : p->res_lo, 4, rdims, rstr, rbox,
+      cuuint64_t rdims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)rw, (cuuint64_t)rh_, (cuuint64_t)d->N};
+      cuuint64_t rstr[3] = {(cuuint64_t)rcs * es, (cuuint64_t)rw * rcs * es, (cuuint64_t)rh_ * rw * rcs * es};
+      cuuint32_t rbox[4] = {32u, (cuuint32_t)(up_tma ? P.TW / 2 : P.TW), (cuuint32_t)(up_tma ? P.TH / 2 : P.TH), (cuuint32_t)P.TN};
+      const void* rbase = up_tma ? (pl == 0 ? p->up_hi : p->up_lo) : (pl == 0 ? p->res_hi : p->res_lo);
+      int rc = encode(fn, &maps.r[pl], rbase, 4, rdims, rstr, rbox,
                       bytes ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B,
                       bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
       if (rc) return rc;

@@ -3,8 +3,9 @@
 # parity / cpu_cfg1 / roofline_aux / train_step / full_pipeline), the TMA stride probe, NMS v1-vs-v2 timing, compute-sanitizer.
 mkdir -p gpurun_out
 T0=$(date +%s)
-timeout 1500 python -m pytest tests/ -q -m gpu -p no:cacheprovider -x > gpurun_out/t_all_gpu.log 2>&1; echo "exit full gpu suite: $?"
+timeout 1500 python -m pytest tests/ -q -m gpu -p no:cacheprovider > gpurun_out/t_all_gpu.log 2>&1; echo "exit full gpu suite: $?"
 tail -5 gpurun_out/t_all_gpu.log | cut -c1-400
+grep -E "^(FAILED|ERROR)" gpurun_out/t_all_gpu.log | cut -c1-250 | head -40
 grep -E "R101 .* 480x640|free-running|PRN (small|prod)" gpurun_out/t_all_gpu.log | head -20
 echo "t=$(( $(date +%s) - T0 ))s"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit smoke: $?"; tail -1 gpurun_out/smoke.log

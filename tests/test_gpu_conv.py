@@ -50,6 +50,11 @@ TC_CASES = [
     (5, 15, 20, 128, 256, 1, 1, 0, dict(bn=True, residual=True, relu=True, bias=False)),  # 15 M tiles: the last pair has a phantom half
     (2, 30, 40, 128, 128, 3, 1, 1, dict(residual=True, relu=True)),                       # 128-wide pair tiles, 3x3 taps
     (32, 30, 40, 64, 1024, 1, 1, 0, dict(bn=True, residual=True, relu=True, bias=False)), # layer3 expansion shape: many tiles per CTA
+    # exact-2x nearest-upsample add through the TMA epilogue (FPN laterals): the tile's source pixels arrive as one half-resolution box
+    (2, 32, 64, 128, 256, 1, 1, 0, dict(up=True)),                                  # 64x2 boxes
+    (3, 30, 40, 256, 256, 1, 1, 0, dict(up=True)),                                  # 20x6 boxes, clipped bottom rows, odd tile count
+    (2, 60, 80, 128, 128, 1, 1, 0, dict(up=True, relu=True)),                       # 128-wide pair tiles
+    (6, 4, 6, 64, 256, 1, 1, 0, dict(up=True)),                                     # whole images per box (TN = 5), 2 tiles
 ]
 
 
