@@ -265,6 +265,23 @@ int mpn_prn_assign(const double* peak_xy, const int32_t* peak_img_start, const i
                    const int32_t* owner, const float* output, double* bbox_keypoints, void* workspace,
                    size_t workspace_bytes, int kmax, void* stream);
 
+/* ---- Multi-scale / flip test-time augmentation, heat-map side: evaluate/tester.py:298-304, :316-331.
+ * mpn_resize_cubic = cv2.resize(..., interpolation=cv2.INTER_CUBIC) on `planes` fp32 planes: the sh x sw valid region of every
+ * source plane (row pitch src_pitch, plane stride src_plane elements) -> dh x dw.  scale_x / scale_y = OpenCV's source step per
+ * destination pixel (1 / fx for cv2.resize(None, fx, fy); 1 / (dw / sw) for an explicit dsize).
+ *   out_mode 0: dst fp32 [planes][dh][dst_pitch] = resized
+ *   out_mode 1: dst fp64 += (double)(resized / div)   (tester.py:304 heatmap_avg + heatmap / len(multiplier)), written to
+ *               plane plane_map[p] (device int32, may be NULL) and mirrored along x when mirror != 0 (the flipped pass of
+ *               Tester._handle_heat, tester.py:316-331)
+ * Same Keys A = -0.75 arithmetic as OpenCV (float32 horizontal pass, then vertical); agreement with cv2 is ~1e-6 of the plane
+ * maximum, not bit-exact (OpenCV's own SIMD and scalar paths differ in FMA use). */
+size_t mpn_resize_cubic_workspace_bytes(int dh, int dw);
+int mpn_resize_cubic(const float* src, long long src_plane, int src_pitch, int sh, int sw, void* dst, long long dst_plane,
+                     int dst_pitch, int dh, int dw, int planes, double scale_x, double scale_y, int out_mode, float div,
+                     int mirror, const int* plane_map, void* workspace, size_t workspace_bytes, void* stream);
+/* out = (normal + flipped) / 2 in float64 (tester.py:329; flipped may be NULL: out = normal), optionally also as fp32 */
+int mpn_tta_combine(const double* normal, const double* flipped, double* out, float* out32, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -258,10 +258,39 @@ __global__ void __launch_bounds__(128) nms_mask_kernel_v2(const float* __restric
     if (j + 1 < nblk) fetch(cblk + 1, nxt);
     if (row_ok) {
       const int col_size = min(n - cblk * 64, 64);
-      const int lo = max(32 * half, cblk == row_start ? r + 1 : 0), hi = min(32 * half + 32, col_size);
+      const int base = 32 * half;
+      const int lo = max(base, cblk == row_start ? r + 1 : 0), hi = min(base + 32, col_size);
       unsigned int t = 0u;
-      for (int i = lo; i < hi; ++i)
-        if (nms_pair_over(rbx, Sa, cbox[buf][i], carea[buf][i], thr, ge, fast_ok)) t |= 1u << (i & 31);
+      if (!fast_ok) {
+        for (int i = lo; i < hi; ++i)
+          if (nms_pair_over(rbx, Sa, cbox[buf][i], carea[buf][i], thr, ge, false)) t |= 1u << (i & 31);
+      } else if (lo < hi) {
+        // all 32 columns of the half, branch-free (the serial, divergent pair loop was latency bound: ~25 % issue efficiency);
+        // the decision tree of nms_pair_over as predicates, the exact division only for pairs inside the guard band (rare);
+        // columns outside [lo, hi) are evaluated on whatever the staging buffer holds (finite zeros) and masked off
+#pragma unroll 8
+        for (int ii = 0; ii < 32; ++ii) {
+          const float4 bb = cbox[buf][base + ii];
+          const float Sb = carea[buf][base + ii];
+          const float w = __fadd_rn(__fsub_rn(fminf(rbx.z, bb.z), fmaxf(rbx.x, bb.x)), 1.f);
+          const float h = __fadd_rn(__fsub_rn(fminf(rbx.w, bb.w), fmaxf(rbx.y, bb.y)), 1.f);
+          const bool disjoint = !(w > 0.f) || !(h > 0.f);
+          const float interS = __fmul_rn(fmaxf(w, 0.f), fmaxf(h, 0.f));
+          const float uni = __fsub_rn(__fadd_rn(Sa, Sb), interS);
+          const float pth = __fmul_rn(thr, uni);
+          const bool pos = uni > 0.f;
+          const bool yes = !disjoint && pos && interS > __fmul_rn(pth, 1.000001f);
+          const bool no = disjoint || (pos && interS < __fmul_rn(pth, 0.999999f));
+          bool over = yes;
+          if (!yes && !no) {
+            const float v = __fdiv_rn(interS, uni);
+            over = ge ? (v >= thr) : (v > thr);
+          }
+          t |= (over ? 1u : 0u) << ii;
+        }
+        const unsigned int upto = (hi - base) >= 32 ? 0xffffffffu : ((1u << (hi - base)) - 1u);
+        t &= upto & ~((1u << (lo - base)) - 1u);
+      }
       mask32[2 * cblk + half] = t;   // little endian: half 0 = columns 0..31 of the 64-bit word
     }
     if (j + 1 < nblk) stage(buf ^ 1, nxt);

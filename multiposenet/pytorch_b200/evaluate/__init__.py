@@ -2,3 +2,4 @@
 (COCO loading, JSON writing, plotting) is out of scope."""
 from .pipeline import process_batch  # noqa: F401
 from .prn_assign import prn_process, prn_process_batch  # noqa: F401
+from .tta import crop_with_factor, get_multiplier, get_outputs, handle_heat, multi_scale_flip  # noqa: F401

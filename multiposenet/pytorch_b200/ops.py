@@ -448,3 +448,35 @@ def prn_assign(peak_xy, peak_img_start, joint_start, boxes_xywh, box_img, box_im
                                     _stream()), "mpn_prn_assign")
     stats["launches"] += 3
     return res
+
+
+# ------------------------------------------------------------------ multi-scale TTA (evaluate/tester.py:298-304, 316-331)
+def resize_cubic(src, sh, sw, dh, dw, scale_x, scale_y, dst=None, out_f64=False, div=1.0, mirror=False, plane_map=None):
+    """cv2.resize(INTER_CUBIC) of the [sh, sw] top-left region of every plane of `src` (fp32 [..., Hs, Ws], leading dims = planes).
+    dst None -> new fp32 [planes, dh, dw]; out_f64: dst (fp64 [planes, dh, dw]) += resized / div, optionally mirrored in x and
+    written to plane plane_map[p]."""
+    assert src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()
+    Hs, Ws = src.shape[-2], src.shape[-1]
+    planes = src.numel() // (Hs * Ws)
+    assert 0 < sh <= Hs and 0 < sw <= Ws
+    L = _lib.lib()
+    if out_f64:
+        assert dst is not None and dst.dtype == torch.float64 and dst.is_contiguous() and dst.shape[-2:] == (dh, dw)
+    else:
+        dst = torch.empty((planes, dh, dw), dtype=torch.float32, device=src.device)
+    wsb = L.mpn_resize_cubic_workspace_bytes(dh, dw)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=src.device)
+    check(L.mpn_resize_cubic(_ptr(src), Hs * Ws, Ws, sh, sw, _ptr(dst), dh * dw, dw, dh, dw, planes, float(scale_x), float(scale_y),
+                             1 if out_f64 else 0, float(div), int(bool(mirror)), _ptr(plane_map), _ptr(ws), wsb, _stream()), "mpn_resize_cubic")
+    stats["launches"] += 3
+    return dst
+
+
+def tta_combine(normal, flipped=None, want_f32=True):
+    """(normal + flipped) / 2 in float64 (tester.py:329), returned as (fp64, fp32 or None)."""
+    assert normal.dtype == torch.float64 and normal.is_contiguous()
+    out = torch.empty_like(normal)
+    out32 = torch.empty(normal.shape, dtype=torch.float32, device=normal.device) if want_f32 else None
+    check(_lib.lib().mpn_tta_combine(_ptr(normal), _ptr(flipped), _ptr(out), _ptr(out32), normal.numel(), _stream()), "mpn_tta_combine")
+    stats["launches"] += 1
+    return out, out32

@@ -234,6 +234,41 @@ def prn_forward_golden():
     print("prn_forward", {k: v.shape for k, v in g.items()})
 
 
+def tta_golden():
+    """tests/golden/tta.npz: Tester._get_multiplier / _get_outputs / _handle_heat of the reference (evaluate/tester.py:256-331)
+    run here on a seeded image with tta_oracle.stub_model in place of the network."""
+    from . import tta_oracle
+    tester = import_reference_tester()
+
+    class Params(object):
+        inp_size, gpus, subnet_name = 96, [0], "both"
+
+    class Self(object):
+        params = Params()
+
+    me = Self()
+
+    def model(args):
+        heat, scores, classes, boxes = tta_oracle.stub_model(args[0].cpu().numpy())
+        return torch.from_numpy(heat), [torch.from_numpy(scores), torch.from_numpy(classes), torch.from_numpy(boxes)]
+    me.model = model
+    img = tta_oracle.test_image()
+    mult = tester.Tester._get_multiplier(me, img)
+    heat_n, bbox_n = tester.Tester._get_outputs(me, mult, img)
+    heat_f, bbox_f = tester.Tester._get_outputs(me, mult, img[:, ::-1, :])
+    avg = tester.Tester._handle_heat(me, heat_n, heat_f)
+    crop, sc, shp = tester.crop_with_factor(img, 150.0, factor=32, pad_val=128)
+    assert heat_n.dtype == np.float64 and avg.dtype == np.float64
+    # stored as float32 (the comparisons carry a 1e-6 tolerance: cv2's cubic resize is not bit-reproducible call to call)
+    g = {"multiplier": np.array(mult), "heat_normal": heat_n.astype(np.float32), "heat_flipped": heat_f.astype(np.float32),
+         "heat_avg": avg.astype(np.float32),
+         "bbox_normal": np.array(json.dumps(bbox_n)), "crop": crop, "crop_scale": np.array(sc), "crop_shape": np.array(shp),
+         "meta": np.array(json.dumps({"inp_size": 96, "image": "tta_oracle.test_image()", "model": "tta_oracle.stub_model",
+                                      "cv2": __import__("cv2").__version__}))}
+    np.savez_compressed(os.path.join(OUT, "tta.npz"), **g)
+    print("tta", mult, heat_n.shape, [len(b) for b in bbox_n])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     meta = {"torch": torch.__version__, "numpy": np.__version__, "reference": refshim.REF_ROOT,
@@ -299,6 +334,7 @@ def main():
     prn_goldens()
     train_golden()
     prn_forward_golden()
+    tta_golden()
     print("wrote", sorted(os.listdir(OUT)))
 
 
@@ -309,4 +345,6 @@ if __name__ == "__main__":
         sys.exit(train_golden())
     if "prn_forward" in sys.argv[1:]:
         sys.exit(prn_forward_golden())
+    if "tta" in sys.argv[1:]:
+        sys.exit(tta_golden())
     sys.exit(main())

@@ -214,3 +214,25 @@ def test_prn_forward_oracle_vs_reference_golden(golden_dir):
         assert out.shape == g[tag + "_out"].shape and saved[0] is out
         np.testing.assert_allclose(out.numpy(), g[tag + "_out"], rtol=2e-5, atol=1e-9)
         assert abs(float(out.sum()) - meta["persons"]) < 1e-3
+
+
+def test_tta_oracle_vs_reference_golden(golden_dir):
+    """f3 pinned: Tester._get_multiplier / crop_with_factor / _get_outputs / _handle_heat of the live reference with a stub model."""
+    pytest.importorskip("cv2")
+    from oracle import tta_oracle as to
+    g = _load(golden_dir, "tta.npz")
+    meta = json.loads(str(g["meta"]))
+    img = to.test_image()
+    mult = to.get_multiplier(img, meta["inp_size"])
+    assert np.array_equal(np.array(mult), g["multiplier"])
+    crop, sc, shp = to.crop_with_factor(img, 150.0, factor=32, pad_val=128)
+    assert np.array_equal(crop, g["crop"]) and sc == float(g["crop_scale"]) and tuple(shp) == tuple(g["crop_shape"])
+    hn, bn = to.get_outputs(to.stub_model, mult, img)
+    hf, _ = to.get_outputs(to.stub_model, mult, img[:, ::-1, :])
+    # cv2's cubic resize is not bit-reproducible between two calls on the same values (vector body vs scalar tail depends on
+    # the buffer alignment, and the two differ in FMA use): ulp-level tolerance, like the device path
+    tol = 1e-6 * np.abs(g["heat_normal"]).max()
+    assert np.abs(hn - g["heat_normal"]).max() <= tol and np.abs(hf - g["heat_flipped"]).max() <= tol
+    assert np.abs(to.handle_heat(hn, hf) - g["heat_avg"]).max() <= tol
+    assert hn.dtype == np.float64
+    assert bn == json.loads(str(g["bbox_normal"]))
