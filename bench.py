@@ -745,11 +745,14 @@ def main():
         ops.stats["conv_events"] = None
         engine_mod.USE_STREAMS = streams_default
         engine_mod.LEVEL_STREAMS = level_default
-        tc = [(a.elapsed_time(b), f) for a, b, f, simt in evs if not simt]
-        conv_ms = sum(t for t, _ in tc) / nprof
+        tc = [(a.elapsed_time(b), f, sl) for a, b, f, simt, sl in evs if not simt]
+        conv_ms = sum(t for t, _, _ in tc) / nprof
         nconv = len(tc) // nprof
+        # bf16-equivalent MMA passes issued per algorithmic MAC, FLOP-weighted over the launches (f16f8: 2, or 2.5 for the
+        # convolutions whose input is stored without its e5m2 copy plane; bf16x3: 3; bf16: 1)
+        passes = sum(f * sl for _, f, sl in tc) / max(1.0, sum(f for _, f, _ in tc))
         stem_flops = 2.0 * 64 * 3 * 49 * (H // 2) * (W // 2)
-        on_cuda_cores = any(simt for _, _, _, simt in evs)  # fp32 mode / MPN_TC_STEM=0: the stem is not a tensor-core launch
+        on_cuda_cores = any(simt for _, _, _, simt, _ in evs)  # fp32 mode / MPN_TC_STEM=0: the stem is not a tensor-core launch
         alg = (flops_img - (stem_flops if on_cuda_cores else 0.0)) * B
         traffic, traffic_src = conv_traffic_record()
         achieved = alg / (conv_ms / 1e3) / 1e12
@@ -757,11 +760,13 @@ def main():
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (%d launches/step)" % nconv, "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_src + " (sustained cuBLAS bf16)",
                 "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / (elapsed_ms / args.steps),
-                "mma_passes": {"bf16x3": 3, "f16f8": 2}.get(args.precision, 1),
-                "tensor_pipe_frac": {"bf16x3": 3, "f16f8": 2}.get(args.precision, 1) * achieved / peak,
+                "mma_passes": passes,
+                "tensor_pipe_frac": passes * achieved / peak,
                 "note": "achieved = algorithmic conv FLOPs (2*MAC, fp32-equivalent) / conv kernel time; bf16x3 issues 3 MMAs per "
                         "algorithmic MAC (hi*hi + lo*hi + hi*lo), so tensor_pipe_frac = 3*frac is the share of the tensor peak the "
-                        "issued MMAs occupy; f16f8 issues 1 fp16 MMA + 2 fp8 MMAs at twice the rate = 2 bf16-equivalent passes"}
+                        "issued MMAs occupy; f16f8 issues 1 fp16 MMA + 2 fp8 MMAs at twice the rate = 2 bf16-equivalent passes (2.5 for the 1x1 "
+                        "convolutions that read a tensor stored without its e5m2 copy plane: 2 fp16 MMAs + 1 fp8 MMA); mma_passes is the "
+                        "FLOP-weighted mean over the launches of a step"}
 
     # ---- optional: single-pass bf16 throughput (not the parity mode; reported beside the headline)
     def side_mode(prec):

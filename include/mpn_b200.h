@@ -50,6 +50,12 @@ extern "C" {
 /* Epilogue flags. */
 #define MPN_EPI_RELU 1
 #define MPN_EPI_SIGMOID 2
+/* MPN_FMT_F16F8 only.  MPN_EPI_NO_H8: the output tensor is stored without its e5m2 copy plane (3 bytes per element); the `lo`
+ * buffer then holds the lo8 plane alone.  MPN_IN_NO_H8: the input tensor has no e5m2 copy plane; the convolution then evaluates
+ * the weight-residual term as x_hi (fp16) * w_lo16 (fp16) and expects the filter packed by mpn_pack_filter_f16f8 with layout 1:
+ * w_hi fp16 [Cout,R,S,Cin]; w_lo = [lo16 fp16 plane][h8 e4m3 plane]. */
+#define MPN_EPI_NO_H8 4
+#define MPN_IN_NO_H8 8
 
 typedef struct mpn_conv_desc {
   /* problem: y = epilogue(conv2d(x, w)); torch.nn.Conv2d semantics (cross-correlation, zero pad) */
@@ -113,10 +119,11 @@ int mpn_pack_filter_bf16_scaled(const float* w_oihw, const float* scale, void* d
                                 void* stream);
 /* MPN_FMT_F16F8 filters: max|w * scale| (device scalar, *amax must be zeroed by the caller) -> the host picks k with
  * max|w * scale| * 2^k in [2^14, 2^15) -> [Cout][R][S][Cin] fp16 hi, e4m3 lo8 / h8 byte planes (dst_lo8h8 = the two planes back
- * to back).  stem = 1: the [64][4][64] space-to-depth layout of mpn_stem_pack_filter (Cin = 3, R = S = 7). */
+ * to back).  layout bit 0: the [64][4][64] space-to-depth layout of mpn_stem_pack_filter (Cin = 3, R = S = 7); bit 1: the planes
+ * of a convolution whose input has no h8 plane (MPN_IN_NO_H8): dst_lo8h8 = [lo16 = fp16(w' - hi) : 2 bytes per element][h8]. */
 int mpn_filter_absmax(const float* w_oihw, const float* scale, int Cout, int per_cout, float* amax, void* stream);
 int mpn_pack_filter_f16f8(const float* w_oihw, const float* scale, float wscale, void* dst_hi, void* dst_lo8h8, int Cout, int Cin,
-                          int R, int S, int stem, void* stream);
+                          int R, int S, int layout, void* stream);
 /* BatchNorm (eval) fold: scale = gamma/sqrt(var+eps), bias = beta - mean*scale   (fpn.py:15-19,25,43) */
 int mpn_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                 float* scale, float* bias, int C, void* stream);
@@ -140,8 +147,10 @@ int mpn_stem_pack_input_u8(const unsigned char* img_nhwc_bgr, void* dst_hi, void
 int mpn_nchw_to_nhwc(const float* src, void* dst_hi, void* dst_lo, int N, int C, int H, int W, int cstride, int fmt, void* stream);
 /* NHWC `fmt` -> fp32 NCHW (first C channels) */
 int mpn_nhwc_to_nchw(const void* src_hi, const void* src_lo, float* dst, int N, int C, int H, int W, int cstride, int fmt, void* stream);
-/* F.max_pool2d(kernel 3, stride 2, pad 1) on NHWC (fpn.py:100) */
-int mpn_maxpool3x3s2(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H, int W, int C, int fmt, void* stream);
+/* F.max_pool2d(kernel 3, stride 2, pad 1) on NHWC (fpn.py:100).  flags: MPN_EPI_NO_H8 = the MPN_FMT_F16F8 output is stored
+ * without its h8 plane (its consumers are 1x1 convolutions running with MPN_IN_NO_H8) */
+int mpn_maxpool3x3s2(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H, int W, int C, int fmt, int flags,
+                     void* stream);
 /* y = relu(x) on n elements (fpn.py:108: conv7(F.relu(p6))) */
 int mpn_relu(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, long long n, int fmt, void* stream);
 
@@ -273,8 +282,8 @@ int mpn_prn_assign(const double* peak_xy, const int32_t* peak_img_start, const i
  *   out_mode 1: dst fp64 += (double)(resized / div)   (tester.py:304 heatmap_avg + heatmap / len(multiplier)), written to
  *               plane plane_map[p] (device int32, may be NULL) and mirrored along x when mirror != 0 (the flipped pass of
  *               Tester._handle_heat, tester.py:316-331)
- * Same Keys A = -0.75 arithmetic as OpenCV (float32 horizontal pass, then vertical); agreement with cv2 is ~1e-6 of the plane
- * maximum, not bit-exact (OpenCV's own SIMD and scalar paths differ in FMA use). */
+ * Same Keys A = -0.75 arithmetic as OpenCV (float32 horizontal pass, then vertical); agreement with cv2 is within 1e-5 of the plane
+ * maximum (measured 3.9e-6), not bit-exact (OpenCV's own SIMD and scalar paths differ in FMA use). */
 size_t mpn_resize_cubic_workspace_bytes(int dh, int dw);
 int mpn_resize_cubic(const float* src, long long src_plane, int src_pitch, int sh, int sw, void* dst, long long dst_plane,
                      int dst_pitch, int dh, int dw, int planes, double scale_x, double scale_y, int out_mode, float div,

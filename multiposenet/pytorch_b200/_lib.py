@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmpn_b200.so")
 
 FMT_F32, FMT_BF16, FMT_BF16X2, FMT_F16F8 = 0, 1, 2, 3
 OUT_ACT, OUT_F32_NHWC, OUT_F32_NCHW = 0, 1, 2
-EPI_RELU, EPI_SIGMOID = 1, 2
+EPI_RELU, EPI_SIGMOID, EPI_NO_H8, IN_NO_H8 = 1, 2, 4, 8
 
 c_void_p, c_int, c_float, c_size_t, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_longlong
 
@@ -54,7 +54,7 @@ _SIGS = {
     "mpn_stem_pack_input_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "mpn_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_relu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "mpn_conv2d_wgrad": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvPtrs), c_void_p, c_void_p]),
     "mpn_pack_filter_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -63,7 +63,7 @@ __device__ __forceinline__ float mpn_load_act(const void* hi, const void* lo, lo
   return v;
 }
 
-// plane = number of elements of one plane of the destination tensor (needed by MPN_FMT_F16F8 to find the h8 plane)
+// plane = number of elements of one plane of the destination tensor (needed by MPN_FMT_F16F8 to find the h8 plane; < 0: no h8 plane)
 __device__ __forceinline__ void mpn_store_act(void* hi, void* lo, long long idx, int fmt, float v, long long plane = 0) {
   if (fmt == MPN_FMT_F32) {
     ((float*)hi)[idx] = v;
@@ -71,7 +71,7 @@ __device__ __forceinline__ void mpn_store_act(void* hi, void* lo, long long idx,
     const __half h = mpn_f16_sat(v);
     ((__half*)hi)[idx] = h;
     ((unsigned char*)lo)[idx] = mpn_float_to_e5m2((v - __half2float(h)) * MPN_F8_LO_SCALE);
-    ((unsigned char*)lo)[plane + idx] = mpn_float_to_e5m2(v);
+    if (plane >= 0) ((unsigned char*)lo)[plane + idx] = mpn_float_to_e5m2(v);   // plane < 0: tensor stored without its h8 plane
   } else {
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     ((__nv_bfloat16*)hi)[idx] = h;

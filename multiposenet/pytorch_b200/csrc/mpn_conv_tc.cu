@@ -132,7 +132,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                : "memory");
 }
 
-enum { MODE_BF16 = 0, MODE_BF16X2 = 1, MODE_F16F8 = 2 };
+// MODE_F16F8B: F16F8 for an activation tensor stored WITHOUT its h8 plane (3 bytes per element in HBM instead of 4): the
+// weight-residual term x * w_lo runs as x_hi(fp16) * w_lo16(fp16) on kind::f16 (4 more K = 16 MMAs per K block: 10 slots
+// instead of 8, and a more accurate term) -- used where the layer is bound by HBM / the epilogue, not by the tensor pipe
+// (every 1x1 conv of the backbone, the FPN laterals).  Filter planes: hi fp16, lo16 fp16, h8 e4m3.
+enum { MODE_BF16 = 0, MODE_BF16X2 = 1, MODE_F16F8 = 2, MODE_F16F8B = 3 };
+__host__ __device__ constexpr int a_stage_bytes(int mode) { return mode == MODE_BF16 ? 16384 : mode == MODE_F16F8B ? 24576 : 32768; }
+__host__ __device__ constexpr int b_row_bytes(int mode) { return mode == MODE_BF16 ? 128 : mode == MODE_F16F8B ? 320 : 256; }
 
 __device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -171,15 +177,19 @@ __device__ __forceinline__ void add_e5m2x4_reg(float* v, uint32_t w) {
   v[2] = fmaf(f16_lo_f(p23), MPN_F8_LO_INV, v[2]);
   v[3] = fmaf(f16_hi_f(p23), MPN_F8_LO_INV, v[3]);
 }
-// 8 floats -> fp16 hi (uint4), lo8 = e5m2((v - hi) * 2^12) (uint2), h8 = e5m2(v) (uint2)
-__device__ __forceinline__ void split_f16f8x8(const float* w, uint4& hi, uint2& lo8, uint2& h8) {
+// 8 floats -> fp16 hi (uint4), lo8 = e5m2((v - hi) * 2^12) (uint2), h8 = e5m2(v) (uint2; skipped for tensors stored without it)
+__device__ __forceinline__ void split_f16f8x8(const float* w, uint4& hi, uint2& lo8, uint2& h8, bool want_h8 = true) {
   hi.x = pack_f16(w[0], w[1]); hi.y = pack_f16(w[2], w[3]); hi.z = pack_f16(w[4], w[5]); hi.w = pack_f16(w[6], w[7]);
   lo8.x = e5m2x4((w[0] - f16_lo_f(hi.x)) * MPN_F8_LO_SCALE, (w[1] - f16_hi_f(hi.x)) * MPN_F8_LO_SCALE,
                  (w[2] - f16_lo_f(hi.y)) * MPN_F8_LO_SCALE, (w[3] - f16_hi_f(hi.y)) * MPN_F8_LO_SCALE);
   lo8.y = e5m2x4((w[4] - f16_lo_f(hi.z)) * MPN_F8_LO_SCALE, (w[5] - f16_hi_f(hi.z)) * MPN_F8_LO_SCALE,
                  (w[6] - f16_lo_f(hi.w)) * MPN_F8_LO_SCALE, (w[7] - f16_hi_f(hi.w)) * MPN_F8_LO_SCALE);
-  h8.x = e5m2x4(w[0], w[1], w[2], w[3]);
-  h8.y = e5m2x4(w[4], w[5], w[6], w[7]);
+  if (want_h8) {
+    h8.x = e5m2x4(w[0], w[1], w[2], w[3]);
+    h8.y = e5m2x4(w[4], w[5], w[6], w[7]);
+  } else {
+    h8.x = h8.y = 0u;
+  }
 }
 
 // PAIR: the kernel runs as 2-CTA clusters (one TPC).  The two CTAs take two consecutive M tiles of the same Cout block; each
@@ -190,12 +200,16 @@ __device__ __forceinline__ void split_f16f8x8(const float* w, uint4& hi, uint2& 
 template <int BN, int MODE, int STAGES, int EPI, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ Maps maps, const TcParams P) {
   constexpr bool SPLIT = MODE == MODE_BF16X2;
-  constexpr bool F8 = MODE == MODE_F16F8;
+  constexpr bool F8B = MODE == MODE_F16F8B;             // operand side: no h8 activation plane, fp16 weight residual
+  constexpr bool F8 = MODE == MODE_F16F8 || F8B;        // format side (epilogue, shortcut): fp16 hi + e5m2 lo8 (+ optional h8)
   // "plane units" of 128 bytes per row and K block: BF16X2 = hi + lo; F16F8 = hi (128 B) + lo8 (64 B) + h8 (64 B)
   constexpr int PLANES = MODE == MODE_BF16 ? 1 : 2;
   constexpr int NMAPS = F8 ? 3 : PLANES;
-  constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BLOCK_K * 2;  // filter rows held by THIS CTA
-  constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + B_TILE_BYTES);
+  constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BLOCK_K * 2;  // one 128-byte plane of the filter rows held by THIS CTA
+  constexpr int A_STAGE = a_stage_bytes(MODE);                      // A planes of one K block
+  constexpr int B_ROW = b_row_bytes(MODE);                          // B bytes per filter row and K block (all planes)
+  constexpr int A_ROW_TX = F8B ? 192 : PLANES * 128;                // A bytes TMA delivers per box row
+  constexpr int STAGE_BYTES = A_STAGE + (PAIR ? BN / 2 : BN) * B_ROW;
   constexpr int MMA_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
   constexpr bool TMAEPI = EPI == EPI_TMA || EPI == EPI_TMA_RES;
   constexpr bool RESLD = EPI == EPI_TMA_RES;
@@ -231,9 +245,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
     for (int p = 0; p < NMAPS; ++p) {
       prefetch_tmap(&maps.b[p]);
-      prefetch_tmap(&maps.a[p][0]);
+      if (!(F8B && p == 2)) prefetch_tmap(&maps.a[p][0]);
       if (P.tail_split > 1) prefetch_tmap(&maps.bs[p]);
-      if (TMAEPI) prefetch_tmap(&maps.y[p]);
+      if (TMAEPI && !(F8 && p == 2 && (P.flags & MPN_EPI_NO_H8))) prefetch_tmap(&maps.y[p]);
       if (TMAEPI && (P.res_mma || RESLD) && p < 2) prefetch_tmap(&maps.r[p]);
     }
     for (int s = 0; s < STAGES; ++s) {
@@ -286,11 +300,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const bool tail = tc.ncols != BN;
       const int brows = PAIR ? tc.ncols / 2 : tc.ncols;                     // filter rows this CTA loads
       // bytes of one K block landing in this CTA; the leader's barrier of a pair expects both CTAs' bytes
-      const uint32_t tx_bytes = (uint32_t)PLANES * (uint32_t)((P.rows + brows) * BLOCK_K * 2) * (PAIR ? 2u : 1u);
+      const uint32_t tx_bytes = (uint32_t)(P.rows * A_ROW_TX + brows * B_ROW) * (PAIR ? 2u : 1u);
       // narrow tail tiles are latency-bound on the ring: pack as many K blocks as fit into one stage (sub-blocks of
       // [A planes][B planes], the B planes ncols*128 bytes apart) so that twice the bytes are in flight
       const uint32_t bplane = tail ? (uint32_t)brows * 128u : (uint32_t)B_TILE_BYTES;
-      const uint32_t sub_bytes = (uint32_t)PLANES * ((uint32_t)A_TILE_BYTES + bplane);
+      const uint32_t sub_bytes = (uint32_t)A_STAGE + (bplane >> 7) * (uint32_t)B_ROW;
       const int kpack = (tail && !PAIR) ? (int)(STAGE_BYTES / sub_bytes) : 1;
       const int ow0 = tc.tw_i * P.TW, oh0 = tc.th_i * P.TH, n0 = tc.tn_i * P.TN, co0 = tc.co0 + cta_rank * brows;
       int u = 0, ki = 0;
@@ -318,11 +332,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (leader) mbar_expect_tx(full_bar(stage), tx_bytes * (uint32_t)group);
           }
           const uint32_t sa = smem_base + stage * STAGE_BYTES + u * sub_bytes;
-          const uint32_t sb = sa + PLANES * A_TILE_BYTES;
+          const uint32_t sb = sa + A_STAGE;
           const int kcol = tap * P.Cin + kb * BLOCK_K;
           if constexpr (PAIR) {
             const uint32_t lb = lead_full0 + 8u * stage;
-            if constexpr (F8) {
+            if constexpr (F8B) {
+              // A: [hi 16 KB][lo8 8 KB]; B: [hi rows*128][lo16 rows*128][h8 rows*64]
+              tma_load_4d_pair(sa, &maps.a[0][ph], lb, kb * BLOCK_K, wc, hc, n0);
+              tma_load_4d_pair(sa + A_TILE_BYTES, &maps.a[1][ph], lb, kb * BLOCK_K, wc, hc, n0);
+              tma_load_2d_pair(sb, tail ? &maps.bs[0] : &maps.b[0], lb, kcol, co0);
+              tma_load_2d_pair(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], lb, kcol, co0);
+              tma_load_2d_pair(sb + 2 * bplane, tail ? &maps.bs[2] : &maps.b[2], lb, kcol, co0);
+            } else if constexpr (F8) {
               tma_load_4d_pair(sa, &maps.a[0][ph], lb, kb * BLOCK_K, wc, hc, n0);
               tma_load_4d_pair(sa + A_TILE_BYTES, &maps.a[1][ph], lb, kb * BLOCK_K, wc, hc, n0);
               tma_load_4d_pair(sa + A_TILE_BYTES + A_TILE_BYTES / 2, &maps.a[2][ph], lb, kb * BLOCK_K, wc, hc, n0);
@@ -336,6 +357,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 tma_load_2d_pair(sb + p * bplane, tail ? &maps.bs[p] : &maps.b[p], lb, kcol, co0);
               }
             }
+          } else if constexpr (F8B) {
+            tma_load_4d(sa, &maps.a[0][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
+            tma_load_4d(sa + A_TILE_BYTES, &maps.a[1][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
+            tma_load_2d(sb, tail ? &maps.bs[0] : &maps.b[0], full_bar(stage), kcol, co0);
+            tma_load_2d(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], full_bar(stage), kcol, co0);
+            tma_load_2d(sb + 2 * bplane, tail ? &maps.bs[2] : &maps.b[2], full_bar(stage), kcol, co0);
           } else if constexpr (F8) {
             // A: [hi 16 KB][lo8 8 KB][h8 8 KB]; B: [hi ncols*128][lo8 ncols*64][h8 ncols*64]
             tma_load_4d(sa, &maps.a[0][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
@@ -364,7 +391,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), (uint32_t)(2 * A_TILE_BYTES + (tc.ncols / 64) * P.rows * 128));
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint32_t sb = sa + PLANES * A_TILE_BYTES;
+          const uint32_t sb = sa + A_STAGE;
           tma_load_2d(sa, &maps.ident, full_bar(stage), 0, 0);
           tma_load_2d(sa + A_TILE_BYTES, &maps.ident, full_bar(stage), 64, 0);
           for (int j = 0; j < tc.ncols / 64; ++j)
@@ -389,7 +416,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const bool res_mma = TMAEPI && !PAIR && P.res_mma;
       const bool tail = ncols != BN;
       const uint32_t bplane = tail ? (uint32_t)(PAIR ? ncols / 2 : ncols) * 128u : (uint32_t)B_TILE_BYTES;
-      const uint32_t sub_bytes = (uint32_t)PLANES * ((uint32_t)A_TILE_BYTES + bplane);
+      const uint32_t sub_bytes = (uint32_t)A_STAGE + (bplane >> 7) * (uint32_t)B_ROW;
       const int kpack = (tail && !PAIR) ? (int)(STAGE_BYTES / sub_bytes) : 1;
       for (int ki = 0; ki < num_k_iters;) {
         mbar_wait(full_bar(stage), phase);
@@ -397,7 +424,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int group = min(kpack, num_k_iters - ki);
         for (int u = 0; u < group; ++u, ++ki) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES + u * sub_bytes;
-          const uint32_t sb = sa + PLANES * A_TILE_BYTES;
+          const uint32_t sb = sa + A_STAGE;
           auto mma16 = [&](uint64_t a, uint64_t b, uint32_t accum) {
             if (PAIR) umma_f16_pair(d_tmem, a, b, IDESC, accum);
             else umma_bf16(d_tmem, a, b, IDESC, accum);
@@ -411,10 +438,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k)  // fp16 hi * fp16 hi, K = 16 per instruction
               mma16(make_sdesc(sa + k * 32), make_sdesc(sb + k * 32), (ki > 0 || k > 0) ? 1u : 0u);
+            if constexpr (F8B) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / 32; ++k) {  // fp8 cross terms, K = 32 per instruction
-              mma8(make_sdesc64(sa + A_TILE_BYTES + k * 32), make_sdesc64(sb + bplane + bplane / 2 + k * 32));  // xlo8 * wh8
-              mma8(make_sdesc64(sa + A_TILE_BYTES + A_TILE_BYTES / 2 + k * 32), make_sdesc64(sb + bplane + k * 32));  // xh8 * wlo8
+              for (int k = 0; k < BLOCK_K / 16; ++k)  // fp16 hi * fp16 weight residual
+                mma16(make_sdesc(sa + k * 32), make_sdesc(sb + bplane + k * 32), 1u);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 32; ++k)  // xlo8 * wh8, K = 32 per instruction
+                mma8(make_sdesc64(sa + A_TILE_BYTES + k * 32), make_sdesc64(sb + 2 * bplane + k * 32));
+            } else {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 32; ++k) {  // fp8 cross terms, K = 32 per instruction
+                mma8(make_sdesc64(sa + A_TILE_BYTES + k * 32), make_sdesc64(sb + bplane + bplane / 2 + k * 32));  // xlo8 * wh8
+                mma8(make_sdesc64(sa + A_TILE_BYTES + A_TILE_BYTES / 2 + k * 32), make_sdesc64(sb + bplane + k * 32));  // xh8 * wlo8
+              }
             }
           } else {
 #pragma unroll
@@ -448,7 +484,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint32_t sb = sa + PLANES * A_TILE_BYTES;
+          const uint32_t sb = sa + A_STAGE;
 #pragma unroll
           for (int k = 0; k < BLOCK_M / 16; ++k) {
             const uint64_t a_id = make_sdesc(sa + (k >> 2) * A_TILE_BYTES + (k & 3) * 32);
@@ -467,6 +503,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // 32-column chunks of parity (w-4)>>2, so each scheduler has two independent instruction streams.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
+    const bool want_h8 = !(P.flags & MPN_EPI_NO_H8);  // F16F8 outputs: the e5m2 copy plane is only stored for tensors a 3x3 conv reads
     const int rep = P.out_rep, OHr = P.OH * rep, OWr = P.OW * rep;
     const long long nstride = P.out_nstride > 0 ? P.out_nstride
                               : (P.out_mode == MPN_OUT_F32_NCHW ? (long long)P.Cout * OHr * OWr : (long long)OHr * OWr * P.out_cstride);
@@ -643,7 +680,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           uint2 l8[4], h8[4];
           if constexpr (F8) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split_f16f8x8(v + 8 * i, hi4[i], l8[i], h8[i]);
+            for (int i = 0; i < 4; ++i) split_f16f8x8(v + 8 * i, hi4[i], l8[i], h8[i], want_h8);
           } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -671,8 +708,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           if constexpr (F8) {  // byte planes: [lo8: rows x 32 B] at +8192, [h8: rows x 32 B] at +12288, unswizzled boxes
             *reinterpret_cast<uint4*>(stg + 8192 + row * 32) = make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y);
             *reinterpret_cast<uint4*>(stg + 8192 + row * 32 + 16) = make_uint4(l8[2].x, l8[2].y, l8[3].x, l8[3].y);
-            *reinterpret_cast<uint4*>(stg + 12288 + row * 32) = make_uint4(h8[0].x, h8[0].y, h8[1].x, h8[1].y);
-            *reinterpret_cast<uint4*>(stg + 12288 + row * 32 + 16) = make_uint4(h8[2].x, h8[2].y, h8[3].x, h8[3].y);
+            if (want_h8) {
+              *reinterpret_cast<uint4*>(stg + 12288 + row * 32) = make_uint4(h8[0].x, h8[0].y, h8[1].x, h8[1].y);
+              *reinterpret_cast<uint4*>(stg + 12288 + row * 32 + 16) = make_uint4(h8[2].x, h8[2].y, h8[3].x, h8[3].y);
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           named_bar_sync(1 + half, 128);
@@ -681,7 +720,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (SPLIT) tma_store_4d(&maps.y[1], stg_u32 + 8192, cbase, ow0, oh0, n0);
             if (F8) {
               tma_store_4d(&maps.y[1], stg_u32 + 8192, cbase, ow0, oh0, n0);
-              tma_store_4d(&maps.y[2], stg_u32 + 12288, cbase, ow0, oh0, n0);
+              if (want_h8) tma_store_4d(&maps.y[2], stg_u32 + 12288, cbase, ow0, oh0, n0);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -791,7 +830,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             uint4 hi4, lo4;
             uint2 l8, h8;
             if constexpr (F8) {
-              split_f16f8x8(v, hi4, l8, h8);
+              split_f16f8x8(v, hi4, l8, h8, want_h8);
               if (pixv[i] >= 0) {
                 unsigned char* ylo = reinterpret_cast<unsigned char*>(P.y_lo);
                 for (int ry = 0; ry < rep; ++ry)
@@ -799,7 +838,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     const long long o = obase[i] + ((long long)ry * OWr + rx) * P.out_cstride + ch;
                     *reinterpret_cast<uint4*>((__half*)P.y_hi + o) = hi4;
                     *reinterpret_cast<uint2*>(ylo + o) = l8;
-                    *reinterpret_cast<uint2*>(ylo + P.y_plane + o) = h8;
+                    if (want_h8) *reinterpret_cast<uint2*>(ylo + P.y_plane + o) = h8;
                   }
               }
               continue;
@@ -955,12 +994,14 @@ void choose_tile(int N, int OH, int OW, int* TW, int* TH, int* TN, bool even = f
 
 template <int BN, int MODE, int EPI, bool PAIR = false>
 int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
-  constexpr int PLANES = MODE == MODE_BF16 ? 1 : 2;
-  constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BLOCK_K * 2);
+  constexpr int STAGE_BYTES = a_stage_bytes(MODE) + (PAIR ? BN / 2 : BN) * b_row_bytes(MODE);
   constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES + (EPI == EPI_TMA_RES ? 4 * RES_STAGE_BYTES : 0);
   constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - BIAS_BYTES - EPI_BYTES) / STAGE_BYTES;
-  constexpr int STAGES = MAXS > 8 ? 8 : MAXS;
-  static_assert(STAGES >= 2, "not enough shared memory for a 2-stage ring");
+  constexpr int STAGES = MAXS > 8 ? 8 : (MAXS < 2 ? 2 : MAXS);
+  if constexpr (MAXS < 2) {   // MODE_F16F8B, 256-wide single-CTA tiles: the host plan never selects them (BN is capped at 128)
+    mpn_set_error("conv(tcgen05): tile configuration does not fit shared memory (BN %d, mode %d)", BN, MODE);
+    return MPN_ERR_UNSUPPORTED;
+  } else {
   static_assert(8 * (2 * STAGES + 9) <= BAR_BYTES, "barrier area too small");
   const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BIAS_BYTES + EPI_BYTES;
   static_assert(STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BIAS_BYTES + EPI_BYTES <= SMEM_LIMIT, "shared memory budget");
@@ -994,6 +1035,7 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
   MPN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, P));
   MPN_LAUNCH_OK();
   return MPN_OK;
+  }
 }
 
 }  // namespace
@@ -1001,7 +1043,9 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
 int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream) {
   const bool split = d->fmt == MPN_FMT_BF16X2;
   const bool f8 = d->fmt == MPN_FMT_F16F8;
+  const bool f8b = f8 && (d->flags & MPN_IN_NO_H8);   // input without its h8 plane: fp16 weight-residual term (MODE_F16F8B)
   MPN_CHECK_ARG(!f8 || (p->x_lo && p->w_lo), "conv(tcgen05): F16F8 needs the byte planes of x and w");
+  MPN_CHECK_ARG(f8 || !(d->flags & (MPN_IN_NO_H8 | MPN_EPI_NO_H8)), "conv(tcgen05): MPN_IN_NO_H8 / MPN_EPI_NO_H8 are MPN_FMT_F16F8 flags");
   MPN_CHECK_ARG(!f8 || (d->in_cstride % 16 == 0 && d->res_cstride % 16 == 0 && d->up_cstride % 16 == 0 &&
                         (d->out_mode != MPN_OUT_ACT || (d->out_cstride % 16 == 0 && d->out_coffset % 16 == 0))),
                 "conv(tcgen05): F16F8 byte planes need channel strides / offsets that are multiples of 16");
@@ -1070,6 +1114,7 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   const bool res_tma = res_tma_on && pair && epi_tma && (d->res_cstride > 0 || up_tma) && d->Cout % 64 == 0;
   const int min_tail_bn = pair ? 64 : res_mma ? 64 : 32;
   int BN = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
+  if (f8b && !pair && BN > 128) BN = 128;   // 256 filter rows x 320 B per K block do not leave room for a 2-stage ring
   int tail_s = 1;
   const long long sched_m = pair ? (m_tiles + 1) / 2 : m_tiles;   // schedulable M units
   const int sched_sms = pair ? sms / 2 : sms;                      // ... and the units that run at once
@@ -1139,13 +1184,14 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
                 "conv(tcgen05): k_overlap needs stride 1, Cin == 64 and a row pitch covering the window");
   const long long x_plane = (long long)d->N * hpitch * wpitch * d->in_cstride;   // F16F8: h8 plane = lo8 plane + x_plane bytes
   const long long w_plane = (long long)d->Cout * d->R * d->S * d->Cin;
-  for (int pl = 0; pl < planes; ++pl) {
+  // ---- activation planes: hi (2-byte elements, 128B swizzle); BF16X2: lo; F16F8: lo8 and (unless MPN_IN_NO_H8) h8 byte planes
+  const int a_planes = f8b ? 2 : planes;
+  for (int pl = 0; pl < a_planes; ++pl) {
     const bool bytes = f8 && pl > 0;                 // byte planes: 1-byte elements, 64-byte swizzle
     const unsigned long long es = bytes ? 1ULL : 2ULL;
     const CUtensorMapSwizzle swz = bytes ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
     const CUtensorMapDataType dt = bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const char* xb = (const char*)(pl == 0 ? p->x_hi : p->x_lo) + (f8 && pl == 2 ? x_plane : 0);
-    const char* wb = (const char*)(pl == 0 ? p->w_hi : p->w_lo) + (f8 && pl == 2 ? w_plane : 0);
     for (int ph = 0; ph < nphase; ++ph) {
       const int hp = ph >> 1, wp = ph & 1;
       const int Hp = (d->H - hp + st - 1) / st, Wp = (d->W - wp + st - 1) / st;
@@ -1162,6 +1208,15 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
       if (rc) return rc;
     }
     MPN_CHECK_ARG(!(P.phase_empty & 1), "conv(tcgen05): empty input");
+  }
+  // ---- filter planes: [Cout, R*S*Cin] K-major.  F16F8: hi fp16 | lo8 bytes | h8 bytes; MPN_IN_NO_H8: hi fp16 | lo16 fp16 | h8 bytes
+  for (int pl = 0; pl < planes; ++pl) {
+    const bool bytes = f8 && (f8b ? pl == 2 : pl > 0);
+    const unsigned long long es = bytes ? 1ULL : 2ULL;
+    const CUtensorMapSwizzle swz = bytes ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapDataType dt = bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const long long off = !f8 || pl < 2 ? 0 : (f8b ? 2 * w_plane : w_plane);   // byte offset of the third plane inside w_lo
+    const char* wb = (const char*)(pl == 0 ? p->w_hi : p->w_lo) + off;
     const cuuint64_t K = (cuuint64_t)d->R * d->S * d->Cin;
     cuuint64_t wdims[2] = {K, (cuuint64_t)d->Cout};
     cuuint64_t wstrides[1] = {K * es};
@@ -1177,6 +1232,7 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   if (epi_tma) {
     const long long nstride = d->out_nstride > 0 ? d->out_nstride : (long long)d->OH * d->OW * d->out_cstride;
     for (int pl = 0; pl < planes; ++pl) {
+      if (f8 && pl == 2 && (d->flags & MPN_EPI_NO_H8)) continue;   // output stored without its h8 plane
       const bool bytes = f8 && pl > 0;
       const unsigned long long es = bytes ? 1ULL : 2ULL;
       cuuint64_t ydims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->OW, (cuuint64_t)d->OH, (cuuint64_t)d->N};
@@ -1224,6 +1280,7 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   cudaStream_t s = (cudaStream_t)stream;
   if (f32out) {  // head outputs (18/19/36/9 channels): the thread-per-row fp32 store path, small-N tiles only
     MPN_CHECK_ARG(BN <= 64, "conv(tcgen05): fp32 outputs are built for Cout <= 64 (got %d)", d->Cout);
+    if (f8b) return BN == 64 ? launch<64, MODE_F16F8B, EPI_F32>(maps, P, s, sms) : launch<32, MODE_F16F8B, EPI_F32>(maps, P, s, sms);
     if (f8) return BN == 64 ? launch<64, MODE_F16F8, EPI_F32>(maps, P, s, sms) : launch<32, MODE_F16F8, EPI_F32>(maps, P, s, sms);
     if (split) return BN == 64 ? launch<64, MODE_BF16X2, EPI_F32>(maps, P, s, sms) : launch<32, MODE_BF16X2, EPI_F32>(maps, P, s, sms);
     return BN == 64 ? launch<64, MODE_BF16, EPI_F32>(maps, P, s, sms) : launch<32, MODE_BF16, EPI_F32>(maps, P, s, sms);
@@ -1243,6 +1300,11 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   if (res_tma) {                                                                      \
     if (BN == 256) return launch<256, SPLIT_, EPI_TMA_RES, true>(maps, P, s, sms);    \
     return launch<128, SPLIT_, EPI_TMA_RES, true>(maps, P, s, sms);                   \
+  }
+  if (f8b) {
+    MPN_TC_DISPATCH_RES(MODE_F16F8B)
+    if (epi_tma) { MPN_TC_DISPATCH(MODE_F16F8B, EPI_TMA) }
+    MPN_TC_DISPATCH(MODE_F16F8B, EPI_LSU)
   }
   if (f8) {
     MPN_TC_DISPATCH_RES(MODE_F16F8)

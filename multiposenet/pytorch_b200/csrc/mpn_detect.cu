@@ -265,31 +265,25 @@ __global__ void __launch_bounds__(128) nms_mask_kernel_v2(const float* __restric
         for (int i = lo; i < hi; ++i)
           if (nms_pair_over(rbx, Sa, cbox[buf][i], carea[buf][i], thr, ge, false)) t |= 1u << (i & 31);
       } else if (lo < hi) {
-        // all 32 columns of the half, branch-free (the serial, divergent pair loop was latency bound: ~25 % issue efficiency);
-        // the decision tree of nms_pair_over as predicates, the exact division only for pairs inside the guard band (rare);
-        // columns outside [lo, hi) are evaluated on whatever the staging buffer holds (finite zeros) and masked off
+        // Phase 1, branch-free over all 32 columns of the half: which column boxes overlap the row box at all?  w > 0 <=> d_w > -1
+        // exactly (w = fl(d_w + 1) and the floats next to -1 are 2^-24 apart), so the test needs 2 min/max + 1 subtract per axis.
+        // Columns outside [lo, hi) are evaluated on whatever the staging buffer holds (finite zeros) and masked off.
+        unsigned int cand = 0u;
 #pragma unroll 8
         for (int ii = 0; ii < 32; ++ii) {
           const float4 bb = cbox[buf][base + ii];
-          const float Sb = carea[buf][base + ii];
-          const float w = __fadd_rn(__fsub_rn(fminf(rbx.z, bb.z), fmaxf(rbx.x, bb.x)), 1.f);
-          const float h = __fadd_rn(__fsub_rn(fminf(rbx.w, bb.w), fmaxf(rbx.y, bb.y)), 1.f);
-          const bool disjoint = !(w > 0.f) || !(h > 0.f);
-          const float interS = __fmul_rn(fmaxf(w, 0.f), fmaxf(h, 0.f));
-          const float uni = __fsub_rn(__fadd_rn(Sa, Sb), interS);
-          const float pth = __fmul_rn(thr, uni);
-          const bool pos = uni > 0.f;
-          const bool yes = !disjoint && pos && interS > __fmul_rn(pth, 1.000001f);
-          const bool no = disjoint || (pos && interS < __fmul_rn(pth, 0.999999f));
-          bool over = yes;
-          if (!yes && !no) {
-            const float v = __fdiv_rn(interS, uni);
-            over = ge ? (v >= thr) : (v > thr);
-          }
-          t |= (over ? 1u : 0u) << ii;
+          const float dw_ = __fsub_rn(fminf(rbx.z, bb.z), fmaxf(rbx.x, bb.x));
+          const float dh_ = __fsub_rn(fminf(rbx.w, bb.w), fmaxf(rbx.y, bb.y));
+          cand |= ((dw_ > -1.f && dh_ > -1.f) ? 1u : 0u) << ii;
         }
         const unsigned int upto = (hi - base) >= 32 ? 0xffffffffu : ((1u << (hi - base)) - 1u);
-        t &= upto & ~((1u << (lo - base)) - 1u);
+        cand &= upto & ~((1u << (lo - base)) - 1u);
+        // Phase 2: the IoU decision proper only for the overlapping pairs (a few per cent of all pairs)
+        while (cand) {
+          const int ii = __ffs((int)cand) - 1;
+          cand &= cand - 1u;
+          if (nms_pair_over(rbx, Sa, cbox[buf][base + ii], carea[buf][base + ii], thr, ge, true)) t |= 1u << ii;
+        }
       }
       mask32[2 * cblk + half] = t;   // little endian: half 0 = columns 0..31 of the 64-bit word
     }

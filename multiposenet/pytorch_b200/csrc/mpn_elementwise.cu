@@ -111,8 +111,8 @@ extern "C" int mpn_filter_absmax(const float* w, const float* scale, int Cout, i
 }
 
 __global__ void pack_filter_f16f8_kernel(const float* __restrict__ w, const float* __restrict__ scale, float wscale, __half* __restrict__ hi,
-                                         unsigned char* __restrict__ lo8, unsigned char* __restrict__ h8, int Cout, int Cin, int R, int S,
-                                         int stem) {
+                                         unsigned char* __restrict__ lo8, unsigned char* __restrict__ h8, __half* __restrict__ lo16,
+                                         int Cout, int Cin, int R, int S, int stem) {
   const long long total = stem ? (long long)Cout * 256 : (long long)Cout * R * S * Cin;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float v = 0.f;
@@ -139,18 +139,22 @@ __global__ void pack_filter_f16f8_kernel(const float* __restrict__ w, const floa
     v = __fmul_rn(v, wscale);  // a power of two: exact
     const __half h = __float2half_rn(v);
     hi[i] = h;
-    lo8[i] = mpn_float_to_e4m3(v - __half2float(h));   // pairs with the activations' e5m2 copy
-    h8[i] = mpn_float_to_e4m3(v * MPN_F8_LO_INV);      // pairs with the activations' lo8 = e5m2((x - hi) * 2^12)
+    if (lo16) lo16[i] = __float2half_rn(v - __half2float(h));   // layout 1: pairs with the activations' fp16 hi plane (MPN_IN_NO_H8)
+    else lo8[i] = mpn_float_to_e4m3(v - __half2float(h));       // layout 0: pairs with the activations' e5m2 copy
+    h8[i] = mpn_float_to_e4m3(v * MPN_F8_LO_INV);               // pairs with the activations' lo8 = e5m2((x - hi) * 2^12)
   }
 }
 
 extern "C" int mpn_pack_filter_f16f8(const float* w, const float* scale, float wscale, void* hi, void* lo8h8, int Cout, int Cin, int R,
-                                     int S, int stem, void* stream) {
+                                     int S, int layout, void* stream) {
+  // layout bit 0: the stem's space-to-depth filter; bit 1: [lo16 fp16 plane][h8 plane] for inputs without an h8 plane
+  const int stem = layout & 1, lay16 = (layout >> 1) & 1;
   MPN_CHECK_ARG(w && hi && lo8h8 && Cout > 0 && Cin > 0 && R > 0 && S > 0 && wscale > 0.f, "mpn_pack_filter_f16f8: bad argument");
   MPN_CHECK_ARG(!stem || (Cin == 3 && R == 7 && S == 7), "mpn_pack_filter_f16f8: the stem layout is for a [Cout,3,7,7] filter");
   const long long total = stem ? (long long)Cout * 256 : (long long)Cout * R * S * Cin;
-  pack_filter_f16f8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, scale, wscale, (__half*)hi, (unsigned char*)lo8h8,
-                                                                                  (unsigned char*)lo8h8 + total, Cout, Cin, R, S, stem);
+  unsigned char* lo = (unsigned char*)lo8h8;
+  pack_filter_f16f8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      w, scale, wscale, (__half*)hi, lo, lay16 ? lo + 2 * total : lo + total, lay16 ? (__half*)lo : nullptr, Cout, Cin, R, S, stem);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -235,7 +239,7 @@ extern "C" int mpn_nhwc_to_nchw(const void* hi, const void* lo, float* dst, int 
 // ---------------------------------------------------------------------------------------------
 // max_pool2d(3, stride 2, pad 1), NHWC.  One thread per (pixel, 4-channel group); -inf padding.
 __global__ void maxpool3x3s2_kernel(const void* __restrict__ xhi, const void* __restrict__ xlo, void* yhi, void* ylo, int N,
-                                    int H, int W, int C, int OH, int OW, int fmt) {
+                                    int H, int W, int C, int OH, int OW, int fmt, int no_h8) {
   long long total = (long long)N * OH * OW * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -256,7 +260,7 @@ __global__ void maxpool3x3s2_kernel(const void* __restrict__ xhi, const void* __
         m = fmaxf(m, mpn_load_act(xhi, xlo, (((long long)n * H + ih) * W + iw) * C + c, fmt));
       }
     }
-    mpn_store_act(yhi, ylo, i, fmt, m, total);
+    mpn_store_act(yhi, ylo, i, fmt, m, no_h8 ? -1 : total);
   }
 }
 
@@ -371,12 +375,13 @@ __global__ void maxpool3x3s2_f16f8_kernel(const uint4* __restrict__ xhi, const u
     }
     yhi[i] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
     ylo[i] = make_uint2(ol2[0], ol2[1]);
-    yh8[i] = make_uint2(og2[0], og2[1]);
+    if (yh8) yh8[i] = make_uint2(og2[0], og2[1]);
   }
 }
 
 extern "C" int mpn_maxpool3x3s2(const void* xhi, const void* xlo, void* yhi, void* ylo, int N, int H, int W, int C, int fmt,
-                                void* stream) {
+                                int flags, void* stream) {
+  const int no_h8 = (fmt == MPN_FMT_F16F8 && (flags & MPN_EPI_NO_H8)) ? 1 : 0;
   MPN_CHECK_ARG(xhi && yhi && N > 0 && H > 0 && W > 0 && C > 0, "mpn_maxpool3x3s2: bad argument");
   int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   long long total = (long long)N * OH * OW * C;
@@ -393,11 +398,12 @@ extern "C" int mpn_maxpool3x3s2(const void* xhi, const void* xlo, void* yhi, voi
   }
   if (fmt == MPN_FMT_F16F8 && C % 8 == 0) {
     maxpool3x3s2_f16f8_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const uint4*)xhi, (const uint2*)xlo, (uint4*)yhi, (uint2*)ylo, (uint2*)((unsigned char*)ylo + total), N, H, W, C / 8, OH, OW);
+        (const uint4*)xhi, (const uint2*)xlo, (uint4*)yhi, (uint2*)ylo, no_h8 ? nullptr : (uint2*)((unsigned char*)ylo + total), N, H, W,
+        C / 8, OH, OW);
     MPN_LAUNCH_OK();
     return MPN_OK;
   }
-  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(xhi, xlo, yhi, ylo, N, H, W, C, OH, OW, fmt);
+  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(xhi, xlo, yhi, ylo, N, H, W, C, OH, OW, fmt, no_h8);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }

@@ -117,16 +117,23 @@ class Engine(object):
             self._packed = {}
             self._sig = sig
 
-    def _pc(self, name, conv, bn=None, fmt=None):
+    def _pc(self, name, conv, bn=None, fmt=None, no_h8=False):
+        """no_h8 (f16f8 only): pack for an input stored without its e5m2 copy plane (ops.pack_conv in_no_h8)."""
         fmt = self.fmt if fmt is None else fmt
-        key = (name, fmt)
+        no_h8 = bool(no_h8) and fmt == ops.FMT_F16F8 and ops.NO_H8
+        key = (name, fmt, no_h8)
         pc = self._packed.get(key)
         if pc is None:
             if not conv.weight.is_cuda:
                 raise RuntimeError("poseNet must be on a CUDA device (no CPU path); call .cuda() first")
-            pc = ops.pack_conv(conv.weight, conv.bias, _bn_tuple(bn) if bn is not None else None, fmt)
+            pc = ops.pack_conv(conv.weight, conv.bias, _bn_tuple(bn) if bn is not None else None, fmt, in_no_h8=no_h8)
             self._packed[key] = pc
         return pc
+
+    @property
+    def _slim(self):
+        """f16f8: tensors that only 1x1 convolutions (and shortcut adds) read are stored without their e5m2 copy plane."""
+        return self.fmt == ops.FMT_F16F8 and ops.NO_H8
 
     # ------------------------------------------------------------------ backbone
     def backbone(self, img):
@@ -146,17 +153,18 @@ class Engine(object):
                 pc = ops.pack_stem_filter(fpn.conv1.weight, _bn_tuple(fpn.bn1), self.fmt)
                 self._packed[key] = pc
             xs = ops.stem_pack_input_u8(img, self.fmt) if raw_u8 else ops.stem_pack_input(img, self.fmt)
-            c1 = ops.conv2d(xs, pc, relu=True)
+            c1 = ops.conv2d(xs, pc, relu=True, want_h8=not self._slim)   # read by the max-pool only
         else:
             x = ops.act_from_nchw(img, FMT_F32)
             # fp32-packed stem filter on the CUDA-core kernel; the epilogue emits the engine's activation format
             c1 = ops.conv2d(x, self._stem_pc(), stride=2, pad=3, relu=True, f32_input=True)
-        c = ops.maxpool3x3s2(c1)
+        c = ops.maxpool3x3s2(c1, want_h8=not self._slim)
         feats = []
         for li in range(1, 5):
             layer = getattr(fpn, "layer%d" % li)
             for bi, blk in enumerate(layer):
-                c = self._bottleneck("fpn.layer%d.%d" % (li, bi), blk, c)
+                # c5 (the last block of layer4) also feeds the 3x3 conv6 (fpn.py:108): it keeps its e5m2 copy plane
+                c = self._bottleneck("fpn.layer%d.%d" % (li, bi), blk, c, out_h8=(li == 4 and bi == len(layer) - 1))
             feats.append(c)
         return feats
 
@@ -172,16 +180,22 @@ class Engine(object):
             self._packed[key] = pc
         return pc
 
-    def _bottleneck(self, name, blk, x):
-        """fpn.py:28-34."""
+    def _bottleneck(self, name, blk, x, out_h8=False):
+        """fpn.py:28-34.  f16f8: the block input / output and the 3x3's output are read by 1x1 convolutions and shortcut adds
+        only -> stored without the e5m2 copy plane (3 B per element), their consumers packed with no_h8; the 1x1 -> 3x3 tensor
+        keeps it."""
         stride = blk.conv2.stride[0]
-        o = ops.conv2d(x, self._pc(name + ".conv1", blk.conv1, blk.bn1), relu=True)
-        o = ops.conv2d(o, self._pc(name + ".conv2", blk.conv2, blk.bn2), stride=stride, pad=1, relu=True)
+        slim = self._slim
+        nh = slim and not x.has_h8
+        o = ops.conv2d(x, self._pc(name + ".conv1", blk.conv1, blk.bn1, no_h8=nh), relu=True)
+        o = ops.conv2d(o, self._pc(name + ".conv2", blk.conv2, blk.bn2), stride=stride, pad=1, relu=True, want_h8=not slim)
         if len(blk.downsample) > 0:
-            sc = ops.conv2d(x, self._pc(name + ".downsample", blk.downsample[0], blk.downsample[1]), stride=stride)
+            sc = ops.conv2d(x, self._pc(name + ".downsample", blk.downsample[0], blk.downsample[1], no_h8=nh), stride=stride,
+                            want_h8=not slim)
         else:
             sc = x
-        return ops.conv2d(o, self._pc(name + ".conv3", blk.conv3, blk.bn3), relu=True, residual=sc)
+        return ops.conv2d(o, self._pc(name + ".conv3", blk.conv3, blk.bn3, no_h8=slim), relu=True, residual=sc,
+                          want_h8=(not slim) or out_h8)
 
     # ------------------------------------------------------------------ necks
     def detection_neck(self, c3, c4, c5):
@@ -189,9 +203,10 @@ class Engine(object):
         f = self.model.fpn
         p6 = ops.conv2d(c5, self._pc("fpn.conv6", f.conv6), stride=2, pad=1)
         p7 = ops.conv2d(ops.relu(p6), self._pc("fpn.conv7", f.conv7), stride=2, pad=1)
-        p5 = ops.conv2d(c5, self._pc("fpn.latlayer1", f.latlayer1))
-        p4 = ops.conv2d(c4, self._pc("fpn.latlayer2", f.latlayer2), up=p5)
-        p3 = ops.conv2d(c3, self._pc("fpn.latlayer3", f.latlayer3), up=p4)
+        nh = lambda t: not t.has_h8   # stage outputs stored without the e5m2 copy plane -> laterals packed accordingly
+        p5 = ops.conv2d(c5, self._pc("fpn.latlayer1", f.latlayer1, no_h8=nh(c5)))
+        p4 = ops.conv2d(c4, self._pc("fpn.latlayer2", f.latlayer2, no_h8=nh(c4)), up=p5)
+        p3 = ops.conv2d(c3, self._pc("fpn.latlayer3", f.latlayer3, no_h8=nh(c3)), up=p4)
         p5 = ops.conv2d(p5, self._pc("fpn.toplayer0", f.toplayer0), pad=1)
         p4 = ops.conv2d(p4, self._pc("fpn.toplayer1", f.toplayer1), pad=1)
         p3 = ops.conv2d(p3, self._pc("fpn.toplayer2", f.toplayer2), pad=1)
@@ -200,10 +215,11 @@ class Engine(object):
     def keypoint_neck(self, c2, c3, c4, c5):
         """fpn.py:117-124 -> [fp2, fp3, fp4, fp5]."""
         f = self.model.fpn
-        fp5 = ops.conv2d(c5, self._pc("fpn.toplayer", f.toplayer))
-        fp4 = ops.conv2d(c4, self._pc("fpn.flatlayer1", f.flatlayer1), up=fp5)
-        fp3 = ops.conv2d(c3, self._pc("fpn.flatlayer2", f.flatlayer2), up=fp4)
-        fp2 = ops.conv2d(c2, self._pc("fpn.flatlayer3", f.flatlayer3), up=fp3)
+        nh = lambda t: not t.has_h8
+        fp5 = ops.conv2d(c5, self._pc("fpn.toplayer", f.toplayer, no_h8=nh(c5)))
+        fp4 = ops.conv2d(c4, self._pc("fpn.flatlayer1", f.flatlayer1, no_h8=nh(c4)), up=fp5)
+        fp3 = ops.conv2d(c3, self._pc("fpn.flatlayer2", f.flatlayer2, no_h8=nh(c3)), up=fp4)
+        fp2 = ops.conv2d(c2, self._pc("fpn.flatlayer3", f.flatlayer3, no_h8=nh(c2)), up=fp3)
         fp4 = ops.conv2d(fp4, self._pc("fpn.smooth1", f.smooth1), pad=1)
         fp3 = ops.conv2d(fp3, self._pc("fpn.smooth2", f.smooth2), pad=1)
         fp2 = ops.conv2d(fp2, self._pc("fpn.smooth3", f.smooth3), pad=1)
@@ -221,8 +237,8 @@ class Engine(object):
                                     (p3, "convt3", "convs3", 2, 256), (p2, "convt4", "convs4", 1, 384)):
             q = ops.conv2d(src, self._pc(t, getattr(m, t)), pad=1)
             ops.conv2d(q, self._pc(s, getattr(m, s)), pad=1, out=cat, out_coffset=off, out_rep=rep)
-        h = ops.conv2d(cat, self._pc("conv2", m.conv2), pad=1, relu=True)
-        return ops.conv2d(h, self._pc("convfin", m.convfin), out_mode=OUT_F32_NCHW)
+        h = ops.conv2d(cat, self._pc("conv2", m.conv2), pad=1, relu=True, want_h8=not self._slim)   # read by the 1x1 convfin only
+        return ops.conv2d(h, self._pc("convfin", m.convfin, no_h8=self._slim), out_mode=OUT_F32_NCHW)
 
     def intermediate_heads(self, p2, p3, p4, p5):
         """posenet.py:296-299."""

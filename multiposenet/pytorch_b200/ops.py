@@ -9,8 +9,8 @@ import torch
 from . import _lib
 import math
 
-from ._lib import (EPI_RELU, EPI_SIGMOID, FMT_BF16, FMT_BF16X2, FMT_F16F8, FMT_F32, OUT_ACT, OUT_F32_NCHW, OUT_F32_NHWC, ConvDesc,
-                   ConvPtrs, check)
+from ._lib import (EPI_NO_H8, EPI_RELU, EPI_SIGMOID, FMT_BF16, FMT_BF16X2, FMT_F16F8, FMT_F32, IN_NO_H8, OUT_ACT, OUT_F32_NCHW,
+                   OUT_F32_NHWC, ConvDesc, ConvPtrs, check)
 
 PRECISIONS = {"fp32": FMT_F32, "bf16": FMT_BF16, "bf16x3": FMT_BF16X2, "f16f8": FMT_F16F8}
 
@@ -36,20 +36,22 @@ def _dtype(fmt):
 
 class Act(object):
     """NHWC activation: `hi` (and `lo` for the split formats) are [N,H,W,cstride] tensors; FMT_F16F8: hi fp16, lo = uint8
-    [2,N,H,W,cstride] (the e5m2 residual plane and the e5m2 copy plane back to back, see mpn_b200.h)."""
-    __slots__ = ("fmt", "N", "H", "W", "C", "cstride", "hi", "lo", "wpitch", "k_overlap")
+    [2,N,H,W,cstride] (the e5m2 residual plane and the e5m2 copy plane back to back, see mpn_b200.h), or [1,...] when the tensor
+    is stored without the copy plane (has_h8 False: 3 bytes per element; only convolutions packed with in_no_h8 can read it)."""
+    __slots__ = ("fmt", "N", "H", "W", "C", "cstride", "hi", "lo", "wpitch", "k_overlap", "has_h8")
 
-    def __init__(self, fmt, N, H, W, C, device, cstride=None, zero=False, wpitch=0, k_overlap=0):
+    def __init__(self, fmt, N, H, W, C, device, cstride=None, zero=False, wpitch=0, k_overlap=0, has_h8=True):
         self.fmt, self.N, self.H, self.W, self.C = fmt, N, H, W, C
         self.cstride = C if cstride is None else cstride
         self.wpitch, self.k_overlap = wpitch, k_overlap  # see mpn_conv_desc.in_wpitch / k_overlap
+        self.has_h8 = bool(has_h8) if fmt == FMT_F16F8 else True
         mk = torch.zeros if zero else torch.empty
         shape = (N, H, wpitch if wpitch else W, self.cstride)
         self.hi = mk(shape, dtype=_dtype(fmt), device=device)
         if fmt == FMT_F16F8:
             if self.cstride % 16:
                 raise ValueError("FMT_F16F8 activations need a channel stride that is a multiple of 16 (got %d)" % self.cstride)
-            self.lo = mk((2,) + shape, dtype=torch.uint8, device=device)
+            self.lo = mk((2 if has_h8 else 1,) + shape, dtype=torch.uint8, device=device)
         else:
             self.lo = mk(shape, dtype=torch.bfloat16, device=device) if fmt == FMT_BF16X2 else None
 
@@ -73,10 +75,16 @@ def act_from_nchw(x, fmt, cstride=None):
 
 class PackedConv(object):
     """Filter + per-channel epilogue constants of one nn.Conv2d (+ folded eval-mode BatchNorm2d)."""
-    __slots__ = ("Cout", "Cin", "R", "S", "fmt", "w_hi", "w_lo", "cout_pad", "scale", "bias", "acc_scale")
+    __slots__ = ("Cout", "Cin", "R", "S", "fmt", "w_hi", "w_lo", "cout_pad", "scale", "bias", "acc_scale", "in_no_h8")
 
 
-def pack_conv(weight, bias, bn, fmt, fold_scale=True):
+# FMT_F16F8 convolutions come in two operand variants (mpn_b200.h MPN_IN_NO_H8): the default reads the input's e5m2 copy plane
+# (8 tensor-core slots per K block); in_no_h8 multiplies the fp16 plane with an fp16 weight residual instead (10 slots) and lets
+# the producer of its input drop that plane from HBM -- the choice for the HBM / epilogue-bound 1x1 convolutions.
+NO_H8 = __import__("os").environ.get("MPN_NO_H8", "1") == "1"
+
+
+def pack_conv(weight, bias, bn, fmt, fold_scale=True, in_no_h8=False):
     """weight OIHW fp32 cuda; bias fp32 or None; bn = (gamma, beta, mean, var, eps) or None.
 
     fold_scale (bf16 formats): the eval-mode BN scale is multiplied into the filter before the hi/lo split, so the
@@ -88,6 +96,7 @@ def pack_conv(weight, bias, bn, fmt, fold_scale=True):
     pc = PackedConv()
     pc.Cout, pc.Cin, pc.R, pc.S = w.shape
     pc.fmt = fmt
+    pc.in_no_h8 = bool(in_no_h8) and fmt == FMT_F16F8
     dev = w.device
     npad = (pc.Cout + 63) // 64 * 64
     pc.scale = pc.bias = None
@@ -138,20 +147,24 @@ def _pack_f16f8(pc, w, scale, stem):
     k = 0 if not (a > 0.0 and math.isfinite(a)) else max(-100, min(100, 14 - math.frexp(a)[1] + 1))   # a * 2^k in [2^14, 2^15)
     shape = (pc.Cout, 4, 1, 64) if stem else (pc.Cout, pc.R, pc.S, pc.Cin)
     pc.w_hi = torch.empty(shape, dtype=torch.float16, device=w.device)
-    pc.w_lo = torch.empty((2,) + shape, dtype=torch.uint8, device=w.device)
+    lay16 = bool(getattr(pc, "in_no_h8", False))          # [lo16 fp16 plane][h8 plane] instead of [lo8 plane][h8 plane]
+    pc.w_lo = torch.empty((3 if lay16 else 2,) + shape, dtype=torch.uint8, device=w.device)
     Cout, Cin, R, S = w.shape
-    check(L.mpn_pack_filter_f16f8(_ptr(w), _ptr(scale), float(2.0 ** k), _ptr(pc.w_hi), _ptr(pc.w_lo), Cout, Cin, R, S, int(stem), _stream()),
-          "mpn_pack_filter_f16f8")
+    check(L.mpn_pack_filter_f16f8(_ptr(w), _ptr(scale), float(2.0 ** k), _ptr(pc.w_hi), _ptr(pc.w_lo), Cout, Cin, R, S,
+                                  int(stem) | (2 if lay16 else 0), _stream()), "mpn_pack_filter_f16f8")
     pc.acc_scale = float(2.0 ** -k)
 
 
 def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=None, out=None, out_mode=OUT_ACT,
-           out_coffset=0, out_rep=1, out_tensor=None, out_elem_offset=0, out_cstride=None, out_nstride=0, f32_input=False):
+           out_coffset=0, out_rep=1, out_tensor=None, out_elem_offset=0, out_cstride=None, out_nstride=0, f32_input=False,
+           want_h8=True):
     """y = epilogue(conv2d(x, w)).  Returns the output Act (OUT_ACT) or the fp32 tensor written.
 
     out          : existing Act to write into (concat buffers), else a new one is allocated
     out_tensor   : fp32 tensor for OUT_F32_* (allocated if None); out_elem_offset shifts the base pointer
     f32_input    : x is an fp32 NHWC Act while the output/epilogue use pc.fmt (stem)
+    want_h8      : FMT_F16F8 activation outputs: False stores the tensor without its e5m2 copy plane (for consumers packed
+                   with in_no_h8)
     """
     L = _lib.lib()
     fmt = pc.fmt
@@ -165,6 +178,11 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
     d.in_cstride = x.cstride
     d.in_wpitch, d.k_overlap = x.wpitch, x.k_overlap
     d.flags = (EPI_RELU if relu else 0) | (EPI_SIGMOID if sigmoid else 0)
+    if fmt == FMT_F16F8 and not f32_input:
+        if getattr(pc, "in_no_h8", False):
+            d.flags |= IN_NO_H8
+        elif not getattr(x, "has_h8", True):
+            raise ValueError("this activation was stored without its h8 plane: the convolution reading it must be packed with in_no_h8=True")
     d.out_mode, d.out_rep, d.out_coffset = out_mode, out_rep, out_coffset
     d.w_cout_pad = pc.cout_pad
     d.acc_scale = getattr(pc, "acc_scale", 0.0)
@@ -183,8 +201,10 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
     ret = None
     if out_mode == OUT_ACT:
         if out is None:
-            out = Act(fmt, x.N, d.OH * out_rep, d.OW * out_rep, pc.Cout, x.hi.device)
+            out = Act(fmt, x.N, d.OH * out_rep, d.OW * out_rep, pc.Cout, x.hi.device, has_h8=want_h8)
         assert out.fmt == fmt and out.N == x.N and out.H == d.OH * out_rep and out.W == d.OW * out_rep
+        if fmt == FMT_F16F8 and not out.has_h8:
+            d.flags |= EPI_NO_H8
         d.out_cstride = out.cstride
         p.y_hi, p.y_lo = _ptr(out.hi), _ptr(out.lo)
         ret = out
@@ -206,7 +226,8 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
     check(fn(ctypes.byref(d), ctypes.byref(p), _stream()), "mpn_conv2d_fwd")
     if ev is not None:
         e1.record()
-        ev.append((e0, e1, 2.0 * x.N * d.OH * d.OW * pc.Cout * pc.Cin * pc.R * pc.S, bool(f32_input or fmt == FMT_F32)))
+        slots = {FMT_BF16: 1.0, FMT_BF16X2: 3.0, FMT_F16F8: 2.5 if (d.flags & IN_NO_H8) else 2.0}.get(fmt, 0.0)  # bf16-equivalent MMA passes
+        ev.append((e0, e1, 2.0 * x.N * d.OH * d.OW * pc.Cout * pc.Cin * pc.R * pc.S, bool(f32_input or fmt == FMT_F32), slots))
     stats["launches"] += 1
     if stats.get("range_check") and fmt == FMT_F16F8 and out_mode == OUT_ACT and not torch.cuda.is_current_stream_capturing():
         amax = float(ret.hi.abs().max())  # debug mode: one reduction + host sync per conv
@@ -285,11 +306,14 @@ def add_softmax_rows(a, res):
     return out
 
 
-def maxpool3x3s2(x):
+def maxpool3x3s2(x, want_h8=True):
     OH, OW = (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1
-    y = Act(x.fmt, x.N, OH, OW, x.C, x.hi.device)
+    if x.fmt == FMT_F16F8 and x.C % 8:
+        want_h8 = True   # the generic (non-vectorised) kernel keeps the full format
+    y = Act(x.fmt, x.N, OH, OW, x.C, x.hi.device, has_h8=want_h8)
     assert x.cstride == x.C
-    check(_lib.lib().mpn_maxpool3x3s2(_ptr(x.hi), _ptr(x.lo), _ptr(y.hi), _ptr(y.lo), x.N, x.H, x.W, x.C, x.fmt, _stream()), "mpn_maxpool3x3s2")
+    check(_lib.lib().mpn_maxpool3x3s2(_ptr(x.hi), _ptr(x.lo), _ptr(y.hi), _ptr(y.lo), x.N, x.H, x.W, x.C, x.fmt,
+                                      0 if y.has_h8 else EPI_NO_H8, _stream()), "mpn_maxpool3x3s2")
     stats["launches"] += 1
     return y
 

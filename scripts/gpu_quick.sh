@@ -12,6 +12,23 @@ grep -E "^(FAILED|ERROR)" gpurun_out/t_gpu.log | cut -c1-250 | head -40
 echo "t=$(( $(date +%s) - T0 ))s"
 timeout 900 python bench.py $BENCH_ARGS > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc $?"; tail -3 gpurun_out/bench_n1.err | cut -c1-300
 echo "t=$(( $(date +%s) - T0 ))s"
+# same-box A/B: AB_ENV="MPN_NO_H8=0;MPN_UP_TMA=0" runs one short bench per setting (device-resident value only)
+if [ -n "$AB_ENV" ]; then
+  IFS=';' read -ra SETS <<< "$AB_ENV"
+  for S in "base" "${SETS[@]}"; do
+    if [ "$S" = "base" ]; then E=""; else E="$S"; fi
+    env $E timeout 300 python bench.py --no-extras --no-cpu-baseline --no-fast --steps 20 > gpurun_out/ab.json 2> gpurun_out/ab.err
+    python -c "
+import json,sys
+try:
+    d=json.loads(open('gpurun_out/ab.json').read().strip().splitlines()[-1]); r=d.get('roofline') or {}
+    print('AB %-28s value %.1f img/s  ms %.3f  conv_ms %.3f  frac %.4f  pipe %.3f  sm %s' % ('$S', d['value'], d['ms_per_step'], r.get('kernel_ms_per_step',0), r.get('frac',0), r.get('tensor_pipe_frac',0), (d.get('clocks') or {}).get('sm_mhz')))
+except Exception as e:
+    print('AB $S failed', e); print(open('gpurun_out/ab.err').read()[-600:])
+"
+  done
+  echo "t=$(( $(date +%s) - T0 ))s"
+fi
 python - <<'PY'
 import json
 try:

@@ -56,7 +56,7 @@ def main():
     torch.cuda.synchronize()
     ops.stats["conv_events"] = None
     rows = []
-    for n, (s, e, fl, simt) in zip(names, evs):
+    for n, (s, e, fl, simt, _slots) in zip(names, evs):
         ms = s.elapsed_time(e)
         rows.append((n, ms, fl / ms / 1e9, simt))
     total = e0.elapsed_time(e1)

@@ -28,8 +28,17 @@ def round_fmt(t, fmt):
     return t
 
 
+def strip_h8(a):
+    """The same f16f8 activation stored WITHOUT its e5m2 copy plane (a new, smaller lo buffer: a stray h8 access would fault
+    or read another allocation, not silently work)."""
+    b = ops.Act(a.fmt, a.N, a.H, a.W, a.C, a.hi.device, cstride=a.cstride, has_h8=False)
+    b.hi.copy_(a.hi)
+    b.lo[0].copy_(a.lo[0])
+    return b
+
+
 def conv_case(fmt, N, H, W, Cin, Cout, R, stride, pad, relu=False, sigmoid=False, residual=False, up=False, bn=False,
-              bias=True, out_mode=OUT_ACT, rep=1, seed=0, coffset=0, ctotal=None):
+              bias=True, out_mode=OUT_ACT, rep=1, seed=0, coffset=0, ctotal=None, no_h8=False):
     """Returns (ours NCHW fp32, reference NCHW fp32 with fmt-rounded operands, reference with fp32 operands)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     dev = "cuda"
@@ -63,16 +72,19 @@ def conv_case(fmt, N, H, W, Cin, Cout, R, stride, pad, relu=False, sigmoid=False
     ref_exact = ref(x, w, res, upt)
     ref_rounded = ref(round_fmt(x, fmt), round_fmt(w, fmt), round_fmt(res, fmt) if res is not None else None,
                       round_fmt(upt, fmt) if upt is not None else None)
-    pc = ops.pack_conv(w, b, bnp, fmt)
+    pc = ops.pack_conv(w, b, bnp, fmt, in_no_h8=no_h8)
     xa = ops.act_from_nchw(x, fmt)
     ra = ops.act_from_nchw(res, fmt) if res is not None else None
     ua = ops.act_from_nchw(upt, fmt) if upt is not None else None
+    if no_h8:   # input, shortcut and upsample source without the copy plane; the output too (unless it is a concat slice)
+        xa, ra, ua = strip_h8(xa), (strip_h8(ra) if ra is not None else None), (strip_h8(ua) if ua is not None else None)
     if out_mode == OUT_ACT:
         out = None
         if ctotal is not None:
             out = ops.Act(fmt, N, OH * rep, OW * rep, ctotal, dev, zero=True)
         o = ops.conv2d(xa, pc, stride=stride, pad=pad, relu=relu, sigmoid=sigmoid, residual=ra, up=ua, out=out,
-                       out_coffset=coffset, out_rep=rep)
+                       out_coffset=coffset, out_rep=rep, want_h8=not no_h8)
+        assert o.has_h8 == (not no_h8 or ctotal is not None)
         ours = o.to_nchw()
         if ctotal is not None:
             ours = ours[:, coffset:coffset + Cout]

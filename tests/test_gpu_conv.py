@@ -93,6 +93,34 @@ def test_conv_tcgen05_f16f8(case):
     _check(3, case, 2e-4, 2e-4)
 
 
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_f16f8_without_h8_plane(case):
+    """MPN_IN_NO_H8 / MPN_EPI_NO_H8: input, shortcut, upsample source and output stored as fp16 + e5m2 residual only (3 bytes per
+    element); the weight-residual term runs as fp16 x fp16 (MODE_F16F8B).  At least as accurate as the default variant."""
+    from gpu_util import conv_case, nerr, no_tf32
+    no_tf32()
+    N, H, W, Cin, Cout, R, stride, pad, kw = case
+    ours, ref_r, ref_e = conv_case(3, N, H, W, Cin, Cout, R, stride, pad, no_h8=True, **kw)
+    assert ours.shape == ref_e.shape and torch.isfinite(ours).all()
+    assert nerr(ours, ref_e) <= 2e-4
+    full, _, _ = conv_case(3, N, H, W, Cin, Cout, R, stride, pad, **kw)
+    assert nerr(ours, full) <= 2e-4
+
+
+def test_maxpool_without_h8_plane_and_guard():
+    import torch.nn.functional as F
+    from gpu_util import strip_h8
+    from multiposenet.pytorch_b200 import ops
+    x = torch.randn(2, 64, 17, 23, generator=torch.Generator().manual_seed(3)).cuda()
+    xa = ops.act_from_nchw(x, 3)
+    y = ops.maxpool3x3s2(strip_h8(xa), want_h8=False)
+    assert not y.has_h8 and y.lo.shape[0] == 1
+    assert torch.equal(y.to_nchw(), F.max_pool2d(xa.to_nchw(), 3, 2, 1))
+    w = torch.randn(64, 64, 3, 3).cuda() * 0.05
+    with pytest.raises(ValueError):   # a default-packed convolution must not read a tensor without its copy plane
+        ops.conv2d(y, ops.pack_conv(w, None, None, 3), pad=1)
+
+
 @pytest.mark.parametrize("fmt,tol", [(2, 1e-4), (1, 2e-2), (3, 2e-4)])
 @pytest.mark.parametrize("shape", [(2, 64, 96), (1, 50, 70), (2, 33, 47)])
 def test_tensor_core_stem_vs_torch(fmt, tol, shape):
