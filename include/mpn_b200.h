@@ -291,6 +291,20 @@ int mpn_resize_cubic(const float* src, long long src_plane, int src_pitch, int s
 /* out = (normal + flipped) / 2 in float64 (tester.py:329; flipped may be NULL: out = normal), optionally also as fp32 */
 int mpn_tta_combine(const double* normal, const double* flipped, double* out, float* out32, long long n, void* stream);
 
+/* ---- Detection-subnet training loss: network/losses.py:5-137 (calc_iou + FocalLoss.forward) for the whole
+ * batch, and its gradients.
+ *   cls fp32 [B][A][C] class scores AFTER the sigmoid (posenet.py:109-117), reg fp32 [B][A][4], anchors fp32 [A][4],
+ *   annotations fp32 [B][M][5] = (x1, y1, x2, y2, class), rows with class == -1 are padding (datasets bbox_collater), M <= 256
+ *   cls_loss / reg_loss fp32 [B]: the per-image values the reference stacks (losses.py:94,131); the caller takes the batch mean
+ *   dcls [B][A][C] / dreg [B][A][4] (may be NULL): gradient of gscale_cls * mean_b(cls_loss) + gscale_reg * mean_b(reg_loss)
+ * Anchor <-> annotation IoU without the +1 convention, first maximum, < 0.4 negative / >= 0.5 positive / else ignored, scores
+ * clamped to [1e-4, 1 - 1e-4] (gradient passes inside the range), alpha .25, gamma 2, smooth-L1 beta 1/9, box targets divided
+ * by (.1, .1, .2, .2).  fp32 per-anchor arithmetic in the reference's order, fp64 sums. */
+size_t mpn_focal_loss_workspace_bytes(int B, int A);
+int mpn_focal_loss(const float* cls, const float* reg, const float* anchors, const float* annotations, int B, int A, int C, int M,
+                   float* cls_loss, float* reg_loss, float* dcls, float* dreg, float gscale_cls, float gscale_reg, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,9 @@ _SIGS = {
     "mpn_resize_cubic": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, ctypes.c_double,
                                  ctypes.c_double, c_int, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mpn_tta_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "mpn_focal_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mpn_focal_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "mpn_prn_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mpn_prn_build_inputs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_double,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),

@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["mpn_elementwise.cu", "mpn_conv_simt.cu", "mpn_conv_tc.cu", "mpn_detect.cu", "mpn_train.cu", "mpn_wgrad_tc.cu", "mpn_peaks.cu", "mpn_prn.cu", "mpn_resize.cu"]
+SOURCES = ["mpn_elementwise.cu", "mpn_conv_simt.cu", "mpn_conv_tc.cu", "mpn_detect.cu", "mpn_train.cu", "mpn_wgrad_tc.cu", "mpn_peaks.cu", "mpn_prn.cu", "mpn_resize.cu", "mpn_focal.cu"]
 OUT = os.path.join(HERE, "libmpn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
