@@ -504,3 +504,28 @@ def tta_combine(normal, flipped=None, want_f32=True):
     check(_lib.lib().mpn_tta_combine(_ptr(normal), _ptr(flipped), _ptr(out), _ptr(out32), normal.numel(), _stream()), "mpn_tta_combine")
     stats["launches"] += 1
     return out, out32
+
+
+# ------------------------------------------------------------------ detection-subnet training loss (network/losses.py:5-137)
+def focal_loss(cls, reg, anchors, annotations, want_grads=True, gscale_cls=1.0, gscale_reg=1.0):
+    """cls [B,A,C] (after the sigmoid), reg [B,A,4], anchors [1,A,4] or [A,4], annotations [B,M,5] (class -1 = padding), CUDA fp32.
+    Returns (cls_loss [B], reg_loss [B], dcls or None, dreg or None): the per-image losses of FocalLoss.forward and the gradients
+    of gscale_cls * mean(cls_loss) + gscale_reg * mean(reg_loss)."""
+    assert cls.is_cuda and cls.dtype == torch.float32 and reg.dtype == torch.float32 and annotations.dtype == torch.float32
+    cls, reg, annotations = cls.contiguous(), reg.contiguous(), annotations.contiguous()
+    anchors = anchors.reshape(-1, 4).contiguous()
+    B, A, C = cls.shape
+    M = annotations.shape[1]
+    assert reg.shape == (B, A, 4) and anchors.shape[0] == A and annotations.shape == (B, M, 5)
+    L = _lib.lib()
+    dev = cls.device
+    cl = torch.empty((B,), dtype=torch.float32, device=dev)
+    rl = torch.empty((B,), dtype=torch.float32, device=dev)
+    dcls = torch.empty_like(cls) if want_grads else None
+    dreg = torch.empty_like(reg) if want_grads else None
+    wsb = L.mpn_focal_loss_workspace_bytes(B, A)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    check(L.mpn_focal_loss(_ptr(cls), _ptr(reg), _ptr(anchors), _ptr(annotations), B, A, C, M, _ptr(cl), _ptr(rl), _ptr(dcls), _ptr(dreg),
+                           float(gscale_cls), float(gscale_reg), _ptr(ws), wsb, _stream()), "mpn_focal_loss")
+    stats["launches"] += 2
+    return cl, rl, dcls, dreg
