@@ -221,17 +221,41 @@ class poseNet(nn.Module):
             engines[key] = e
         return e
 
+    def detection_train_engine(self, precision=None):
+        from ..detect_train import DetectionTrainEngine
+        precision = precision or self._precision or _engine.DEFAULT_PRECISION
+        if precision in ("f16f8", "fp32"):  # the weight-gradient kernel reads bf16 planes
+            precision = "bf16x3"
+        engines = self.__dict__.setdefault("_engines", {})
+        key = ("train-det", precision, id(self))
+        e = engines.get(key)
+        if e is None or e.model is not self:
+            e = DetectionTrainEngine(self, precision)
+            engines[key] = e
+        return e
+
     def forward(self, x):
         img_batch, subnet_name = x
         if subnet_name == "prn_subnet":
             return self.prn_forward(img_batch)
         bn_batch_stats = self.training and self.fpn.bn1.training  # model.train() without freeze_bn (trainer.py:170-174)
         wants_grad = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
+        if wants_grad and subnet_name == "detection_subnet":
+            # detection-subnet training (training/multipose_detection_train.py): frozen trunk and BatchNorm, RetinaNet neck + towers
+            if not (torch.is_tensor(img_batch) and img_batch.is_cuda):
+                raise RuntimeError("poseNet.forward needs a CUDA image batch (no CPU / eager fallback)")
+            from ..detect_train import DetectionTrainFunction
+            deng = self.detection_train_engine()
+            deng.check_frozen()
+            with torch.cuda.device(img_batch.device):
+                params = [p for _, p in deng.trainable_parameters()]
+                cls, reg, anchors = DetectionTrainFunction.apply(deng, img_batch, *params)
+            return [], [cls, reg, anchors]
         if wants_grad or (bn_batch_stats and subnet_name == "keypoint_subnet"):
             if subnet_name != "keypoint_subnet":
                 raise NotImplementedError(
-                    "only the keypoint-subnet training step (BASELINE config 4, SURVEY 8(a17)) has backward kernels; "
-                    "detection-subnet training (network/losses.py) is SURVEY 8(f) rank 4 and there is no eager fallback")
+                    "the keypoint-subnet (BASELINE config 4) and detection-subnet training steps have backward kernels; "
+                    "training through the entire_net branch is not a reference configuration and there is no eager fallback")
             if not bn_batch_stats:
                 raise NotImplementedError("keypoint-subnet training with frozen BatchNorm (freeze_bn() in train mode) is not "
                                           "built: the reference trains this subnet with batch statistics (trainer.py:170-174)")
@@ -280,7 +304,7 @@ class poseNet(nn.Module):
         if subnet_name == "keypoint_subnet":
             return build_keypoint_loss(saved_for_loss, args[1], args[2])
         if subnet_name == "detection_subnet":
-            raise NotImplementedError("detection training loss (network/losses.py) is outside the hot path (SURVEY 8(f) rank 4)")
+            return build_detection_loss(saved_for_loss, args[1])
         if subnet_name == "prn_subnet":
             return build_prn_loss(saved_for_loss, args[1])
         return 0
@@ -309,6 +333,20 @@ def build_keypoint_loss(saved_for_loss, heat_temp, heat_weight):
     last = saved_for_loss[-1].detach()[:, :18]
     log["max_ht"] = last.max().item()
     log["min_ht"] = last.min().item()
+    return total, log
+
+
+def build_detection_loss(saved_for_loss, anno):
+    """posenet.py:405-424: saved_for_loss = [classifications, regressions, anchors]; mean focal + smooth-L1 loss."""
+    from .losses import FocalLoss
+    log = OrderedDict()
+    classification_loss, regression_loss = FocalLoss()(*saved_for_loss, anno)
+    classification_loss = classification_loss.mean()
+    regression_loss = regression_loss.mean()
+    total = classification_loss + regression_loss
+    log["total_loss"] = total.item()
+    log["classification_loss"] = classification_loss.item()
+    log["regression_loss"] = regression_loss.item()
     return total, log
 
 

@@ -269,6 +269,36 @@ def tta_golden():
     print("tta", mult, heat_n.shape, [len(b) for b in bbox_n])
 
 
+def focal_golden():
+    """tests/golden/focal_loss.npz: the reference's own FocalLoss (network/losses.py:27-137) and its autograd gradients on
+    losses_oracle.focal_case()."""
+    from . import losses_oracle as lo
+    refshim.import_reference()
+    from network.losses import FocalLoss
+    cls, reg, anchors, ann = (torch.from_numpy(a) for a in lo.focal_case(with_empty=False))
+    cls.requires_grad_(True)
+    reg.requires_grad_(True)
+    # torch >= 1.2 compatibility shim (third shim beside refshim's two): losses.py:120 computes `1 - positive_indices` on what
+    # torch 0.4 returned as a ByteTensor and torch 2.x returns as a bool tensor, for which `-` raises.  The value is never used
+    # (negative_indices is dead code), so the shim only lets the line execute: bool operands of __rsub__ are viewed as uint8.
+    real_rsub = torch.Tensor.__rsub__
+
+    def rsub(self, other):
+        return real_rsub(self.to(torch.uint8) if self.dtype == torch.bool else self, other)
+    torch.Tensor.__rsub__ = rsub
+    try:
+        with torch.enable_grad():
+            cl, rl = FocalLoss()(cls, reg, anchors, ann)
+            total = cl.mean() + rl.mean()                                       # posenet.py:413-416
+            total.backward()
+    finally:
+        torch.Tensor.__rsub__ = real_rsub
+    g = {"cls_loss": cl.detach().numpy(), "reg_loss": rl.detach().numpy(), "dcls": cls.grad.numpy(), "dreg": reg.grad.numpy(),
+         "meta": np.array(json.dumps({"case": "losses_oracle.focal_case(with_empty=False)", "torch": torch.__version__}))}
+    np.savez_compressed(os.path.join(OUT, "focal_loss.npz"), **g)
+    print("focal", float(cl), float(rl), int((cls.grad != 0).sum()), int((reg.grad != 0).sum()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     meta = {"torch": torch.__version__, "numpy": np.__version__, "reference": refshim.REF_ROOT,
@@ -335,6 +365,7 @@ def main():
     train_golden()
     prn_forward_golden()
     tta_golden()
+    focal_golden()
     print("wrote", sorted(os.listdir(OUT)))
 
 
@@ -347,4 +378,6 @@ if __name__ == "__main__":
         sys.exit(prn_forward_golden())
     if "tta" in sys.argv[1:]:
         sys.exit(tta_golden())
+    if "focal" in sys.argv[1:]:
+        sys.exit(focal_golden())
     sys.exit(main())

@@ -236,3 +236,26 @@ def test_tta_oracle_vs_reference_golden(golden_dir):
     assert np.abs(to.handle_heat(hn, hf) - g["heat_avg"]).max() <= tol
     assert hn.dtype == np.float64
     assert bn == json.loads(str(g["bbox_normal"]))
+
+
+def test_focal_loss_oracle_vs_reference_golden(golden_dir):
+    """f4 pinned: the reference's own FocalLoss.forward values and autograd gradients (tests/golden/focal_loss.npz)."""
+    from oracle import losses_oracle as lo
+    g = _load(golden_dir, "focal_loss.npz")
+    cls, reg, anchors, ann = (torch.from_numpy(a) for a in lo.focal_case(with_empty=False))
+    cls.requires_grad_(True)
+    reg.requires_grad_(True)
+    with torch.enable_grad():
+        cl, rl, _, _ = lo.focal_loss(cls, reg, anchors, ann)
+        (cl.mean() + rl.mean()).backward()
+    np.testing.assert_allclose(cl.detach().numpy(), g["cls_loss"], rtol=1e-6)
+    np.testing.assert_allclose(rl.detach().numpy(), g["reg_loss"], rtol=1e-6)
+    np.testing.assert_allclose(cls.grad.numpy(), g["dcls"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(reg.grad.numpy(), g["dreg"], rtol=1e-5, atol=1e-9)
+    # an image without annotations contributes zero to both losses (losses.py:53-57) and gets zero gradients
+    cls2, reg2, anchors2, ann2 = (torch.from_numpy(a) for a in lo.focal_case(with_empty=True))
+    cls2.requires_grad_(True)
+    with torch.enable_grad():
+        cl2, rl2, per_c, per_r = lo.focal_loss(cls2, reg2, anchors2, ann2)
+        (cl2.mean() + rl2.mean()).backward()
+    assert float(per_c[1]) == 0.0 and float(per_r[1]) == 0.0 and float(cls2.grad[1].abs().max()) == 0.0
