@@ -104,6 +104,12 @@ int mpn_device_supports_tcgen05(void);
 /* ---- conv2d (+BN-fold/bias/residual/upsample-add/ReLU/sigmoid): fpn.py:14-25,42-74,99-124,
  *      posenet.py:37-49,79-92,165-187.  fmt F32 -> CUDA-core kernel, BF16/BF16X2 -> tcgen05+TMA. */
 int mpn_conv2d_fwd(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream);
+/* One layer applied to several tensors with SHARED weights in ONE persistent launch -- a RetinaNet tower layer over the five
+ * pyramid levels (posenet.py:262-263: `torch.cat([self.regressionModel(feature) for feature in features])`).  descs / ptrs are
+ * arrays of nseg (<= 5) entries that differ only in N, H, W, OH, OW and the x / y pointers; stride 1, no shortcut / upsample /
+ * replication; tensor-core formats only.  The levels' tiles form one tile list, so the small levels fill the SMs the large
+ * ones leave idle instead of running as latency-bound launches of their own. */
+int mpn_conv2d_fwd_multi(const mpn_conv_desc* descs, const mpn_conv_ptrs* ptrs, int nseg, void* stream);
 /* fp32-input variant used for the stem: x is fp32 NHWC (Cin may be 3), output in d->fmt. */
 int mpn_conv2d_fwd_f32in(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream);
 

@@ -41,6 +41,7 @@ _SIGS = {
     "mpn_sizeof_conv_ptrs": (c_int, []),
     "mpn_device_supports_tcgen05": (c_int, []),
     "mpn_conv2d_fwd": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvPtrs), c_void_p]),
+    "mpn_conv2d_fwd_multi": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvPtrs), c_int, c_void_p]),
     "mpn_conv2d_fwd_f32in": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvPtrs), c_void_p]),
     "mpn_pack_filter_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_pack_filter_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -209,6 +209,19 @@ extern "C" int mpn_conv2d_fwd(const mpn_conv_desc* d, const mpn_conv_ptrs* p, vo
   return MPN_ERR_ARG;
 }
 
+int mpn_conv_tc_launch_multi(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg, void* stream);  // mpn_conv_tc.cu
+
+extern "C" int mpn_conv2d_fwd_multi(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg, void* stream) {
+  MPN_CHECK_ARG(ds && ps && nseg >= 1, "conv (multi-level): null descriptor array");
+  MPN_CHECK_ARG(ds->fmt == MPN_FMT_BF16 || ds->fmt == MPN_FMT_BF16X2 || ds->fmt == MPN_FMT_F16F8,
+                "conv (multi-level): tensor-core formats only (got fmt %d)", ds->fmt);
+  for (int i = 0; i < nseg; ++i) {
+    int rc = check_desc(ds + i, ps + i);
+    if (rc) return rc;
+  }
+  return mpn_conv_tc_launch_multi(ds, ps, nseg, stream);
+}
+
 extern "C" int mpn_conv2d_fwd_f32in(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream) {
   MPN_CHECK_ARG(d, "conv: null descriptor");
   MPN_CHECK_ARG(d->fmt != MPN_FMT_F16F8, "conv(fp32 input): F16F8 outputs come from the tensor-core stem only (MPN_TC_STEM=1)");

@@ -47,15 +47,28 @@ constexpr int BIAS_BYTES = 1024;  // EPI_TMA: the tile's folded-BN bias, 2 halve
 constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 32 fp32 accumulators, 16B chunks XOR-swizzled
 
 struct Maps {
-  CUtensorMap a[3][4];  // [plane hi/lo(/h8)][phase hp*2+wp]; F16F8: planes 1, 2 are byte tensors, 64B swizzle
+  CUtensorMap a[3][5];  // [plane hi/lo(/h8)][phase hp*2+wp, or the segment of a multi-level launch]; F16F8: planes 1, 2 are byte tensors, 64B swizzle
   CUtensorMap b[3];     // [plane]
   CUtensorMap bs[3];    // [plane] filter map with a tail_bn-row box (tail sub-tiles)
-  CUtensorMap y[3];     // [plane] output tensor (EPI_TMA): box {32 ch, TW, TH, TN}, 64B swizzle (F16F8 byte planes: none)
+  CUtensorMap y[3][5];  // [plane][segment] output tensor (EPI_TMA): box {32 ch, TW, TH, TN}, 64B swizzle (F16F8 byte planes: none)
   CUtensorMap r[2];     // [plane] residual tensor (res_mma): box {64 ch, TW, TH, TN}, 128B swizzle = MN-major B operand
   CUtensorMap ident;    // 128 x 128 bf16 identity matrix (res_mma): box {64, 128}, K-major A operand
 };
 
+// Multi-level launches (mpn_conv2d_fwd_multi: one layer of a RetinaNet tower over the five pyramid levels, posenet.py:262-263):
+// the persistent tile list is the concatenation of the levels' tiles; a level ("segment") has its own geometry, input / output
+// tensor maps and, for fp32 outputs, its offset in the concatenated output.  Single launches are one segment.
+constexpr int MAX_SEG = 5;
+struct Seg {
+  int N, OH, OW, TW, TH, TN, rows;
+  int tiles_w, tiles_h, tiles_n, m_tiles;
+  int unit0;           // first schedulable M unit (pair kernels: pair of M tiles) of this segment
+  long long out_off;   // EPI_F32: element offset of this segment's output inside y_hi
+};
+
 struct TcParams {
+  int nseg;
+  Seg seg[MAX_SEG];
   int N, OH, OW, Cout;
   int TW, TH, TN, rows;
   int tiles_w, tiles_h, tiles_n, tiles_co, total_tiles;
@@ -86,7 +99,7 @@ struct TcParams {
 };
 
 struct TileCoord {
-  int co0, ncols, tw_i, th_i, tn_i;
+  int co0, ncols, tw_i, th_i, tn_i, seg;
 };
 
 template <int BN, bool PAIR = false>
@@ -101,20 +114,25 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, in
     c.ncols = P.tail_bn;
   }
   const int co_t = t % P.tiles_co;
-  int mt = t / P.tiles_co;
+  int mt = t / P.tiles_co;   // M unit over all segments
   c.co0 = co_t * BN + sub * c.ncols;
+  int sg = 0;
+  while (sg + 1 < P.nseg && mt >= P.seg[sg + 1].unit0) ++sg;
+  const Seg& g = P.seg[sg];
+  c.seg = sg;
+  mt -= g.unit0;
   if (PAIR) {
     mt = 2 * mt + rank;
-    if (mt >= P.m_tiles) {  // odd tile count: the pair's second half is a box beyond the last image (zero loads, clipped stores)
+    if (mt >= g.m_tiles) {  // odd tile count: the pair's second half is a box beyond the last image (zero loads, clipped stores)
       c.tw_i = c.th_i = 0;
-      c.tn_i = P.tiles_n;
+      c.tn_i = g.tiles_n;
       return c;
     }
   }
-  c.tw_i = mt % P.tiles_w;
-  mt /= P.tiles_w;
-  c.th_i = mt % P.tiles_h;
-  c.tn_i = mt / P.tiles_h;
+  c.tw_i = mt % g.tiles_w;
+  mt /= g.tiles_w;
+  c.th_i = mt % g.tiles_h;
+  c.tn_i = mt / g.tiles_h;
   return c;
 }
 
@@ -245,9 +263,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
     for (int p = 0; p < NMAPS; ++p) {
       prefetch_tmap(&maps.b[p]);
-      if (!(F8B && p == 2)) prefetch_tmap(&maps.a[p][0]);
+      for (int sg = 0; sg < P.nseg; ++sg) {
+        if (!(F8B && p == 2)) prefetch_tmap(&maps.a[p][sg]);
+        if (TMAEPI && !(F8 && p == 2 && (P.flags & MPN_EPI_NO_H8))) prefetch_tmap(&maps.y[p][sg]);
+      }
       if (P.tail_split > 1) prefetch_tmap(&maps.bs[p]);
-      if (TMAEPI && !(F8 && p == 2 && (P.flags & MPN_EPI_NO_H8))) prefetch_tmap(&maps.y[p]);
       if (TMAEPI && (P.res_mma || RESLD) && p < 2) prefetch_tmap(&maps.r[p]);
     }
     for (int s = 0; s < STAGES; ++s) {
@@ -300,13 +320,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       const bool tail = tc.ncols != BN;
       const int brows = PAIR ? tc.ncols / 2 : tc.ncols;                     // filter rows this CTA loads
       // bytes of one K block landing in this CTA; the leader's barrier of a pair expects both CTAs' bytes
-      const uint32_t tx_bytes = (uint32_t)(P.rows * A_ROW_TX + brows * B_ROW) * (PAIR ? 2u : 1u);
+      const Seg& g = P.seg[tc.seg];
+      const uint32_t tx_bytes = (uint32_t)(g.rows * A_ROW_TX + brows * B_ROW) * (PAIR ? 2u : 1u);
       // narrow tail tiles are latency-bound on the ring: pack as many K blocks as fit into one stage (sub-blocks of
       // [A planes][B planes], the B planes ncols*128 bytes apart) so that twice the bytes are in flight
       const uint32_t bplane = tail ? (uint32_t)brows * 128u : (uint32_t)B_TILE_BYTES;
       const uint32_t sub_bytes = (uint32_t)A_STAGE + (bplane >> 7) * (uint32_t)B_ROW;
       const int kpack = (tail && !PAIR) ? (int)(STAGE_BYTES / sub_bytes) : 1;
-      const int ow0 = tc.tw_i * P.TW, oh0 = tc.th_i * P.TH, n0 = tc.tn_i * P.TN, co0 = tc.co0 + cta_rank * brows;
+      const int ow0 = tc.tw_i * g.TW, oh0 = tc.th_i * g.TH, n0 = tc.tn_i * g.TN, co0 = tc.co0 + cta_rank * brows;
       int u = 0, ki = 0;
       for (int tap = 0; tap < P.R * P.S; ++tap) {
         const int r = tap / P.S, s = tap - r * P.S;
@@ -325,6 +346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           ph = 0;
           hc = 1 << 24;
         }
+        if (P.nseg > 1) ph = tc.seg;   // multi-level launches are stride 1: the map slot is the segment
         for (int kb = 0; kb < P.kb_per_tap; ++kb) {
           if (u == 0) {
             const int group = min(kpack, num_k_iters - ki);
@@ -549,7 +571,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
         const int rsw = (rrow >> 1) & 3;
         const bool issuer = (q == 0 && lane == 0);
-        const int ow0 = tw_i * P.TW, oh0 = th_i * P.TH, n0 = tn_i * P.TN;
+        const Seg& g = P.seg[tc.seg];
+        const int ow0 = tw_i * g.TW, oh0 = th_i * g.TH, n0 = tn_i * g.TN;
         long long res_off = 0;
         const bool res_lsu = !RESLD && P.res_cstride > 0 && !P.res_mma;
         if (res_lsu) {
@@ -716,11 +739,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           named_bar_sync(1 + half, 128);
           if (issuer) {
-            tma_store_4d(&maps.y[0], stg_u32, cbase, ow0, oh0, n0);
-            if (SPLIT) tma_store_4d(&maps.y[1], stg_u32 + 8192, cbase, ow0, oh0, n0);
+            tma_store_4d(&maps.y[0][tc.seg], stg_u32, cbase, ow0, oh0, n0);
+            if (SPLIT) tma_store_4d(&maps.y[1][tc.seg], stg_u32 + 8192, cbase, ow0, oh0, n0);
             if (F8) {
-              tma_store_4d(&maps.y[1], stg_u32 + 8192, cbase, ow0, oh0, n0);
-              if (want_h8) tma_store_4d(&maps.y[2], stg_u32 + 12288, cbase, ow0, oh0, n0);
+              tma_store_4d(&maps.y[1][tc.seg], stg_u32 + 8192, cbase, ow0, oh0, n0);
+              if (want_h8) tma_store_4d(&maps.y[2][tc.seg], stg_u32 + 12288, cbase, ow0, oh0, n0);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -869,9 +892,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       } else {
         // ---- fp32 outputs (heads: Cout <= 64): thread-per-row, 16 columns at a time
         const int row = q * 32 + lane;
-        const int tw = row % P.TW, th = (row / P.TW) % P.TH, tn = row / (P.TW * P.TH);
-        const int ow = tw_i * P.TW + tw, oh = th_i * P.TH + th, n = tn_i * P.TN + tn;
-        const bool valid = row < P.rows && ow < P.OW && oh < P.OH && n < P.N;
+        const Seg& g = P.seg[tc.seg];
+        const int tw = row % g.TW, th = (row / g.TW) % g.TH, tn = row / (g.TW * g.TH);
+        const int ow = tw_i * g.TW + tw, oh = th_i * g.TH + th, n = tn_i * g.TN + tn;
+        const bool valid = row < g.rows && ow < g.OW && oh < g.OH && n < g.N;
+        const int OHr = g.OH * rep, OWr = g.OW * rep;   // shadows the launch-wide values: per segment
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
 #pragma unroll 1
@@ -899,7 +924,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           for (int ry = 0; ry < rep; ++ry)
             for (int rx = 0; rx < rep; ++rx) {
               if (P.out_mode == MPN_OUT_F32_NHWC) {
-                float* dst = (float*)P.y_hi + (long long)n * nstride +
+                float* dst = (float*)P.y_hi + g.out_off + (long long)n * nstride +
                              ((long long)(oh * rep + ry) * OWr + (ow * rep + rx)) * P.out_cstride + P.out_coffset + cbase;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) if (j < nc) dst[j] = v[j];
@@ -1040,7 +1065,31 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
 
 }  // namespace
 
-int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream) {
+// ds / ps: nseg descriptors that differ only in N, H, W, OH, OW and the x / y pointers (one per pyramid level); nseg == 1 is the
+// ordinary launch.
+static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg, void* stream) {
+  const mpn_conv_desc* d = ds;
+  const mpn_conv_ptrs* p = ps;
+  MPN_CHECK_ARG(nseg >= 1 && nseg <= MAX_SEG, "conv(tcgen05): 1..%d segments per launch", MAX_SEG);
+  for (int sg = 1; sg < nseg; ++sg) {
+    const mpn_conv_desc* e = ds + sg;
+    MPN_CHECK_ARG(e->Cin == d->Cin && e->Cout == d->Cout && e->R == d->R && e->S == d->S && e->stride == d->stride && e->pad == d->pad &&
+                      e->fmt == d->fmt && e->flags == d->flags && e->out_mode == d->out_mode && e->in_cstride == d->in_cstride &&
+                      e->out_cstride == d->out_cstride && e->out_coffset == d->out_coffset && e->out_nstride == d->out_nstride &&
+                      e->acc_scale == d->acc_scale,
+                  "conv(tcgen05) multi-level launch: the levels must share filter, format, flags and output strides");
+    MPN_CHECK_ARG(ps[sg].w_hi == p->w_hi && ps[sg].w_lo == p->w_lo && ps[sg].bias == p->bias && ps[sg].scale == p->scale,
+                  "conv(tcgen05) multi-level launch: the levels must share the packed filter and bias");
+  }
+  if (nseg > 1) {
+    for (int sg = 0; sg < nseg; ++sg) {
+      const mpn_conv_desc* e = ds + sg;
+      MPN_CHECK_ARG(e->stride == 1 && e->res_cstride == 0 && e->up_cstride == 0 && e->out_rep == 1 && !e->k_overlap && !e->in_wpitch &&
+                        !e->in_hpitch && e->OH == e->H + 2 * e->pad - e->R + 1 && e->OW == e->W + 2 * e->pad - e->S + 1 && e->N > 0,
+                    "conv(tcgen05) multi-level launch: stride-1 convolutions without shortcut / upsample / replication only");
+      MPN_CHECK_ARG(e->out_mode == MPN_OUT_ACT || e->out_nstride > 0, "conv(tcgen05) multi-level launch: fp32 outputs need out_nstride");
+    }
+  }
   const bool split = d->fmt == MPN_FMT_BF16X2;
   const bool f8 = d->fmt == MPN_FMT_F16F8;
   const bool f8b = f8 && (d->flags & MPN_IN_NO_H8);   // input without its h8 plane: fp16 weight-residual term (MODE_F16F8B)
@@ -1076,6 +1125,23 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   P.tiles_w = mpn_divup(d->OW, P.TW);
   P.tiles_h = mpn_divup(d->OH, P.TH);
   P.tiles_n = mpn_divup(d->N, P.TN);
+  // per-segment geometry (segment 0 = the values above); unit0 is filled in once pair / single-CTA scheduling is known
+  P.nseg = nseg;
+  long long m_tiles_all = 0;
+  for (int sg = 0; sg < nseg; ++sg) {
+    const mpn_conv_desc* e = ds + sg;
+    Seg& g = P.seg[sg];
+    g.N = e->N; g.OH = e->OH; g.OW = e->OW;
+    if (sg == 0) { g.TW = P.TW; g.TH = P.TH; g.TN = P.TN; }
+    else choose_tile(e->N, e->OH, e->OW, &g.TW, &g.TH, &g.TN, false);
+    g.rows = g.TW * g.TH * g.TN;
+    g.tiles_w = mpn_divup(e->OW, g.TW);
+    g.tiles_h = mpn_divup(e->OH, g.TH);
+    g.tiles_n = mpn_divup(e->N, g.TN);
+    g.m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+    g.out_off = (long long)(((const char*)ps[sg].y_hi - (const char*)p->y_hi) / 4);   // fp32 outputs: element offset of the level
+    m_tiles_all += g.m_tiles;
+  }
   // ---- tile plan.  A persistent launch runs `rounds` full rounds of G = min(tiles, SMs) tiles plus a partial round of
   // `rem` tiles that would leave most SMs idle; the plan cuts those rem tiles into s sub-tiles of BN/s columns (>= 32)
   // so the tail costs one narrow tile instead of one full tile.  Relative tile cost ~ (columns + 64): the fixed part is
@@ -1089,7 +1155,7 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   }
   static const int split256 = getenv("MPN_SPLIT_BN256") ? atoi(getenv("MPN_SPLIT_BN256")) : -1;
   static const int tail_on = getenv("MPN_TAIL_SPLIT") ? atoi(getenv("MPN_TAIL_SPLIT")) : 1;
-  const long long m_tiles = (long long)P.tiles_w * P.tiles_h * P.tiles_n;
+  const long long m_tiles = m_tiles_all;
   const bool f32out = d->out_mode != MPN_OUT_ACT;
   // Activation outputs without upsample-add / replication go through the TMA-store epilogue (MPN_EPI_TMA=0 forces the LSU
   // one); there a split-format residual without an epilogue scale is added by the tensor core (MPN_RES_MMA=0: by the LSU).
@@ -1116,7 +1182,12 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   int BN = d->Cout > 128 ? 256 : d->Cout > 64 ? 128 : d->Cout > 32 ? 64 : 32;
   if (f8b && !pair && BN > 128) BN = 128;   // 256 filter rows x 320 B per K block do not leave room for a 2-stage ring
   int tail_s = 1;
-  const long long sched_m = pair ? (m_tiles + 1) / 2 : m_tiles;   // schedulable M units
+  long long sched_m = 0;                                           // schedulable M units (pair kernels: pairs of M tiles of a level)
+  for (int sg = 0; sg < nseg; ++sg) {
+    P.seg[sg].unit0 = (int)sched_m;
+    sched_m += pair ? (P.seg[sg].m_tiles + 1) / 2 : P.seg[sg].m_tiles;
+  }
+  MPN_CHECK_ARG(nseg == 1 || f32out || (epi_tma && !res_tma && !res_mma), "conv(tcgen05) multi-level launch: TMA-store or fp32 epilogue only");
   const int sched_sms = pair ? sms / 2 : sms;                      // ... and the units that run at once
   {
     int cand[3] = {BN, 0, 0};
@@ -1208,6 +1279,19 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
       if (rc) return rc;
     }
     MPN_CHECK_ARG(!(P.phase_empty & 1), "conv(tcgen05): empty input");
+    for (int sg = 1; sg < nseg; ++sg) {   // multi-level launch (stride 1, dense tensors): map slot = segment
+      const mpn_conv_desc* e = ds + sg;
+      const Seg& g = P.seg[sg];
+      const long long xpl = (long long)e->N * e->H * e->W * e->in_cstride;
+      const char* xs = (const char*)(pl == 0 ? ps[sg].x_hi : ps[sg].x_lo) + (f8 && pl == 2 ? xpl : 0);
+      MPN_CHECK_ARG(ps[sg].x_hi && (pl == 0 || ps[sg].x_lo), "conv(tcgen05) multi-level launch: missing input plane");
+      cuuint64_t dims[4] = {(cuuint64_t)e->Cin, (cuuint64_t)e->W, (cuuint64_t)e->H, (cuuint64_t)e->N};
+      cuuint64_t strides[3] = {(cuuint64_t)e->in_cstride * es, (cuuint64_t)e->W * e->in_cstride * es,
+                               (cuuint64_t)e->H * e->W * e->in_cstride * es};
+      cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TN};
+      int rc = encode(fn, &maps.a[pl][sg], xs, 4, dims, strides, box, swz, dt);
+      if (rc) return rc;
+    }
   }
   // ---- filter planes: [Cout, R*S*Cin] K-major.  F16F8: hi fp16 | lo8 bytes | h8 bytes; MPN_IN_NO_H8: hi fp16 | lo16 fp16 | h8 bytes
   for (int pl = 0; pl < planes; ++pl) {
@@ -1230,18 +1314,24 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
     }
   }
   if (epi_tma) {
-    const long long nstride = d->out_nstride > 0 ? d->out_nstride : (long long)d->OH * d->OW * d->out_cstride;
-    for (int pl = 0; pl < planes; ++pl) {
-      if (f8 && pl == 2 && (d->flags & MPN_EPI_NO_H8)) continue;   // output stored without its h8 plane
-      const bool bytes = f8 && pl > 0;
-      const unsigned long long es = bytes ? 1ULL : 2ULL;
-      cuuint64_t ydims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->OW, (cuuint64_t)d->OH, (cuuint64_t)d->N};
-      cuuint64_t ystr[3] = {(cuuint64_t)d->out_cstride * es, (cuuint64_t)d->OW * d->out_cstride * es, (cuuint64_t)nstride * es};
-      cuuint32_t ybox[4] = {32u, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
-      const char* yb = (const char*)(pl == 0 ? p->y_hi : p->y_lo) + (f8 && pl == 2 ? P.y_plane : 0) + (long long)d->out_coffset * (long long)es;
-      int rc = encode(fn, &maps.y[pl], yb, 4, ydims, ystr, ybox, bytes ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B,
-                      bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-      if (rc) return rc;
+    for (int sg = 0; sg < nseg; ++sg) {
+      const mpn_conv_desc* e = ds + sg;
+      const Seg& g = P.seg[sg];
+      const long long nstride = e->out_nstride > 0 ? e->out_nstride : (long long)e->OH * e->OW * e->out_cstride;
+      const long long ypl = (long long)e->N * nstride;   // elements of one output plane of this level (F16F8: h8 follows lo8)
+      for (int pl = 0; pl < planes; ++pl) {
+        if (f8 && pl == 2 && (d->flags & MPN_EPI_NO_H8)) continue;   // output stored without its h8 plane
+        const bool bytes = f8 && pl > 0;
+        const unsigned long long es = bytes ? 1ULL : 2ULL;
+        cuuint64_t ydims[4] = {(cuuint64_t)e->Cout, (cuuint64_t)e->OW, (cuuint64_t)e->OH, (cuuint64_t)e->N};
+        cuuint64_t ystr[3] = {(cuuint64_t)e->out_cstride * es, (cuuint64_t)e->OW * e->out_cstride * es, (cuuint64_t)nstride * es};
+        cuuint32_t ybox[4] = {32u, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TN};
+        MPN_CHECK_ARG(ps[sg].y_hi && (pl == 0 || ps[sg].y_lo), "conv(tcgen05): missing output plane");
+        const char* yb = (const char*)(pl == 0 ? ps[sg].y_hi : ps[sg].y_lo) + (f8 && pl == 2 ? ypl : 0) + (long long)e->out_coffset * (long long)es;
+        int rc = encode(fn, &maps.y[pl][sg], yb, 4, ydims, ystr, ybox, bytes ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B,
+                        bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        if (rc) return rc;
+      }
     }
   }
   if (res_mma) {
@@ -1321,4 +1411,10 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
   MPN_TC_DISPATCH(MODE_BF16, EPI_LSU)
 #undef MPN_TC_DISPATCH
 #undef MPN_TC_DISPATCH_RES
+}
+
+int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* stream) { return tc_launch(d, p, 1, stream); }
+
+int mpn_conv_tc_launch_multi(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg, void* stream) {
+  return tc_launch(ds, ps, nseg, stream);
 }

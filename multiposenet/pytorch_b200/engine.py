@@ -40,6 +40,8 @@ MAX_GRAPHS = int(os.environ.get("MPN_MAX_GRAPHS", "4"))
 TC_STEM = os.environ.get("MPN_TC_STEM", "1") == "1"
 USE_STREAMS = os.environ.get("MPN_STREAMS", "0") == "1"  # measured: no gain on B200 (r01c), kept as an option
 LEVEL_STREAMS = os.environ.get("MPN_LEVEL_STREAMS", "1") == "1"  # small pyramid levels of the RetinaNet towers side by side
+# one launch per tower layer over the five pyramid levels (mpn_conv2d_fwd_multi): 10 launches per step instead of 50
+TOWER_MULTI = os.environ.get("MPN_TOWER_MULTI", "1") == "1"
 SMALL_LEVEL_PIXELS = 120 * 80  # batch x H x W of a level that cannot fill the GPU (<= 40 CTA pairs of 2 x 120 pixels)
 
 
@@ -273,7 +275,21 @@ class Engine(object):
         cls = torch.empty((B, A, 1), dtype=torch.float32, device=dev)
         reg = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
         small = [i for i, f in enumerate(feats) if f.N * f.H * f.W <= SMALL_LEVEL_PIXELS]
-        if LEVEL_STREAMS and small and len(small) < len(feats):
+        if TOWER_MULTI and self.fmt != FMT_F32 and len(feats) <= 5:
+            # posenet.py:262-263: the tower's weights are shared by the levels -> one persistent launch per layer whose tile
+            # list is the concatenation of the five levels' tiles (the P5-P7 levels alone are latency-bound launches that
+            # leave most SMs idle); the two towers alternate so that consecutive launches are independent
+            cells = [f.H * f.W for f in feats]
+            offs = [9 * sum(cells[:i]) for i in range(len(feats))]
+            hr, hc = list(feats), list(feats)
+            for n in ("conv1", "conv2", "conv3", "conv4"):
+                hr = ops.conv2d_multi(hr, self._pc("regressionModel." + n, getattr(m.regressionModel, n)), pad=1, relu=True)
+                hc = ops.conv2d_multi(hc, self._pc("classificationModel." + n, getattr(m.classificationModel, n)), pad=1, relu=True)
+            ops.conv2d_multi(hr, self._pc("regressionModel.output", m.regressionModel.output), pad=1, out_mode=OUT_F32_NHWC,
+                             out_tensor=reg, out_elem_offsets=[o * 4 for o in offs], out_cstride=36, out_nstride=A * 4)
+            ops.conv2d_multi(hc, self._pc("classificationModel.output", m.classificationModel.output), pad=1, sigmoid=True,
+                             out_mode=OUT_F32_NHWC, out_tensor=cls, out_elem_offsets=offs, out_cstride=9, out_nstride=A)
+        elif LEVEL_STREAMS and small and len(small) < len(feats):
             # The five convs of a small pyramid level (P5-P7: at most 40 CTA pairs, a serial K loop per CTA) are latency
             # bound and leave most SMs idle.  The large levels run first on the current stream (their persistent kernels
             # want every SM); then the small-level chains of both towers run side by side, one stream per (tower, level).

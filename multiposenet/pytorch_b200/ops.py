@@ -238,6 +238,60 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
     return ret
 
 
+def conv2d_multi(xs, pc, pad=0, relu=False, sigmoid=False, out_mode=OUT_ACT, out_tensor=None, out_elem_offsets=None,
+                 out_cstride=None, out_nstride=0, want_h8=True):
+    """The same stride-1 convolution (shared packed filter) applied to several Acts in ONE persistent launch
+    (mpn_conv2d_fwd_multi): a RetinaNet tower layer over the pyramid levels.  OUT_ACT: returns the list of output Acts;
+    fp32 modes: every level writes at out_elem_offsets[i] of out_tensor (strides as in conv2d)."""
+    L = _lib.lib()
+    n = len(xs)
+    fmt = pc.fmt
+    D, Pp = (ConvDesc * n)(), (ConvPtrs * n)()
+    outs = []
+    flops = 0.0
+    for i, x in enumerate(xs):
+        d, p = D[i], Pp[i]
+        assert x.C == pc.Cin and x.fmt == fmt and not x.wpitch and not x.k_overlap
+        d.N, d.H, d.W, d.Cin = x.N, x.H, x.W, pc.Cin
+        d.Cout, d.R, d.S, d.stride, d.pad = pc.Cout, pc.R, pc.S, 1, pad
+        d.OH, d.OW = x.H + 2 * pad - pc.R + 1, x.W + 2 * pad - pc.S + 1
+        d.fmt, d.in_cstride = fmt, x.cstride
+        d.flags = (EPI_RELU if relu else 0) | (EPI_SIGMOID if sigmoid else 0)
+        if fmt == FMT_F16F8:
+            if getattr(pc, "in_no_h8", False):
+                d.flags |= IN_NO_H8
+            elif not x.has_h8:
+                raise ValueError("this activation was stored without its h8 plane: the convolution reading it must be packed with in_no_h8=True")
+        d.out_mode, d.out_rep, d.out_coffset = out_mode, 1, 0
+        d.w_cout_pad, d.acc_scale = pc.cout_pad, getattr(pc, "acc_scale", 0.0)
+        p.x_hi, p.x_lo = _ptr(x.hi), _ptr(x.lo)
+        p.w_hi, p.w_lo, p.scale, p.bias = _ptr(pc.w_hi), _ptr(pc.w_lo), _ptr(pc.scale), _ptr(pc.bias)
+        if out_mode == OUT_ACT:
+            o = Act(fmt, x.N, d.OH, d.OW, pc.Cout, x.hi.device, has_h8=want_h8)
+            d.out_cstride = o.cstride
+            if fmt == FMT_F16F8 and not o.has_h8:
+                d.flags |= EPI_NO_H8
+            p.y_hi, p.y_lo = _ptr(o.hi), _ptr(o.lo)
+            outs.append(o)
+        else:
+            assert out_tensor is not None and out_tensor.dtype == torch.float32 and out_tensor.is_contiguous() and out_nstride > 0
+            d.out_cstride = pc.Cout if out_cstride is None else out_cstride
+            d.out_nstride = out_nstride
+            p.y_hi = ctypes.c_void_p(out_tensor.data_ptr() + 4 * out_elem_offsets[i])
+        flops += 2.0 * x.N * d.OH * d.OW * pc.Cout * pc.Cin * pc.R * pc.S
+    ev = stats["conv_events"]
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(L.mpn_conv2d_fwd_multi(D, Pp, n, _stream()), "mpn_conv2d_fwd_multi")
+    if ev is not None:
+        e1.record()
+        slots = {FMT_BF16: 1.0, FMT_BF16X2: 3.0, FMT_F16F8: 2.5 if (D[0].flags & IN_NO_H8) else 2.0}.get(fmt, 0.0)
+        ev.append((e0, e1, flops, False, slots))
+    stats["launches"] += 1
+    return outs if out_mode == OUT_ACT else out_tensor
+
+
 def stem_pack_input(img, fmt):
     """fp32 NCHW image -> zero-padded space-to-depth Act [N, H/2+3, W/2 (+3 pitch), 64-wide windows of 16 ch]
     (mpn_stem_pack_input); with pack_stem_filter the 7x7/2 stem becomes a tcgen05 conv (R=4, S=1, Cin=64)."""

@@ -83,5 +83,5 @@ def focal_case(seed=0, hw=(96, 128), batch=3, max_ann=6, with_empty=True):
             w, h = rng.uniform(12, 70), rng.uniform(16, 90)
             x, y = rng.uniform(0, hw[1] - w), rng.uniform(0, hw[0] - h)
             ann[b, i] = [x, y, x + w, y + h, 0]
-    ann[2, 1, 2:4] = ann[2, 1, 0:2] + np.float32(0.4)                        # a sub-pixel box: gt width / height clamp at 1
+    ann[batch - 1, 1, 2:4] = ann[batch - 1, 1, 0:2] + np.float32(0.4)                        # a sub-pixel box: gt width / height clamp at 1
     return cls, reg, anchors, ann

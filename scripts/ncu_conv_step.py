@@ -44,6 +44,12 @@ def main():
 
     if a.names_out:
         ops.conv2d = named
+        real_multi = ops.conv2d_multi
+
+        def named_multi(xs, pc, **kw):
+            names.append("multi[%s] c%d->%d k%d s1" % (",".join("%dx%d" % (t.H, t.W) for t in xs), pc.Cin, pc.Cout, pc.R))
+            return real_multi(xs, pc, **kw)
+        ops.conv2d_multi = named_multi
     for i in range(a.steps):
         ops.stats["conv_events"] = evs = []
         eng.entire_forward_device(x, max_cand=4096)

@@ -38,6 +38,13 @@ def main():
         return real(xa, pc, **kw)
 
     ops.conv2d = named
+    real_multi = ops.conv2d_multi
+
+    def named_multi(xs, pc, **kw):
+        names.append("multi[%s] c%d->%d k%d s1" % (",".join("%dx%d" % (t.H, t.W) for t in xs), pc.Cin, pc.Cout, pc.R))
+        return real_multi(xs, pc, **kw)
+
+    ops.conv2d_multi = named_multi
     for _ in range(2):
         eng.entire_forward_device(x, max_cand=8192)
     torch.cuda.synchronize()

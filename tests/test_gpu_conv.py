@@ -161,3 +161,41 @@ def test_maxpool3x3s2_vs_torch(fmt, shape):
     ref = F.max_pool2d(xr, 3, 2, 1)
     assert y.shape == ref.shape
     assert torch.equal(y, ref)
+
+
+@pytest.mark.parametrize("fmt", [3, 2, 1])
+@pytest.mark.parametrize("B,sizes", [(3, [(12, 16), (6, 8), (3, 4), (2, 2), (1, 1)]), (32, [(30, 40), (15, 20), (8, 10), (4, 5)]), (2, [(60, 80), (7, 9)])])
+def test_multi_level_launch_equals_per_level_launches(fmt, B, sizes):
+    """mpn_conv2d_fwd_multi (one tower layer over the pyramid levels, posenet.py:262-263): the concatenated tile list must give
+    exactly the tensors of the per-level launches -- activation outputs (TMA-store epilogue, CTA pairs, odd tile counts) and the
+    fp32 outputs written at the levels' anchor offsets."""
+    from multiposenet.pytorch_b200 import ops
+    from multiposenet.pytorch_b200._lib import OUT_F32_NHWC
+    g = torch.Generator().manual_seed(1)
+    xs = [ops.act_from_nchw(torch.randn(B, 256, h, w, generator=g).cuda(), fmt) for h, w in sizes]
+    w1 = (torch.randn(256, 256, 3, 3, generator=g) / 48.0).cuda()
+    b1 = torch.randn(256, generator=g).cuda()
+    pc = ops.pack_conv(w1, b1, None, fmt)
+    multi = ops.conv2d_multi(xs, pc, pad=1, relu=True)
+    for x, o in zip(xs, multi):
+        ref = ops.conv2d(x, pc, pad=1, relu=True)
+        assert torch.equal(o.hi, ref.hi) and (o.lo is None or torch.equal(o.lo, ref.lo))
+    # fp32 head outputs (36 = 9 anchors x 4) into the concatenated [B, A, 4] tensor, sigmoid variant with 9 channels
+    for cout, sig in ((36, False), (9, True)):
+        per = cout // 9
+        w2 = (torch.randn(cout, 256, 3, 3, generator=g) / 48.0).cuda()
+        b2 = torch.randn(cout, generator=g).cuda()
+        pc2 = ops.pack_conv(w2, b2, None, fmt)
+        cells = [h * w for h, w in sizes]
+        A = 9 * sum(cells)
+        offs = [9 * sum(cells[:i]) * per for i in range(len(sizes))]
+        out_m = torch.zeros((B, A, per), dtype=torch.float32, device="cuda")
+        out_s = torch.zeros_like(out_m)
+        ops.conv2d_multi(multi, pc2, pad=1, sigmoid=sig, out_mode=OUT_F32_NHWC, out_tensor=out_m, out_elem_offsets=offs, out_cstride=cout,
+                         out_nstride=A * per)
+        for o, off in zip(multi, offs):
+            ops.conv2d(o, pc2, pad=1, sigmoid=sig, out_mode=OUT_F32_NHWC, out_tensor=out_s, out_elem_offset=off, out_cstride=cout,
+                       out_nstride=A * per)
+        torch.cuda.synchronize()
+        assert torch.equal(out_m, out_s)
+        assert float(out_m.abs().min()) > 0.0 or sig   # every anchor slot was written
