@@ -140,6 +140,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, in
 // EPI_TMA_RES = EPI_TMA with the shortcut tensor brought in by TMA as well (32-channel boxes, double-buffered per epilogue half)
 enum { EPI_LSU = 0, EPI_F32 = 1, EPI_TMA = 2, EPI_TMA_RES = 3 };
 constexpr int RES_STAGE_BYTES = 16384;  // per (half, buffer): [hi: rows x 64 B, 64B swizzle][lo: rows x 64 B | lo8: rows x 32 B]
+// Wide epilogue (NG = 4 column groups of four warps, F16F8 shortcut convolutions whose output is stored without h8): per group
+// one 12 KB output staging box and one 12 KB shortcut box, each [hi: rows x 64 B, 64B swizzle][lo8: rows x 32 B at +8192]
+constexpr int WIDE_BOX_BYTES = 12288;
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -215,8 +218,11 @@ __device__ __forceinline__ void split_f16f8x8(const float* w, uint4& hi, uint2& 
 // tcgen05.mma.cta_group::2 per K step for both, so every SM reads half the B operand from shared memory and fills half of
 // it by TMA -- the single-CTA kernel is bound by shared-memory bandwidth (96 B/clk of MMA operand reads + the TMA fill
 // against 128 B/clk), not by the tensor pipe.
-template <int BN, int MODE, int STAGES, int EPI, bool PAIR>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ Maps maps, const TcParams P) {
+template <int BN, int MODE, int STAGES, int EPI, bool PAIR, int NG = 2>
+__global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid_constant__ Maps maps, const TcParams P) {
+  constexpr bool WIDE = NG == 4;             // 16 epilogue warps: four per TMEM lane quarter, each group owns every 4th 32-column chunk
+  constexpr int NEPI = 4 * NG;               // epilogue warps
+  constexpr int NTHREADS = 128 + 128 * NG;   // 4 control warps + the epilogue warps
   constexpr bool SPLIT = MODE == MODE_BF16X2;
   constexpr bool F8B = MODE == MODE_F16F8B;             // operand side: no h8 activation plane, fp16 weight residual
   constexpr bool F8 = MODE == MODE_F16F8 || F8B;        // format side (epilogue, shortcut): fp16 hi + e5m2 lo8 (+ optional h8)
@@ -231,7 +237,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   constexpr int MMA_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
   constexpr bool TMAEPI = EPI == EPI_TMA || EPI == EPI_TMA_RES;
   constexpr bool RESLD = EPI == EPI_TMA_RES;
-  constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES + (RESLD ? 4 * RES_STAGE_BYTES : 0);
+  constexpr int EPI_BYTES = WIDE ? 8 * WIDE_BOX_BYTES : NUM_EPI_WARPS * EPI_STAGE_BYTES + (RESLD ? 4 * RES_STAGE_BYTES : 0);
+  static_assert(!WIDE || (RESLD && PAIR && (MODE == MODE_F16F8 || MODE == MODE_F16F8B)), "the wide epilogue is the F16F8 shortcut epilogue");
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   // c = F32; a, b = BF16 (1) or, for F16F8, F16 (0);  | (N >> 3) << 17 per tile
   constexpr uint32_t IDESC_BASE = (1u << 4) | (F8 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(MMA_M >> 4) << 24);
@@ -276,7 +283,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // pair: the epilogue warps of both CTAs release the leader
+      mbar_init(tempty_bar(a), PAIR ? 2 * NEPI : NEPI);  // pair: the epilogue warps of both CTAs release the leader
     }
     if (RESLD) {
       for (int i = 0; i < 4; ++i) mbar_init(res_full_bar(i >> 1, i & 1), 1);
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // rows >= P.rows of a residual box are never written by TMA but are read (times a zero of I) by the MMA:
     // make sure no stale NaN/Inf bit pattern of an earlier kernel sits there
     uint4* z = reinterpret_cast<uint4*>(smem_gen);
-    for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += NUM_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += NTHREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
@@ -525,6 +532,138 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // 32-column chunks of parity (w-4)>>2, so each scheduler has two independent instruction streams.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
+    if constexpr (WIDE) {
+      // =============== wide epilogue: 4 column groups x 4 warps (one per TMEM lane quarter) ===============
+      // The 1x1 convolutions with a shortcut (bottleneck conv3) are bound by this epilogue, not by the tensor pipe or HBM (ncu
+      // r02d: 10 instructions per output element, two warps per SM sub-partition, issue slots 37 % active).  Here every
+      // sub-partition runs four epilogue warps; group `half` (0..3) owns the 32-column chunks half, half + 4, ... of a tile and
+      // works in 16-column register blocks (<= 96 registers per thread at 640 threads).  Per group: one output staging box and
+      // ONE shortcut box; the shortcut box of the group's next chunk is requested as soon as every thread of the group has read
+      // the current one (barrier B below), the other three groups cover its latency.
+      const int grp = half;
+      const int row = q * 32 + lane;
+      const int sw = (row >> 1) & 3;
+      const bool issuer = (q == 0 && lane == 0);
+      uint8_t* stg = epi_stage + grp * WIDE_BOX_BYTES;
+      const uint32_t stg_u32 = smem_base + STAGES * STAGE_BYTES + grp * WIDE_BOX_BYTES;
+      const uint8_t* rs = epi_stage + (4 + grp) * WIDE_BOX_BYTES;
+      const uint32_t rs_u32 = smem_base + STAGES * STAGE_BYTES + (4 + grp) * WIDE_BOX_BYTES;
+      const uint32_t rbar = res_full_bar(grp >> 1, grp & 1);
+      const uint32_t res_bytes = (uint32_t)P.rows * 96u;
+      float* bias_g = bias_smem + grp * 64;
+      const uint32_t lead_tempty0 = mapa_shared(tempty_bar(0), 0);
+      const float as = P.acc_scale;
+      // prefetch cursor (issuer thread only): the next (tile, chunk) of this group's sequence whose shortcut box is not requested yet
+      int pf_tile = tile0, pf_c0 = grp * 32;
+      auto pf_issue = [&]() {
+        while (pf_tile < P.total_tiles) {
+          const TileCoord t = decode_tile<BN, PAIR>(P, pf_tile, cta_rank);
+          if (pf_c0 < t.ncols && t.co0 + pf_c0 < P.Cout) {
+            mbar_expect_tx(rbar, res_bytes);
+            tma_load_4d(rs_u32, &maps.r[0], rbar, t.co0 + pf_c0, t.tw_i * P.TW, t.th_i * P.TH, t.tn_i * P.TN);
+            tma_load_4d(rs_u32 + 8192, &maps.r[1], rbar, t.co0 + pf_c0, t.tw_i * P.TW, t.th_i * P.TH, t.tn_i * P.TN);
+            pf_c0 += 128;
+            return;
+          }
+          pf_tile += tile_step;   // no (further) chunk of this group in that tile
+          pf_c0 = grp * 32;
+        }
+      };
+      if (issuer) pf_issue();
+      uint32_t res_n = 0;
+      bool store_pending = false;
+      int it = 0;
+      for (int tile = tile0; tile < P.total_tiles; tile += tile_step, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        const TileCoord tc = decode_tile<BN, PAIR>(P, tile, cta_rank);
+        const int co0 = tc.co0, ncols = tc.ncols;
+        const int ow0 = tc.tw_i * P.TW, oh0 = tc.th_i * P.TH, n0 = tc.tn_i * P.TN;
+        if (P.bias) {   // the group's (up to) two chunks x 32 bias values of this tile
+          const int tq = q * 32 + lane;
+          if (tq < 64) {
+            const int col = grp * 32 + 128 * (tq >> 5) + (tq & 31);
+            bias_g[tq] = (col < ncols && co0 + col < P.Cout) ? __ldg(P.bias + co0 + col) : 0.f;
+          }
+          named_bar_sync(1 + grp, 128);
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = grp * 32; c0 < ncols; c0 += 128) {
+          const int cbase = co0 + c0;
+          if (cbase >= P.Cout) break;  // uniform over the group
+          mbar_wait(rbar, res_n & 1u);
+          ++res_n;
+          uint32_t ohi[16], olo[8];   // the chunk's 32 outputs of this row: fp16 pairs, e5m2 residual bytes
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t raw[16];
+            TMEM_LD_32x32b_X16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0 + 16 * sub), raw);
+            const uint4 rh0 = *reinterpret_cast<const uint4*>(rs + row * 64 + (((2 * sub) ^ sw) << 4));
+            const uint4 rh1 = *reinterpret_cast<const uint4*>(rs + row * 64 + (((2 * sub + 1) ^ sw) << 4));
+            const uint4 rl = *reinterpret_cast<const uint4*>(rs + 8192 + row * 32 + (sub << 4));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float v[16];
+            if (P.bias) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias_g + (c0 >> 7) * 32 + 16 * sub);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 t = b4[j];
+                v[4 * j] = fmaf(__uint_as_float(raw[4 * j]), as, t.x); v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), as, t.y);
+                v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), as, t.z); v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), as, t.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * as;
+            }
+            add_f16x8_reg(v, rh0);
+            add_f16x8_reg(v + 8, rh1);
+            add_e5m2x4_reg(v, rl.x); add_e5m2x4_reg(v + 4, rl.y); add_e5m2x4_reg(v + 8, rl.z); add_e5m2x4_reg(v + 12, rl.w);
+            if (P.flags & MPN_EPI_RELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (P.flags & MPN_EPI_SIGMOID) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint4 h4;
+              uint2 l8, h8;
+              split_f16f8x8(v + 8 * i, h4, l8, h8, false);
+              const int o = 8 * sub + 4 * i;
+              ohi[o] = h4.x; ohi[o + 1] = h4.y; ohi[o + 2] = h4.z; ohi[o + 3] = h4.w;
+              olo[4 * sub + 2 * i] = l8.x; olo[4 * sub + 2 * i + 1] = l8.y;
+            }
+          }
+          // A: the previous store of this group has finished READING the staging box
+          if (store_pending && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          named_bar_sync(1 + grp, 128);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(stg + row * 64 + ((i ^ sw) << 4)) = make_uint4(ohi[4 * i], ohi[4 * i + 1], ohi[4 * i + 2], ohi[4 * i + 3]);
+          *reinterpret_cast<uint4*>(stg + 8192 + row * 32) = make_uint4(olo[0], olo[1], olo[2], olo[3]);
+          *reinterpret_cast<uint4*>(stg + 8192 + row * 32 + 16) = make_uint4(olo[4], olo[5], olo[6], olo[7]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          // B: staging box complete; every thread of the group is also done reading the shortcut box (its generic-proxy reads
+          // are ordered before the async-proxy refill by the fence above)
+          named_bar_sync(1 + grp, 128);
+          if (issuer) {
+            pf_issue();
+            tma_store_4d(&maps.y[0][0], stg_u32, cbase, ow0, oh0, n0);
+            tma_store_4d(&maps.y[1][0], stg_u32 + 8192, cbase, ow0, oh0, n0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          store_pending = true;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_tempty0 + 8u * acc);  // the leader's MMA issuer waits for both CTAs' epilogues
+      }
+      if (store_pending && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
     const bool want_h8 = !(P.flags & MPN_EPI_NO_H8);  // F16F8 outputs: the e5m2 copy plane is only stored for tensors a 3x3 conv reads
     const int rep = P.out_rep, OHr = P.OH * rep, OWr = P.OW * rep;
     const long long nstride = P.out_nstride > 0 ? P.out_nstride
@@ -945,6 +1084,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       }
     }
     if (TMAEPI && store_pending && (warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }  // !WIDE
   }
   // =============================== teardown ===============================
   tc_fence_before();
@@ -1017,10 +1157,10 @@ void choose_tile(int N, int OH, int OW, int* TW, int* TH, int* TN, bool even = f
   *TW = bw; *TH = bh; *TN = bn;
 }
 
-template <int BN, int MODE, int EPI, bool PAIR = false>
+template <int BN, int MODE, int EPI, bool PAIR = false, int NG = 2>
 int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
   constexpr int STAGE_BYTES = a_stage_bytes(MODE) + (PAIR ? BN / 2 : BN) * b_row_bytes(MODE);
-  constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES + (EPI == EPI_TMA_RES ? 4 * RES_STAGE_BYTES : 0);
+  constexpr int EPI_BYTES = NG == 4 ? 8 * WIDE_BOX_BYTES : NUM_EPI_WARPS * EPI_STAGE_BYTES + (EPI == EPI_TMA_RES ? 4 * RES_STAGE_BYTES : 0);
   constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - BIAS_BYTES - EPI_BYTES) / STAGE_BYTES;
   constexpr int STAGES = MAXS > 8 ? 8 : (MAXS < 2 ? 2 : MAXS);
   if constexpr (MAXS < 2) {   // MODE_F16F8B, 256-wide single-CTA tiles: the host plan never selects them (BN is capped at 128)
@@ -1030,7 +1170,7 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
   static_assert(8 * (2 * STAGES + 9) <= BAR_BYTES, "barrier area too small");
   const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BIAS_BYTES + EPI_BYTES;
   static_assert(STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BIAS_BYTES + EPI_BYTES <= SMEM_LIMIT, "shared memory budget");
-  auto kern = conv_tc_kernel<BN, MODE, STAGES, EPI, PAIR>;
+  auto kern = conv_tc_kernel<BN, MODE, STAGES, EPI, PAIR, NG>;
   MPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = P.total_tiles < sms ? P.total_tiles : sms;
   if (PAIR) grid = 2 * (P.total_tiles < sms / 2 ? P.total_tiles : sms / 2);  // one 2-CTA cluster per pair tile, <= SMs/2 clusters
@@ -1038,7 +1178,7 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(128 + 128 * NG);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -1385,6 +1525,13 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
     case 128: return launch<128, SPLIT_, EPI_>(maps, P, s, sms);           \
     case 64: return launch<64, SPLIT_, EPI_>(maps, P, s, sms);             \
     default: return launch<32, SPLIT_, EPI_>(maps, P, s, sms);             \
+  }
+  // wide epilogue (MPN_EPI_WIDE=0 disables): F16F8 shortcut convolutions whose output is stored without the e5m2 copy plane
+  static const int wide_on = getenv("MPN_EPI_WIDE") ? atoi(getenv("MPN_EPI_WIDE")) : 1;
+  const bool wide = wide_on && res_tma && !up_tma && f8 && (d->flags & MPN_EPI_NO_H8) && !p->scale && nseg == 1 && P.tail_split <= 4;
+  if (wide) {
+    if (f8b) return BN == 256 ? launch<256, MODE_F16F8B, EPI_TMA_RES, true, 4>(maps, P, s, sms) : launch<128, MODE_F16F8B, EPI_TMA_RES, true, 4>(maps, P, s, sms);
+    return BN == 256 ? launch<256, MODE_F16F8, EPI_TMA_RES, true, 4>(maps, P, s, sms) : launch<128, MODE_F16F8, EPI_TMA_RES, true, 4>(maps, P, s, sms);
   }
 #define MPN_TC_DISPATCH_RES(SPLIT_)                                                  \
   if (res_tma) {                                                                      \
