@@ -1528,7 +1528,11 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
   }
   // wide epilogue (MPN_EPI_WIDE=0 disables): F16F8 shortcut convolutions whose output is stored without the e5m2 copy plane
   static const int wide_on = getenv("MPN_EPI_WIDE") ? atoi(getenv("MPN_EPI_WIDE")) : 1;
-  const bool wide = wide_on && res_tma && !up_tma && f8 && (d->flags & MPN_EPI_NO_H8) && !p->scale && nseg == 1 && P.tail_split <= 4;
+  // and whose reduction is short (K <= 256: with eight K blocks per tile the MMA phase covers the epilogue and the single shortcut
+  // buffer of the wide variant costs more than the extra warps win -- 15x20 c512->2048: 64 vs 60 us, 30x40 c256->1024: 80 vs 81 us,
+  // 120x160 c64->256: 234 vs 241 us, profiles/r02i)
+  const bool wide = wide_on && res_tma && !up_tma && f8 && (d->flags & MPN_EPI_NO_H8) && !p->scale && nseg == 1 && P.tail_split <= 4 &&
+                    d->Cin * d->R * d->S <= 256;
   if (wide) {
     if (f8b) return BN == 256 ? launch<256, MODE_F16F8B, EPI_TMA_RES, true, 4>(maps, P, s, sms) : launch<128, MODE_F16F8B, EPI_TMA_RES, true, 4>(maps, P, s, sms);
     return BN == 256 ? launch<256, MODE_F16F8, EPI_TMA_RES, true, 4>(maps, P, s, sms) : launch<128, MODE_F16F8, EPI_TMA_RES, true, 4>(maps, P, s, sms);

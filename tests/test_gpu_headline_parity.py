@@ -176,3 +176,15 @@ def test_dataparallel_replica_path():
         hk, saved = dp([x[:1], "keypoint_subnet"])
     assert torch.equal(heat1, heat0[:1]) and torch.equal(s1, s0) and torch.equal(b1, b0)
     assert hk.shape == (1, 18, 24, 32) and len(saved) == 5
+    if torch.cuda.device_count() >= 2:
+        # two replicas on two devices (trainer.py:170 / tester.py:126 with gpus = [0, 1]): the batch is scattered, the str is
+        # replicated, the nested outputs are gathered on device 0 -- and equal the bare module's
+        with torch.no_grad():
+            want_h, want_saved = m([x, "keypoint_subnet"])
+            got_h, got_saved = dp([x, "keypoint_subnet"])
+            _, (cls_w, reg_w, anc_w) = m([x, "detection_subnet"])
+        assert got_h.device.index == 0 and torch.equal(got_h, want_h)
+        assert all(torch.equal(a, b) for a, b in zip(got_saved[:4], want_saved[:4]))
+        from multiposenet.pytorch_b200 import pth_nms
+        d1 = torch.cat([torch.rand(40, 2) * 100, torch.rand(40, 2) * 100 + 100, torch.rand(40, 1)], 1)
+        assert torch.equal(pth_nms(d1.to("cuda:1"), 0.5).cpu(), pth_nms(d1.to("cuda:0"), 0.5).cpu())   # per-device workspaces / streams
