@@ -37,6 +37,8 @@ class TrainEngine(object):
         self.fmt = ops.PRECISIONS[precision]
         self.grads = {}
         self.trace = None  # dict -> records d loss / d (block output) during backward (diagnostics)
+        self._bucket_hook = None  # called once inside backward() when the gradients of head + neck + layer4 + layer3 are complete
+        self._ov = {}
 
     # ------------------------------------------------------------------ helpers
     def _pc(self, conv):
@@ -174,6 +176,10 @@ class TrainEngine(object):
             d = self._conv_grads(name + ".conv1", blk.conv1, b.x, dy1, residual=dsc)
             if id(b.x) in extra:  # b.x is a stage output (c2 / c3 / c4) that also feeds a lateral conv
                 d = T.add(d, extra[id(b.x)])
+            if self._bucket_hook is not None and name == "fpn.layer3.0":
+                # ~88 % of the trainable parameters (head, neck, layer4, layer3) have their gradients now, ~40 % of the backward's
+                # time is still ahead (layer2, layer1 and the stem work on the large maps): the allreduce of this bucket overlaps it
+                self._bucket_hook()
         # stem
         d_z = T.maxpool_backward(S.stem_z, d)
         dy, _, dg, db = T.bn_train_backward(d_z, S.stem_st, fpn.bn1)
@@ -240,6 +246,99 @@ class TrainEngine(object):
         sx.copy_(img, non_blocking=True); sg.copy_(heat_gt, non_blocking=True); sw.copy_(heat_weight, non_blocking=True)
         graph.replay()
         return out
+
+    # ------------------------------------------------------------------ overlapped data-parallel step
+    def _build_overlapped(self, img, heat_gt, heat_weight):
+        """Two CUDA graphs that share one memory pool: graph 1 = forward + loss + backward down to the first block of layer3,
+        graph 2 = the rest of the backward.  Each ends by copying its gradients into its slice of ONE flat fp32 buffer, so the
+        NCCL allreduce of the first (large) bucket can run on a side stream while graph 2 replays."""
+        st = _Saved()
+        st.sx, st.sg, st.sw = torch.empty_like(img), torch.empty_like(heat_gt), torch.empty_like(heat_weight)
+        st.sx.copy_(img); st.sg.copy_(heat_gt); st.sw.copy_(heat_weight)
+        bn_state = [(m, m.running_mean.clone(), m.running_var.clone(), m.num_batches_tracked.clone())
+                    for m in self.model.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+
+        def restore():
+            for m, rm, rv, nb in bn_state:
+                m.running_mean.copy_(rm); m.running_var.copy_(rv); m.num_batches_tracked.copy_(nb)
+        # eager dry run: warms allocator pools / function attributes and records which gradients exist at the hook
+        at_hook = []
+        self._bucket_hook = lambda: at_hook.extend(self.grads.keys())
+        side = torch.cuda.Stream(device=img.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            _, _, grads = self.forward_backward(st.sx, st.sg, st.sw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._bucket_hook = None
+        restore()
+        named = [(n, p) for n, p in self.trainable_parameters() if n in grads]
+        first = set(at_hook)
+        order = [(n, p) for n, p in named if n in first] + [(n, p) for n, p in named if n not in first]
+        st.index, off = [], 0
+        for n, p in order:
+            st.index.append((n, p, off, p.numel()))
+            off += p.numel()
+        st.n_first = sum(k for n, _, _, k in st.index if n in first)
+        st.flat = torch.zeros(off, dtype=torch.float32, device=img.device)
+        st.flat_a, st.flat_b = st.flat[:st.n_first], st.flat[st.n_first:]
+
+        def gather(keys):   # inside the capture: this bucket's gradients -> the flat buffer
+            for n, p, o, k in st.index:
+                if (n in first) == keys:
+                    st.flat[o:o + k].copy_(self.grads[n].reshape(-1))
+        st.g1, st.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        pool = torch.cuda.graph_pool_handle()
+        cap = torch.cuda.Stream(device=img.device)
+        cap.wait_stream(torch.cuda.current_stream())
+
+        def split():
+            gather(True)
+            st.g1.capture_end()
+            st.g2.capture_begin(pool=pool)
+        self._bucket_hook = split
+        try:
+            with torch.cuda.stream(cap):
+                st.g1.capture_begin(pool=pool)
+                st.loss, st.outs, st.grads = self.forward_backward(st.sx, st.sg, st.sw)
+                gather(False)
+                st.g2.capture_end()
+        finally:
+            self._bucket_hook = None
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
+        restore()
+        st.comm = torch.cuda.Stream(device=img.device)
+        return st
+
+    def train_step_overlapped(self, img, heat_gt, heat_weight, world_size=1):
+        """forward + backward + gradient allreduce of one data-parallel step (reference: the DataParallel reduce-add of
+        training/trainer.py:170, 245-259), with the allreduce of the first gradient bucket overlapped with the tail of the
+        backward.  Leaves the averaged gradients in param.grad (views of one flat buffer) and returns the loss (fp64 [1])."""
+        import torch.distributed as dist
+        key = (tuple(img.shape), str(img.device))
+        st = self._ov.get(key)
+        if st is None:
+            st = self._ov[key] = self._build_overlapped(img, heat_gt, heat_weight)
+        st.sx.copy_(img, non_blocking=True); st.sg.copy_(heat_gt, non_blocking=True); st.sw.copy_(heat_weight, non_blocking=True)
+        multi = world_size > 1 and dist.is_available() and dist.is_initialized()
+        st.g1.replay()
+        if multi:
+            cur = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(st.comm):
+                st.comm.wait_event(ev)
+                w1 = dist.all_reduce(st.flat_a, async_op=True)      # runs under graph 2
+        st.g2.replay()
+        if multi:
+            w2 = dist.all_reduce(st.flat_b, async_op=True)
+            w1.wait()
+            w2.wait()
+            st.flat.div_(world_size)
+        for n, p, o, k in st.index:
+            p.grad = st.flat[o:o + k].view_as(p)
+        return st.loss
 
     def trainable_parameters(self):
         return [(n, p) for n, p in self.model.named_parameters() if p.requires_grad]

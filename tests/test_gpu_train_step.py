@@ -139,3 +139,30 @@ def test_graphed_train_step_matches_eager():
     assert all(torch.equal(a, b) for a, b in zip(outs_g, outs_ref)), "forward not reproducible"
     assert errs[-1] <= 1e-4, errs[-1]
     assert int(m.fpn.bn1.num_batches_tracked) == nb + 2  # the capture/warm-up runs did not count as steps
+
+
+def test_overlapped_step_matches_single_graph_step():
+    """train_step_overlapped: two graphs sharing a pool, gradients gathered into one flat buffer in two buckets -- same loss and
+    gradients as the single-graph step, BatchNorm running statistics advanced once per step."""
+    from gpu_util import nerr
+    m, w, x, gt, wt = _problem()
+    m.train()
+    eng = m.train_engine()
+    loss_e, outs_e, grads_e = eng.forward_backward(x, gt, wt)
+    ref = {k: v.clone() for k, v in grads_e.items()}
+    loss_e = float(loss_e)
+    nb = int(m.fpn.bn1.num_batches_tracked)
+    for _ in range(2):
+        loss_o = eng.train_step_overlapped(x, gt, wt, 1)
+    torch.cuda.synchronize()
+    assert abs(float(loss_o) - loss_e) <= 1e-5 * max(1.0, abs(loss_e))
+    st = eng._ov[(tuple(x.shape), str(x.device))]
+    names = [n for n, _, _, _ in st.index]
+    assert set(names) == set(ref) and 0 < st.n_first < st.flat.numel()
+    assert st.n_first > 0.8 * st.flat.numel()                       # head + neck + layer4 + layer3 are the large bucket
+    first = [n for n, _, o, _ in st.index if o < st.n_first]
+    assert any(n.startswith("fpn.layer3.0.") for n in first) and not any(n.startswith(("fpn.layer2", "fpn.layer1", "fpn.conv1")) for n in first)
+    params = dict(m.named_parameters())
+    errs = sorted(nerr(params[n].grad, ref[n]) for n in names if float(ref[n].abs().max()) > 0)
+    assert errs[-1] <= 1e-4, errs[-1]
+    assert int(m.fpn.bn1.num_batches_tracked) == nb + 2             # the dry run and the capture did not count as steps
