@@ -324,10 +324,10 @@ __global__ void __launch_bounds__(256) channel_stats_v8_kernel(const uint4* __re
                                                                double* __restrict__ sumsq) {
   // fp64 accumulators: the cross-thread sums must not depend on the (non-deterministic) order of the atomics, otherwise
   // batch statistics differ in the last fp32 bit from run to run and the bf16 hi/lo re-split turns that into ~1e-5 jitter
-  __shared__ double sh[2][256];
-  sh[0][threadIdx.x] = 0.0;
-  sh[1][threadIdx.x] = 0.0;
-  __syncthreads();
+  // per-thread fp32 partials -> shared memory [lane][channel] -> one fp64 column sum per channel -> ONE fp64 global atomic per
+  // channel and CTA (r02: the 4096 contended fp64 shared-memory atomics per CTA and the un-unrolled load loop held these
+  // reductions at 1.2-2 TB/s)
+  __shared__ float part[2][2048];
   const int groups = C8 < 32 ? C8 : 32;          // channel vectors of this CTA's slice (power of two)
   const int cg = blockIdx.y * 32 + (threadIdx.x % groups);
   const int lanes = 256 / groups, lane = threadIdx.x / groups;
@@ -336,32 +336,31 @@ __global__ void __launch_bounds__(256) channel_stats_v8_kernel(const uint4* __re
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+#pragma unroll 4
   for (long long p = p0 + lane; p < p1; p += lanes) {
     float v[8];
     load8<SPLIT>(hi, lo, p * C8 + cg, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
   }
-  for (int o = groups; o < 32; o <<= 1) {  // same-slice threads of a warp sit `groups` apart
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-      q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
-    }
-  }
-  if (groups >= 32 || (threadIdx.x & 31) < groups) {
+  {
     const int g = threadIdx.x % groups;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[0][g * 8 + j], (double)s[j]);
-      atomicAdd(&sh[1][g * 8 + j], (double)q[j]);
+      part[0][lane * (groups * 8) + g * 8 + j] = s[j];
+      part[1][lane * (groups * 8) + g * 8 + j] = q[j];
     }
   }
   __syncthreads();
   if (threadIdx.x < groups * 8) {
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < lanes; ++l) {
+      a += (double)part[0][l * (groups * 8) + threadIdx.x];
+      b += (double)part[1][l * (groups * 8) + threadIdx.x];
+    }
     const int c = blockIdx.y * 256 + threadIdx.x;
-    atomicAdd(sum + c, sh[0][threadIdx.x]);
-    if (sumsq) atomicAdd(sumsq + c, sh[1][threadIdx.x]);
+    atomicAdd(sum + c, a);
+    if (sumsq) atomicAdd(sumsq + c, b);
   }
 }
 
@@ -407,10 +406,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v8_kernel(const uint4* __re
                                                                double* __restrict__ s1, double* __restrict__ s2) {
   // fp64 accumulators: the cross-thread sums must not depend on the (non-deterministic) order of the atomics, otherwise
   // batch statistics differ in the last fp32 bit from run to run and the bf16 hi/lo re-split turns that into ~1e-5 jitter
-  __shared__ double sh[2][256];
-  sh[0][threadIdx.x] = 0.0;
-  sh[1][threadIdx.x] = 0.0;
-  __syncthreads();
+  __shared__ float part[2][2048];
   const int groups = C8 < 32 ? C8 : 32;
   const int cg = blockIdx.y * 32 + (threadIdx.x % groups);
   const int lanes = 256 / groups, lane = threadIdx.x / groups;
@@ -423,6 +419,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v8_kernel(const uint4* __re
     m[j] = mean[cg * 8 + j];
     is[j] = rsqrtf(var[cg * 8 + j] + eps);
   }
+#pragma unroll 2
   for (long long p = p0 + lane; p < p1; p += lanes) {
     float g[8], z[8], y[8];
     load8<SPLIT>(dzhi, dzlo, p * C8 + cg, g);
@@ -435,26 +432,24 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v8_kernel(const uint4* __re
       b[j] = fmaf(gg, (y[j] - m[j]) * is[j], b[j]);
     }
   }
-  for (int o = groups; o < 32; o <<= 1) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
-      b[j] += __shfl_xor_sync(0xffffffffu, b[j], o);
-    }
-  }
-  if (groups >= 32 || (threadIdx.x & 31) < groups) {
+  {
     const int g2 = threadIdx.x % groups;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[0][g2 * 8 + j], (double)a[j]);
-      atomicAdd(&sh[1][g2 * 8 + j], (double)b[j]);
+      part[0][lane * (groups * 8) + g2 * 8 + j] = a[j];
+      part[1][lane * (groups * 8) + g2 * 8 + j] = b[j];
     }
   }
   __syncthreads();
   if (threadIdx.x < groups * 8) {
+    double sa = 0.0, sb = 0.0;
+    for (int l = 0; l < lanes; ++l) {
+      sa += (double)part[0][l * (groups * 8) + threadIdx.x];
+      sb += (double)part[1][l * (groups * 8) + threadIdx.x];
+    }
     const int c = blockIdx.y * 256 + threadIdx.x;
-    atomicAdd(s1 + c, sh[0][threadIdx.x]);
-    atomicAdd(s2 + c, sh[1][threadIdx.x]);
+    atomicAdd(s1 + c, sa);
+    atomicAdd(s2 + c, sb);
   }
 }
 
