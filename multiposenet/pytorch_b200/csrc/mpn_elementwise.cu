@@ -422,23 +422,69 @@ extern "C" int mpn_relu(const void* xhi, const void* xlo, void* yhi, void* ylo, 
 
 // ---------------------------------------------------------------------------------------------
 // Tensor-core stem helpers (see mpn_b200.h).  X2[n][hp][wp][cc], cc = (ph*2+pw)*3 + c, hp = h/2 + 2.
+// One thread per (image, hp, wp) position of the space-to-depth tensor: 16 channels = the 2 x 2 pixel block (ph, pw) x 3 colours
+// + 4 zero pads, written with vector stores (32 B hi + the format's second / third plane) -- r02: the element-per-thread version
+// ran at 0.8 TB/s and its uint8 twin was slower than the fp32 one although it reads 4x fewer bytes.
+__device__ __forceinline__ void stem_store16(void* hi, void* lo, long long pos, int fmt, const float* v, long long plane) {
+  if (fmt == MPN_FMT_F16F8) {
+    unsigned h[8], l[4], g[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = mpn_pack_f16x2_sat(v[2 * j], v[2 * j + 1]);
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+      const unsigned l0 = mpn_float_to_e5m2((v[2 * j] - f.x) * MPN_F8_LO_SCALE), l1 = mpn_float_to_e5m2((v[2 * j + 1] - f.y) * MPN_F8_LO_SCALE);
+      const unsigned g0 = mpn_float_to_e5m2(v[2 * j]), g1 = mpn_float_to_e5m2(v[2 * j + 1]);
+      if ((j & 1) == 0) { l[j >> 1] = l0 | (l1 << 8); g[j >> 1] = g0 | (g1 << 8); }
+      else { l[j >> 1] |= (l0 | (l1 << 8)) << 16; g[j >> 1] |= (g0 | (g1 << 8)) << 16; }
+    }
+    uint4* ph = reinterpret_cast<uint4*>((__half*)hi + pos * 16);
+    ph[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4*>((unsigned char*)lo + pos * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>((unsigned char*)lo + plane + pos * 16) = make_uint4(g[0], g[1], g[2], g[3]);
+  } else {
+    unsigned h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      h[j] = *reinterpret_cast<const unsigned*>(&t);
+      const __nv_bfloat162 r = __floats2bfloat162_rn(v[2 * j] - __uint_as_float(h[j] << 16), v[2 * j + 1] - __uint_as_float(h[j] & 0xFFFF0000u));
+      l[j] = *reinterpret_cast<const unsigned*>(&r);
+    }
+    uint4* ph = reinterpret_cast<uint4*>((__nv_bfloat16*)hi + pos * 16);
+    ph[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    if (fmt == MPN_FMT_BF16X2) {
+      uint4* pl = reinterpret_cast<uint4*>((__nv_bfloat16*)lo + pos * 16);
+      pl[0] = make_uint4(l[0], l[1], l[2], l[3]);
+      pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+    }
+  }
+}
+
 __global__ void stem_pack_input_kernel(const float* __restrict__ img, void* hi, void* lo, int N, int H, int W, int H2p, int W2p,
                                        int fmt) {
-  long long total = (long long)N * H2p * W2p * 16;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int cc = (int)(i & 15);
-    long long p = i >> 4;
-    int wp = (int)(p % W2p);
-    long long q = p / W2p;
-    int hp = (int)(q % H2p);
-    int n = (int)(q / H2p);
-    float v = 0.f;
-    if (cc < 12) {
-      int c = cc % 3, ph = (cc / 3) >> 1, pw = (cc / 3) & 1;
-      int ih = 2 * (hp - 2) + ph, iw = 2 * (wp - 2) + pw;
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = img[(((long long)n * 3 + c) * H + ih) * W + iw];
+  const long long npos = (long long)N * H2p * W2p;
+  for (long long pos = blockIdx.x * (long long)blockDim.x + threadIdx.x; pos < npos; pos += (long long)gridDim.x * blockDim.x) {
+    const int wp = (int)(pos % W2p);
+    const long long q = pos / W2p;
+    const int hp = (int)(q % H2p), n = (int)(q / H2p);
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+      const int ih = 2 * (hp - 2) + ph;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw) {
+        const int iw = 2 * (wp - 2) + pw;
+        if (iw < 0 || iw >= W) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(ph * 2 + pw) * 3 + c] = __ldg(img + (((long long)n * 3 + c) * H + ih) * W + iw);
+      }
     }
-    mpn_store_act(hi, lo, i, fmt, v, total);
+    stem_store16(hi, lo, pos, fmt, v, npos * 16);
   }
 }
 
@@ -446,7 +492,7 @@ extern "C" int mpn_stem_pack_input(const float* img, void* hi, void* lo, int N, 
   MPN_CHECK_ARG(img && hi && N > 0 && H > 0 && W > 0, "mpn_stem_pack_input: bad argument");
   MPN_CHECK_ARG(fmt == MPN_FMT_BF16 || ((fmt == MPN_FMT_BF16X2 || fmt == MPN_FMT_F16F8) && lo), "mpn_stem_pack_input: fmt must be BF16, BF16X2 or F16F8 (with lo)");
   int H2p = (H + 1) / 2 + 3, W2p = (W + 1) / 2 + 3;
-  long long total = (long long)N * H2p * W2p * 16;
+  long long total = (long long)N * H2p * W2p;
   stem_pack_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, hi, lo, N, H, W, H2p, W2p, fmt);
   MPN_LAUNCH_OK();
   return MPN_OK;
@@ -569,21 +615,28 @@ __global__ void stem_pack_input_u8_kernel(const unsigned char* __restrict__ img,
     lut[t >> 8][t & 255] = resnet_preprocess_px(fake, t >> 8);
   }
   __syncthreads();
-  long long total = (long long)N * H2p * W2p * 16;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int cc = (int)(i & 15);
-    long long p = i >> 4;
-    int wp = (int)(p % W2p);
-    long long q = p / W2p;
-    int hp = (int)(q % H2p);
-    int n = (int)(q / H2p);
-    float v = 0.f;
-    if (cc < 12) {
-      int c = cc % 3, ph = (cc / 3) >> 1, pw = (cc / 3) & 1;
-      int ih = 2 * (hp - 2) + ph, iw = 2 * (wp - 2) + pw;
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = lut[c][img[(((long long)n * H + ih) * W + iw) * 3 + (2 - c)]];
+  const long long npos = (long long)N * H2p * W2p;
+  for (long long pos = blockIdx.x * (long long)blockDim.x + threadIdx.x; pos < npos; pos += (long long)gridDim.x * blockDim.x) {
+    const int wp = (int)(pos % W2p);
+    const long long q = pos / W2p;
+    const int hp = (int)(q % H2p), n = (int)(q / H2p);
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+      const int ih = 2 * (hp - 2) + ph;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw) {
+        const int iw = 2 * (wp - 2) + pw;
+        if (iw < 0 || iw >= W) continue;
+        const unsigned char* px = img + (((long long)n * H + ih) * W + iw) * 3;   // BGR
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(ph * 2 + pw) * 3 + c] = lut[c][px[2 - c]];
+      }
     }
-    mpn_store_act(hi, lo, i, fmt, v, total);
+    stem_store16(hi, lo, pos, fmt, v, npos * 16);
   }
 }
 
@@ -592,7 +645,7 @@ extern "C" int mpn_stem_pack_input_u8(const unsigned char* img_nhwc_bgr, void* h
   MPN_CHECK_ARG(img_nhwc_bgr && hi && N > 0 && H > 0 && W > 0, "mpn_stem_pack_input_u8: bad argument");
   MPN_CHECK_ARG(fmt == MPN_FMT_BF16 || ((fmt == MPN_FMT_BF16X2 || fmt == MPN_FMT_F16F8) && lo), "mpn_stem_pack_input_u8: fmt must be BF16, BF16X2 or F16F8 (with lo)");
   int H2p = (H + 1) / 2 + 3, W2p = (W + 1) / 2 + 3;
-  long long total = (long long)N * H2p * W2p * 16;
+  long long total = (long long)N * H2p * W2p;
   stem_pack_input_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img_nhwc_bgr, hi, lo, N, H, W, H2p, W2p, fmt);
   MPN_LAUNCH_OK();
   return MPN_OK;
