@@ -5,7 +5,8 @@ training/multipose_keypoint_train.py:11) and `from lib.nms.pth_nms import pth_nm
 (network/posenet.py:16).  install_dropin() aliases those module names to this package's mirrors, so
 evaluate/ and training/ scripts import the B200 implementation without being edited.  Other
 `network.*` / `lib.*` submodules of a reference checkout on sys.path (joint_utils, net_utils, lib.utils)
-keep resolving to the checkout: only the hot-path modules are replaced.
+keep resolving to the checkout: only the hot-path modules are replaced, plus `network.losses` (FocalLoss on the device) and
+`training.batch_processor` (the reference's file is a SyntaxError on Python >= 3.7).
 """
 import importlib
 import sys
@@ -33,10 +34,15 @@ def install_dropin(reference_root=None):
             sys.modules[name] = m
         return m
 
-    for pkg in ("network", "lib", "lib.nms"):
+    from .network import losses as _losses
+    _bp = importlib.import_module(__package__ + ".training.batch_processor")   # the module (the package re-exports the function)
+    for pkg in ("network", "lib", "lib.nms", "training"):
         _pkg(pkg)
+    # network.losses: FocalLoss on the device (the reference's own file needs two torch-0.4 idioms that fail on torch >= 1.2);
+    # training.batch_processor: the reference file is a SyntaxError on Python >= 3.7 (`async=` keyword)
     for name, mod in (("network.posenet", _posenet), ("network.fpn", _fpn), ("network.anchors", _anchors),
-                      ("network.utils", _utils), ("lib.nms.pth_nms", _pth)):
+                      ("network.utils", _utils), ("network.losses", _losses), ("lib.nms.pth_nms", _pth),
+                      ("training.batch_processor", _bp)):
         sys.modules[name] = mod
         parent, _, leaf = name.rpartition(".")
         setattr(sys.modules[parent], leaf, mod)

@@ -159,3 +159,37 @@ def test_prn_degenerate_boxes_follow_the_reference():
     kps = [[50.0, 60.0, 0.9, i, i] for i in range(16)]
     with pytest.raises(ZeroDivisionError):
         prn_oracle.prn_process(kps, [[10, 10, 110, 210], [10, 10, 9.5, 60]], prn_oracle.synthetic_prn(0))
+
+
+def test_compat_batch_processor_contract():
+    """training/batch_processor.py:10-60: (inputs, gts, saved_for_eval) for the three subnets; the mirror must import on this
+    Python (the reference file does not: `async=` keyword) and be registered by install_dropin()."""
+    import sys
+    import types
+    from multiposenet.pytorch_b200 import install_dropin
+    from multiposenet.pytorch_b200.training import batch_processor
+    install_dropin()
+    assert sys.modules["training.batch_processor"].batch_processor is batch_processor
+    assert hasattr(sys.modules["network.losses"], "FocalLoss")
+    moved = []
+
+    class T(object):   # stands in for a CPU tensor: records the device it is sent to
+        def to(self, dev, non_blocking=False):
+            moved.append(str(dev))
+            return self
+
+        def float(self):
+            return self
+    state = types.SimpleNamespace(params=types.SimpleNamespace(gpus=[0], subnet_name="keypoint_subnet"),
+                                  model=types.SimpleNamespace(training=True))
+    a, b, c = T(), T(), T()
+    inputs, gts, saved = batch_processor(state, (a, b, c))
+    assert inputs == [[a, "keypoint_subnet"]] and gts == ["keypoint_subnet", b, c] and saved == []
+    assert moved == ["cuda:0"] * 3
+    state.params.subnet_name = "detection_subnet"
+    state.model.training = False
+    inputs, gts, _ = batch_processor(state, (a, b))
+    assert inputs == [[a, "detection_subnet"]] and gts == ["detection_subnet", b]
+    state.params.subnet_name = "prn_subnet"
+    inputs, gts, _ = batch_processor(state, (a, b))
+    assert inputs[0][1] == "prn_subnet" and gts[0] == "prn_subnet"
