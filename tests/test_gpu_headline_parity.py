@@ -13,6 +13,14 @@ pytestmark = pytest.mark.gpu
 BAR = 1e-3  # north_star: max|a-b| / max|b| per output tensor vs the fp32 reference
 
 
+def _record(tag, payload):
+    """Measured margins go to gpurun_out/headline_parity.jsonl (pytest -q swallows the prints of passing tests)."""
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "headline_parity.jsonl"), "a") as f:
+            f.write(json.dumps(dict(test=tag, **payload)) + "\n")
+
+
 @pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
 def test_r101_480x640_batch2_all_outputs_vs_fp32_oracle(precision):
     from gpu_util import image, load_model, nerr, no_tf32
@@ -36,6 +44,7 @@ def test_r101_480x640_batch2_all_outputs_vs_fp32_oracle(precision):
     for i in range(4):
         errs["k%d" % (i + 2)] = nerr(saved[i], osaved[i])
     print("R101 %s 480x640 b%d: %s" % (precision, B, json.dumps({k: float("%.3g" % v) for k, v in errs.items()})))
+    _record("r101_480x640_b2", {"precision": precision, **{k: float("%.3g" % v) for k, v in errs.items()}})
     assert torch.equal(anc, oanc)
     assert max(errs.values()) <= BAR, errs
     # elementwise view of the same outputs (README 'parity metric'): the share of elements off by more than 1e-3 of the tensor's
@@ -90,6 +99,7 @@ def test_train_step_vs_reference_golden(golden_dir):
         worst_max = max(worst_max, (emax, k))
         worst_l2 = max(worst_l2, (el2, k))
     print("free-running gradients vs the reference: worst max-norm %.3g (%s), worst L2-relative %.3g (%s)" % (worst_max + worst_l2))
+    _record("train_step_vs_reference_golden", {"worst_max_norm": worst_max[0], "at": worst_max[1], "worst_l2_rel": worst_l2[0], "at_l2": worst_l2[1]})
     # measured on B200 (r02): worst L2-relative 0.040 (fpn.layer1.0.bn3.weight), worst max-norm 0.23 (fpn.layer4.2.conv3.weight):
     # the footprint of a handful of flipped ReLU / max-pool decisions, cf. test_gpu_train_step (6e-4 with the patterns imposed)
     assert worst_l2[0] <= 0.1, worst_l2
@@ -120,6 +130,7 @@ def test_prn_forward_vs_reference_golden(golden_dir, tag, precision):
     assert out.shape == want.shape and saved[0] is out
     e = nerr(out, want)
     print("PRN %s %s: %.3g" % (tag, precision, e))
+    _record("prn_forward", {"shape": tag, "precision": precision, "err": e})
     assert e <= BAR
     assert torch.allclose(out.reshape(out.shape[0], -1).sum(1), torch.ones(out.shape[0], device="cuda"), atol=1e-4)
     m.train()   # model.train(): dropout is live in the reference -> the library path, not the engine
