@@ -748,7 +748,12 @@ def main():
         level_default, engine_mod.LEVEL_STREAMS = engine_mod.LEVEL_STREAMS, False
         ops.stats["conv_events"] = evs = []
         for i in range(nprof):
-            eng.entire_forward_device(devin[i % len(devin)], max_cand=MAXC)  # eager: events around each launch
+            # eager: events around each launch.  The GPU first spins for ~40 ms so that the host enqueues the whole step ahead
+            # of it: otherwise the start event of a short kernel is reached while the stream is empty and the interval
+            # includes the host's launch gap (~10 us x 139 launches), not just the kernel
+            torch.cuda._sleep(int(7e7))
+            eng.entire_forward_device(devin[i % len(devin)], max_cand=MAXC)
+            torch.cuda.synchronize()
         torch.cuda.synchronize()
         ops.stats["conv_events"] = None
         engine_mod.USE_STREAMS = streams_default

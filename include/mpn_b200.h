@@ -138,7 +138,8 @@ int mpn_fold_bn(const float* gamma, const float* beta, const float* mean, const 
  * space-to-depth tensor X2[n, H/2+3, W/2+3, 16] (channel = (row parity, col parity, rgb), 12 used) in
  * which the 7x7/2 conv is a 4x4/1 conv; one filter row (4 pixels x 16 ch = 64 contiguous elements) is one
  * K block, so mpn_conv2d_fwd runs it with R=4, S=1, Cin=64, in_cstride=16, k_overlap=1. */
-int mpn_stem_pack_input(const float* img_nchw, void* dst_hi, void* dst_lo, int N, int H, int W, int fmt, void* stream);
+int mpn_stem_pack_input(const float* img_nchw, void* dst_hi, void* dst_lo, int N, int H, int W, int fmt, int flags /* MPN_EPI_NO_H8 */,
+                        void* stream);
 /* OIHW [64,3,7,7] fp32 -> [64][4][64] bf16 hi (+lo) matching that layout */
 int mpn_stem_pack_filter(const float* w_oihw, void* dst_hi, void* dst_lo, int Cout, void* stream);
 
@@ -146,7 +147,8 @@ int mpn_stem_pack_filter(const float* w_oihw, void* dst_hi, void* dst_lo, int Co
  * img: uint8 [N,H,W,3] BGR (cv2.imread layout).  Bit-identical to the numpy code (fp32 divide / subtract / divide). */
 int mpn_preprocess_u8_nchw(const unsigned char* img_nhwc_bgr, float* out_nchw, int N, int H, int W, void* stream);
 /* ... fused into mpn_stem_pack_input: uint8 image -> normalised, zero-padded space-to-depth stem operand */
-int mpn_stem_pack_input_u8(const unsigned char* img_nhwc_bgr, void* dst_hi, void* dst_lo, int N, int H, int W, int fmt, void* stream);
+int mpn_stem_pack_input_u8(const unsigned char* img_nhwc_bgr, void* dst_hi, void* dst_lo, int N, int H, int W, int fmt, int flags,
+                           void* stream);
 
 /* ---- layout / elementwise */
 /* fp32 NCHW -> NHWC in `fmt` (dst_lo for BF16X2); cstride >= C, padding channels are zeroed */

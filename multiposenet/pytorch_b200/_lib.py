@@ -49,10 +49,10 @@ _SIGS = {
     "mpn_filter_absmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mpn_pack_filter_f16f8": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_fold_bn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p]),
-    "mpn_stem_pack_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_stem_pack_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_stem_pack_filter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mpn_preprocess_u8_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "mpn_stem_pack_input_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpn_stem_pack_input_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mpn_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -441,7 +441,7 @@ __device__ __forceinline__ void stem_store16(void* hi, void* lo, long long pos, 
     ph[0] = make_uint4(h[0], h[1], h[2], h[3]);
     ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
     *reinterpret_cast<uint4*>((unsigned char*)lo + pos * 16) = make_uint4(l[0], l[1], l[2], l[3]);
-    *reinterpret_cast<uint4*>((unsigned char*)lo + plane + pos * 16) = make_uint4(g[0], g[1], g[2], g[3]);
+    if (plane >= 0) *reinterpret_cast<uint4*>((unsigned char*)lo + plane + pos * 16) = make_uint4(g[0], g[1], g[2], g[3]);   // < 0: no h8 plane
   } else {
     unsigned h[8], l[8];
 #pragma unroll
@@ -463,7 +463,7 @@ __device__ __forceinline__ void stem_store16(void* hi, void* lo, long long pos, 
 }
 
 __global__ void stem_pack_input_kernel(const float* __restrict__ img, void* hi, void* lo, int N, int H, int W, int H2p, int W2p,
-                                       int fmt) {
+                                       int fmt, int no_h8) {
   const long long npos = (long long)N * H2p * W2p;
   for (long long pos = blockIdx.x * (long long)blockDim.x + threadIdx.x; pos < npos; pos += (long long)gridDim.x * blockDim.x) {
     const int wp = (int)(pos % W2p);
@@ -484,16 +484,17 @@ __global__ void stem_pack_input_kernel(const float* __restrict__ img, void* hi, 
         for (int c = 0; c < 3; ++c) v[(ph * 2 + pw) * 3 + c] = __ldg(img + (((long long)n * 3 + c) * H + ih) * W + iw);
       }
     }
-    stem_store16(hi, lo, pos, fmt, v, npos * 16);
+    stem_store16(hi, lo, pos, fmt, v, no_h8 ? -1 : npos * 16);
   }
 }
 
-extern "C" int mpn_stem_pack_input(const float* img, void* hi, void* lo, int N, int H, int W, int fmt, void* stream) {
+extern "C" int mpn_stem_pack_input(const float* img, void* hi, void* lo, int N, int H, int W, int fmt, int flags, void* stream) {
+  const int no_h8 = (fmt == MPN_FMT_F16F8 && (flags & MPN_EPI_NO_H8)) ? 1 : 0;
   MPN_CHECK_ARG(img && hi && N > 0 && H > 0 && W > 0, "mpn_stem_pack_input: bad argument");
   MPN_CHECK_ARG(fmt == MPN_FMT_BF16 || ((fmt == MPN_FMT_BF16X2 || fmt == MPN_FMT_F16F8) && lo), "mpn_stem_pack_input: fmt must be BF16, BF16X2 or F16F8 (with lo)");
   int H2p = (H + 1) / 2 + 3, W2p = (W + 1) / 2 + 3;
   long long total = (long long)N * H2p * W2p;
-  stem_pack_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, hi, lo, N, H, W, H2p, W2p, fmt);
+  stem_pack_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, hi, lo, N, H, W, H2p, W2p, fmt, no_h8);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -607,7 +608,7 @@ extern "C" int mpn_preprocess_u8_nchw(const unsigned char* img_nhwc_bgr, float* 
 
 // the same, fused into the tensor-core stem's space-to-depth packing (see mpn_stem_pack_input)
 __global__ void stem_pack_input_u8_kernel(const unsigned char* __restrict__ img, void* hi, void* lo, int N, int H, int W, int H2p,
-                                          int W2p, int fmt) {
+                                          int W2p, int fmt, int no_h8) {
   // a byte has 256 values: tabulate the exact (IEEE-division) result per channel once per CTA instead of dividing per pixel
   __shared__ float lut[3][256];
   for (int t = threadIdx.x; t < 768; t += blockDim.x) {
@@ -636,17 +637,18 @@ __global__ void stem_pack_input_u8_kernel(const unsigned char* __restrict__ img,
         for (int c = 0; c < 3; ++c) v[(ph * 2 + pw) * 3 + c] = lut[c][px[2 - c]];
       }
     }
-    stem_store16(hi, lo, pos, fmt, v, npos * 16);
+    stem_store16(hi, lo, pos, fmt, v, no_h8 ? -1 : npos * 16);
   }
 }
 
 extern "C" int mpn_stem_pack_input_u8(const unsigned char* img_nhwc_bgr, void* hi, void* lo, int N, int H, int W, int fmt,
-                                      void* stream) {
+                                      int flags, void* stream) {
+  const int no_h8 = (fmt == MPN_FMT_F16F8 && (flags & MPN_EPI_NO_H8)) ? 1 : 0;
   MPN_CHECK_ARG(img_nhwc_bgr && hi && N > 0 && H > 0 && W > 0, "mpn_stem_pack_input_u8: bad argument");
   MPN_CHECK_ARG(fmt == MPN_FMT_BF16 || ((fmt == MPN_FMT_BF16X2 || fmt == MPN_FMT_F16F8) && lo), "mpn_stem_pack_input_u8: fmt must be BF16, BF16X2 or F16F8 (with lo)");
   int H2p = (H + 1) / 2 + 3, W2p = (W + 1) / 2 + 3;
   long long total = (long long)N * H2p * W2p;
-  stem_pack_input_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img_nhwc_bgr, hi, lo, N, H, W, H2p, W2p, fmt);
+  stem_pack_input_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img_nhwc_bgr, hi, lo, N, H, W, H2p, W2p, fmt, no_h8);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }

@@ -149,12 +149,14 @@ class Engine(object):
             raise RuntimeError("expected a CUDA fp32 [B,3,H,W] image batch (or uint8 [B,H,W,3] BGR raw images)")
         if self.fmt != FMT_F32 and TC_STEM:
             # tensor-core stem: 7x7/2 on the image == 4x4/1 on the zero-padded space-to-depth tensor
-            key = ("fpn.conv1", "tcstem", self.fmt)
+            # with 64 output channels the stem is bound by its A-operand traffic (L2 -> shared memory), not by the tensor pipe:
+            # the no-h8 operand variant moves 192 instead of 256 bytes per pixel and K block
+            key = ("fpn.conv1", "tcstem", self.fmt, self._slim)
             pc = self._packed.get(key)
             if pc is None:
-                pc = ops.pack_stem_filter(fpn.conv1.weight, _bn_tuple(fpn.bn1), self.fmt)
+                pc = ops.pack_stem_filter(fpn.conv1.weight, _bn_tuple(fpn.bn1), self.fmt, in_no_h8=self._slim)
                 self._packed[key] = pc
-            xs = ops.stem_pack_input_u8(img, self.fmt) if raw_u8 else ops.stem_pack_input(img, self.fmt)
+            xs = (ops.stem_pack_input_u8 if raw_u8 else ops.stem_pack_input)(img, self.fmt, want_h8=not self._slim)
             c1 = ops.conv2d(xs, pc, relu=True, want_h8=not self._slim)   # read by the max-pool only
         else:
             x = ops.act_from_nchw(img, FMT_F32)
@@ -189,8 +191,11 @@ class Engine(object):
         stride = blk.conv2.stride[0]
         slim = self._slim
         nh = slim and not x.has_h8
-        o = ops.conv2d(x, self._pc(name + ".conv1", blk.conv1, blk.bn1, no_h8=nh), relu=True)
-        o = ops.conv2d(o, self._pc(name + ".conv2", blk.conv2, blk.bn2), stride=stride, pad=1, relu=True, want_h8=not slim)
+        # a 3x3 with <= 64 output channels (layer1) is bound by its A-operand traffic, not by the tensor pipe: it takes the no-h8
+        # operand variant too, and its input is then stored without the copy plane
+        thin = slim and blk.conv2.out_channels <= 64
+        o = ops.conv2d(x, self._pc(name + ".conv1", blk.conv1, blk.bn1, no_h8=nh), relu=True, want_h8=not thin)
+        o = ops.conv2d(o, self._pc(name + ".conv2", blk.conv2, blk.bn2, no_h8=thin), stride=stride, pad=1, relu=True, want_h8=not slim)
         if len(blk.downsample) > 0:
             sc = ops.conv2d(x, self._pc(name + ".downsample", blk.downsample[0], blk.downsample[1], no_h8=nh), stride=stride,
                             want_h8=not slim)
@@ -282,12 +287,14 @@ class Engine(object):
             cells = [f.H * f.W for f in feats]
             offs = [9 * sum(cells[:i]) for i in range(len(feats))]
             hr, hc = list(feats), list(feats)
+            slim = self._slim   # the 36- / 9-channel output convs are A-traffic bound: no-h8 operand variant, conv4 stores no h8
             for n in ("conv1", "conv2", "conv3", "conv4"):
-                hr = ops.conv2d_multi(hr, self._pc("regressionModel." + n, getattr(m.regressionModel, n)), pad=1, relu=True)
-                hc = ops.conv2d_multi(hc, self._pc("classificationModel." + n, getattr(m.classificationModel, n)), pad=1, relu=True)
-            ops.conv2d_multi(hr, self._pc("regressionModel.output", m.regressionModel.output), pad=1, out_mode=OUT_F32_NHWC,
+                h8 = not (slim and n == "conv4")
+                hr = ops.conv2d_multi(hr, self._pc("regressionModel." + n, getattr(m.regressionModel, n)), pad=1, relu=True, want_h8=h8)
+                hc = ops.conv2d_multi(hc, self._pc("classificationModel." + n, getattr(m.classificationModel, n)), pad=1, relu=True, want_h8=h8)
+            ops.conv2d_multi(hr, self._pc("regressionModel.output", m.regressionModel.output, no_h8=slim), pad=1, out_mode=OUT_F32_NHWC,
                              out_tensor=reg, out_elem_offsets=[o * 4 for o in offs], out_cstride=36, out_nstride=A * 4)
-            ops.conv2d_multi(hc, self._pc("classificationModel.output", m.classificationModel.output), pad=1, sigmoid=True,
+            ops.conv2d_multi(hc, self._pc("classificationModel.output", m.classificationModel.output, no_h8=slim), pad=1, sigmoid=True,
                              out_mode=OUT_F32_NHWC, out_tensor=cls, out_elem_offsets=offs, out_cstride=9, out_nstride=A)
         elif LEVEL_STREAMS and small and len(small) < len(feats):
             # The five convs of a small pyramid level (P5-P7: at most 40 CTA pairs, a serial K loop per CTA) are latency

@@ -292,15 +292,16 @@ def conv2d_multi(xs, pc, pad=0, relu=False, sigmoid=False, out_mode=OUT_ACT, out
     return outs if out_mode == OUT_ACT else out_tensor
 
 
-def stem_pack_input(img, fmt):
+def stem_pack_input(img, fmt, want_h8=True):
     """fp32 NCHW image -> zero-padded space-to-depth Act [N, H/2+3, W/2 (+3 pitch), 64-wide windows of 16 ch]
     (mpn_stem_pack_input); with pack_stem_filter the 7x7/2 stem becomes a tcgen05 conv (R=4, S=1, Cin=64)."""
     assert img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3
     img = img.contiguous()
     N, _, H, W = img.shape
     H2, W2 = (H + 1) // 2, (W + 1) // 2
-    a = Act(fmt, N, H2 + 3, W2, 64, img.device, cstride=16, wpitch=W2 + 3, k_overlap=1)
-    check(_lib.lib().mpn_stem_pack_input(_ptr(img), _ptr(a.hi), _ptr(a.lo), N, H, W, fmt, _stream()), "mpn_stem_pack_input")
+    a = Act(fmt, N, H2 + 3, W2, 64, img.device, cstride=16, wpitch=W2 + 3, k_overlap=1, has_h8=want_h8)
+    check(_lib.lib().mpn_stem_pack_input(_ptr(img), _ptr(a.hi), _ptr(a.lo), N, H, W, fmt, 0 if a.has_h8 else EPI_NO_H8, _stream()),
+          "mpn_stem_pack_input")
     stats["launches"] += 1
     return a
 
@@ -316,25 +317,27 @@ def resnet_preprocess_u8(img_u8):
     return out
 
 
-def stem_pack_input_u8(img_u8, fmt):
+def stem_pack_input_u8(img_u8, fmt, want_h8=True):
     """uint8 [N,H,W,3] BGR image -> the tensor-core stem operand with resnet_preprocess fused in."""
     assert img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[3] == 3
     img_u8 = img_u8.contiguous()
     N, H, W, _ = img_u8.shape
     H2, W2 = (H + 1) // 2, (W + 1) // 2
-    a = Act(fmt, N, H2 + 3, W2, 64, img_u8.device, cstride=16, wpitch=W2 + 3, k_overlap=1)
-    check(_lib.lib().mpn_stem_pack_input_u8(_ptr(img_u8), _ptr(a.hi), _ptr(a.lo), N, H, W, fmt, _stream()), "mpn_stem_pack_input_u8")
+    a = Act(fmt, N, H2 + 3, W2, 64, img_u8.device, cstride=16, wpitch=W2 + 3, k_overlap=1, has_h8=want_h8)
+    check(_lib.lib().mpn_stem_pack_input_u8(_ptr(img_u8), _ptr(a.hi), _ptr(a.lo), N, H, W, fmt, 0 if a.has_h8 else EPI_NO_H8, _stream()),
+          "mpn_stem_pack_input_u8")
     stats["launches"] += 1
     return a
 
 
-def pack_stem_filter(weight, bn, fmt):
+def pack_stem_filter(weight, bn, fmt, in_no_h8=False):
     L = _lib.lib()
     w = weight.detach().contiguous()
     assert tuple(w.shape[1:]) == (3, 7, 7)
     pc = PackedConv()
     pc.Cout, pc.Cin, pc.R, pc.S, pc.fmt, pc.cout_pad = w.shape[0], 64, 4, 1, fmt, w.shape[0]
     pc.acc_scale = 0.0
+    pc.in_no_h8 = bool(in_no_h8) and fmt == FMT_F16F8
     if fmt == FMT_F16F8:
         _pack_f16f8(pc, w, None, stem=True)   # the BN scale stays in the epilogue, as for the bf16 stem
     else:

@@ -199,3 +199,31 @@ def test_multi_level_launch_equals_per_level_launches(fmt, B, sizes):
         torch.cuda.synchronize()
         assert torch.equal(out_m, out_s)
         assert float(out_m.abs().min()) > 0.0 or sig   # every anchor slot was written
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 50, 70)])
+def test_tensor_core_stem_without_h8_plane(shape):
+    """The stem on the no-h8 operand variant (its 64 output channels make it A-traffic bound): space-to-depth operand packed without
+    the e5m2 copy plane, filter packed with the fp16 residual plane, overlapping K windows; fp32 and uint8 inputs."""
+    import numpy as np
+    import torch.nn.functional as F
+    from gpu_util import nerr, no_tf32
+    from multiposenet.pytorch_b200 import ops
+    no_tf32()
+    N, H, W = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, 3, H, W, generator=g).cuda()
+    w = (torch.randn(64, 3, 7, 7, generator=g) / 12.0).cuda()
+    bn = (torch.rand(64, generator=g).cuda() + 0.5, torch.randn(64, generator=g).cuda() * 0.1,
+          torch.randn(64, generator=g).cuda() * 0.1, torch.rand(64, generator=g).cuda() + 0.5, 1e-5)
+    ref = F.relu(F.batch_norm(F.conv2d(x, w, None, stride=2, padding=3), bn[2], bn[3], bn[0], bn[1], False, 0.0, 1e-5))
+    pc = ops.pack_stem_filter(w, bn, 3, in_no_h8=True)
+    xs = ops.stem_pack_input(x, 3, want_h8=False)
+    assert not xs.has_h8 and xs.lo.shape[0] == 1
+    y = ops.conv2d(xs, pc, relu=True, want_h8=False)
+    assert not y.has_h8 and nerr(y.to_nchw(), ref) <= 2e-4
+    full = ops.conv2d(ops.stem_pack_input(x, 3), ops.pack_stem_filter(w, bn, 3), relu=True)
+    assert nerr(y.to_nchw(), full.to_nchw()) <= 2e-4
+    u8 = torch.from_numpy(np.random.Generator(np.random.PCG64(2)).integers(0, 256, (N, H, W, 3), dtype=np.uint8)).cuda()
+    a, b = ops.stem_pack_input_u8(u8, 3, want_h8=False), ops.stem_pack_input_u8(u8, 3)
+    assert torch.equal(a.hi, b.hi) and torch.equal(a.lo[0], b.lo[0])
