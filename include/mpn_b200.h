@@ -81,6 +81,16 @@ typedef struct mpn_conv_desc {
                                 Cin/in_cstride neighbouring pixels (stem as a space-to-depth conv) */
   float acc_scale;           /* MPN_FMT_F16F8: the accumulator is multiplied by this (2^-k of the filter packing) before
                                 scale/bias; 0 is read as 1 */
+  /* Phase-class addends (tcgen05 path, MPN_OUT_ACT through the TMA-store epilogue; posenet.py:243-257 without the concat): a
+   * 3x3 convolution over a x2^shift nearest-upsampled map equals, per output pixel, ONE of nine 3x3 convolutions of the
+   * low-resolution map -- which one depends only on (oh mod 2^shift, ow mod 2^shift): class = rc*3 + cc with rc / cc = 0 on the
+   * first row / column of a block, 2 on the last, 1 inside.  The caller evaluates the nine class convolutions at low resolution
+   * (one convolution with 9*Cout output channels, class-major) and this epilogue adds, for g < gat_n,
+   *   v[c] += G_g[n, oh >> gat_shift[g], ow >> gat_shift[g], class * Cout + c]   before ReLU / sigmoid. */
+  int gat_n;                 /* 0, 1 or 2 gathered addends                                                     */
+  int gat_shift[2];          /* log2 of the upsampling factor (2 -> x4, 3 -> x8)                             */
+  int gat_h[2], gat_w[2];    /* low-resolution map size                                                        */
+  int gat_cstride[2];        /* channel stride of G_g (>= 9 * Cout)                                            */
 } mpn_conv_desc;
 
 typedef struct mpn_conv_ptrs {
@@ -90,6 +100,7 @@ typedef struct mpn_conv_ptrs {
   const void* res_hi; const void* res_lo;
   const void* up_hi;  const void* up_lo;
   void* y_hi;         void* y_lo;
+  const void* gat_hi[2]; const void* gat_lo[2];   /* phase-class addends (fmt planes: hi, lo / lo8) */
 } mpn_conv_ptrs;
 
 const char* mpn_last_error(void);

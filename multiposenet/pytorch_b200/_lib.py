@@ -20,12 +20,14 @@ class ConvDesc(ctypes.Structure):
         "N", "H", "W", "Cin", "Cout", "R", "S", "stride", "pad", "OH", "OW", "fmt", "in_cstride", "flags",
         "res_cstride", "up_h", "up_w", "up_cstride", "out_mode", "out_cstride", "out_coffset", "out_rep")] + [
         ("out_nstride", c_ll), ("w_cout_pad", c_int), ("in_wpitch", c_int), ("in_hpitch", c_int), ("k_overlap", c_int),
-        ("acc_scale", c_float)]
+        ("acc_scale", c_float), ("gat_n", c_int), ("gat_shift", c_int * 2), ("gat_h", c_int * 2), ("gat_w", c_int * 2),
+        ("gat_cstride", c_int * 2)]
 
 
 class ConvPtrs(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in (
-        "x_hi", "x_lo", "w_hi", "w_lo", "scale", "bias", "res_hi", "res_lo", "up_hi", "up_lo", "y_hi", "y_lo")]
+        "x_hi", "x_lo", "w_hi", "w_lo", "scale", "bias", "res_hi", "res_lo", "up_hi", "up_lo", "y_hi", "y_lo")] + [
+        ("gat_hi", c_void_p * 2), ("gat_lo", c_void_p * 2)]
 
 
 class MpnError(RuntimeError):

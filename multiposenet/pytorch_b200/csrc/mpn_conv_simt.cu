@@ -176,6 +176,7 @@ int launch_simt(const mpn_conv_desc* d, const mpn_conv_ptrs* p, int in_fmt, void
   if (rc) return rc;
   MPN_CHECK_ARG(d->w_cout_pad >= d->Cout && d->w_cout_pad % 4 == 0, "conv(fp32): w_cout_pad must be >= Cout and a multiple of 4");
   MPN_CHECK_ARG(!d->k_overlap && !d->in_wpitch && !d->in_hpitch, "conv(fp32): pitched / overlapped inputs are a tcgen05-path feature");
+  MPN_CHECK_ARG(d->gat_n == 0, "conv(fp32): phase-class addends are a tcgen05-path feature");
   MPN_CHECK_ARG(in_fmt != MPN_FMT_BF16X2 || p->x_lo, "conv: BF16X2 input needs x_lo");
   SimtParams P;
   P.d = *d;

@@ -92,6 +92,10 @@ struct TcParams {
   int up_tma;  // EPI_TMA_RES brings in the 2x-nearest-upsample source (box {32 ch, TW/2, TH/2, TN}) instead of a shortcut tensor
   int flags, out_mode, out_cstride, out_coffset, out_rep;
   long long out_nstride;
+  // phase-class addends (mpn_conv_desc.gat_*): per output pixel a low-resolution pixel and one of nine Cout-wide channel slices
+  int gat_n, gat_shift[2], gat_h[2], gat_w[2], gat_cstride[2];
+  const void* gat_hi[2];
+  const void* gat_lo[2];
   void* y_hi;
   void* y_lo;
   long long y_plane;  // F16F8: elements of one output plane (the h8 plane starts y_plane bytes after y_lo)
@@ -720,6 +724,22 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
           const bool ok = row < P.rows && ow2 < P.OW && oh2 < P.OH && n2 < P.N;
           res_off = ok ? ((long long)(n2 * P.OH + oh2) * P.OW + ow2) * P.res_cstride : 0;  // invalid rows read pixel 0 (never stored)
         }
+        // phase-class addends: element offset of this row's (low-resolution pixel, class slice) in each gathered tensor
+        long long gat_off[2] = {0, 0};
+        if (!RESLD && P.gat_n > 0) {
+          const int tw2 = row % P.TW, th2 = (row / P.TW) % P.TH, tn2 = row / (P.TW * P.TH);
+          const int ow2 = ow0 + tw2, oh2 = oh0 + th2, n2 = n0 + tn2;
+          const bool ok = row < P.rows && ow2 < P.OW && oh2 < P.OH && n2 < P.N;
+#pragma unroll
+          for (int gi = 0; gi < 2; ++gi) {
+            if (gi < P.gat_n && ok) {
+              const int sh = P.gat_shift[gi], m = (1 << sh) - 1;
+              const int a = oh2 & m, b = ow2 & m;
+              const int cls = (a == 0 ? 0 : a == m ? 2 : 1) * 3 + (b == 0 ? 0 : b == m ? 2 : 1);
+              gat_off[gi] = ((long long)(n2 * P.gat_h[gi] + (oh2 >> sh)) * P.gat_w[gi] + (ow2 >> sh)) * P.gat_cstride[gi] + (long long)cls * P.Cout;
+            }
+          }
+        }
         // The shortcut operand does not depend on the accumulator: the 64 (+64 / +32) bytes of a row's next 32-channel chunk are
         // requested one chunk ahead -- the first one before the accumulator is even complete -- so the global-load latency
         // hides behind the previous chunk's convert / stage / store instead of stalling every chunk (4 per tile and warp).
@@ -811,6 +831,34 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
             for (int j = 0; j < 8; ++j) {
               const float4 t = bias4[j];
               v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
+          }
+          if (!RESLD && P.gat_n > 0) {   // += G_g[low-res pixel][class * Cout + channel], straight from L2 (the MMA phase of these
+                                         // 3x3 convolutions is long: the epilogue has slack)
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+              if (gi >= P.gat_n) break;
+              if constexpr (F8) {
+                const uint4* gh = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(P.gat_hi[gi]) + gat_off[gi] + cbase);
+                const uint4* gl = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(P.gat_lo[gi]) + gat_off[gi] + cbase);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) add_f16x8_reg(v + 8 * i, __ldg(gh + i));
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const uint4 t = __ldg(gl + i);
+                  add_e5m2x4_reg(v + 16 * i, t.x); add_e5m2x4_reg(v + 16 * i + 4, t.y);
+                  add_e5m2x4_reg(v + 16 * i + 8, t.z); add_e5m2x4_reg(v + 16 * i + 12, t.w);
+                }
+              } else {
+                const uint4* gh = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(P.gat_hi[gi]) + gat_off[gi] + cbase);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) add_bf16x8_reg(v + 8 * i, __ldg(gh + i));
+                if (SPLIT) {
+                  const uint4* gl = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(P.gat_lo[gi]) + gat_off[gi] + cbase);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) add_bf16x8_reg(v + 8 * i, __ldg(gl + i));
+                }
+              }
             }
           }
           if (res_lsu || RESLD) {
@@ -1376,6 +1424,20 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
   P.out_rep = d->out_rep; P.out_nstride = d->out_nstride;
   P.y_hi = p->y_hi; P.y_lo = p->y_lo;
   P.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
+  P.gat_n = d->gat_n;
+  MPN_CHECK_ARG(d->gat_n >= 0 && d->gat_n <= 2, "conv(tcgen05): gat_n must be 0, 1 or 2");
+  if (d->gat_n > 0) {
+    MPN_CHECK_ARG(epi_tma && !res_tma && nseg == 1 && d->Cout % 32 == 0, "conv(tcgen05): phase-class addends need the TMA-store epilogue without a shortcut");
+    for (int gi = 0; gi < d->gat_n; ++gi) {
+      const int sh = d->gat_shift[gi];
+      MPN_CHECK_ARG(sh >= 1 && sh <= 4 && (d->gat_h[gi] << sh) == d->OH && (d->gat_w[gi] << sh) == d->OW &&
+                        d->gat_cstride[gi] >= 9 * d->Cout && d->gat_cstride[gi] % 16 == 0 && p->gat_hi[gi] &&
+                        (p->gat_lo[gi] || d->fmt == MPN_FMT_BF16),
+                    "conv(tcgen05): phase-class addend %d: needs OH = gat_h << shift, OW = gat_w << shift, cstride >= 9*Cout", gi);
+      P.gat_shift[gi] = sh; P.gat_h[gi] = d->gat_h[gi]; P.gat_w[gi] = d->gat_w[gi]; P.gat_cstride[gi] = d->gat_cstride[gi];
+      P.gat_hi[gi] = p->gat_hi[gi]; P.gat_lo[gi] = p->gat_lo[gi];
+    }
+  }
   {
     const long long rep2 = (long long)d->out_rep * d->out_rep;
     const long long ns = d->out_nstride > 0 ? d->out_nstride : (long long)d->OH * d->OW * rep2 * d->out_cstride;

@@ -42,6 +42,8 @@ USE_STREAMS = os.environ.get("MPN_STREAMS", "0") == "1"  # measured: no gain on 
 LEVEL_STREAMS = os.environ.get("MPN_LEVEL_STREAMS", "1") == "1"  # small pyramid levels of the RetinaNet towers side by side
 # one launch per tower layer over the five pyramid levels (mpn_conv2d_fwd_multi): 10 launches per step instead of 50
 TOWER_MULTI = os.environ.get("MPN_TOWER_MULTI", "1") == "1"
+# keypoint head: the x8 / x4 quarters of conv2 evaluated at low resolution as phase-class convolutions (no replicated concat)
+CONV2_GATHER = os.environ.get("MPN_CONV2_GATHER", "1") == "1"
 SMALL_LEVEL_PIXELS = 120 * 80  # batch x H x W of a level that cannot fill the GPU (<= 40 CTA pairs of 2 x 120 pixels)
 
 
@@ -239,6 +241,8 @@ class Engine(object):
         if not (p3.H * 2 == p2.H and p4.H * 4 == p2.H and p5.H * 8 == p2.H and p3.W * 2 == p2.W and p4.W * 4 == p2.W
                 and p5.W * 8 == p2.W):
             raise RuntimeError("keypoint head needs H and W to be multiples of 32 (evaluate/tester.py:285 pads to 32)")
+        if CONV2_GATHER and self.fmt != FMT_F32:
+            return self._keypoint_head_classes(p2, p3, p4, p5)
         cat = ops.Act(self.fmt, p2.N, p2.H, p2.W, 512, p2.hi.device)
         for src, t, s, rep, off in ((p5, "convt1", "convs1", 8, 0), (p4, "convt2", "convs2", 4, 128),
                                     (p3, "convt3", "convs3", 2, 256), (p2, "convt4", "convs4", 1, 384)):
@@ -246,6 +250,36 @@ class Engine(object):
             ops.conv2d(q, self._pc(s, getattr(m, s)), pad=1, out=cat, out_coffset=off, out_rep=rep)
         h = ops.conv2d(cat, self._pc("conv2", m.conv2), pad=1, relu=True, want_h8=not self._slim)   # read by the 1x1 convfin only
         return ops.conv2d(h, self._pc("convfin", m.convfin, no_h8=self._slim), out_mode=OUT_F32_NCHW)
+
+    def _keypoint_head_classes(self, p2, p3, p4, p5):
+        """The same head without materialising the x8 / x4 upsampled quarters of the concat (posenet.py:250-254): conv2 is
+        linear in its input channels, and a 3x3 convolution of a nearest-upsampled map is, per output phase, one of nine 3x3
+        convolutions of the low-resolution map (ops.phase_class_filter).  The q5 / q4 quarters of conv2 are evaluated at 1/32 and
+        1/16 resolution (9 * 256 output channels: 0.14x and 0.56x the tensor work of their quarter) and conv2 -- now over the
+        256 channels of q3 (x2, still replicated into the concat) and q2 -- adds them per pixel in its epilogue."""
+        m = self.model
+        slim = self._slim
+        key = ("conv2.classes", self.fmt, slim)
+        pcs = self._packed.get(key)
+        if pcs is None:
+            w = m.conv2.weight.detach()
+            if not w.is_cuda:
+                raise RuntimeError("poseNet must be on a CUDA device (no CPU path); call .cuda() first")
+            pcs = (ops.pack_conv(ops.phase_class_filter(w[:, 0:128]), None, None, self.fmt),
+                   ops.pack_conv(ops.phase_class_filter(w[:, 128:256]), None, None, self.fmt),
+                   ops.pack_conv(w[:, 256:512].contiguous(), m.conv2.bias, None, self.fmt))
+            self._packed[key] = pcs
+        z = []
+        for src, t, s, pcz in ((p5, "convt1", "convs1", pcs[0]), (p4, "convt2", "convs2", pcs[1])):
+            q = ops.conv2d(src, self._pc(t, getattr(m, t)), pad=1)
+            q = ops.conv2d(q, self._pc(s, getattr(m, s)), pad=1)
+            z.append(ops.conv2d(q, pcz, pad=1, want_h8=False))            # read by conv2's epilogue only
+        cat = ops.Act(self.fmt, p2.N, p2.H, p2.W, 256, p2.hi.device)
+        for src, t, s, rep, off in ((p3, "convt3", "convs3", 2, 0), (p2, "convt4", "convs4", 1, 128)):
+            q = ops.conv2d(src, self._pc(t, getattr(m, t)), pad=1)
+            ops.conv2d(q, self._pc(s, getattr(m, s)), pad=1, out=cat, out_coffset=off, out_rep=rep)
+        h = ops.conv2d(cat, pcs[2], pad=1, relu=True, want_h8=not slim, gather=[(z[0], 3), (z[1], 2)])
+        return ops.conv2d(h, self._pc("convfin", m.convfin, no_h8=slim), out_mode=OUT_F32_NCHW)
 
     def intermediate_heads(self, p2, p3, p4, p5):
         """posenet.py:296-299."""

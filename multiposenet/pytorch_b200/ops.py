@@ -157,7 +157,7 @@ def _pack_f16f8(pc, w, scale, stem):
 
 def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=None, out=None, out_mode=OUT_ACT,
            out_coffset=0, out_rep=1, out_tensor=None, out_elem_offset=0, out_cstride=None, out_nstride=0, f32_input=False,
-           want_h8=True):
+           want_h8=True, gather=None):
     """y = epilogue(conv2d(x, w)).  Returns the output Act (OUT_ACT) or the fp32 tensor written.
 
     out          : existing Act to write into (concat buffers), else a new one is allocated
@@ -165,6 +165,8 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
     f32_input    : x is an fp32 NHWC Act while the output/epilogue use pc.fmt (stem)
     want_h8      : FMT_F16F8 activation outputs: False stores the tensor without its e5m2 copy plane (for consumers packed
                    with in_no_h8)
+    gather       : up to two (Act, shift) phase-class addends (mpn_conv_desc.gat_*): Act is the 9*Cout-channel class
+                   convolution of a map 2^shift times smaller than the output (phase_class_filter below)
     """
     L = _lib.lib()
     fmt = pc.fmt
@@ -198,6 +200,15 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
         assert up.N == x.N and up.C == pc.Cout and up.fmt == fmt
         d.up_h, d.up_w, d.up_cstride = up.H, up.W, up.cstride
         p.up_hi, p.up_lo = _ptr(up.hi), _ptr(up.lo)
+    keep = []
+    if gather:
+        assert len(gather) <= 2 and out_mode == OUT_ACT and out_rep == 1
+        d.gat_n = len(gather)
+        for i, (g, sh) in enumerate(gather):
+            assert g.fmt == fmt and g.N == x.N and g.C == 9 * pc.Cout and (g.H << sh, g.W << sh) == (d.OH, d.OW), (g.H, g.W, g.C, sh)
+            d.gat_shift[i], d.gat_h[i], d.gat_w[i], d.gat_cstride[i] = sh, g.H, g.W, g.cstride
+            p.gat_hi[i], p.gat_lo[i] = g.hi.data_ptr(), g.lo.data_ptr() if g.lo is not None else None
+            keep.append(g)
     ret = None
     if out_mode == OUT_ACT:
         if out is None:
@@ -236,6 +247,22 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
                                 "clamped by the saturating fp16 store; run this model with precision='bf16x3'"
                                 % (d.OH, d.OW, pc.Cin, pc.Cout, pc.R, pc.S))
     return ret
+
+
+def phase_class_filter(weight):
+    """3x3 pad-1 filter W [Cout, Cin, 3, 3] applied to a nearest-upsampled map == per output phase one of nine 3x3 pad-1
+    filters on the low-resolution map (mpn_conv_desc.gat_*).  Returns V [9*Cout, Cin, 3, 3], class-major, class = rc*3 + cc:
+    along one axis, class 0 (first row of a block) sends tap 0 to the previous low-resolution row and taps 1,2 to the same
+    row; class 1 (inside) sends all three taps to the same row; class 2 (last row) sends taps 0,1 to the same row and tap 2
+    to the next one.  Holds for every upsampling factor >= 2 (factor 2 has no class 1)."""
+    w = weight.detach().double()
+    assert w.dim() == 4 and w.shape[2:] == (3, 3)
+    M = torch.zeros(3, 3, 3, dtype=torch.float64, device=w.device)   # [class][low-res tap i][tap r]
+    M[0, 0, 0] = M[0, 1, 1] = M[0, 1, 2] = 1
+    M[1, 1, :] = 1
+    M[2, 1, 0] = M[2, 1, 1] = M[2, 2, 2] = 1
+    v = torch.einsum("air,bjs,ocrs->abocij", M, M, w)
+    return v.reshape(9 * w.shape[0], w.shape[1], 3, 3).float().contiguous()
 
 
 def conv2d_multi(xs, pc, pad=0, relu=False, sigmoid=False, out_mode=OUT_ACT, out_tensor=None, out_elem_offsets=None,

@@ -227,3 +227,41 @@ def test_tensor_core_stem_without_h8_plane(shape):
     u8 = torch.from_numpy(np.random.Generator(np.random.PCG64(2)).integers(0, 256, (N, H, W, 3), dtype=np.uint8)).cuda()
     a, b = ops.stem_pack_input_u8(u8, 3, want_h8=False), ops.stem_pack_input_u8(u8, 3)
     assert torch.equal(a.hi, b.hi) and torch.equal(a.lo[0], b.lo[0])
+
+
+@pytest.mark.parametrize("fmt,tol", [(3, 2e-4), (2, 1e-4), (1, 2e-2)])
+@pytest.mark.parametrize("shape", [(2, 32, 64), (3, 24, 40), (1, 8, 8), (32, 120, 160)])
+def test_phase_class_addends_equal_the_replicated_concat(fmt, tol, shape):
+    """Keypoint head conv2 (posenet.py:250-256) with the x8 / x4 quarters evaluated at low resolution as phase-class convolutions and
+    added in the epilogue == the same 3x3 convolution over the replicated 512-channel concat."""
+    import torch.nn.functional as F
+    from gpu_util import nerr, no_tf32
+    from multiposenet.pytorch_b200 import ops
+    no_tf32()
+    N, H, W = shape
+    big = N * H * W > 100000
+    Cout = 256
+    g = torch.Generator().manual_seed(11)
+    q5 = torch.randn(N, 128, H // 8, W // 8, generator=g).cuda()
+    q4 = torch.randn(N, 128, H // 4, W // 4, generator=g).cuda()
+    q32 = torch.randn(N, 256, H, W, generator=g).cuda()
+    w = (torch.randn(Cout, 512, 3, 3, generator=g) / 68.0).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    z5 = ops.conv2d(ops.act_from_nchw(q5, fmt), ops.pack_conv(ops.phase_class_filter(w[:, :128]), None, None, fmt), pad=1, want_h8=False)
+    z4 = ops.conv2d(ops.act_from_nchw(q4, fmt), ops.pack_conv(ops.phase_class_filter(w[:, 128:256]), None, None, fmt), pad=1, want_h8=False)
+    y = ops.conv2d(ops.act_from_nchw(q32, fmt), ops.pack_conv(w[:, 256:].contiguous(), b, None, fmt), pad=1, relu=True,
+                   gather=[(z5, 3), (z4, 2)]).to_nchw()
+    # the replicated-concat formulation on the device (the previous product path) and, for the small cases, torch fp32
+    cat = ops.Act(fmt, N, H, W, 512, "cuda")
+    eye = torch.eye(128).reshape(128, 128, 1, 1).cuda()
+    pe = ops.pack_conv(eye, None, None, fmt)
+    ops.conv2d(ops.act_from_nchw(q5, fmt), pe, out=cat, out_coffset=0, out_rep=8)
+    ops.conv2d(ops.act_from_nchw(q4, fmt), pe, out=cat, out_coffset=128, out_rep=4)
+    ops.conv2d(ops.act_from_nchw(q32, fmt), ops.pack_conv(torch.eye(256).reshape(256, 256, 1, 1).cuda(), None, None, fmt), out=cat, out_coffset=256)
+    y_cat = ops.conv2d(cat, ops.pack_conv(w, b, None, fmt), pad=1, relu=True).to_nchw()
+    torch.cuda.synchronize()
+    assert nerr(y, y_cat) <= tol
+    if not big:
+        x = torch.cat([F.interpolate(q5, scale_factor=8, mode="nearest"), F.interpolate(q4, scale_factor=4, mode="nearest"), q32], 1)
+        ref = F.relu(F.conv2d(x, w, b, padding=1))
+        assert nerr(y, ref) <= tol

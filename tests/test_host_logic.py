@@ -193,3 +193,23 @@ def test_compat_batch_processor_contract():
     state.params.subnet_name = "prn_subnet"
     inputs, gts, _ = batch_processor(state, (a, b))
     assert inputs[0][1] == "prn_subnet" and gts[0] == "prn_subnet"
+
+
+def test_phase_class_filter_identity():
+    """ops.phase_class_filter: conv3x3(nearest_upsample(x, f), W) == per output phase one of nine 3x3 convolutions of x
+    (the identity behind mpn_conv_desc.gat_*), for f = 2, 4, 8 including the zero-padded borders."""
+    import torch
+    import torch.nn.functional as F
+    from multiposenet.pytorch_b200.ops import phase_class_filter
+    g = torch.Generator().manual_seed(0)
+    for sh in (1, 2, 3):
+        f = 1 << sh
+        x = torch.randn(2, 5, 3, 4, generator=g, dtype=torch.float64)
+        w = torch.randn(7, 5, 3, 3, generator=g)
+        ref = F.conv2d(F.interpolate(x, scale_factor=f, mode="nearest"), w.double(), padding=1)
+        z = F.conv2d(x, phase_class_filter(w).double(), padding=1).reshape(2, 9, 7, 3, 4)
+        oh, ow = torch.arange(3 * f), torch.arange(4 * f)
+        rc = torch.where(oh % f == 0, 0, torch.where(oh % f == f - 1, 2, 1))
+        cc = torch.where(ow % f == 0, 0, torch.where(ow % f == f - 1, 2, 1))
+        out = z[:, rc[:, None] * 3 + cc[None, :], :, (oh // f)[:, None], (ow // f)[None, :]].permute(2, 3, 0, 1)
+        assert float((out - ref).abs().max()) < 1e-5
