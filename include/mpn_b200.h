@@ -56,6 +56,15 @@ extern "C" {
  * w_hi fp16 [Cout,R,S,Cin]; w_lo = [lo16 fp16 plane][h8 e4m3 plane]. */
 #define MPN_EPI_NO_H8 4
 #define MPN_IN_NO_H8 8
+/* MPN_IN_DERIVE_H8: the input tensor has no e5m2 copy plane and the kernel derives the copy in shared memory from the fp16 tile
+ * TMA delivered (two converter warps per CTA); the filter is packed in the ordinary layout 0 (hi | lo8 | h8) and the MMA schedule
+ * is the 8-slot one.  With it no activation needs its copy plane in HBM at all: the plane exists because TMA cannot gather every
+ * second byte, and its 64-byte box rows cost the TMA unit as much as 128-byte ones (~2.25 cycles per row). */
+#define MPN_IN_DERIVE_H8 16
+/* MPN_W_MERGED: the filter's two byte planes were packed interleaved (mpn_pack_filter_f16f8 layout bit 2: per filter row and 64 K
+ * elements one 128-byte group [64 lo8 | 64 h8]), so a K block's filter tile arrives as two TMA boxes of 128-byte rows instead of
+ * three.  Not combinable with MPN_IN_NO_H8 (whose residual plane is fp16). */
+#define MPN_W_MERGED 32
 
 typedef struct mpn_conv_desc {
   /* problem: y = epilogue(conv2d(x, w)); torch.nn.Conv2d semantics (cross-correlation, zero pad) */

@@ -6,11 +6,12 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmpn_b200.so")
+# MPN_B200_LIB: an instrumented build of the same ABI (csrc/build.py --trace -> libmpn_b200_trace.so, scripts/exp/trace_conv.py)
+LIB_PATH = os.environ.get("MPN_B200_LIB") or os.path.join(_HERE, "csrc", "libmpn_b200.so")
 
 FMT_F32, FMT_BF16, FMT_BF16X2, FMT_F16F8 = 0, 1, 2, 3
 OUT_ACT, OUT_F32_NHWC, OUT_F32_NCHW = 0, 1, 2
-EPI_RELU, EPI_SIGMOID, EPI_NO_H8, IN_NO_H8 = 1, 2, 4, 8
+EPI_RELU, EPI_SIGMOID, EPI_NO_H8, IN_NO_H8, IN_DERIVE_H8, W_MERGED = 1, 2, 4, 8, 16, 32
 
 c_void_p, c_int, c_float, c_size_t, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_longlong
 

@@ -20,15 +20,18 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, trace=False):
+    """trace=True: the instrumented debug build (-DMPN_CONV_TRACE: clock64 stamps inside conv_tc_kernel) -> libmpn_b200_trace.so,
+    loaded through MPN_B200_LIB by scripts/exp/trace_conv.py; never the product library."""
+    out_path = OUT.replace(".so", "_trace.so") if trace else OUT
+    if not trace and not force and not needs_build():
         return OUT
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(HERE, s.replace(".cu", ".o"))
+        o = os.path.join(HERE, s.replace(".cu", ".trace.o" if trace else ".o"))
         objs.append(o)
-        cmd = [NVCC] + FLAGS + ["-c", os.path.join(HERE, s), "-o", o]
+        cmd = [NVCC] + FLAGS + (["-DMPN_CONV_TRACE"] if trace else []) + ["-c", os.path.join(HERE, s), "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -36,10 +39,10 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
         if verbose and out.strip():
             print(out)
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lcudart"]
+    cmd = [NVCC, "-shared", "-o", out_path] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
-    return OUT
+    return out_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, trace="--trace" in sys.argv))

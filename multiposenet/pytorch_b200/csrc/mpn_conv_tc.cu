@@ -39,8 +39,37 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;           // bf16 elements = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 384;
+
+// Debug build only (-DMPN_CONV_TRACE, scripts/exp/trace_conv.py): clock64 stamps of the producer / MMA issuer / epilogue issuers of
+// the first CTAs into a global buffer -- the timeline of a persistent CTA.  Compiled out of the product library.
+#ifdef MPN_CONV_TRACE
+__device__ unsigned long long* g_trace_buf = nullptr;
+__device__ int g_trace_cap = 0;
+constexpr int TRACE_CTAS = 4, TRACE_ROLES = 8;
+struct Tracer {
+  unsigned long long* p;
+  int n, cap;
+  __device__ __forceinline__ void init(int role) {
+    n = 0;
+    cap = (blockIdx.x < TRACE_CTAS && g_trace_buf) ? g_trace_cap : 0;
+    p = g_trace_buf + ((size_t)(blockIdx.x * TRACE_ROLES + role) * (size_t)g_trace_cap) * 2;
+  }
+  __device__ __forceinline__ void rec(int ev, int a, int b) {
+    if (n < cap) {
+      p[2 * n] = (unsigned long long)clock64();
+      p[2 * n + 1] = (unsigned long long)ev | ((unsigned long long)(unsigned)a << 8) | ((unsigned long long)(unsigned)b << 32);
+      ++n;
+    }
+  }
+};
+#define TRACE_INIT(role) Tracer tr_; tr_.init(role)
+#define TRACE(ev, a, b) tr_.rec(ev, a, b)
+#else
+#define TRACE_INIT(role)
+#define TRACE(ev, a, b)
+#endif
+constexpr int NUM_EPI_WARPS = 8;   // NUM_THREADS = 4 control warps (TMA, MMA, TMEM alloc / h8 converters) + 8 epilogue warps
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 256;
 constexpr int BIAS_BYTES = 1024;  // EPI_TMA: the tile's folded-BN bias, 2 halves x 4 chunks x 32 channels (behind the barriers)
@@ -93,6 +122,11 @@ struct TcParams {
   int flags, out_mode, out_cstride, out_coffset, out_rep;
   long long out_nstride;
   // phase-class addends (mpn_conv_desc.gat_*): per output pixel a low-resolution pixel and one of nine Cout-wide channel slices
+#ifdef MPN_CONV_TRACE
+  int dbg_skip;   // timing experiment (results are garbage): bit 0 skips the B h8 plane load, bit 1 the A h8 plane load
+#endif
+  int w_merged; // F16F8 / F16F8C: filter byte planes interleaved per K block (MPN_W_MERGED): one 128B-swizzled tile [lo8 | h8]
+  int res_pf;   // EPI_TMA_RES: L2 prefetch of the next tile's shortcut boxes (MPN_RES_PF=0 disables)
   int gat_n, gat_shift[2], gat_h[2], gat_w[2], gat_cstride[2];
   const void* gat_hi[2];
   const void* gat_lo[2];
@@ -161,7 +195,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 // weight-residual term x * w_lo runs as x_hi(fp16) * w_lo16(fp16) on kind::f16 (4 more K = 16 MMAs per K block: 10 slots
 // instead of 8, and a more accurate term) -- used where the layer is bound by HBM / the epilogue, not by the tensor pipe
 // (every 1x1 conv of the backbone, the FPN laterals).  Filter planes: hi fp16, lo16 fp16, h8 e4m3.
-enum { MODE_BF16 = 0, MODE_BF16X2 = 1, MODE_F16F8 = 2, MODE_F16F8B = 3 };
+// MODE_F16F8C: F16F8 for an activation tensor stored without its h8 plane, the plane DERIVED in shared memory: TMA pays ~2.25
+// cycles per box row whatever its width (32..128 B: scripts/exp/tma_row_rate_probe.cu), so the 64-byte h8 rows cost as much as
+// the 128-byte fp16 rows they copy.  Warps 2 and 3 round the fp16 tile TMA delivered to e5m2 (top byte, round half up, clamped
+// to the largest finite e5m2) into the stage's h8 tile; 8 MMA slots per K block like MODE_F16F8, filter planes hi | lo8 | h8.
+enum { MODE_BF16 = 0, MODE_BF16X2 = 1, MODE_F16F8 = 2, MODE_F16F8B = 3, MODE_F16F8C = 4 };
 __host__ __device__ constexpr int a_stage_bytes(int mode) { return mode == MODE_BF16 ? 16384 : mode == MODE_F16F8B ? 24576 : 32768; }
 __host__ __device__ constexpr int b_row_bytes(int mode) { return mode == MODE_BF16 ? 128 : mode == MODE_F16F8B ? 320 : 256; }
 
@@ -202,6 +240,14 @@ __device__ __forceinline__ void add_e5m2x4_reg(float* v, uint32_t w) {
   v[2] = fmaf(f16_lo_f(p23), MPN_F8_LO_INV, v[2]);
   v[3] = fmaf(f16_hi_f(p23), MPN_F8_LO_INV, v[3]);
 }
+// four fp16 (two words) -> their e5m2 roundings (top byte after adding half an e5m2 ulp; the carry runs into the exponent as it
+// should), magnitude clamped to 0x7B = 57344, the largest finite e5m2: a saturated activation must not become inf * w
+__device__ __forceinline__ uint32_t h8_round4(uint32_t w0, uint32_t w1) {
+  // magnitude + half an e5m2 ulp, clamped below the first inf pattern (one VIADDMNMX.U16x2 per word), top bytes, signs back in
+  const uint32_t m0 = __viaddmin_u16x2(w0 & 0x7FFF7FFFu, 0x00800080u, 0x7BFF7BFFu);
+  const uint32_t m1 = __viaddmin_u16x2(w1 & 0x7FFF7FFFu, 0x00800080u, 0x7BFF7BFFu);
+  return __byte_perm(m0, m1, 0x7531) | (__byte_perm(w0, w1, 0x7531) & 0x80808080u);
+}
 // 8 floats -> fp16 hi (uint4), lo8 = e5m2((v - hi) * 2^12) (uint2), h8 = e5m2(v) (uint2; skipped for tensors stored without it)
 __device__ __forceinline__ void split_f16f8x8(const float* w, uint4& hi, uint2& lo8, uint2& h8, bool want_h8 = true) {
   hi.x = pack_f16(w[0], w[1]); hi.y = pack_f16(w[2], w[3]); hi.z = pack_f16(w[4], w[5]); hi.w = pack_f16(w[6], w[7]);
@@ -229,20 +275,21 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
   constexpr int NTHREADS = 128 + 128 * NG;   // 4 control warps + the epilogue warps
   constexpr bool SPLIT = MODE == MODE_BF16X2;
   constexpr bool F8B = MODE == MODE_F16F8B;             // operand side: no h8 activation plane, fp16 weight residual
-  constexpr bool F8 = MODE == MODE_F16F8 || F8B;        // format side (epilogue, shortcut): fp16 hi + e5m2 lo8 (+ optional h8)
+  constexpr bool F8C = MODE == MODE_F16F8C;             // operand side: no h8 activation plane, derived in shared memory
+  constexpr bool F8 = MODE == MODE_F16F8 || F8B || F8C; // format side (epilogue, shortcut): fp16 hi + e5m2 lo8 (+ optional h8)
   // "plane units" of 128 bytes per row and K block: BF16X2 = hi + lo; F16F8 = hi (128 B) + lo8 (64 B) + h8 (64 B)
   constexpr int PLANES = MODE == MODE_BF16 ? 1 : 2;
   constexpr int NMAPS = F8 ? 3 : PLANES;
   constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BLOCK_K * 2;  // one 128-byte plane of the filter rows held by THIS CTA
   constexpr int A_STAGE = a_stage_bytes(MODE);                      // A planes of one K block
   constexpr int B_ROW = b_row_bytes(MODE);                          // B bytes per filter row and K block (all planes)
-  constexpr int A_ROW_TX = F8B ? 192 : PLANES * 128;                // A bytes TMA delivers per box row
+  constexpr int A_ROW_TX = (F8B || F8C) ? 192 : PLANES * 128;       // A bytes TMA delivers per box row
   constexpr int STAGE_BYTES = A_STAGE + (PAIR ? BN / 2 : BN) * B_ROW;
   constexpr int MMA_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
   constexpr bool TMAEPI = EPI == EPI_TMA || EPI == EPI_TMA_RES;
   constexpr bool RESLD = EPI == EPI_TMA_RES;
   constexpr int EPI_BYTES = WIDE ? 8 * WIDE_BOX_BYTES : NUM_EPI_WARPS * EPI_STAGE_BYTES + (RESLD ? 4 * RES_STAGE_BYTES : 0);
-  static_assert(!WIDE || (RESLD && PAIR && (MODE == MODE_F16F8 || MODE == MODE_F16F8B)), "the wide epilogue is the F16F8 shortcut epilogue");
+  static_assert(!WIDE || (RESLD && PAIR && F8), "the wide epilogue is the F16F8 shortcut epilogue");
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   // c = F32; a, b = BF16 (1) or, for F16F8, F16 (0);  | (N >> 3) << 17 per tile
   constexpr uint32_t IDESC_BASE = (1u << 4) | (F8 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(MMA_M >> 4) << 24);
@@ -257,6 +304,11 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   auto res_full_bar = [&](int h, int b) { return bar_base + 8u * (2 * STAGES + 5 + 2 * h + b); };
+  // F8C: afull = this CTA's activation planes of a stage have landed (the converter warps wait for it); conv = the h8 tiles of the
+  // stage are complete in every CTA of the pair (on the leader; the MMA issuer waits for it in addition to `full`, which counts
+  // the filter bytes there)
+  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 9 + s); };
+  auto conv_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + 9 + s); };
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + EPI_BYTES + 8 * (2 * STAGES + 4));
@@ -275,7 +327,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
     for (int p = 0; p < NMAPS; ++p) {
       prefetch_tmap(&maps.b[p]);
       for (int sg = 0; sg < P.nseg; ++sg) {
-        if (!(F8B && p == 2)) prefetch_tmap(&maps.a[p][sg]);
+        if (!((F8B || F8C) && p == 2)) prefetch_tmap(&maps.a[p][sg]);
         if (TMAEPI && !(F8 && p == 2 && (P.flags & MPN_EPI_NO_H8))) prefetch_tmap(&maps.y[p][sg]);
       }
       if (P.tail_split > 1) prefetch_tmap(&maps.bs[p]);
@@ -291,6 +343,12 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
     }
     if (RESLD) {
       for (int i = 0; i < 4; ++i) mbar_init(res_full_bar(i >> 1, i & 1), 1);
+    }
+    if (F8C) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(afull_bar(s), 1);
+        mbar_init(conv_bar(s), PAIR ? 4 : 2);   // one arrival per converter warp of each CTA
+      }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -325,6 +383,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
     // =============================== TMA producer ===============================
     int stage = 0;
     uint32_t phase = 0;
+    TRACE_INIT(0);
     const uint32_t lead_full0 = PAIR ? mapa_shared(full_bar(0), 0) : 0u;  // the leader's full barriers, as cluster addresses
     for (int tile = tile0; tile < P.total_tiles; tile += tile_step) {
       const TileCoord tc = decode_tile<BN, PAIR>(P, tile, cta_rank);
@@ -332,7 +391,11 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
       const int brows = PAIR ? tc.ncols / 2 : tc.ncols;                     // filter rows this CTA loads
       // bytes of one K block landing in this CTA; the leader's barrier of a pair expects both CTAs' bytes
       const Seg& g = P.seg[tc.seg];
+#ifdef MPN_CONV_TRACE
+      const uint32_t tx_bytes = (uint32_t)(g.rows * (A_ROW_TX - ((P.dbg_skip & 2) ? 64 : 0)) + brows * (B_ROW - ((P.dbg_skip & 1) ? 64 : 0))) * (PAIR ? 2u : 1u);
+#else
       const uint32_t tx_bytes = (uint32_t)(g.rows * A_ROW_TX + brows * B_ROW) * (PAIR ? 2u : 1u);
+#endif
       // narrow tail tiles are latency-bound on the ring: pack as many K blocks as fit into one stage (sub-blocks of
       // [A planes][B planes], the B planes ncols*128 bytes apart) so that twice the bytes are in flight
       const uint32_t bplane = tail ? (uint32_t)brows * 128u : (uint32_t)B_TILE_BYTES;
@@ -362,14 +425,31 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
           if (u == 0) {
             const int group = min(kpack, num_k_iters - ki);
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            if (leader) mbar_expect_tx(full_bar(stage), tx_bytes * (uint32_t)group);
+            TRACE(1, tile, ki);
+            if constexpr (F8C) {   // activation bytes -> this CTA's afull barrier, filter bytes -> the (leader's) full barrier
+              mbar_expect_tx(afull_bar(stage), (uint32_t)(g.rows * A_ROW_TX) * (uint32_t)group);
+              if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)(brows * B_ROW) * (PAIR ? 2u : 1u) * (uint32_t)group);
+            } else {
+              if (leader) mbar_expect_tx(full_bar(stage), tx_bytes * (uint32_t)group);
+            }
           }
           const uint32_t sa = smem_base + stage * STAGE_BYTES + u * sub_bytes;
           const uint32_t sb = sa + A_STAGE;
           const int kcol = tap * P.Cin + kb * BLOCK_K;
           if constexpr (PAIR) {
             const uint32_t lb = lead_full0 + 8u * stage;
-            if constexpr (F8B) {
+            if constexpr (F8C) {
+              // A: [hi 16 KB][lo8 8 KB][h8 8 KB, written by the converter warps]; B: [hi rows*128][lo8 rows*64][h8 rows*64]
+              tma_load_4d(sa, &maps.a[0][ph], afull_bar(stage), kb * BLOCK_K, wc, hc, n0);
+              tma_load_4d(sa + A_TILE_BYTES, &maps.a[1][ph], afull_bar(stage), kb * BLOCK_K, wc, hc, n0);
+              tma_load_2d_pair(sb, tail ? &maps.bs[0] : &maps.b[0], lb, kcol, co0);
+              if (P.w_merged) {
+                tma_load_2d_pair(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], lb, 2 * kcol, co0);
+              } else {
+                tma_load_2d_pair(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], lb, kcol, co0);
+                tma_load_2d_pair(sb + bplane + bplane / 2, tail ? &maps.bs[2] : &maps.b[2], lb, kcol, co0);
+              }
+            } else if constexpr (F8B) {
               // A: [hi 16 KB][lo8 8 KB]; B: [hi rows*128][lo16 rows*128][h8 rows*64]
               tma_load_4d_pair(sa, &maps.a[0][ph], lb, kb * BLOCK_K, wc, hc, n0);
               tma_load_4d_pair(sa + A_TILE_BYTES, &maps.a[1][ph], lb, kb * BLOCK_K, wc, hc, n0);
@@ -379,16 +459,36 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
             } else if constexpr (F8) {
               tma_load_4d_pair(sa, &maps.a[0][ph], lb, kb * BLOCK_K, wc, hc, n0);
               tma_load_4d_pair(sa + A_TILE_BYTES, &maps.a[1][ph], lb, kb * BLOCK_K, wc, hc, n0);
+#ifdef MPN_CONV_TRACE
+              if (!(P.dbg_skip & 2))
+#endif
               tma_load_4d_pair(sa + A_TILE_BYTES + A_TILE_BYTES / 2, &maps.a[2][ph], lb, kb * BLOCK_K, wc, hc, n0);
               tma_load_2d_pair(sb, tail ? &maps.bs[0] : &maps.b[0], lb, kcol, co0);
+              if (P.w_merged) {
+                tma_load_2d_pair(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], lb, 2 * kcol, co0);
+              } else {
               tma_load_2d_pair(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], lb, kcol, co0);
+#ifdef MPN_CONV_TRACE
+              if (!(P.dbg_skip & 1))
+#endif
               tma_load_2d_pair(sb + bplane + bplane / 2, tail ? &maps.bs[2] : &maps.b[2], lb, kcol, co0);
+              }
             } else {
 #pragma unroll
               for (int p = 0; p < PLANES; ++p) {
                 tma_load_4d_pair(sa + p * A_TILE_BYTES, &maps.a[p][ph], lb, kb * BLOCK_K, wc, hc, n0);
                 tma_load_2d_pair(sb + p * bplane, tail ? &maps.bs[p] : &maps.b[p], lb, kcol, co0);
               }
+            }
+          } else if constexpr (F8C) {
+            tma_load_4d(sa, &maps.a[0][ph], afull_bar(stage), kb * BLOCK_K, wc, hc, n0);
+            tma_load_4d(sa + A_TILE_BYTES, &maps.a[1][ph], afull_bar(stage), kb * BLOCK_K, wc, hc, n0);
+            tma_load_2d(sb, tail ? &maps.bs[0] : &maps.b[0], full_bar(stage), kcol, co0);
+            if (P.w_merged) {
+              tma_load_2d(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], full_bar(stage), 2 * kcol, co0);
+            } else {
+              tma_load_2d(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], full_bar(stage), kcol, co0);
+              tma_load_2d(sb + bplane + bplane / 2, tail ? &maps.bs[2] : &maps.b[2], full_bar(stage), kcol, co0);
             }
           } else if constexpr (F8B) {
             tma_load_4d(sa, &maps.a[0][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
@@ -402,8 +502,12 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
             tma_load_4d(sa + A_TILE_BYTES, &maps.a[1][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
             tma_load_4d(sa + A_TILE_BYTES + A_TILE_BYTES / 2, &maps.a[2][ph], full_bar(stage), kb * BLOCK_K, wc, hc, n0);
             tma_load_2d(sb, tail ? &maps.bs[0] : &maps.b[0], full_bar(stage), kcol, co0);
-            tma_load_2d(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], full_bar(stage), kcol, co0);
-            tma_load_2d(sb + bplane + bplane / 2, tail ? &maps.bs[2] : &maps.b[2], full_bar(stage), kcol, co0);
+            if (P.w_merged) {
+              tma_load_2d(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], full_bar(stage), 2 * kcol, co0);
+            } else {
+              tma_load_2d(sb + bplane, tail ? &maps.bs[1] : &maps.b[1], full_bar(stage), kcol, co0);
+              tma_load_2d(sb + bplane + bplane / 2, tail ? &maps.bs[2] : &maps.b[2], full_bar(stage), kcol, co0);
+            }
           } else {
 #pragma unroll
             for (int p = 0; p < PLANES; ++p) {
@@ -438,10 +542,12 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    TRACE_INIT(1);
     for (int tile = tile0; tile < P.total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      TRACE(2, tile, 0);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       const int ncols = decode_tile<BN, PAIR>(P, tile, 0).ncols;
@@ -453,6 +559,9 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
       const int kpack = (tail && !PAIR) ? (int)(STAGE_BYTES / sub_bytes) : 1;
       for (int ki = 0; ki < num_k_iters;) {
         mbar_wait(full_bar(stage), phase);
+        TRACE(16, tile, ki);
+        if constexpr (F8C) mbar_wait(conv_bar(stage), phase);
+        TRACE(3, tile, ki);
         tc_fence_after();
         const int group = min(kpack, num_k_iters - ki);
         for (int u = 0; u < group; ++u, ++ki) {
@@ -481,8 +590,11 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
             } else {
 #pragma unroll
               for (int k = 0; k < BLOCK_K / 32; ++k) {  // fp8 cross terms, K = 32 per instruction
-                mma8(make_sdesc64(sa + A_TILE_BYTES + k * 32), make_sdesc64(sb + bplane + bplane / 2 + k * 32));  // xlo8 * wh8
-                mma8(make_sdesc64(sa + A_TILE_BYTES + A_TILE_BYTES / 2 + k * 32), make_sdesc64(sb + bplane + k * 32));  // xh8 * wlo8
+                // merged filter planes: one 128B-swizzled tile of 128-byte rows, lo8 in bytes 0..63 and h8 in bytes 64..127
+                const uint64_t b_h8 = P.w_merged ? make_sdesc(sb + bplane + 64 + k * 32) : make_sdesc64(sb + bplane + bplane / 2 + k * 32);
+                const uint64_t b_lo8 = P.w_merged ? make_sdesc(sb + bplane + k * 32) : make_sdesc64(sb + bplane + k * 32);
+                mma8(make_sdesc64(sa + A_TILE_BYTES + k * 32), b_h8);                          // xlo8 * wh8
+                mma8(make_sdesc64(sa + A_TILE_BYTES + A_TILE_BYTES / 2 + k * 32), b_lo8);      // xh8 * wlo8
               }
             }
           } else {
@@ -530,6 +642,65 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
         }
       }
     }
+  } else if (F8C && (warp == 2 || warp == 3)) {
+    // =============================== h8 converters (MODE_F16F8C) ===============================
+    // Per K block: the 128 x 64 fp16 tile (128-byte rows, 128B swizzle) -> its e5m2 rounding as a 128 x 64 byte tile (64-byte rows,
+    // 64B swizzle) behind the lo8 tile.  Lane = row: a quarter-warp's eight rows read / write eight different 16-byte columns.
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t conv0 = PAIR ? mapa_shared(conv_bar(0), 0) : conv_bar(0);
+    TRACE_INIT(6 + (warp - 2));
+#ifdef MPN_CONV_TRACE
+    if (lane != 0) tr_.cap = 0;
+#endif
+    for (int tile = tile0; tile < P.total_tiles; tile += tile_step) {
+      const TileCoord tc = decode_tile<BN, PAIR>(P, tile, cta_rank);
+      const bool tail = tc.ncols != BN;
+      const int brows = PAIR ? tc.ncols / 2 : tc.ncols;
+      const uint32_t bplane = tail ? (uint32_t)brows * 128u : (uint32_t)B_TILE_BYTES;
+      const uint32_t sub_bytes = (uint32_t)A_STAGE + (bplane >> 7) * (uint32_t)B_ROW;
+      const int kpack = (tail && !PAIR) ? (int)(STAGE_BYTES / sub_bytes) : 1;
+      for (int ki = 0; ki < num_k_iters;) {
+        const int group = min(kpack, num_k_iters - ki);
+        TRACE(12, tile, ki);
+        mbar_wait(afull_bar(stage), phase);
+        TRACE(13, tile, ki);
+        for (int u = 0; u < group; ++u) {
+          uint8_t* a_hi = smem_gen + stage * STAGE_BYTES + u * sub_bytes;
+          uint8_t* a_h8 = a_hi + A_TILE_BYTES + A_TILE_BYTES / 2;
+          // all sixteen loads of the thread's two rows first (the stores below may alias them for all the compiler knows)
+          uint4 x[2][8];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int r = (warp - 2) * 64 + i * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) x[i][c] = *reinterpret_cast<const uint4*>(a_hi + r * 128 + ((c ^ (r & 7)) << 4));
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int r = (warp - 2) * 64 + i * 32 + lane;
+            uint8_t* dst = a_h8 + r * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 x0 = x[i][2 * j], x1 = x[i][2 * j + 1];
+              uint4 o;
+              o.x = h8_round4(x0.x, x0.y); o.y = h8_round4(x0.z, x0.w); o.z = h8_round4(x1.x, x1.y); o.w = h8_round4(x1.z, x1.w);
+              *reinterpret_cast<uint4*>(dst + ((j ^ ((r >> 1) & 3)) << 4)) = o;
+            }
+          }
+        }
+        ki += group;
+        TRACE(14, tile, ki);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(conv0 + 8u * stage);
+          else mbar_arrive(conv_bar(stage));
+        }
+        TRACE(15, tile, ki);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
   } else if (warp >= 4) {
     // =============================== epilogue (8 warps) ===============================
     // Two warps per TMEM lane quarter (one per SM sub-partition pair): warp w owns quarter w&3 and the
@@ -573,6 +744,12 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
           pf_c0 = grp * 32;
         }
       };
+      TRACE_INIT(2 + grp);
+      if (!issuer) {
+#ifdef MPN_CONV_TRACE
+        tr_.cap = 0;
+#endif
+      }
       if (issuer) pf_issue();
       uint32_t res_n = 0;
       bool store_pending = false;
@@ -583,6 +760,15 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
         const TileCoord tc = decode_tile<BN, PAIR>(P, tile, cta_rank);
         const int co0 = tc.co0, ncols = tc.ncols;
         const int ow0 = tc.tw_i * P.TW, oh0 = tc.th_i * P.TH, n0 = tc.tn_i * P.TN;
+        if (issuer && P.res_pf && tile + tile_step < P.total_tiles) {
+          // The group holds ONE shortcut box, requested when the previous one has been read: every chunk pays a full TMA load
+          // latency.  Asking L2 for the next tile's boxes a whole tile ahead turns that latency from an HBM miss into an L2 hit.
+          const TileCoord t2 = decode_tile<BN, PAIR>(P, tile + tile_step, cta_rank);
+          for (int c2 = grp * 32; c2 < t2.ncols && t2.co0 + c2 < P.Cout; c2 += 128) {
+            tma_prefetch_l2_4d(&maps.r[0], t2.co0 + c2, t2.tw_i * P.TW, t2.th_i * P.TH, t2.tn_i * P.TN);
+            tma_prefetch_l2_4d(&maps.r[1], t2.co0 + c2, t2.tw_i * P.TW, t2.th_i * P.TH, t2.tn_i * P.TN);
+          }
+        }
         if (P.bias) {   // the group's (up to) two chunks x 32 bias values of this tile
           const int tq = q * 32 + lane;
           if (tq < 64) {
@@ -591,13 +777,16 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
           }
           named_bar_sync(1 + grp, 128);
         }
+        TRACE(4, tile, 0);
         mbar_wait(tfull_bar(acc), acc_phase);
+        TRACE(5, tile, 0);
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = grp * 32; c0 < ncols; c0 += 128) {
           const int cbase = co0 + c0;
           if (cbase >= P.Cout) break;  // uniform over the group
           mbar_wait(rbar, res_n & 1u);
+          TRACE(6, tile, c0);
           ++res_n;
           uint32_t ohi[16], olo[8];   // the chunk's 32 outputs of this row: fp16 pairs, e5m2 residual bytes
 #pragma unroll
@@ -643,8 +832,11 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
             }
           }
           // A: the previous store of this group has finished READING the staging box
+          TRACE(7, tile, c0);
           if (store_pending && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          TRACE(8, tile, c0);
           named_bar_sync(1 + grp, 128);
+          TRACE(9, tile, c0);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<uint4*>(stg + row * 64 + ((i ^ sw) << 4)) = make_uint4(ohi[4 * i], ohi[4 * i + 1], ohi[4 * i + 2], ohi[4 * i + 3]);
@@ -654,6 +846,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
           // B: staging box complete; every thread of the group is also done reading the shortcut box (its generic-proxy reads
           // are ordered before the async-proxy refill by the fence above)
           named_bar_sync(1 + grp, 128);
+          TRACE(10, tile, c0);
           if (issuer) {
             pf_issue();
             tma_store_4d(&maps.y[0][0], stg_u32, cbase, ow0, oh0, n0);
@@ -665,6 +858,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(lead_tempty0 + 8u * acc);  // the leader's MMA issuer waits for both CTAs' epilogues
+        TRACE(11, tile, 0);
       }
       if (store_pending && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
@@ -716,6 +910,17 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
         const bool issuer = (q == 0 && lane == 0);
         const Seg& g = P.seg[tc.seg];
         const int ow0 = tw_i * g.TW, oh0 = th_i * g.TH, n0 = tn_i * g.TN;
+        if (RESLD && issuer && P.res_pf && tile + tile_step < P.total_tiles) {
+          // the shortcut boxes are requested one chunk ahead only (two buffers per half): L2 is asked for the next tile's boxes a
+          // whole tile ahead, so that those requests find their lines there instead of in HBM
+          const TileCoord t2 = decode_tile<BN, PAIR>(P, tile + tile_step, cta_rank);
+          int w2 = t2.tw_i * P.TW, h2 = t2.th_i * P.TH;
+          if (P.up_tma) { w2 >>= 1; h2 >>= 1; }
+          for (int c2 = half * 32; c2 < t2.ncols && t2.co0 + c2 < P.Cout; c2 += 64) {
+            tma_prefetch_l2_4d(&maps.r[0], t2.co0 + c2, w2, h2, t2.tn_i * P.TN);
+            if (SPLIT || F8) tma_prefetch_l2_4d(&maps.r[1], t2.co0 + c2, w2, h2, t2.tn_i * P.TN);
+          }
+        }
         long long res_off = 0;
         const bool res_lsu = !RESLD && P.res_cstride > 0 && !P.res_mma;
         if (res_lsu) {
@@ -1215,7 +1420,7 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
     mpn_set_error("conv(tcgen05): tile configuration does not fit shared memory (BN %d, mode %d)", BN, MODE);
     return MPN_ERR_UNSUPPORTED;
   } else {
-  static_assert(8 * (2 * STAGES + 9) <= BAR_BYTES, "barrier area too small");
+  static_assert(8 * ((MODE == MODE_F16F8C ? 4 : 2) * STAGES + 9) <= BAR_BYTES, "barrier area too small");
   const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BIAS_BYTES + EPI_BYTES;
   static_assert(STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BIAS_BYTES + EPI_BYTES <= SMEM_LIMIT, "shared memory budget");
   auto kern = conv_tc_kernel<BN, MODE, STAGES, EPI, PAIR, NG>;
@@ -1280,7 +1485,8 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
   }
   const bool split = d->fmt == MPN_FMT_BF16X2;
   const bool f8 = d->fmt == MPN_FMT_F16F8;
-  const bool f8b = f8 && (d->flags & MPN_IN_NO_H8);   // input without its h8 plane: fp16 weight-residual term (MODE_F16F8B)
+  const bool f8c = f8 && (d->flags & MPN_IN_DERIVE_H8);              // input without its h8 plane, derived in shared memory (MODE_F16F8C)
+  const bool f8b = f8 && !f8c && (d->flags & MPN_IN_NO_H8);          // input without its h8 plane: fp16 weight-residual term (MODE_F16F8B)
   MPN_CHECK_ARG(!f8 || (p->x_lo && p->w_lo), "conv(tcgen05): F16F8 needs the byte planes of x and w");
   MPN_CHECK_ARG(f8 || !(d->flags & (MPN_IN_NO_H8 | MPN_EPI_NO_H8)), "conv(tcgen05): MPN_IN_NO_H8 / MPN_EPI_NO_H8 are MPN_FMT_F16F8 flags");
   MPN_CHECK_ARG(!f8 || (d->in_cstride % 16 == 0 && d->res_cstride % 16 == 0 && d->up_cstride % 16 == 0 &&
@@ -1424,6 +1630,13 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
   P.out_rep = d->out_rep; P.out_nstride = d->out_nstride;
   P.y_hi = p->y_hi; P.y_lo = p->y_lo;
   P.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
+#ifdef MPN_CONV_TRACE
+  P.dbg_skip = getenv("MPN_DEBUG_SKIP") ? atoi(getenv("MPN_DEBUG_SKIP")) : 0;
+#endif
+  P.w_merged = (f8 && !f8b && (d->flags & MPN_W_MERGED)) ? 1 : 0;
+  MPN_CHECK_ARG(!(f8b && (d->flags & MPN_W_MERGED)), "conv(tcgen05): MPN_W_MERGED filters cannot serve MPN_IN_NO_H8 (fp16 residual plane)");
+  static const int res_pf_on = getenv("MPN_RES_PF") ? atoi(getenv("MPN_RES_PF")) : 0;
+  P.res_pf = res_pf_on;
   P.gat_n = d->gat_n;
   MPN_CHECK_ARG(d->gat_n >= 0 && d->gat_n <= 2, "conv(tcgen05): gat_n must be 0, 1 or 2");
   if (d->gat_n > 0) {
@@ -1458,7 +1671,7 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
   const long long x_plane = (long long)d->N * hpitch * wpitch * d->in_cstride;   // F16F8: h8 plane = lo8 plane + x_plane bytes
   const long long w_plane = (long long)d->Cout * d->R * d->S * d->Cin;
   // ---- activation planes: hi (2-byte elements, 128B swizzle); BF16X2: lo; F16F8: lo8 and (unless MPN_IN_NO_H8) h8 byte planes
-  const int a_planes = f8b ? 2 : planes;
+  const int a_planes = (f8b || f8c) ? 2 : planes;
   for (int pl = 0; pl < a_planes; ++pl) {
     const bool bytes = f8 && pl > 0;                 // byte planes: 1-byte elements, 64-byte swizzle
     const unsigned long long es = bytes ? 1ULL : 2ULL;
@@ -1496,21 +1709,23 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
     }
   }
   // ---- filter planes: [Cout, R*S*Cin] K-major.  F16F8: hi fp16 | lo8 bytes | h8 bytes; MPN_IN_NO_H8: hi fp16 | lo16 fp16 | h8 bytes
+  const bool wm = P.w_merged != 0;
   for (int pl = 0; pl < planes; ++pl) {
     const bool bytes = f8 && (f8b ? pl == 2 : pl > 0);
+    const bool mrg = wm && pl > 0;                   // merged byte planes: [Cout][2K] bytes, boxes of 128-byte rows (slot 2 repeats slot 1)
     const unsigned long long es = bytes ? 1ULL : 2ULL;
-    const CUtensorMapSwizzle swz = bytes ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle swz = (bytes && !mrg) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
     const CUtensorMapDataType dt = bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    const long long off = !f8 || pl < 2 ? 0 : (f8b ? 2 * w_plane : w_plane);   // byte offset of the third plane inside w_lo
+    const long long off = !f8 || pl < 2 || mrg ? 0 : (f8b ? 2 * w_plane : w_plane);   // byte offset of the third plane inside w_lo
     const char* wb = (const char*)(pl == 0 ? p->w_hi : p->w_lo) + off;
-    const cuuint64_t K = (cuuint64_t)d->R * d->S * d->Cin;
+    const cuuint64_t K = (cuuint64_t)d->R * d->S * d->Cin * (mrg ? 2 : 1);
     cuuint64_t wdims[2] = {K, (cuuint64_t)d->Cout};
     cuuint64_t wstrides[1] = {K * es};
-    cuuint32_t wbox[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(pair ? BN / 2 : BN)};   // pair: each CTA loads half of the filter rows
+    cuuint32_t wbox[2] = {(cuuint32_t)(mrg ? 2 * BLOCK_K : BLOCK_K), (cuuint32_t)(pair ? BN / 2 : BN)};   // pair: each CTA loads half of the filter rows
     int rc = encode(fn, &maps.b[pl], wb, 2, wdims, wstrides, wbox, swz, dt);
     if (rc) return rc;
     if (P.tail_split > 1) {
-      cuuint32_t sbox[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(pair ? P.tail_bn / 2 : P.tail_bn)};
+      cuuint32_t sbox[2] = {(cuuint32_t)(mrg ? 2 * BLOCK_K : BLOCK_K), (cuuint32_t)(pair ? P.tail_bn / 2 : P.tail_bn)};
       rc = encode(fn, &maps.bs[pl], wb, 2, wdims, wstrides, sbox, swz, dt);
       if (rc) return rc;
     }
@@ -1573,6 +1788,7 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
   if (f32out) {  // head outputs (18/19/36/9 channels): the thread-per-row fp32 store path, small-N tiles only
     MPN_CHECK_ARG(BN <= 64, "conv(tcgen05): fp32 outputs are built for Cout <= 64 (got %d)", d->Cout);
     if (f8b) return BN == 64 ? launch<64, MODE_F16F8B, EPI_F32>(maps, P, s, sms) : launch<32, MODE_F16F8B, EPI_F32>(maps, P, s, sms);
+    if (f8c) return BN == 64 ? launch<64, MODE_F16F8C, EPI_F32>(maps, P, s, sms) : launch<32, MODE_F16F8C, EPI_F32>(maps, P, s, sms);
     if (f8) return BN == 64 ? launch<64, MODE_F16F8, EPI_F32>(maps, P, s, sms) : launch<32, MODE_F16F8, EPI_F32>(maps, P, s, sms);
     if (split) return BN == 64 ? launch<64, MODE_BF16X2, EPI_F32>(maps, P, s, sms) : launch<32, MODE_BF16X2, EPI_F32>(maps, P, s, sms);
     return BN == 64 ? launch<64, MODE_BF16, EPI_F32>(maps, P, s, sms) : launch<32, MODE_BF16, EPI_F32>(maps, P, s, sms);
@@ -1597,6 +1813,7 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
                     d->Cin * d->R * d->S <= 256;
   if (wide) {
     if (f8b) return BN == 256 ? launch<256, MODE_F16F8B, EPI_TMA_RES, true, 4>(maps, P, s, sms) : launch<128, MODE_F16F8B, EPI_TMA_RES, true, 4>(maps, P, s, sms);
+    if (f8c) return BN == 256 ? launch<256, MODE_F16F8C, EPI_TMA_RES, true, 4>(maps, P, s, sms) : launch<128, MODE_F16F8C, EPI_TMA_RES, true, 4>(maps, P, s, sms);
     return BN == 256 ? launch<256, MODE_F16F8, EPI_TMA_RES, true, 4>(maps, P, s, sms) : launch<128, MODE_F16F8, EPI_TMA_RES, true, 4>(maps, P, s, sms);
   }
 #define MPN_TC_DISPATCH_RES(SPLIT_)                                                  \
@@ -1608,6 +1825,11 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
     MPN_TC_DISPATCH_RES(MODE_F16F8B)
     if (epi_tma) { MPN_TC_DISPATCH(MODE_F16F8B, EPI_TMA) }
     MPN_TC_DISPATCH(MODE_F16F8B, EPI_LSU)
+  }
+  if (f8c) {
+    MPN_TC_DISPATCH_RES(MODE_F16F8C)
+    if (epi_tma) { MPN_TC_DISPATCH(MODE_F16F8C, EPI_TMA) }
+    MPN_TC_DISPATCH(MODE_F16F8C, EPI_LSU)
   }
   if (f8) {
     MPN_TC_DISPATCH_RES(MODE_F16F8)
@@ -1631,3 +1853,12 @@ int mpn_conv_tc_launch(const mpn_conv_desc* d, const mpn_conv_ptrs* p, void* str
 int mpn_conv_tc_launch_multi(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg, void* stream) {
   return tc_launch(ds, ps, nseg, stream);
 }
+
+#ifdef MPN_CONV_TRACE
+extern "C" int mpn_debug_conv_trace(void* buf, int cap) {
+  unsigned long long* b = (unsigned long long*)buf;
+  MPN_CUDA_OK(cudaMemcpyToSymbol(g_trace_buf, &b, sizeof(b)));
+  MPN_CUDA_OK(cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap)));
+  return MPN_OK;
+}
+#endif

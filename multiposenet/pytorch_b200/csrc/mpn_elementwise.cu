@@ -112,7 +112,7 @@ extern "C" int mpn_filter_absmax(const float* w, const float* scale, int Cout, i
 
 __global__ void pack_filter_f16f8_kernel(const float* __restrict__ w, const float* __restrict__ scale, float wscale, __half* __restrict__ hi,
                                          unsigned char* __restrict__ lo8, unsigned char* __restrict__ h8, __half* __restrict__ lo16,
-                                         int Cout, int Cin, int R, int S, int stem) {
+                                         int Cout, int Cin, int R, int S, int stem, int merged) {
   const long long total = stem ? (long long)Cout * 256 : (long long)Cout * R * S * Cin;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float v = 0.f;
@@ -139,6 +139,12 @@ __global__ void pack_filter_f16f8_kernel(const float* __restrict__ w, const floa
     v = __fmul_rn(v, wscale);  // a power of two: exact
     const __half h = __float2half_rn(v);
     hi[i] = h;
+    if (merged) {   // layout bit 2: one 128-byte group per 64 K elements, [64 lo8 | 64 h8] (h8 == lo8 + 64 on entry)
+      const long long j = (i >> 6) * 128 + (i & 63);
+      lo8[j] = mpn_float_to_e4m3(v - __half2float(h));
+      h8[j] = mpn_float_to_e4m3(v * MPN_F8_LO_INV);
+      continue;
+    }
     if (lo16) lo16[i] = __float2half_rn(v - __half2float(h));   // layout 1: pairs with the activations' fp16 hi plane (MPN_IN_NO_H8)
     else lo8[i] = mpn_float_to_e4m3(v - __half2float(h));       // layout 0: pairs with the activations' e5m2 copy
     h8[i] = mpn_float_to_e4m3(v * MPN_F8_LO_INV);               // pairs with the activations' lo8 = e5m2((x - hi) * 2^12)
@@ -147,14 +153,19 @@ __global__ void pack_filter_f16f8_kernel(const float* __restrict__ w, const floa
 
 extern "C" int mpn_pack_filter_f16f8(const float* w, const float* scale, float wscale, void* hi, void* lo8h8, int Cout, int Cin, int R,
                                      int S, int layout, void* stream) {
-  // layout bit 0: the stem's space-to-depth filter; bit 1: [lo16 fp16 plane][h8 plane] for inputs without an h8 plane
-  const int stem = layout & 1, lay16 = (layout >> 1) & 1;
+  // layout bit 0: the stem's space-to-depth filter; bit 1: [lo16 fp16 plane][h8 plane] for inputs without an h8 plane; bit 2: the
+  // lo8 and h8 planes interleaved per 64 K elements ([Cout][K/64][64 lo8 | 64 h8]): one 128-byte TMA row instead of two 64-byte
+  // ones (MPN_W_MERGED) -- the TMA unit is paced per row, not per byte
+  const int stem = layout & 1, lay16 = (layout >> 1) & 1, merged = (layout >> 2) & 1;
+  MPN_CHECK_ARG(!(merged && lay16), "mpn_pack_filter_f16f8: layouts 2 and 4 exclude each other");
+  MPN_CHECK_ARG(!merged || stem || ((long long)R * S * Cin) % 64 == 0, "mpn_pack_filter_f16f8: the merged layout needs K %% 64 == 0");
   MPN_CHECK_ARG(w && hi && lo8h8 && Cout > 0 && Cin > 0 && R > 0 && S > 0 && wscale > 0.f, "mpn_pack_filter_f16f8: bad argument");
   MPN_CHECK_ARG(!stem || (Cin == 3 && R == 7 && S == 7), "mpn_pack_filter_f16f8: the stem layout is for a [Cout,3,7,7] filter");
   const long long total = stem ? (long long)Cout * 256 : (long long)Cout * R * S * Cin;
   unsigned char* lo = (unsigned char*)lo8h8;
   pack_filter_f16f8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      w, scale, wscale, (__half*)hi, lo, lay16 ? lo + 2 * total : lo + total, lay16 ? (__half*)lo : nullptr, Cout, Cin, R, S, stem);
+      w, scale, wscale, (__half*)hi, lo, merged ? lo + 64 : (lay16 ? lo + 2 * total : lo + total), lay16 ? (__half*)lo : nullptr, Cout, Cin, R,
+      S, stem, merged);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }

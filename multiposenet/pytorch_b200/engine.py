@@ -124,7 +124,7 @@ class Engine(object):
     def _pc(self, name, conv, bn=None, fmt=None, no_h8=False):
         """no_h8 (f16f8 only): pack for an input stored without its e5m2 copy plane (ops.pack_conv in_no_h8)."""
         fmt = self.fmt if fmt is None else fmt
-        no_h8 = bool(no_h8) and fmt == ops.FMT_F16F8 and ops.NO_H8
+        no_h8 = bool(no_h8) and fmt == ops.FMT_F16F8 and ops.NO_H8 and not ops.DERIVE_H8   # derived copy plane: ordinary packing
         key = (name, fmt, no_h8)
         pc = self._packed.get(key)
         if pc is None:
@@ -137,7 +137,12 @@ class Engine(object):
     @property
     def _slim(self):
         """f16f8: tensors that only 1x1 convolutions (and shortcut adds) read are stored without their e5m2 copy plane."""
-        return self.fmt == ops.FMT_F16F8 and ops.NO_H8
+        return self.fmt == ops.FMT_F16F8 and (ops.NO_H8 or ops.DERIVE_H8)
+
+    @property
+    def _derive(self):
+        """f16f8: the kernels derive the e5m2 copy in shared memory (ops.DERIVE_H8): no tensor stores it."""
+        return self.fmt == ops.FMT_F16F8 and ops.DERIVE_H8
 
     # ------------------------------------------------------------------ backbone
     def backbone(self, img):
@@ -195,7 +200,7 @@ class Engine(object):
         nh = slim and not x.has_h8
         # a 3x3 with <= 64 output channels (layer1) is bound by its A-operand traffic, not by the tensor pipe: it takes the no-h8
         # operand variant too, and its input is then stored without the copy plane
-        thin = slim and blk.conv2.out_channels <= 64
+        thin = slim and (blk.conv2.out_channels <= 64 or self._derive)
         o = ops.conv2d(x, self._pc(name + ".conv1", blk.conv1, blk.bn1, no_h8=nh), relu=True, want_h8=not thin)
         o = ops.conv2d(o, self._pc(name + ".conv2", blk.conv2, blk.bn2, no_h8=thin), stride=stride, pad=1, relu=True, want_h8=not slim)
         if len(blk.downsample) > 0:
@@ -204,7 +209,7 @@ class Engine(object):
         else:
             sc = x
         return ops.conv2d(o, self._pc(name + ".conv3", blk.conv3, blk.bn3, no_h8=slim), relu=True, residual=sc,
-                          want_h8=(not slim) or out_h8)
+                          want_h8=((not slim) or out_h8) and not self._derive)
 
     # ------------------------------------------------------------------ necks
     def detection_neck(self, c3, c4, c5):
@@ -243,7 +248,7 @@ class Engine(object):
             raise RuntimeError("keypoint head needs H and W to be multiples of 32 (evaluate/tester.py:285 pads to 32)")
         if CONV2_GATHER and self.fmt != FMT_F32:
             return self._keypoint_head_classes(p2, p3, p4, p5)
-        cat = ops.Act(self.fmt, p2.N, p2.H, p2.W, 512, p2.hi.device)
+        cat = ops.Act(self.fmt, p2.N, p2.H, p2.W, 512, p2.hi.device, has_h8=not self._derive)
         for src, t, s, rep, off in ((p5, "convt1", "convs1", 8, 0), (p4, "convt2", "convs2", 4, 128),
                                     (p3, "convt3", "convs3", 2, 256), (p2, "convt4", "convs4", 1, 384)):
             q = ops.conv2d(src, self._pc(t, getattr(m, t)), pad=1)
@@ -274,7 +279,7 @@ class Engine(object):
             q = ops.conv2d(src, self._pc(t, getattr(m, t)), pad=1)
             q = ops.conv2d(q, self._pc(s, getattr(m, s)), pad=1)
             z.append(ops.conv2d(q, pcz, pad=1, want_h8=False))            # read by conv2's epilogue only
-        cat = ops.Act(self.fmt, p2.N, p2.H, p2.W, 256, p2.hi.device)
+        cat = ops.Act(self.fmt, p2.N, p2.H, p2.W, 256, p2.hi.device, has_h8=not self._derive)
         for src, t, s, rep, off in ((p3, "convt3", "convs3", 2, 0), (p2, "convt4", "convs4", 1, 128)):
             q = ops.conv2d(src, self._pc(t, getattr(m, t)), pad=1)
             ops.conv2d(q, self._pc(s, getattr(m, s)), pad=1, out=cat, out_coffset=off, out_rep=rep)
@@ -323,7 +328,7 @@ class Engine(object):
             hr, hc = list(feats), list(feats)
             slim = self._slim   # the 36- / 9-channel output convs are A-traffic bound: no-h8 operand variant, conv4 stores no h8
             for n in ("conv1", "conv2", "conv3", "conv4"):
-                h8 = not (slim and n == "conv4")
+                h8 = not (slim and n == "conv4") and not self._derive
                 hr = ops.conv2d_multi(hr, self._pc("regressionModel." + n, getattr(m.regressionModel, n)), pad=1, relu=True, want_h8=h8)
                 hc = ops.conv2d_multi(hc, self._pc("classificationModel." + n, getattr(m.classificationModel, n)), pad=1, relu=True, want_h8=h8)
             ops.conv2d_multi(hr, self._pc("regressionModel.output", m.regressionModel.output, no_h8=slim), pad=1, out_mode=OUT_F32_NHWC,

@@ -9,7 +9,7 @@ import torch
 from . import _lib
 import math
 
-from ._lib import (EPI_NO_H8, EPI_RELU, EPI_SIGMOID, FMT_BF16, FMT_BF16X2, FMT_F16F8, FMT_F32, IN_NO_H8, OUT_ACT, OUT_F32_NCHW,
+from ._lib import (EPI_NO_H8, EPI_RELU, EPI_SIGMOID, FMT_BF16, FMT_BF16X2, FMT_F16F8, FMT_F32, IN_DERIVE_H8, IN_NO_H8, OUT_ACT, OUT_F32_NCHW, W_MERGED,
                    OUT_F32_NHWC, ConvDesc, ConvPtrs, check)
 
 PRECISIONS = {"fp32": FMT_F32, "bf16": FMT_BF16, "bf16x3": FMT_BF16X2, "f16f8": FMT_F16F8}
@@ -75,13 +75,43 @@ def act_from_nchw(x, fmt, cstride=None):
 
 class PackedConv(object):
     """Filter + per-channel epilogue constants of one nn.Conv2d (+ folded eval-mode BatchNorm2d)."""
-    __slots__ = ("Cout", "Cin", "R", "S", "fmt", "w_hi", "w_lo", "cout_pad", "scale", "bias", "acc_scale", "in_no_h8")
+    __slots__ = ("Cout", "Cin", "R", "S", "fmt", "w_hi", "w_lo", "cout_pad", "scale", "bias", "acc_scale", "in_no_h8", "w_merged")
 
 
 # FMT_F16F8 convolutions come in two operand variants (mpn_b200.h MPN_IN_NO_H8): the default reads the input's e5m2 copy plane
 # (8 tensor-core slots per K block); in_no_h8 multiplies the fp16 plane with an fp16 weight residual instead (10 slots) and lets
 # the producer of its input drop that plane from HBM -- the choice for the HBM / epilogue-bound 1x1 convolutions.
 NO_H8 = __import__("os").environ.get("MPN_NO_H8", "1") == "1"
+# Third variant (MPN_IN_DERIVE_H8, opt-in with MPN_DERIVE_H8=1): the kernel derives the e5m2 copy in shared memory from the fp16
+# tile (two converter warps per CTA), so NO activation needs the plane in HBM and every convolution runs the 8-slot schedule on
+# ordinarily packed filters with one TMA box less per K block.  Measured (profiles/r02q_derive_h8_ab.txt): bit-compatible parity,
+# shortcut convolutions 6 % faster, but the large 3x3 convolutions -- 92-94 % tensor-bound in cycles with the stored plane --
+# wait ~260 cycles per K block for the converters: the step is 3-4 % slower, so the stored-plane plan stays the default.
+DERIVE_H8 = __import__("os").environ.get("MPN_DERIVE_H8", "0") == "1"
+
+
+# FMT_F16F8 filters: the two byte planes interleaved per K block (mpn_b200.h MPN_W_MERGED) -- one TMA box less per K block
+W_MERGE = __import__("os").environ.get("MPN_W_MERGED", "1") == "1"
+
+
+def _auto_h8(want_h8):
+    """want_h8=None (the default of every producer): store the copy plane only when the kernels do not derive it."""
+    return (not DERIVE_H8) if want_h8 is None else bool(want_h8)
+
+
+def _input_flags(pc, x, derive):
+    """Operand variant of an FMT_F16F8 convolution reading Act x with filter pc: 0 (copy plane loaded by TMA), IN_NO_H8 (filter
+    packed with the fp16 residual plane) or IN_DERIVE_H8.  derive: None = derive when enabled or when x has no copy plane."""
+    if getattr(pc, "in_no_h8", False):
+        return IN_NO_H8
+    wm = W_MERGED if getattr(pc, "w_merged", False) else 0
+    if derive is None:
+        derive = DERIVE_H8 or not getattr(x, "has_h8", True)
+    if derive:
+        return IN_DERIVE_H8 | wm
+    if not getattr(x, "has_h8", True):
+        raise ValueError("this activation was stored without its h8 plane: read it with derive=True or a filter packed with in_no_h8=True")
+    return wm
 
 
 def pack_conv(weight, bias, bn, fmt, fold_scale=True, in_no_h8=False):
@@ -148,23 +178,26 @@ def _pack_f16f8(pc, w, scale, stem):
     shape = (pc.Cout, 4, 1, 64) if stem else (pc.Cout, pc.R, pc.S, pc.Cin)
     pc.w_hi = torch.empty(shape, dtype=torch.float16, device=w.device)
     lay16 = bool(getattr(pc, "in_no_h8", False))          # [lo16 fp16 plane][h8 plane] instead of [lo8 plane][h8 plane]
-    pc.w_lo = torch.empty((3 if lay16 else 2,) + shape, dtype=torch.uint8, device=w.device)
     Cout, Cin, R, S = w.shape
+    pc.w_merged = W_MERGE and not lay16 and (stem or (Cin * R * S) % 64 == 0)   # [Cout][K/64][64 lo8 | 64 h8]
+    pc.w_lo = torch.empty((3 if lay16 else 2,) + shape, dtype=torch.uint8, device=w.device)
     check(L.mpn_pack_filter_f16f8(_ptr(w), _ptr(scale), float(2.0 ** k), _ptr(pc.w_hi), _ptr(pc.w_lo), Cout, Cin, R, S,
-                                  int(stem) | (2 if lay16 else 0), _stream()), "mpn_pack_filter_f16f8")
+                                  int(stem) | (2 if lay16 else 0) | (4 if pc.w_merged else 0), _stream()), "mpn_pack_filter_f16f8")
     pc.acc_scale = float(2.0 ** -k)
 
 
 def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=None, out=None, out_mode=OUT_ACT,
            out_coffset=0, out_rep=1, out_tensor=None, out_elem_offset=0, out_cstride=None, out_nstride=0, f32_input=False,
-           want_h8=True, gather=None):
+           want_h8=None, gather=None, derive=None):
     """y = epilogue(conv2d(x, w)).  Returns the output Act (OUT_ACT) or the fp32 tensor written.
 
     out          : existing Act to write into (concat buffers), else a new one is allocated
     out_tensor   : fp32 tensor for OUT_F32_* (allocated if None); out_elem_offset shifts the base pointer
     f32_input    : x is an fp32 NHWC Act while the output/epilogue use pc.fmt (stem)
-    want_h8      : FMT_F16F8 activation outputs: False stores the tensor without its e5m2 copy plane (for consumers packed
-                   with in_no_h8)
+    want_h8      : FMT_F16F8 activation outputs: False stores the tensor without its e5m2 copy plane (for consumers that derive
+                   it or are packed with in_no_h8); None = only when the kernels do not derive it (DERIVE_H8)
+    derive       : FMT_F16F8 input: True = the kernel derives the copy plane in shared memory, False = TMA loads the stored one,
+                   None = automatic (_input_flags)
     gather       : up to two (Act, shift) phase-class addends (mpn_conv_desc.gat_*): Act is the 9*Cout-channel class
                    convolution of a map 2^shift times smaller than the output (phase_class_filter below)
     """
@@ -181,10 +214,7 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
     d.in_wpitch, d.k_overlap = x.wpitch, x.k_overlap
     d.flags = (EPI_RELU if relu else 0) | (EPI_SIGMOID if sigmoid else 0)
     if fmt == FMT_F16F8 and not f32_input:
-        if getattr(pc, "in_no_h8", False):
-            d.flags |= IN_NO_H8
-        elif not getattr(x, "has_h8", True):
-            raise ValueError("this activation was stored without its h8 plane: the convolution reading it must be packed with in_no_h8=True")
+        d.flags |= _input_flags(pc, x, derive)
     d.out_mode, d.out_rep, d.out_coffset = out_mode, out_rep, out_coffset
     d.w_cout_pad = pc.cout_pad
     d.acc_scale = getattr(pc, "acc_scale", 0.0)
@@ -212,7 +242,7 @@ def conv2d(x, pc, stride=1, pad=0, relu=False, sigmoid=False, residual=None, up=
     ret = None
     if out_mode == OUT_ACT:
         if out is None:
-            out = Act(fmt, x.N, d.OH * out_rep, d.OW * out_rep, pc.Cout, x.hi.device, has_h8=want_h8)
+            out = Act(fmt, x.N, d.OH * out_rep, d.OW * out_rep, pc.Cout, x.hi.device, has_h8=_auto_h8(want_h8))
         assert out.fmt == fmt and out.N == x.N and out.H == d.OH * out_rep and out.W == d.OW * out_rep
         if fmt == FMT_F16F8 and not out.has_h8:
             d.flags |= EPI_NO_H8
@@ -266,7 +296,7 @@ def phase_class_filter(weight):
 
 
 def conv2d_multi(xs, pc, pad=0, relu=False, sigmoid=False, out_mode=OUT_ACT, out_tensor=None, out_elem_offsets=None,
-                 out_cstride=None, out_nstride=0, want_h8=True):
+                 out_cstride=None, out_nstride=0, want_h8=None, derive=None):
     """The same stride-1 convolution (shared packed filter) applied to several Acts in ONE persistent launch
     (mpn_conv2d_fwd_multi): a RetinaNet tower layer over the pyramid levels.  OUT_ACT: returns the list of output Acts;
     fp32 modes: every level writes at out_elem_offsets[i] of out_tensor (strides as in conv2d)."""
@@ -285,16 +315,13 @@ def conv2d_multi(xs, pc, pad=0, relu=False, sigmoid=False, out_mode=OUT_ACT, out
         d.fmt, d.in_cstride = fmt, x.cstride
         d.flags = (EPI_RELU if relu else 0) | (EPI_SIGMOID if sigmoid else 0)
         if fmt == FMT_F16F8:
-            if getattr(pc, "in_no_h8", False):
-                d.flags |= IN_NO_H8
-            elif not x.has_h8:
-                raise ValueError("this activation was stored without its h8 plane: the convolution reading it must be packed with in_no_h8=True")
+            d.flags |= _input_flags(pc, x, derive)
         d.out_mode, d.out_rep, d.out_coffset = out_mode, 1, 0
         d.w_cout_pad, d.acc_scale = pc.cout_pad, getattr(pc, "acc_scale", 0.0)
         p.x_hi, p.x_lo = _ptr(x.hi), _ptr(x.lo)
         p.w_hi, p.w_lo, p.scale, p.bias = _ptr(pc.w_hi), _ptr(pc.w_lo), _ptr(pc.scale), _ptr(pc.bias)
         if out_mode == OUT_ACT:
-            o = Act(fmt, x.N, d.OH, d.OW, pc.Cout, x.hi.device, has_h8=want_h8)
+            o = Act(fmt, x.N, d.OH, d.OW, pc.Cout, x.hi.device, has_h8=_auto_h8(want_h8))
             d.out_cstride = o.cstride
             if fmt == FMT_F16F8 and not o.has_h8:
                 d.flags |= EPI_NO_H8
@@ -319,14 +346,14 @@ def conv2d_multi(xs, pc, pad=0, relu=False, sigmoid=False, out_mode=OUT_ACT, out
     return outs if out_mode == OUT_ACT else out_tensor
 
 
-def stem_pack_input(img, fmt, want_h8=True):
+def stem_pack_input(img, fmt, want_h8=None):
     """fp32 NCHW image -> zero-padded space-to-depth Act [N, H/2+3, W/2 (+3 pitch), 64-wide windows of 16 ch]
     (mpn_stem_pack_input); with pack_stem_filter the 7x7/2 stem becomes a tcgen05 conv (R=4, S=1, Cin=64)."""
     assert img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3
     img = img.contiguous()
     N, _, H, W = img.shape
     H2, W2 = (H + 1) // 2, (W + 1) // 2
-    a = Act(fmt, N, H2 + 3, W2, 64, img.device, cstride=16, wpitch=W2 + 3, k_overlap=1, has_h8=want_h8)
+    a = Act(fmt, N, H2 + 3, W2, 64, img.device, cstride=16, wpitch=W2 + 3, k_overlap=1, has_h8=_auto_h8(want_h8))
     check(_lib.lib().mpn_stem_pack_input(_ptr(img), _ptr(a.hi), _ptr(a.lo), N, H, W, fmt, 0 if a.has_h8 else EPI_NO_H8, _stream()),
           "mpn_stem_pack_input")
     stats["launches"] += 1
@@ -344,13 +371,13 @@ def resnet_preprocess_u8(img_u8):
     return out
 
 
-def stem_pack_input_u8(img_u8, fmt, want_h8=True):
+def stem_pack_input_u8(img_u8, fmt, want_h8=None):
     """uint8 [N,H,W,3] BGR image -> the tensor-core stem operand with resnet_preprocess fused in."""
     assert img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[3] == 3
     img_u8 = img_u8.contiguous()
     N, H, W, _ = img_u8.shape
     H2, W2 = (H + 1) // 2, (W + 1) // 2
-    a = Act(fmt, N, H2 + 3, W2, 64, img_u8.device, cstride=16, wpitch=W2 + 3, k_overlap=1, has_h8=want_h8)
+    a = Act(fmt, N, H2 + 3, W2, 64, img_u8.device, cstride=16, wpitch=W2 + 3, k_overlap=1, has_h8=_auto_h8(want_h8))
     check(_lib.lib().mpn_stem_pack_input_u8(_ptr(img_u8), _ptr(a.hi), _ptr(a.lo), N, H, W, fmt, 0 if a.has_h8 else EPI_NO_H8, _stream()),
           "mpn_stem_pack_input_u8")
     stats["launches"] += 1
@@ -390,8 +417,9 @@ def add_softmax_rows(a, res):
     return out
 
 
-def maxpool3x3s2(x, want_h8=True):
+def maxpool3x3s2(x, want_h8=None):
     OH, OW = (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1
+    want_h8 = _auto_h8(want_h8)
     if x.fmt == FMT_F16F8 and x.C % 8:
         want_h8 = True   # the generic (non-vectorised) kernel keeps the full format
     y = Act(x.fmt, x.N, OH, OW, x.C, x.hi.device, has_h8=want_h8)

@@ -38,8 +38,10 @@ def strip_h8(a):
 
 
 def conv_case(fmt, N, H, W, Cin, Cout, R, stride, pad, relu=False, sigmoid=False, residual=False, up=False, bn=False,
-              bias=True, out_mode=OUT_ACT, rep=1, seed=0, coffset=0, ctotal=None, no_h8=False):
-    """Returns (ours NCHW fp32, reference NCHW fp32 with fmt-rounded operands, reference with fp32 operands)."""
+              bias=True, out_mode=OUT_ACT, rep=1, seed=0, coffset=0, ctotal=None, no_h8=False, derive=None):
+    """Returns (ours NCHW fp32, reference NCHW fp32 with fmt-rounded operands, reference with fp32 operands).
+    FMT_F16F8 operand variants: no_h8 = filter packed with the fp16 residual plane, tensors without the copy plane (MODE_F16F8B);
+    derive = True: tensors without the copy plane, derived in shared memory (MODE_F16F8C); False: the stored plane is loaded."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     dev = "cuda"
     x = torch.randn(N, Cin, H, W, generator=g).to(dev)
@@ -76,24 +78,27 @@ def conv_case(fmt, N, H, W, Cin, Cout, R, stride, pad, relu=False, sigmoid=False
     xa = ops.act_from_nchw(x, fmt)
     ra = ops.act_from_nchw(res, fmt) if res is not None else None
     ua = ops.act_from_nchw(upt, fmt) if upt is not None else None
-    if no_h8:   # input, shortcut and upsample source without the copy plane; the output too (unless it is a concat slice)
+    if fmt == 3 and derive is None and not no_h8:
+        derive = ops.DERIVE_H8
+    if no_h8 or (derive and fmt == 3):   # input, shortcut and upsample source without the copy plane; the output too (unless it is a concat slice)
         xa, ra, ua = strip_h8(xa), (strip_h8(ra) if ra is not None else None), (strip_h8(ua) if ua is not None else None)
+    slim_out = no_h8 or bool(derive and fmt == 3)
     if out_mode == OUT_ACT:
         out = None
         if ctotal is not None:
             out = ops.Act(fmt, N, OH * rep, OW * rep, ctotal, dev, zero=True)
         o = ops.conv2d(xa, pc, stride=stride, pad=pad, relu=relu, sigmoid=sigmoid, residual=ra, up=ua, out=out,
-                       out_coffset=coffset, out_rep=rep, want_h8=not no_h8)
-        assert o.has_h8 == (not no_h8 or ctotal is not None)
+                       out_coffset=coffset, out_rep=rep, want_h8=not slim_out, derive=derive)
+        assert o.has_h8 == (not slim_out or ctotal is not None)
         ours = o.to_nchw()
         if ctotal is not None:
             ours = ours[:, coffset:coffset + Cout]
     elif out_mode == OUT_F32_NCHW:
         ours = ops.conv2d(xa, pc, stride=stride, pad=pad, relu=relu, sigmoid=sigmoid, residual=ra, up=ua,
-                          out_mode=out_mode, out_rep=rep)
+                          out_mode=out_mode, out_rep=rep, derive=derive)
     else:
         ours = ops.conv2d(xa, pc, stride=stride, pad=pad, relu=relu, sigmoid=sigmoid, residual=ra, up=ua,
-                          out_mode=out_mode, out_rep=rep).permute(0, 3, 1, 2).contiguous()
+                          out_mode=out_mode, out_rep=rep, derive=derive).permute(0, 3, 1, 2).contiguous()
     torch.cuda.synchronize()
     return ours, ref_rounded, ref_exact
 

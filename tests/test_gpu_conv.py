@@ -90,7 +90,29 @@ def test_conv_tcgen05_bf16(case):
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_tcgen05_f16f8(case):
     # fp16 hi*hi on kind::f16 + the two fp8 cross terms on kind::f8f6f4: product error ~2^-15, output re-split 2^-15
+    # (the default operand variant: MPN_IN_DERIVE_H8 unless MPN_DERIVE_H8=0)
     _check(3, case, 2e-4, 2e-4)
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_f16f8_stored_copy_plane(case):
+    """MODE_F16F8: the e5m2 copy plane of the input is stored in HBM and loaded by TMA."""
+    N, H, W, Cin, Cout, R, stride, pad, kw = case
+    _check(3, (N, H, W, Cin, Cout, R, stride, pad, dict(kw, derive=False)), 2e-4, 2e-4)
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_f16f8_derived_copy_plane(case):
+    """MODE_F16F8C: tensors without the copy plane, the converter warps derive it from the fp16 tile in shared memory; agrees with
+    the stored-plane variant to the rounding of the 3-bit cross term."""
+    from gpu_util import conv_case, nerr, no_tf32
+    no_tf32()
+    N, H, W, Cin, Cout, R, stride, pad, kw = case
+    ours, ref_r, ref_e = conv_case(3, N, H, W, Cin, Cout, R, stride, pad, derive=True, **kw)
+    assert ours.shape == ref_e.shape and torch.isfinite(ours).all()
+    assert nerr(ours, ref_e) <= 2e-4
+    full, _, _ = conv_case(3, N, H, W, Cin, Cout, R, stride, pad, derive=False, **kw)
+    assert nerr(ours, full) <= 2e-4
 
 
 @pytest.mark.parametrize("case", TC_CASES)
@@ -107,6 +129,20 @@ def test_conv_tcgen05_f16f8_without_h8_plane(case):
     assert nerr(ours, full) <= 2e-4
 
 
+@pytest.mark.parametrize("derive", [False, True])
+@pytest.mark.parametrize("case", TC_CASES[::3])
+def test_conv_tcgen05_f16f8_separate_filter_planes(case, derive, monkeypatch):
+    """MPN_W_MERGED off: the filter's lo8 and h8 planes as two tensors of 64-byte rows (the round-1 layout) give the same result as
+    the interleaved default to the bit."""
+    from gpu_util import conv_case
+    from multiposenet.pytorch_b200 import ops
+    N, H, W, Cin, Cout, R, stride, pad, kw = case
+    merged, _, _ = conv_case(3, N, H, W, Cin, Cout, R, stride, pad, derive=derive, **kw)
+    monkeypatch.setattr(ops, "W_MERGE", False)
+    planar, _, ref = conv_case(3, N, H, W, Cin, Cout, R, stride, pad, derive=derive, **kw)
+    assert torch.equal(merged, planar)
+
+
 def test_maxpool_without_h8_plane_and_guard():
     import torch.nn.functional as F
     from gpu_util import strip_h8
@@ -117,8 +153,8 @@ def test_maxpool_without_h8_plane_and_guard():
     assert not y.has_h8 and y.lo.shape[0] == 1
     assert torch.equal(y.to_nchw(), F.max_pool2d(xa.to_nchw(), 3, 2, 1))
     w = torch.randn(64, 64, 3, 3).cuda() * 0.05
-    with pytest.raises(ValueError):   # a default-packed convolution must not read a tensor without its copy plane
-        ops.conv2d(y, ops.pack_conv(w, None, None, 3), pad=1)
+    with pytest.raises(ValueError):   # the stored-plane variant must not read a tensor without its copy plane
+        ops.conv2d(y, ops.pack_conv(w, None, None, 3), pad=1, derive=False)
 
 
 @pytest.mark.parametrize("fmt,tol", [(2, 1e-4), (1, 2e-2), (3, 2e-4)])
@@ -222,8 +258,10 @@ def test_tensor_core_stem_without_h8_plane(shape):
     assert not xs.has_h8 and xs.lo.shape[0] == 1
     y = ops.conv2d(xs, pc, relu=True, want_h8=False)
     assert not y.has_h8 and nerr(y.to_nchw(), ref) <= 2e-4
-    full = ops.conv2d(ops.stem_pack_input(x, 3), ops.pack_stem_filter(w, bn, 3), relu=True)
+    full = ops.conv2d(ops.stem_pack_input(x, 3, want_h8=True), ops.pack_stem_filter(w, bn, 3), relu=True, derive=False)
     assert nerr(y.to_nchw(), full.to_nchw()) <= 2e-4
+    der = ops.conv2d(ops.stem_pack_input(x, 3, want_h8=False), ops.pack_stem_filter(w, bn, 3), relu=True, derive=True)   # MODE_F16F8C
+    assert nerr(der.to_nchw(), full.to_nchw()) <= 2e-4 and nerr(der.to_nchw(), ref) <= 2e-4
     u8 = torch.from_numpy(np.random.Generator(np.random.PCG64(2)).integers(0, 256, (N, H, W, 3), dtype=np.uint8)).cuda()
     a, b = ops.stem_pack_input_u8(u8, 3, want_h8=False), ops.stem_pack_input_u8(u8, 3)
     assert torch.equal(a.hi, b.hi) and torch.equal(a.lo[0], b.lo[0])
