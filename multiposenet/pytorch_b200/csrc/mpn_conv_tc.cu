@@ -178,9 +178,10 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, in
 // EPI_TMA_RES = EPI_TMA with the shortcut tensor brought in by TMA as well (32-channel boxes, double-buffered per epilogue half)
 enum { EPI_LSU = 0, EPI_F32 = 1, EPI_TMA = 2, EPI_TMA_RES = 3 };
 constexpr int RES_STAGE_BYTES = 16384;  // per (half, buffer): [hi: rows x 64 B, 64B swizzle][lo: rows x 64 B | lo8: rows x 32 B]
-// Wide epilogue (NG = 4 column groups of four warps, F16F8 shortcut convolutions whose output is stored without h8): per group
-// one 12 KB output staging box and one 12 KB shortcut box, each [hi: rows x 64 B, 64B swizzle][lo8: rows x 32 B at +8192]
-constexpr int WIDE_BOX_BYTES = 12288;
+// Wide epilogue (NG = 4 column groups of four warps, F16F8 shortcut convolutions whose output is stored without h8): per
+// group pair one 24 KB output staging box and one 24 KB shortcut box of 64 channels, each [hi: rows x 128 B, 128B swizzle][lo8:
+// rows x 64 B, 64B swizzle, at +16384]
+constexpr int WIDE_BOX_BYTES = 24576;
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -288,8 +289,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
   constexpr int MMA_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
   constexpr bool TMAEPI = EPI == EPI_TMA || EPI == EPI_TMA_RES;
   constexpr bool RESLD = EPI == EPI_TMA_RES;
-  constexpr int EPI_BYTES = WIDE ? 8 * WIDE_BOX_BYTES : NUM_EPI_WARPS * EPI_STAGE_BYTES + (RESLD ? 4 * RES_STAGE_BYTES : 0);
-  static_assert(!WIDE || (RESLD && PAIR && F8), "the wide epilogue is the F16F8 shortcut epilogue");
+  constexpr int EPI_BYTES = WIDE ? 4 * WIDE_BOX_BYTES : NUM_EPI_WARPS * EPI_STAGE_BYTES + (RESLD ? 4 * RES_STAGE_BYTES : 0);
+  static_assert(!WIDE || (RESLD && PAIR && F8 && !F8C), "the wide epilogue is the F16F8 shortcut epilogue (its agents are the F8C converter warps)");
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   // c = F32; a, b = BF16 (1) or, for F16F8, F16 (0);  | (N >> 3) << 17 per tile
   constexpr uint32_t IDESC_BASE = (1u << 4) | (F8 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(MMA_M >> 4) << 24);
@@ -642,6 +643,54 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
         }
       }
     }
+  } else if (WIDE && (warp == 2 || warp == 3)) {
+    // =============================== wide epilogue: TMA agents ===============================
+    // Warp 2 + pg issues every bulk-tensor instruction of group pair pg (see the wide epilogue below): the shortcut box of chunk
+    // n lands in buffer n & 1, the 256 math threads turn it into the output in place and meet this warp at named barrier 5 + pg,
+    // lane 0 stores the buffer, waits until the store has read it and requests chunk n + 2 into it.
+    const int pg = warp - 2;
+    constexpr int LO_OFF = 16384;
+    const uint32_t buf0 = smem_base + STAGES * STAGE_BYTES + (uint32_t)(pg * 2) * WIDE_BOX_BYTES;
+    const uint32_t res_bytes = (uint32_t)P.rows * 192u;
+    int pf_tile = tile0, pf_c0 = pg * 64;   // cursor: the next (tile, chunk) of this pair whose shortcut box is not requested yet
+    uint32_t pf_n = 0;
+    auto pf_issue = [&]() {
+      while (pf_tile < P.total_tiles) {
+        const TileCoord t = decode_tile<BN, PAIR>(P, pf_tile, cta_rank);
+        if (pf_c0 < t.ncols && t.co0 + pf_c0 < P.Cout) {
+          const uint32_t bar = res_full_bar(pg, (int)(pf_n & 1u)), dst = buf0 + (pf_n & 1u) * WIDE_BOX_BYTES;
+          mbar_expect_tx(bar, res_bytes);
+          tma_load_4d(dst, &maps.r[0], bar, t.co0 + pf_c0, t.tw_i * P.TW, t.th_i * P.TH, t.tn_i * P.TN);
+          tma_load_4d(dst + LO_OFF, &maps.r[1], bar, t.co0 + pf_c0, t.tw_i * P.TW, t.th_i * P.TH, t.tn_i * P.TN);
+          pf_c0 += 128;
+          ++pf_n;
+          return;
+        }
+        pf_tile += tile_step;   // no (further) chunk of this pair in that tile
+        pf_c0 = pg * 64;
+      }
+    };
+    if (lane == 0) { pf_issue(); pf_issue(); }
+    uint32_t n = 0;
+    for (int tile = tile0; tile < P.total_tiles; tile += tile_step) {
+      const TileCoord tc = decode_tile<BN, PAIR>(P, tile, cta_rank);
+      const int ow0 = tc.tw_i * P.TW, oh0 = tc.th_i * P.TH, n0 = tc.tn_i * P.TN;
+      for (int c0 = pg * 64; c0 < tc.ncols; c0 += 128) {
+        const int cbase = tc.co0 + c0;
+        if (cbase >= P.Cout) break;
+        named_bar_sync(5 + pg, 288);
+        if (lane == 0) {
+          const uint32_t src = buf0 + (n & 1u) * WIDE_BOX_BYTES;
+          tma_store_4d(&maps.y[0][0], src, cbase, ow0, oh0, n0);
+          tma_store_4d(&maps.y[1][0], src + LO_OFF, cbase, ow0, oh0, n0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          pf_issue();   // chunk n + 2 into the buffer just read
+        }
+        ++n;
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (F8C && (warp == 2 || warp == 3)) {
     // =============================== h8 converters (MODE_F16F8C) ===============================
     // Per K block: the 128 x 64 fp16 tile (128-byte rows, 128B swizzle) -> its e5m2 rounding as a 128 x 64 byte tile (64-byte rows,
@@ -709,67 +758,36 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
     const int half = (warp - 4) >> 2;
     if constexpr (WIDE) {
       // =============== wide epilogue: 4 column groups x 4 warps (one per TMEM lane quarter) ===============
-      // The 1x1 convolutions with a shortcut (bottleneck conv3) are bound by this epilogue, not by the tensor pipe or HBM (ncu
-      // r02d: 10 instructions per output element, two warps per SM sub-partition, issue slots 37 % active).  Here every
-      // sub-partition runs four epilogue warps; group `half` (0..3) owns the 32-column chunks half, half + 4, ... of a tile and
-      // works in 16-column register blocks (<= 96 registers per thread at 640 threads).  Per group: one output staging box and
-      // ONE shortcut box; the shortcut box of the group's next chunk is requested as soon as every thread of the group has read
-      // the current one (barrier B below), the other three groups cover its latency.
-      const int grp = half;
+      // The 1x1 convolutions with a shortcut (bottleneck conv3) are bound by their epilogue, and the epilogue by its TMA traffic and
+      // the latency of the shortcut boxes (clock64 timelines, profiles/r02q and r02r): the unit is paced per box ROW (~2 cycles
+      // whatever the row width) and a thread that issues a bulk-tensor instruction stalls until the unit accepts it.  Here
+      //  * every sub-partition runs four epilogue warps working in 16-column register blocks (<= 96 registers at 640 threads);
+      //  * two neighbouring groups share 64-channel boxes (128-byte fp16 rows, 64-byte e5m2 rows: half the rows of 32-channel boxes):
+      //    group pair `pg` owns the 64-column chunks pg, pg + 2 of a tile, group 2 * pg + sub the 32-column half `sub` of each;
+      //  * the shortcut box IS the output staging box: a thread adds its row's 32 values in place (same layout, no other thread
+      //    touches them), so the pair's two buffers double-buffer the shortcut loads -- chunk n + 2 is requested as soon as the
+      //    store of chunk n has read its buffer;
+      //  * all bulk-tensor instructions of the pair are issued by an otherwise idle control warp (warp 2 + pg, below): the 256 math
+      //    threads never wait on the TMA unit, they meet the agent at one named barrier per chunk.
+      const int grp = half, pg = half >> 1, sub = half & 1;
       const int row = q * 32 + lane;
-      const int sw = (row >> 1) & 3;
-      const bool issuer = (q == 0 && lane == 0);
-      uint8_t* stg = epi_stage + grp * WIDE_BOX_BYTES;
-      const uint32_t stg_u32 = smem_base + STAGES * STAGE_BYTES + grp * WIDE_BOX_BYTES;
-      const uint8_t* rs = epi_stage + (4 + grp) * WIDE_BOX_BYTES;
-      const uint32_t rs_u32 = smem_base + STAGES * STAGE_BYTES + (4 + grp) * WIDE_BOX_BYTES;
-      const uint32_t rbar = res_full_bar(grp >> 1, grp & 1);
-      const uint32_t res_bytes = (uint32_t)P.rows * 96u;
+      const int sw7 = row & 7, sw3 = (row >> 1) & 3;   // 128B swizzle of the fp16 rows, 64B swizzle of the e5m2 rows
+      constexpr int LO_OFF = 16384;                      // [hi: rows x 128 B][lo8: rows x 64 B]
       float* bias_g = bias_smem + grp * 64;
       const uint32_t lead_tempty0 = mapa_shared(tempty_bar(0), 0);
       const float as = P.acc_scale;
-      // prefetch cursor (issuer thread only): the next (tile, chunk) of this group's sequence whose shortcut box is not requested yet
-      int pf_tile = tile0, pf_c0 = grp * 32;
-      auto pf_issue = [&]() {
-        while (pf_tile < P.total_tiles) {
-          const TileCoord t = decode_tile<BN, PAIR>(P, pf_tile, cta_rank);
-          if (pf_c0 < t.ncols && t.co0 + pf_c0 < P.Cout) {
-            mbar_expect_tx(rbar, res_bytes);
-            tma_load_4d(rs_u32, &maps.r[0], rbar, t.co0 + pf_c0, t.tw_i * P.TW, t.th_i * P.TH, t.tn_i * P.TN);
-            tma_load_4d(rs_u32 + 8192, &maps.r[1], rbar, t.co0 + pf_c0, t.tw_i * P.TW, t.th_i * P.TH, t.tn_i * P.TN);
-            pf_c0 += 128;
-            return;
-          }
-          pf_tile += tile_step;   // no (further) chunk of this group in that tile
-          pf_c0 = grp * 32;
-        }
-      };
       TRACE_INIT(2 + grp);
-      if (!issuer) {
 #ifdef MPN_CONV_TRACE
-        tr_.cap = 0;
+      if (!(q == 0 && lane == 0)) tr_.cap = 0;
 #endif
-      }
-      if (issuer) pf_issue();
-      uint32_t res_n = 0;
-      bool store_pending = false;
+      uint32_t res_n = 0;   // chunks of this pair consumed so far: buffer = res_n & 1, mbarrier parity = (res_n >> 1) & 1
       int it = 0;
       for (int tile = tile0; tile < P.total_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         const TileCoord tc = decode_tile<BN, PAIR>(P, tile, cta_rank);
         const int co0 = tc.co0, ncols = tc.ncols;
-        const int ow0 = tc.tw_i * P.TW, oh0 = tc.th_i * P.TH, n0 = tc.tn_i * P.TN;
-        if (issuer && P.res_pf && tile + tile_step < P.total_tiles) {
-          // The group holds ONE shortcut box, requested when the previous one has been read: every chunk pays a full TMA load
-          // latency.  Asking L2 for the next tile's boxes a whole tile ahead turns that latency from an HBM miss into an L2 hit.
-          const TileCoord t2 = decode_tile<BN, PAIR>(P, tile + tile_step, cta_rank);
-          for (int c2 = grp * 32; c2 < t2.ncols && t2.co0 + c2 < P.Cout; c2 += 128) {
-            tma_prefetch_l2_4d(&maps.r[0], t2.co0 + c2, t2.tw_i * P.TW, t2.th_i * P.TH, t2.tn_i * P.TN);
-            tma_prefetch_l2_4d(&maps.r[1], t2.co0 + c2, t2.tw_i * P.TW, t2.th_i * P.TH, t2.tn_i * P.TN);
-          }
-        }
-        if (P.bias) {   // the group's (up to) two chunks x 32 bias values of this tile
+        if (P.bias) {   // the group's (up to) two half-chunks x 32 bias values of this tile
           const int tq = q * 32 + lane;
           if (tq < 64) {
             const int col = grp * 32 + 128 * (tq >> 5) + (tq & 31);
@@ -782,24 +800,25 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
         TRACE(5, tile, 0);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = grp * 32; c0 < ncols; c0 += 128) {
-          const int cbase = co0 + c0;
-          if (cbase >= P.Cout) break;  // uniform over the group
-          mbar_wait(rbar, res_n & 1u);
+        for (int c0 = pg * 64; c0 < ncols; c0 += 128) {
+          if (co0 + c0 >= P.Cout) break;  // uniform over the pair
+          const int b = (int)(res_n & 1u);
+          uint8_t* buf = epi_stage + (pg * 2 + b) * WIDE_BOX_BYTES;
+          mbar_wait(res_full_bar(pg, b), (res_n >> 1) & 1u);
           TRACE(6, tile, c0);
           ++res_n;
-          uint32_t ohi[16], olo[8];   // the chunk's 32 outputs of this row: fp16 pairs, e5m2 residual bytes
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
+          for (int s2 = 0; s2 < 2; ++s2) {
             uint32_t raw[16];
-            TMEM_LD_32x32b_X16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0 + 16 * sub), raw);
-            const uint4 rh0 = *reinterpret_cast<const uint4*>(rs + row * 64 + (((2 * sub) ^ sw) << 4));
-            const uint4 rh1 = *reinterpret_cast<const uint4*>(rs + row * 64 + (((2 * sub + 1) ^ sw) << 4));
-            const uint4 rl = *reinterpret_cast<const uint4*>(rs + 8192 + row * 32 + (sub << 4));
+            TMEM_LD_32x32b_X16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0 + sub * 32 + 16 * s2), raw);
+            uint4* ph0 = reinterpret_cast<uint4*>(buf + row * 128 + (((sub * 4 + 2 * s2) ^ sw7) << 4));
+            uint4* ph1 = reinterpret_cast<uint4*>(buf + row * 128 + (((sub * 4 + 2 * s2 + 1) ^ sw7) << 4));
+            uint4* pl = reinterpret_cast<uint4*>(buf + LO_OFF + row * 64 + (((sub * 2 + s2) ^ sw3) << 4));
+            const uint4 rh0 = *ph0, rh1 = *ph1, rl = *pl;
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             float v[16];
             if (P.bias) {
-              const float4* b4 = reinterpret_cast<const float4*>(bias_g + (c0 >> 7) * 32 + 16 * sub);
+              const float4* b4 = reinterpret_cast<const float4*>(bias_g + (c0 >> 7) * 32 + 16 * s2);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 t = b4[j];
@@ -821,46 +840,24 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
             }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              uint4 h4;
-              uint2 l8, h8;
-              split_f16f8x8(v + 8 * i, h4, l8, h8, false);
-              const int o = 8 * sub + 4 * i;
-              ohi[o] = h4.x; ohi[o + 1] = h4.y; ohi[o + 2] = h4.z; ohi[o + 3] = h4.w;
-              olo[4 * sub + 2 * i] = l8.x; olo[4 * sub + 2 * i + 1] = l8.y;
-            }
+            uint4 h0, h1;
+            uint2 l0, l1, unused;
+            split_f16f8x8(v, h0, l0, unused, false);
+            split_f16f8x8(v + 8, h1, l1, unused, false);
+            *ph0 = h0;   // in place: this thread's own 16 values of the shortcut box become the output
+            *ph1 = h1;
+            *pl = make_uint4(l0.x, l0.y, l1.x, l1.y);
           }
-          // A: the previous store of this group has finished READING the staging box
           TRACE(7, tile, c0);
-          if (store_pending && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          TRACE(8, tile, c0);
-          named_bar_sync(1 + grp, 128);
-          TRACE(9, tile, c0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(stg + row * 64 + ((i ^ sw) << 4)) = make_uint4(ohi[4 * i], ohi[4 * i + 1], ohi[4 * i + 2], ohi[4 * i + 3]);
-          *reinterpret_cast<uint4*>(stg + 8192 + row * 32) = make_uint4(olo[0], olo[1], olo[2], olo[3]);
-          *reinterpret_cast<uint4*>(stg + 8192 + row * 32 + 16) = make_uint4(olo[4], olo[5], olo[6], olo[7]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          // B: staging box complete; every thread of the group is also done reading the shortcut box (its generic-proxy reads
-          // are ordered before the async-proxy refill by the fence above)
-          named_bar_sync(1 + grp, 128);
+          named_bar_sync(5 + pg, 288);   // buffer complete: the pair's agent warp stores it and refills it with chunk n + 2
           TRACE(10, tile, c0);
-          if (issuer) {
-            pf_issue();
-            tma_store_4d(&maps.y[0][0], stg_u32, cbase, ow0, oh0, n0);
-            tma_store_4d(&maps.y[1][0], stg_u32 + 8192, cbase, ow0, oh0, n0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          store_pending = true;
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(lead_tempty0 + 8u * acc);  // the leader's MMA issuer waits for both CTAs' epilogues
         TRACE(11, tile, 0);
       }
-      if (store_pending && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
     const bool want_h8 = !(P.flags & MPN_EPI_NO_H8);  // F16F8 outputs: the e5m2 copy plane is only stored for tensors a 3x3 conv reads
     const int rep = P.out_rep, OHr = P.OH * rep, OWr = P.OW * rep;
@@ -1413,7 +1410,7 @@ void choose_tile(int N, int OH, int OW, int* TW, int* TH, int* TN, bool even = f
 template <int BN, int MODE, int EPI, bool PAIR = false, int NG = 2>
 int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
   constexpr int STAGE_BYTES = a_stage_bytes(MODE) + (PAIR ? BN / 2 : BN) * b_row_bytes(MODE);
-  constexpr int EPI_BYTES = NG == 4 ? 8 * WIDE_BOX_BYTES : NUM_EPI_WARPS * EPI_STAGE_BYTES + (EPI == EPI_TMA_RES ? 4 * RES_STAGE_BYTES : 0);
+  constexpr int EPI_BYTES = NG == 4 ? 4 * WIDE_BOX_BYTES : NUM_EPI_WARPS * EPI_STAGE_BYTES + (EPI == EPI_TMA_RES ? 4 * RES_STAGE_BYTES : 0);
   constexpr int MAXS = (SMEM_LIMIT - 1024 - BAR_BYTES - BIAS_BYTES - EPI_BYTES) / STAGE_BYTES;
   constexpr int STAGES = MAXS > 8 ? 8 : (MAXS < 2 ? 2 : MAXS);
   if constexpr (MAXS < 2) {   // MODE_F16F8B, 256-wide single-CTA tiles: the host plan never selects them (BN is capped at 128)
@@ -1621,6 +1618,14 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
   }
   P.res_mma = res_mma ? 1 : 0;
   P.up_tma = up_tma ? 1 : 0;
+  // wide epilogue (MPN_EPI_WIDE=0 disables): F16F8 shortcut convolutions whose output is stored without the e5m2 copy plane; its
+  // output and shortcut boxes are 64 channels wide (half the TMA rows of the 32-channel boxes of the other epilogues)
+  static const int wide_on = getenv("MPN_EPI_WIDE") ? atoi(getenv("MPN_EPI_WIDE")) : 1;
+  static const int wide_maxk = getenv("MPN_EPI_WIDE_MAXK") ? atoi(getenv("MPN_EPI_WIDE_MAXK")) : 256;
+  // ... and whose reduction is short (r02i, 32-channel boxes: with eight K blocks per tile the MMA phase covers the epilogue and
+  // the single shortcut buffer cost more than the extra warps won)
+  const bool wide = wide_on && res_tma && !up_tma && f8 && !f8c && (d->flags & MPN_EPI_NO_H8) && !p->scale && nseg == 1 && P.tail_split <= 4 &&
+                    d->Cin * d->R * d->S <= wide_maxk;
   P.R = d->R; P.S = d->S; P.stride = d->stride; P.pad = d->pad; P.Cin = d->Cin; P.kb_per_tap = d->Cin / BLOCK_K;
   P.scale = p->scale; P.bias = p->bias;
   P.res_hi = (const __nv_bfloat16*)p->res_hi; P.res_lo = (const __nv_bfloat16*)p->res_lo; P.res_cstride = d->res_cstride;
@@ -1742,10 +1747,12 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
         const unsigned long long es = bytes ? 1ULL : 2ULL;
         cuuint64_t ydims[4] = {(cuuint64_t)e->Cout, (cuuint64_t)e->OW, (cuuint64_t)e->OH, (cuuint64_t)e->N};
         cuuint64_t ystr[3] = {(cuuint64_t)e->out_cstride * es, (cuuint64_t)e->OW * e->out_cstride * es, (cuuint64_t)nstride * es};
-        cuuint32_t ybox[4] = {32u, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TN};
+        cuuint32_t ybox[4] = {wide ? 64u : 32u, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TN};
         MPN_CHECK_ARG(ps[sg].y_hi && (pl == 0 || ps[sg].y_lo), "conv(tcgen05): missing output plane");
         const char* yb = (const char*)(pl == 0 ? ps[sg].y_hi : ps[sg].y_lo) + (f8 && pl == 2 ? ypl : 0) + (long long)e->out_coffset * (long long)es;
-        int rc = encode(fn, &maps.y[pl][sg], yb, 4, ydims, ystr, ybox, bytes ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B,
+        int rc = encode(fn, &maps.y[pl][sg], yb, 4, ydims, ystr, ybox,
+                        wide ? (bytes ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)
+                             : (bytes ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B),
                         bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
         if (rc) return rc;
       }
@@ -1776,10 +1783,11 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
       const unsigned long long es = bytes ? 1ULL : 2ULL;
       cuuint64_t rdims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)rw, (cuuint64_t)rh_, (cuuint64_t)d->N};
       cuuint64_t rstr[3] = {(cuuint64_t)rcs * es, (cuuint64_t)rw * rcs * es, (cuuint64_t)rh_ * rw * rcs * es};
-      cuuint32_t rbox[4] = {32u, (cuuint32_t)(up_tma ? P.TW / 2 : P.TW), (cuuint32_t)(up_tma ? P.TH / 2 : P.TH), (cuuint32_t)P.TN};
+      cuuint32_t rbox[4] = {wide ? 64u : 32u, (cuuint32_t)(up_tma ? P.TW / 2 : P.TW), (cuuint32_t)(up_tma ? P.TH / 2 : P.TH), (cuuint32_t)P.TN};
       const void* rbase = up_tma ? (pl == 0 ? p->up_hi : p->up_lo) : (pl == 0 ? p->res_hi : p->res_lo);
       int rc = encode(fn, &maps.r[pl], rbase, 4, rdims, rstr, rbox,
-                      bytes ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B,
+                      wide ? (bytes ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)
+                           : (bytes ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B),
                       bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
       if (rc) return rc;
     }
@@ -1804,16 +1812,8 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
     case 64: return launch<64, SPLIT_, EPI_>(maps, P, s, sms);             \
     default: return launch<32, SPLIT_, EPI_>(maps, P, s, sms);             \
   }
-  // wide epilogue (MPN_EPI_WIDE=0 disables): F16F8 shortcut convolutions whose output is stored without the e5m2 copy plane
-  static const int wide_on = getenv("MPN_EPI_WIDE") ? atoi(getenv("MPN_EPI_WIDE")) : 1;
-  // and whose reduction is short (K <= 256: with eight K blocks per tile the MMA phase covers the epilogue and the single shortcut
-  // buffer of the wide variant costs more than the extra warps win -- 15x20 c512->2048: 64 vs 60 us, 30x40 c256->1024: 80 vs 81 us,
-  // 120x160 c64->256: 234 vs 241 us, profiles/r02i)
-  const bool wide = wide_on && res_tma && !up_tma && f8 && (d->flags & MPN_EPI_NO_H8) && !p->scale && nseg == 1 && P.tail_split <= 4 &&
-                    d->Cin * d->R * d->S <= 256;
   if (wide) {
     if (f8b) return BN == 256 ? launch<256, MODE_F16F8B, EPI_TMA_RES, true, 4>(maps, P, s, sms) : launch<128, MODE_F16F8B, EPI_TMA_RES, true, 4>(maps, P, s, sms);
-    if (f8c) return BN == 256 ? launch<256, MODE_F16F8C, EPI_TMA_RES, true, 4>(maps, P, s, sms) : launch<128, MODE_F16F8C, EPI_TMA_RES, true, 4>(maps, P, s, sms);
     return BN == 256 ? launch<256, MODE_F16F8, EPI_TMA_RES, true, 4>(maps, P, s, sms) : launch<128, MODE_F16F8, EPI_TMA_RES, true, 4>(maps, P, s, sms);
   }
 #define MPN_TC_DISPATCH_RES(SPLIT_)                                                  \
