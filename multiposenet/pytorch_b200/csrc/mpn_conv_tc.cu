@@ -865,6 +865,10 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
                               : (P.out_mode == MPN_OUT_F32_NCHW ? (long long)P.Cout * OHr * OWr : (long long)OHr * OWr * P.out_cstride);
     int it = 0;
     bool store_pending = false;  // EPI_TMA: a bulk store of this half may still be reading its staging box
+    TRACE_INIT(2 + half);
+#ifdef MPN_CONV_TRACE
+    if (!(q == 0 && lane == 0)) tr_.cap = 0;
+#endif
     const uint32_t lead_tempty0 = PAIR ? mapa_shared(tempty_bar(0), 0) : 0u;
     // RESLD: the shortcut box of 32-channel chunk n + 1 of this half (next chunk of the tile, or the first one of the CTA's next
     // tile) is requested by TMA when chunk n starts, into the buffer chunk n - 1 was read from (every thread of the half has
@@ -967,7 +971,9 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
             bias_h[tq] = (col < ncols && co0 + col < P.Cout) ? __ldg(P.bias + co0 + col) : 0.f;
             named_bar_sync(1 + half, 128);
         }
+        TRACE(4, tile, 0);
         mbar_wait(tfull_bar(acc), acc_phase);
+        TRACE(5, tile, 0);
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = half * 32; c0 < ncols; c0 += 64) {
@@ -1108,10 +1114,13 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
           }
           }
           // the previous store of this half must have finished READING the staging box before it is overwritten
+          TRACE(7, tile, c0);
           if (store_pending) {
             if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            TRACE(8, tile, c0);
             named_bar_sync(1 + half, 128);
           }
+          TRACE(9, tile, c0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             *reinterpret_cast<uint4*>(stg + row * 64 + ((i ^ sw) << 4)) = hi4[i];
@@ -1127,6 +1136,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           named_bar_sync(1 + half, 128);
+          TRACE(10, tile, c0);
           if (issuer) {
             tma_store_4d(&maps.y[0][tc.seg], stg_u32, cbase, ow0, oh0, n0);
             if (SPLIT) tma_store_4d(&maps.y[1][tc.seg], stg_u32 + 8192, cbase, ow0, oh0, n0);
@@ -1136,6 +1146,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          TRACE(17, tile, c0);
           store_pending = true;
         }
       } else if constexpr (EPI == EPI_LSU) {

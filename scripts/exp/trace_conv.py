@@ -22,10 +22,10 @@ from multiposenet.pytorch_b200 import _lib, ops
 # (H, W, Cin, Cout, k, shortcut)
 SHAPES = {"l3": (30, 40, 256, 1024, 1, True), "l2": (60, 80, 128, 512, 1, True), "l1": (120, 160, 64, 256, 1, True),
           "l4": (15, 20, 512, 2048, 1, True), "h60": (60, 80, 256, 256, 3, False), "kp": (120, 160, 512, 256, 3, False),
-          "l3c1": (30, 40, 1024, 256, 1, False)}
+          "l3c1": (30, 40, 1024, 256, 1, False), "l3c2": (30, 40, 256, 256, 3, False)}
 EV = {1: "P.issue", 2: "M.acc_free", 3: "M.stage_full", 4: "E.tile_start", 5: "E.acc_full", 6: "E.res_arrived", 7: "E.math_done",
       8: "E.store_read", 9: "E.barA", 10: "E.barB", 11: "E.tile_done", 12: "C.wait", 13: "C.a_landed", 14: "C.converted", 15: "C.arrived",
-      16: "M.b_full"}
+      16: "M.b_full", 17: "E.store_issued"}
 CTAS, ROLES = 4, 8
 
 
@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--cap", type=int, default=4096)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--dump", default=None, help="write every event of CTA 0 (role, cycle, event, tile, arg) to this file")
+    ap.add_argument("--out-h8", action="store_true", help="the output keeps its e5m2 copy plane (three store boxes per chunk)")
     ap.add_argument("--stored", action="store_true", help="MODE_F16F8: the input keeps its e5m2 copy plane and TMA loads it")
     ap.add_argument("--lo16", action="store_true", help="MODE_F16F8B (filter packed with the fp16 residual plane) instead of the derived copy plane")
     a = ap.parse_args()
@@ -60,7 +62,7 @@ def main():
     derive = False if a.stored else None
     ra = strip(ops.act_from_nchw(torch.randn(a.batch, Cout, H, W, device=dev, generator=g), fmt)) if res else None
     pc = ops.pack_conv(w, None, bn, fmt, in_no_h8=a.lo16)
-    out = ops.Act(fmt, a.batch, H, W, Cout, dev, has_h8=False)
+    out = ops.Act(fmt, a.batch, H, W, Cout, dev, has_h8=a.out_h8)
     buf = torch.zeros(CTAS * ROLES * a.cap * 2, dtype=torch.int64, device=dev)
     L.mpn_debug_conv_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
     for _ in range(3):
@@ -101,6 +103,18 @@ def main():
                 sel = [i for i in range(n) if tile[i] in (tiles[3:6] if len(tiles) > 6 else tiles[1:2])][:60]
                 base = clk[sel[0]] if sel else 0
                 lines.append("    raw: " + " ".join("%s@%d(t%d,%d)" % (EV[int(ev[i])].split(".")[1], clk[i] - base, tile[i], arg[i]) for i in sel))
+    if a.dump:
+        ev_all = []
+        for role in range(ROLES):
+            r = t[0, role]
+            n = int((r[:, 0] != 0).sum())
+            for i in range(n):
+                ev_all.append((int(r[i, 0]), role, int(r[i, 1] & 0xFF), int((r[i, 1] >> 8) & 0xFFFFFF), int(r[i, 1] >> 32)))
+        ev_all.sort()
+        t0 = ev_all[0][0] if ev_all else 0
+        with open(a.dump, "w") as f:
+            for c, role, e, tl, ar in ev_all:
+                f.write("%8d role %d %-16s tile %d arg %d\n" % (c - t0, role, EV[e], tl, ar))
     txt = "\n".join(lines)
     print(txt)
     if a.out:
