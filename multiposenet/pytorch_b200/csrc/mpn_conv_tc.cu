@@ -310,9 +310,6 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
   // the filter bytes there)
   auto afull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 9 + s); };
   auto conv_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + 9 + s); };
-  // aland (on the leader) = the activation planes of the stage have landed in every CTA of the pair: the MMA issuer runs the six
-  // MMAs that do not read the derived tile behind it and only the last two behind `conv`
-  auto aland_bar = [&](int s) { return bar_base + 8u * (4 * STAGES + 9 + s); };
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + EPI_BYTES + 8 * (2 * STAGES + 4));
@@ -352,7 +349,6 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(afull_bar(s), 1);
         mbar_init(conv_bar(s), PAIR ? 4 : 2);   // one arrival per converter warp of each CTA
-        mbar_init(aland_bar(s), PAIR ? 2 : 1);  // one arrival per CTA (converter warp 2, after its afull wait)
       }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -565,7 +561,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
       for (int ki = 0; ki < num_k_iters;) {
         mbar_wait(full_bar(stage), phase);
         TRACE(16, tile, ki);
-        if constexpr (F8C) mbar_wait(aland_bar(stage), phase);
+        if constexpr (F8C) mbar_wait(conv_bar(stage), phase);
         TRACE(3, tile, ki);
         tc_fence_after();
         const int group = min(kpack, num_k_iters - ki);
@@ -594,22 +590,11 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
                 mma8(make_sdesc64(sa + A_TILE_BYTES + k * 32), make_sdesc64(sb + 2 * bplane + k * 32));
             } else {
 #pragma unroll
-              // fp8 cross terms, K = 32 per instruction.  Merged filter planes: one 128B-swizzled tile of 128-byte rows, lo8 in bytes
-              // 0..63 and h8 in bytes 64..127
-#pragma unroll
-              for (int k = 0; k < BLOCK_K / 32; ++k) {
+              for (int k = 0; k < BLOCK_K / 32; ++k) {  // fp8 cross terms, K = 32 per instruction
+                // merged filter planes: one 128B-swizzled tile of 128-byte rows, lo8 in bytes 0..63 and h8 in bytes 64..127
                 const uint64_t b_h8 = P.w_merged ? make_sdesc(sb + bplane + 64 + k * 32) : make_sdesc64(sb + bplane + bplane / 2 + k * 32);
-                mma8(make_sdesc64(sa + A_TILE_BYTES + k * 32), b_h8);                          // xlo8 * wh8
-              }
-              if constexpr (F8C) {   // the derived e5m2 tile is only needed from here on: the converters had six MMAs of time
-                if (u == 0) {
-                  mbar_wait(conv_bar(stage), phase);
-                  tc_fence_after();
-                }
-              }
-#pragma unroll
-              for (int k = 0; k < BLOCK_K / 32; ++k) {
                 const uint64_t b_lo8 = P.w_merged ? make_sdesc(sb + bplane + k * 32) : make_sdesc64(sb + bplane + k * 32);
+                mma8(make_sdesc64(sa + A_TILE_BYTES + k * 32), b_h8);                          // xlo8 * wh8
                 mma8(make_sdesc64(sa + A_TILE_BYTES + A_TILE_BYTES / 2 + k * 32), b_lo8);      // xh8 * wlo8
               }
             }
@@ -713,7 +698,6 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t conv0 = PAIR ? mapa_shared(conv_bar(0), 0) : conv_bar(0);
-    const uint32_t aland0 = PAIR ? mapa_shared(aland_bar(0), 0) : aland_bar(0);
     TRACE_INIT(6 + (warp - 2));
 #ifdef MPN_CONV_TRACE
     if (lane != 0) tr_.cap = 0;
@@ -729,10 +713,6 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
         const int group = min(kpack, num_k_iters - ki);
         TRACE(12, tile, ki);
         mbar_wait(afull_bar(stage), phase);
-        if (warp == 2 && lane == 0) {   // this CTA's activation planes are in shared memory
-          if (PAIR) mbar_arrive_cluster(aland0 + 8u * stage);
-          else mbar_arrive(aland_bar(stage));
-        }
         TRACE(13, tile, ki);
         for (int u = 0; u < group; ++u) {
           uint8_t* a_hi = smem_gen + stage * STAGE_BYTES + u * sub_bytes;
@@ -1448,7 +1428,7 @@ int launch(const Maps& maps, const TcParams& P, cudaStream_t st, int sms) {
     mpn_set_error("conv(tcgen05): tile configuration does not fit shared memory (BN %d, mode %d)", BN, MODE);
     return MPN_ERR_UNSUPPORTED;
   } else {
-  static_assert(8 * ((MODE == MODE_F16F8C ? 5 : 2) * STAGES + 9) <= BAR_BYTES, "barrier area too small");
+  static_assert(8 * ((MODE == MODE_F16F8C ? 4 : 2) * STAGES + 9) <= BAR_BYTES, "barrier area too small");
   const int smem = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BIAS_BYTES + EPI_BYTES;
   static_assert(STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BIAS_BYTES + EPI_BYTES <= SMEM_LIMIT, "shared memory budget");
   auto kern = conv_tc_kernel<BN, MODE, STAGES, EPI, PAIR, NG>;
