@@ -126,6 +126,7 @@ struct TcParams {
   int dbg_skip;   // timing experiment (results are garbage): bit 0 skips the B h8 plane load, bit 1 the A h8 plane load
 #endif
   int w_merged; // F16F8 / F16F8C: filter byte planes interleaved per K block (MPN_W_MERGED): one 128B-swizzled tile [lo8 | h8]
+  int epi_agent;  // EPI_TMA: the stores are issued by the agent warps (MPN_EPI_AGENT=0: by a thread of each epilogue half)
   int res_pf;   // EPI_TMA_RES: L2 prefetch of the next tile's shortcut boxes (MPN_RES_PF=0 disables)
   int gat_n, gat_shift[2], gat_h[2], gat_w[2], gat_cstride[2];
   const void* gat_hi[2];
@@ -289,6 +290,9 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
   constexpr int MMA_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
   constexpr bool TMAEPI = EPI == EPI_TMA || EPI == EPI_TMA_RES;
   constexpr bool RESLD = EPI == EPI_TMA_RES;
+  // TMA-store epilogue without a shortcut: the bulk-tensor stores of epilogue half h are issued by control warp 2 + h (a thread
+  // that issues one stalls until the TMA unit accepts it -- ~500 cycles per chunk on the math threads' critical path otherwise)
+  constexpr bool AGENT = EPI == EPI_TMA && MODE != MODE_F16F8C;
   constexpr int EPI_BYTES = WIDE ? 4 * WIDE_BOX_BYTES : NUM_EPI_WARPS * EPI_STAGE_BYTES + (RESLD ? 4 * RES_STAGE_BYTES : 0);
   static_assert(!WIDE || (RESLD && PAIR && F8 && !F8C), "the wide epilogue is the F16F8 shortcut epilogue (its agents are the F8C converter warps)");
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -643,6 +647,37 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
         }
       }
     }
+  } else if (AGENT && P.epi_agent && (warp == 2 || warp == 3)) {
+    // =============================== TMA-store agents (EPI_TMA) ===============================
+    // Warp 2 + h walks the (tile, chunk) sequence of epilogue half h: barrier 3 + h = "the staging box of the half is free" (this
+    // warp arrives once its previous store has read it), barrier 5 + h = "the box is complete", then lane 0 stores the planes.
+    const int half = warp - 2;
+    const uint32_t stg_u32 = smem_base + STAGES * STAGE_BYTES + half * (4 * EPI_STAGE_BYTES);
+    const bool want_h8 = !(P.flags & MPN_EPI_NO_H8);
+    bool pending = false;
+    for (int tile = tile0; tile < P.total_tiles; tile += tile_step) {
+      const TileCoord tc = decode_tile<BN, PAIR>(P, tile, cta_rank);
+      const Seg& g = P.seg[tc.seg];
+      const int ow0 = tc.tw_i * g.TW, oh0 = tc.th_i * g.TH, n0 = tc.tn_i * g.TN;
+      for (int c0 = half * 32; c0 < tc.ncols; c0 += 64) {
+        const int cbase = tc.co0 + c0;
+        if (cbase >= P.Cout) break;
+        named_bar_sync(3 + half, 160);
+        named_bar_sync(5 + half, 160);
+        if (lane == 0) {
+          tma_store_4d(&maps.y[0][tc.seg], stg_u32, cbase, ow0, oh0, n0);
+          if (SPLIT) tma_store_4d(&maps.y[1][tc.seg], stg_u32 + 8192, cbase, ow0, oh0, n0);
+          if (F8) {
+            tma_store_4d(&maps.y[1][tc.seg], stg_u32 + 8192, cbase, ow0, oh0, n0);
+            if (want_h8) tma_store_4d(&maps.y[2][tc.seg], stg_u32 + 12288, cbase, ow0, oh0, n0);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          pending = true;
+        }
+      }
+    }
+    if (lane == 0 && pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (WIDE && (warp == 2 || warp == 3)) {
     // =============================== wide epilogue: TMA agents ===============================
     // Warp 2 + pg issues every bulk-tensor instruction of group pair pg (see the wide epilogue below): the shortcut box of chunk
@@ -1115,7 +1150,9 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
           }
           // the previous store of this half must have finished READING the staging box before it is overwritten
           TRACE(7, tile, c0);
-          if (store_pending) {
+          if (AGENT && P.epi_agent) {
+            named_bar_sync(3 + half, 160);   // the agent warp joins once its previous store has read the box
+          } else if (store_pending) {
             if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             TRACE(8, tile, c0);
             named_bar_sync(1 + half, 128);
@@ -1135,6 +1172,11 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) conv_tc_kernel(const __grid
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (AGENT && P.epi_agent) {
+            named_bar_sync(5 + half, 160);   // box complete: the agent stores it
+            TRACE(10, tile, c0);
+            continue;
+          }
           named_bar_sync(1 + half, 128);
           TRACE(10, tile, c0);
           if (issuer) {
@@ -1651,6 +1693,8 @@ static int tc_launch(const mpn_conv_desc* ds, const mpn_conv_ptrs* ps, int nseg,
 #endif
   P.w_merged = (f8 && !f8b && (d->flags & MPN_W_MERGED)) ? 1 : 0;
   MPN_CHECK_ARG(!(f8b && (d->flags & MPN_W_MERGED)), "conv(tcgen05): MPN_W_MERGED filters cannot serve MPN_IN_NO_H8 (fp16 residual plane)");
+  static const int epi_agent_on = getenv("MPN_EPI_AGENT") ? atoi(getenv("MPN_EPI_AGENT")) : 1;
+  P.epi_agent = epi_agent_on;
   static const int res_pf_on = getenv("MPN_RES_PF") ? atoi(getenv("MPN_RES_PF")) : 0;
   P.res_pf = res_pf_on;
   P.gat_n = d->gat_n;
