@@ -8,9 +8,9 @@ libmpn_b200 launches on NHWC activations:
   backbone : per Bottleneck 3 launches (4 with a projection shortcut); BN folded to scale/bias,
              residual add + ReLU fused in conv3's epilogue
   necks    : lateral 1x1 with the nearest-upsample-add fused in its epilogue, then 3x3 smooth
-  kp head  : convt/convs per level; convs writes straight into its channel slice of the 512-channel
-             concat buffer with the x8/x4/x2 nearest replication fused in the store; conv2+ReLU; convfin
-             writes fp32 NCHW directly
+  kp head  : convt/convs per level; the x8 / x4 quarters of conv2 are evaluated at low resolution as phase-class
+             convolutions and gathered in conv2's epilogue, the x2 and native quarters go through a 256-channel
+             concat buffer (replication fused in the store); conv2+ReLU; convfin writes fp32 NCHW directly
   det head : shared tower on 5 levels; outputs land in the concatenated [B, A, 1|4] tensors
   post     : decode+clip, filter, radix sort, bit-mask NMS, gather -- all on the device
 
