@@ -213,3 +213,22 @@ def test_uint8_input_with_fused_resnet_preprocess(golden_dir):
         _, (cls_u8, _, anc) = m([torch.from_numpy(u8).cuda(), "detection_subnet"])
     assert torch.equal(h_ref, h_u8) and torch.equal(cls_ref, cls_u8)   # same bits in, same bits out
     assert anc.shape[1] == ops.anchors_for(64, 96, anc.device).shape[1]
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
+def test_keypoint_head_with_and_without_the_replicated_concat(precision, monkeypatch):
+    """engine.CONV2_GATHER: the x8 / x4 quarters of conv2 as low-resolution phase-class convolutions gathered in its epilogue
+    (default) against the replicated 512-channel concat of round 1 (MPN_CONV2_GATHER=0): same heat maps to the rounding of the
+    regrouped sums."""
+    from gpu_util import image, load_model, nerr
+    from multiposenet.pytorch_b200 import engine as eng_mod
+    m, _ = load_model(50, "conditioned", precision)
+    x = image(5, (2, 3, 128, 192))
+    eng = m.engine()
+    monkeypatch.setattr(eng_mod, "CONV2_GATHER", True)
+    h1 = eng.keypoint_forward(x)[0].clone()
+    monkeypatch.setattr(eng_mod, "CONV2_GATHER", False)
+    h0 = eng.keypoint_forward(x)[0].clone()
+    torch.cuda.synchronize()
+    assert h1.shape == h0.shape and torch.isfinite(h1).all()
+    assert nerr(h1, h0) <= 2e-4
