@@ -9,16 +9,24 @@
 // four "phase" views of the input (tensor maps with doubled pixel strides and an offset base), so no
 // im2col buffer ever exists in HBM.  The filter is a plain 2-D [Cout, R*S*Cin] K-major tensor.
 //
-// Warp roles (384 threads, 1 CTA/SM, persistent over tiles):
+// Warp roles (384 threads, or 640 with the wide epilogue; 1 CTA/SM or one CTA pair per TPC, persistent over tiles):
 //   warp 0 lane 0 : TMA producer           (mbarrier full/empty ring of STAGES stages)
-//   warp 1 lane 0 : tcgen05.mma issuer     (accumulators double-buffered in TMEM, 2 x BN columns)
+//   warp 1 lane 0 : tcgen05.mma issuer     (accumulators double-buffered in TMEM, 2 x BN columns; pair kernels: the leader CTA)
 //   warp 2        : TMEM allocate / free
-//   warps 4..11   : epilogue (two warps per TMEM lane quarter), three variants (template EPI):
+//   warps 2, 3    : after that, "agents": they issue the epilogue's bulk-tensor instructions (EPI_TMA: the stores of epilogue
+//                   half 0 / 1; wide epilogue: shortcut loads and stores of group pair 0 / 1) -- a thread that issues one stalls
+//                   until the TMA unit accepts it, which the math threads must not pay; MODE_F16F8C: the e5m2 converters
+//   warps 4..11   : epilogue (two warps per TMEM lane quarter; wide: warps 4..19, four per quarter), variants (template EPI):
 //                   EPI_TMA  tcgen05.ld (thread = pixel row) -> BN-fold scale/bias, residual, ReLU/sigmoid -> bf16 hi/lo
-//                            -> 64B-swizzled smem box -> cp.async.bulk.tensor store (no per-row address math, no LSU stores)
+//                            -> 64B-swizzled smem box -> cp.async.bulk.tensor store (no per-row address math, no LSU stores);
+//                            optional phase-class addends gathered per pixel (keypoint head conv2)
+//                   EPI_TMA_RES  the same with the shortcut (or the 2x-upsample source) brought in by TMA boxes; NG = 4: the
+//                            wide variant (64-channel boxes, shortcut added in place)
 //                   EPI_LSU  same math through a swizzled smem transpose and 64-byte row segments per 4 lanes; handles the
-//                            nearest-upsample add and x2/x4/x8 replicated outputs (FPN laterals, keypoint concat)
+//                            ragged nearest-upsample add and x2/x4/x8 replicated outputs (FPN laterals, keypoint concat)
 //                   EPI_F32  fp32 NHWC / NCHW heads (Cout <= 64), thread-per-row stores
+// The TMA unit is paced per box ROW (~2.25 cycles for any row <= 128 bytes, scripts/exp/tma_row_rate_probe.cu): operand and
+// epilogue boxes are laid out for 128-byte rows wherever the formats allow (merged filter byte planes, 64-channel wide boxes).
 // Precision modes: MPN_FMT_BF16   one bf16 plane per operand, one MMA per K step;
 //                  MPN_FMT_BF16X2 hi/lo bf16 planes (x = hi + lo to ~2^-17), three MMAs per K step
 //                  (hi*hi + lo*hi + hi*lo) accumulated in fp32 -> fp32-grade parity with the reference.
@@ -26,6 +34,8 @@
 //                  prescaled by 2^k: fp16 hi, lo8 = e4m3(w' - hi), h8 = e4m3(w' * 2^-12).  Per 64-channel K block:
 //                  4 kind::f16 MMAs (hi*hi) + 2 + 2 kind::f8f6f4 MMAs of K = 32 (xlo8*wh8, xh8*wlo8) into the SAME fp32
 //                  accumulator = 8 MMA slots instead of 12, product error ~2^-15 (tests/tools/precision_study.py).
+//                  Operand variants: MODE_F16F8 (copy plane stored), MODE_F16F8B (input without it: fp16 weight residual, 10
+//                  slots), MODE_F16F8C (input without it: derived in shared memory by warps 2, 3; opt-in).
 #include <cuda.h>
 #include <stdlib.h>
 
