@@ -769,15 +769,21 @@ def main():
         alg = (flops_img - (stem_flops if on_cuda_cores else 0.0)) * B
         traffic, traffic_src = conv_traffic_record()
         achieved = alg / (conv_ms / 1e3) / 1e12
+        # FLOPs the launches actually issue (2*MAC of every launch as launched): fewer than the reference graph's where the
+        # algebra was changed (keypoint head conv2 without the replicated concat), more where operands are padded (stem K window)
+        executed = sum(f for _, f, _ in tc) / nprof / (conv_ms / 1e3) / 1e12
+        issued = sum(f * sl for _, f, sl in tc) / nprof / (conv_ms / 1e3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (%d launches/step)" % nconv, "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_src + " (sustained cuBLAS bf16)",
                 "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / (elapsed_ms / args.steps),
                 "mma_passes": passes,
-                "tensor_pipe_frac": passes * achieved / peak,
-                "note": "achieved = algorithmic conv FLOPs (2*MAC, fp32-equivalent) / conv kernel time; bf16x3 issues 3 MMAs per "
-                        "algorithmic MAC (hi*hi + lo*hi + hi*lo), so tensor_pipe_frac = 3*frac is the share of the tensor peak the "
-                        "issued MMAs occupy; f16f8 issues 1 fp16 MMA + 2 fp8 MMAs at twice the rate = 2 bf16-equivalent passes (2.5 for the 1x1 "
+                "executed_tflops": executed, "executed_frac": executed / peak,
+                "tensor_pipe_frac": issued / peak,
+                "note": "achieved = algorithmic conv FLOPs of the REFERENCE graph (2*MAC, fp32-equivalent) / conv kernel time; executed_* = the FLOPs "
+                        "of the launches as issued (the keypoint head's conv2 is evaluated without its replicated concat: fewer MACs than "
+                        "the reference graph), and tensor_pipe_frac = issued bf16-equivalent MMA passes of those launches / peak; bf16x3 issues 3 MMAs per "
+                        "MAC (hi*hi + lo*hi + hi*lo); f16f8 issues 1 fp16 MMA + 2 fp8 MMAs at twice the rate = 2 bf16-equivalent passes (2.5 for the 1x1 "
                         "convolutions that read a tensor stored without its e5m2 copy plane: 2 fp16 MMAs + 1 fp8 MMA); mma_passes is the "
                         "FLOP-weighted mean over the launches of a step"}
 
