@@ -535,6 +535,19 @@ class Engine(object):
         return True
 
     @torch.no_grad()
+    def _counts_to_host(self, det):
+        """Candidate and keep counts of the batch with ONE stream synchronisation (two async copies into a pinned buffer): the
+        GPU idles while the host reads them, every separate `.cpu()` / `.item()` is another round trip."""
+        B = det.cand_cnt.numel()
+        key = (B, str(det.cand_cnt.device))
+        pin = self.__dict__.setdefault("_cnt_pin", {}).get(key)
+        if pin is None:
+            pin = self._cnt_pin[key] = torch.empty((2, B), dtype=torch.int32).pin_memory()
+        pin[0].copy_(det.cand_cnt, non_blocking=True)
+        pin[1].copy_(det.keep_cnt, non_blocking=True)
+        torch.cuda.current_stream(det.cand_cnt.device).synchronize()
+        return pin[0].clone(), pin[1].clone()
+
     def entire_forward(self, img, max_cand=4096):
         """posenet.py:236-285: (heat, [nms_scores, nms_class, boxes]) for image 0, like the reference;
         the per-image results of the whole batch stay in self.last_detections."""
@@ -543,14 +556,14 @@ class Engine(object):
             heat = heat.clone()  # static graph output -> caller-owned
         else:
             heat, cls, reg, boxes, det = self.entire_forward_device(img, max_cand=max_cand)
-        cnt = det.cand_cnt.cpu()
+        cnt, kcnt = self._counts_to_host(det)
         if int(cnt.max()) > det.max_cand:  # rare: more survivors than the fast-path capacity -> redo with room
             det = ops.filter_sort_nms(cls, boxes, 0.05, 0.5, max_cand=int(cnt.max()))
-            cnt = det.cand_cnt.cpu()
+            cnt, kcnt = self._counts_to_host(det)
         self.last_detections = det
         if int(cnt[0]) == 0:  # posenet.py:273-275 (CPU tensors, as in the reference)
             return heat, [torch.zeros(0), torch.zeros(0), torch.zeros(0, 4)]
-        k = int(det.keep_cnt[0].item())
+        k = int(kcnt[0])
         scores = det.scores[0, :k].clone()
         classes = torch.zeros((k,), dtype=torch.int64, device=img.device)  # single class: argmax over 1 column
         return heat, [scores, classes, det.boxes[0, :k].clone()]
